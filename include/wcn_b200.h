@@ -1,0 +1,158 @@
+/* SPDX-License-Identifier: Apache-2.0
+ *
+ * wcn_b200 — C-ABI of the B200-native sparse-convolution hot path.
+ *
+ * This header is the drop-in boundary: every entry point replaces one pybind11 binding of the
+ * reference's `warpconvnet._C` extension (cited per function as file:line under the reference
+ * tree). Conventions shared by all functions:
+ *   - plain device pointers + sizes, no framework types; the CALLER owns and allocates every
+ *     buffer including outputs and scratch (same ownership rule as the reference, whose Python
+ *     side allocates all tensors: detail/mask_gemm.py:723,874,934);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); every call only
+ *     enqueues work on it and never synchronises;
+ *   - return value: 0 = success, negative = error (same "int status" convention as
+ *     csrc/include/gemm_error_codes.h:7-15): -1 invalid argument, -2 unsupported shape,
+ *     -3 misaligned pointer/stride, -4 unsupported dtype, -5 CUDA launch error,
+ *     -6 workspace too small;
+ *   - dtype codes: 0 = bf16, 1 = fp16, 2 = fp32 (computed as TF32 on the tensor cores);
+ *     accumulation is always fp32;
+ *   - device-side failures (hash table full, coordinate out of the packed-key range) are reported
+ *     through a caller-provided int status word, like the reference's status tensor
+ *     (csrc/include/cuhash/hash_table.cuh:59-62).
+ */
+#ifndef WCN_B200_H_
+#define WCN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WCN_OK 0
+#define WCN_ERR_INVALID_ARG (-1)
+#define WCN_ERR_UNSUPPORTED_SHAPE (-2)
+#define WCN_ERR_ALIGNMENT (-3)
+#define WCN_ERR_UNSUPPORTED_DTYPE (-4)
+#define WCN_ERR_CUDA (-5)
+#define WCN_ERR_WORKSPACE (-6)
+
+#define WCN_BF16 0
+#define WCN_F16 1
+#define WCN_F32 2
+
+/* library / build identification (reference: csrc/warpconvnet_pybind.cpp:21-32 `__build_commit__`) */
+const char* wcn_version(void);
+/* 1 when the library was compiled for sm_100a (always, this build has no other target). */
+int wcn_built_for_sm100a(void);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Packed-coordinate hash table  (replaces _C.cuhash.packed_prepare / packed_insert /        */
+/* packed_search: csrc/bindings/cuhash_bindings.cpp:241-330, csrc/cuhash_hash_table.cu:19-100) */
+/* keys: uint64[capacity], values: int32[capacity], capacity a power of two >= 2*n.           */
+/* Key layout 1|9b batch|18b x|18b y|18b z (csrc/include/cuhash/hash_functions.cuh:29-44).    */
+/* ------------------------------------------------------------------------------------------ */
+int wcn_hash_prepare(uint64_t* keys, int32_t* values, int capacity, void* stream);
+/* coords: int32[n][4] = (batch, x, y, z). value = insertion index (smallest index wins for
+ * duplicates). status (device int, caller-zeroed): bit0 = table full, bit1 = coordinate outside
+ * batch [0,511] / xyz [-131072,131071] (the reference checks the range on the host,
+ * geometry/coords/search/packed_hashmap.py:66-82). */
+int wcn_hash_insert(uint64_t* keys, int32_t* values, const int32_t* coords, int n, int capacity,
+                    int32_t* status, void* stream);
+/* results[i] = stored index of queries[i] or -1. */
+int wcn_hash_search(const uint64_t* keys, const int32_t* values, const int32_t* queries,
+                    int32_t* results, int n, int capacity, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Kernel map  (replaces _C.cuhash.packed_kernel_map_size / packed_kernel_map_offset /        */
+/* postprocess_count / postprocess_scatter: csrc/cuhash_kernel_map.cu:93-134,508-599; call    */
+/* sites geometry/coords/search/torch_discrete.py:154,254-287)                                */
+/* ------------------------------------------------------------------------------------------ */
+/* number of 256-query blocks the search/scatter passes use for M queries */
+int wcn_kernel_map_num_blocks(int M);
+/* pair_table[k*M + m] = index of the input voxel at out_coords[m]*stride + offsets3[k], or -1.
+ * offsets3: device int32[K][3] (x,y,z offset of kernel element k, reference order
+ * csrc/include/cuhash/kernel_map.cuh:34-54). block_counts: int32[K][num_blocks] (optional, may be
+ * NULL) receives per-block hit counts; mask_keys: uint64[M] (optional) receives the per-row offset
+ * bitmask (bit k, folded modulo 64 when K > 64). */
+int wcn_kernel_map_search(const uint64_t* keys, const int32_t* values, int capacity,
+                          const int32_t* out_coords, int M, const int32_t* offsets3, int K,
+                          int stride_x, int stride_y, int stride_z, int32_t* pair_table,
+                          int32_t* block_counts, uint64_t* mask_keys, void* stream);
+/* In-place exclusive scan of block_counts per offset; counts[K], offsets[K+1] (exclusive scan of
+ * counts, offsets[K] = total pairs L). */
+int wcn_kernel_map_count(int32_t* block_counts, int K, int num_blocks, int32_t* counts,
+                         int32_t* offsets, void* stream);
+/* CSR emission, ascending output row inside every offset: in_maps/out_maps int32[L]. */
+int wcn_kernel_map_scatter(const int32_t* pair_table, const int32_t* block_prefix,
+                           const int32_t* offsets, int32_t* in_maps, int32_t* out_maps, int K,
+                           int M, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Mask / tile preparation  (replaces _C.mask_gemm build_pair_mask / mask_argsort /           */
+/* build_reverse_mask_data: csrc/mask_data_kernels.cu:23-220, detail/mask_gemm.py:127-377)    */
+/* ------------------------------------------------------------------------------------------ */
+/* rev[k*n_in + i] = m for every pair_table[k*M + m] = i >= 0, -1 elsewhere. */
+int wcn_reverse_pair_table(const int32_t* pair_table, int K, int M, int32_t* rev, int n_in,
+                           void* stream);
+int wcn_mask_keys(const int32_t* table, int K, int M, uint64_t* keys, void* stream);
+size_t wcn_sort_workspace_bytes(int M);
+/* rows_out = stable argsort of keys (low min(K,64) bits). */
+int wcn_sort_rows_by_key(const uint64_t* keys, int M, int K, int32_t* rows_out, void* workspace,
+                         size_t workspace_bytes, void* stream);
+/* Tile tables in mask-sorted order, m_pad = ceil(M/128)*128:
+ *   nbr[k*m_pad + p]   = table[k*M + sorted_rows[p]]  (-1 for padding)
+ *   rows_padded[p]     = sorted_rows[p]               (-1 for padding)
+ *   tile_ks[t*k_stride + i], tile_nk[t] = offsets active in tile t (rows 128t..128t+127). */
+int wcn_build_tiles(const int32_t* table, int K, int M, const int32_t* sorted_rows, int m_pad,
+                    int32_t* nbr, int32_t* rows_padded, uint16_t* tile_ks, int k_stride,
+                    int32_t* tile_nk, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Weight image for the gather-GEMM kernel                                                    */
+/* (replaces weight.transpose(1,2).contiguous(), detail/unified.py:654-671)                   */
+/* ------------------------------------------------------------------------------------------ */
+/* bytes of the image for the given problem */
+size_t wcn_weight_image_bytes(int K, int groups, int cin_g, int cout_g, int dtype, int transpose_w,
+                              int* n_slabs_out, int* gps_out);
+/* weight: [K][groups][cin_g][cout_g] contiguous (groups = 1 for a dense conv).
+ * transpose_w = 0: forward image (rows = output channels, contraction over input channels);
+ * transpose_w = 1: dgrad image (rows = input channels, contraction over output channels). */
+int wcn_weight_image(const void* weight, void* image, int K, int groups, int cin_g, int cout_g,
+                     int dtype, int transpose_w, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* The three sparse-conv GEMMs                                                                */
+/* ------------------------------------------------------------------------------------------ */
+/* forward AB_gather_scatter and dgrad ABt_gather_scatter
+ * (replaces _C.mask_gemm.fwd / .dgrad: csrc/bindings/mask_gemm_bindings.cu:993-1750,2071-2116;
+ *  semantics detail/explicit.py:22-57,60-101):
+ *   out[rows[p], :] = sum_k feats[nbr[k][p], :] @ Wk      (rows not listed are untouched;
+ *   every listed row is overwritten, so `out` needs no zero-fill)
+ * feats [n_in, in_ld], out [n_out, out_ld]; channels: cin_total = groups*cin_g gathered per row
+ * (dgrad: pass cout/cin swapped and a transpose_w=1 image); bias (optional fp32[groups*cout_g]);
+ * kflip=1 uses weight K-1-k for table row k (dgrad of a submanifold conv on the forward table). */
+int wcn_gather_gemm(const void* feats, long long in_ld, const void* wimg, void* out,
+                    long long out_ld, const int32_t* nbr, const int32_t* rows,
+                    const uint16_t* tile_ks, int k_stride, const int32_t* tile_nk, int num_tiles,
+                    int m_pad, int K, int groups, int cin_g, int cout_g, int dtype,
+                    const float* bias, int relu, int kflip, int max_ctas, void* stream);
+
+/* wgrad AtB_gather_gather
+ * (replaces _C.mask_gemm.wgrad: csrc/bindings/mask_gemm_bindings.cu:1755-2040 and
+ *  _C.gemm.cutlass_gemm_trAB_gather: csrc/bindings/gemm_bindings.cpp:810-918;
+ *  semantics detail/explicit.py:95-97):
+ *   dw[k][g][ci][co] += alpha * sum over pairs j of offset k of feats[in_maps[j], g*cin_g+ci] *
+ *                                                     gout[out_maps[j], g*cout_g+co]
+ * dw is fp32 [K][groups][cin_g][cout_g], accumulated into (caller zero-fills);
+ * offsets: device int32[K+1]. */
+int wcn_wgrad(const void* feats, long long in_ld, const void* gout, long long out_ld, float* dw,
+              const int32_t* in_maps, const int32_t* out_maps, const int32_t* offsets, int K,
+              int groups, int cin_g, int cout_g, int dtype, float alpha, int unit_pairs,
+              int max_ctas, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WCN_B200_H_ */

@@ -1,0 +1,15 @@
+#!/usr/bin/env bash
+# Builds libwcn_b200.so in-tree for sm_100a. nvcc cross-compiles without a GPU.
+set -euo pipefail
+cd "$(dirname "$0")"
+NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -diag-suppress 177"
+mkdir -p build
+pids=()
+for f in cuhash conv_fwd conv_wgrad weight_prep capi; do
+  $NVCC $FLAGS -c $f.cu -o build/$f.o &
+  pids+=($!)
+done
+for p in "${pids[@]}"; do wait $p; done
+$NVCC -shared -o libwcn_b200.so build/cuhash.o build/conv_fwd.o build/conv_wgrad.o build/weight_prep.o build/capi.o
+echo "built $(pwd)/libwcn_b200.so"

@@ -1,0 +1,315 @@
+// SPDX-License-Identifier: Apache-2.0
+// extern "C" boundary of libwcn_b200.so — see include/wcn_b200.h for the contract and the
+// reference bindings each entry point replaces.
+#include "../../include/wcn_b200.h"
+
+#include "common.cuh"
+#include "conv_gemm.cuh"
+
+namespace wcn {
+// cuhash.cu
+int hash_prepare(uint64_t*, int*, int, cudaStream_t);
+int hash_insert(uint64_t*, int*, const int*, int, int, int*, cudaStream_t);
+int hash_search(const uint64_t*, const int*, const int*, int*, int, int, cudaStream_t);
+int kernel_map_num_blocks(int);
+int kernel_map_search(const uint64_t*, const int*, int, const int*, int, const int*, int, int, int,
+                      int, int*, int*, unsigned long long*, cudaStream_t);
+int kernel_map_count(int*, int, int, int*, int*, cudaStream_t);
+int kernel_map_scatter(const int*, const int*, const int*, int*, int*, int, int, cudaStream_t);
+int reverse_pair_table(const int*, int, int, int*, int, cudaStream_t);
+int mask_keys_from_table(const int*, int, int, unsigned long long*, cudaStream_t);
+size_t sort_workspace_bytes(int);
+int sort_rows_by_key(const unsigned long long*, int, int, int*, void*, size_t, cudaStream_t);
+int build_tiles(const int*, int, int, const int*, int, int*, int*, uint16_t*, int, int*,
+                cudaStream_t);
+// weight_prep.cu
+int launch_weight_image(const WeightPrepParams&, cudaStream_t);
+// conv_fwd.cu / conv_wgrad.cu
+int launch_gather_gemm(const GatherGemmParams&, int dtype, int n_slabs, int max_ctas, cudaStream_t);
+int launch_wgrad(const WgradParams&, int dtype, int y_slabs, int z_slabs, int max_ctas, cudaStream_t);
+
+static int sm_count() {
+  static int cached = 0;
+  if (cached == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      cached = n;
+    else
+      cached = kNumSMsB200;
+  }
+  return cached;
+}
+
+// Slab plan shared by the weight image, the gather-GEMM and wgrad.
+//   rows = channels produced per group (rg), contraction = channels consumed per group (cg)
+struct SlabPlan {
+  int n_slabs;  // grid.y
+  int gps;      // groups per slab (1 for dense)
+  int bn;       // rows per slab
+  int cdim;     // contraction channels per slab
+};
+
+static int plan_slabs(int groups, int rg, int cg, SlabPlan* plan) {
+  if (groups < 1 || rg < 1 || cg < 1) return kErrInvalidArg;
+  if (groups == 1) {
+    int n = (rg + 255) / 256;
+    while (n <= rg && (rg % n != 0 || (rg / n) % 16 != 0)) ++n;
+    if (n > rg) return kErrUnsupportedShape;
+    plan->n_slabs = n;
+    plan->gps = 1;
+    plan->bn = rg / n;
+    plan->cdim = cg;
+    return kOk;
+  }
+  // group conv: densify `gps` groups block-diagonally per slab
+  int best = 0;
+  for (int g = 1; g <= groups; ++g) {
+    if (groups % g) continue;
+    if (g * rg <= 128 && g * cg <= 128 && (g * rg) % 16 == 0) best = g;
+  }
+  if (best == 0) {
+    // large groups: one group per slab if it fits a single tile
+    if (rg <= 256 && rg % 16 == 0) best = 1; else return kErrUnsupportedShape;
+  }
+  plan->gps = best;
+  plan->n_slabs = groups / best;
+  plan->bn = best * rg;
+  plan->cdim = best * cg;
+  return kOk;
+}
+
+}  // namespace wcn
+
+using namespace wcn;
+
+static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+extern "C" {
+
+const char* wcn_version(void) { return "wcn_b200 0.1.0 (sm_100a, tcgen05)"; }
+int wcn_built_for_sm100a(void) { return 1; }
+
+int wcn_hash_prepare(uint64_t* keys, int32_t* values, int capacity, void* stream) {
+  if (!keys || !values) return kErrInvalidArg;
+  return hash_prepare(keys, values, capacity, S(stream));
+}
+int wcn_hash_insert(uint64_t* keys, int32_t* values, const int32_t* coords, int n, int capacity,
+                    int32_t* status, void* stream) {
+  if (!keys || !values || !status || (n > 0 && !coords)) return kErrInvalidArg;
+  if ((long long)n * 2 > (long long)capacity) return kErrInvalidArg;  // load factor <= 0.5
+  return hash_insert(keys, values, coords, n, capacity, status, S(stream));
+}
+int wcn_hash_search(const uint64_t* keys, const int32_t* values, const int32_t* queries,
+                    int32_t* results, int n, int capacity, void* stream) {
+  if (!keys || !values || (n > 0 && (!queries || !results))) return kErrInvalidArg;
+  return hash_search(keys, values, queries, results, n, capacity, S(stream));
+}
+
+int wcn_kernel_map_num_blocks(int M) { return kernel_map_num_blocks(M); }
+int wcn_kernel_map_search(const uint64_t* keys, const int32_t* values, int capacity,
+                          const int32_t* out_coords, int M, const int32_t* offsets3, int K,
+                          int stride_x, int stride_y, int stride_z, int32_t* pair_table,
+                          int32_t* block_counts, uint64_t* mask_keys, void* stream) {
+  if (!keys || !values || !offsets3 || (M > 0 && (!out_coords || !pair_table)))
+    return kErrInvalidArg;
+  return kernel_map_search(keys, values, capacity, out_coords, M, offsets3, K, stride_x, stride_y,
+                           stride_z, pair_table, block_counts,
+                           reinterpret_cast<unsigned long long*>(mask_keys), S(stream));
+}
+int wcn_kernel_map_count(int32_t* block_counts, int K, int num_blocks, int32_t* counts,
+                         int32_t* offsets, void* stream) {
+  if (!counts || !offsets || (num_blocks > 0 && !block_counts)) return kErrInvalidArg;
+  return kernel_map_count(block_counts, K, num_blocks, counts, offsets, S(stream));
+}
+int wcn_kernel_map_scatter(const int32_t* pair_table, const int32_t* block_prefix,
+                           const int32_t* offsets, int32_t* in_maps, int32_t* out_maps, int K,
+                           int M, void* stream) {
+  if (M > 0 && (!pair_table || !block_prefix || !offsets)) return kErrInvalidArg;
+  return kernel_map_scatter(pair_table, block_prefix, offsets, in_maps, out_maps, K, M, S(stream));
+}
+
+int wcn_reverse_pair_table(const int32_t* pair_table, int K, int M, int32_t* rev, int n_in,
+                           void* stream) {
+  if (K < 1 || M < 0 || n_in < 0 || (n_in > 0 && !rev)) return kErrInvalidArg;
+  return reverse_pair_table(pair_table, K, M, rev, n_in, S(stream));
+}
+int wcn_mask_keys(const int32_t* table, int K, int M, uint64_t* keys, void* stream) {
+  if (M > 0 && (!table || !keys)) return kErrInvalidArg;
+  return mask_keys_from_table(table, K, M, reinterpret_cast<unsigned long long*>(keys), S(stream));
+}
+size_t wcn_sort_workspace_bytes(int M) { return sort_workspace_bytes(M); }
+int wcn_sort_rows_by_key(const uint64_t* keys, int M, int K, int32_t* rows_out, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+  if (M > 0 && (!keys || !rows_out || !workspace)) return kErrInvalidArg;
+  return sort_rows_by_key(reinterpret_cast<const unsigned long long*>(keys), M, K, rows_out,
+                          workspace, workspace_bytes, S(stream));
+}
+int wcn_build_tiles(const int32_t* table, int K, int M, const int32_t* sorted_rows, int m_pad,
+                    int32_t* nbr, int32_t* rows_padded, uint16_t* tile_ks, int k_stride,
+                    int32_t* tile_nk, void* stream) {
+  if (m_pad > 0 && (!table || !sorted_rows || !nbr || !rows_padded || !tile_ks || !tile_nk))
+    return kErrInvalidArg;
+  return build_tiles(table, K, M, sorted_rows, m_pad, nbr, rows_padded, tile_ks, k_stride, tile_nk,
+                     S(stream));
+}
+
+size_t wcn_weight_image_bytes(int K, int groups, int cin_g, int cout_g, int dtype, int transpose_w,
+                              int* n_slabs_out, int* gps_out) {
+  const int rg = transpose_w ? cin_g : cout_g;
+  const int cg = transpose_w ? cout_g : cin_g;
+  SlabPlan plan;
+  if (plan_slabs(groups, rg, cg, &plan) != kOk) return 0;
+  if (n_slabs_out) *n_slabs_out = plan.n_slabs;
+  if (gps_out) *gps_out = plan.gps;
+  const int ce = 128 / dtype_size(dtype);
+  const int n_chunks = (plan.cdim + ce - 1) / ce;
+  return (size_t)plan.n_slabs * K * n_chunks * plan.bn * 128;
+}
+
+int wcn_weight_image(const void* weight, void* image, int K, int groups, int cin_g, int cout_g,
+                     int dtype, int transpose_w, void* stream) {
+  if (!weight || !image || K < 1) return kErrInvalidArg;
+  if (dtype < 0 || dtype > 2) return kErrUnsupportedDtype;
+  const int rg = transpose_w ? cin_g : cout_g;
+  const int cg = transpose_w ? cout_g : cin_g;
+  SlabPlan plan;
+  int st = plan_slabs(groups, rg, cg, &plan);
+  if (st != kOk) return st;
+  WeightPrepParams p;
+  p.w = weight;
+  p.img = image;
+  p.es = dtype_size(dtype);
+  p.K = K;
+  p.n_slabs = plan.n_slabs;
+  p.gps = plan.gps;
+  p.w_k_stride = (long long)groups * cin_g * cout_g;
+  // element (k, g, ci, co) sits at k*K_stride + g*cin_g*cout_g + ci*cout_g + co
+  const long long r_stride = transpose_w ? cout_g : 1;  // step of a row (rows = ci for dgrad)
+  const long long c_stride = transpose_w ? 1 : cout_g;  // step of a contraction channel
+  p.w_r_stride = r_stride;
+  p.w_c_stride = c_stride;
+  if (groups == 1) {
+    // slabs are windows of rows of the single group
+    p.rg = plan.bn;
+    p.cg = cg;
+    p.w_g_stride = (long long)plan.bn * r_stride;
+  } else {
+    p.rg = rg;
+    p.cg = cg;
+    p.w_g_stride = (long long)cin_g * cout_g;
+  }
+  const int ce = 128 / p.es;
+  p.n_chunks = (plan.cdim + ce - 1) / ce;
+  return launch_weight_image(p, S(stream));
+}
+
+int wcn_gather_gemm(const void* feats, long long in_ld, const void* wimg, void* out,
+                    long long out_ld, const int32_t* nbr, const int32_t* rows,
+                    const uint16_t* tile_ks, int k_stride, const int32_t* tile_nk, int num_tiles,
+                    int m_pad, int K, int groups, int cin_g, int cout_g, int dtype,
+                    const float* bias, int relu, int kflip, int max_ctas, void* stream) {
+  if (!feats || !wimg || !out || !nbr || !rows || !tile_ks || !tile_nk) return kErrInvalidArg;
+  if (dtype < 0 || dtype > 2) return kErrUnsupportedDtype;
+  if (num_tiles == 0) return kOk;
+  SlabPlan plan;
+  int st = plan_slabs(groups, cout_g, cin_g, &plan);
+  if (st != kOk) return st;
+  GatherGemmParams p;
+  p.feats = feats;
+  p.wimg = wimg;
+  p.out = out;
+  p.nbr = nbr;
+  p.rows = rows;
+  p.tile_ks = tile_ks;
+  p.tile_nk = tile_nk;
+  p.bias = bias;
+  p.in_ld = in_ld;
+  p.out_ld = out_ld;
+  p.in_coff = 0;
+  p.in_slab_stride = (groups == 1) ? 0 : plan.cdim;
+  p.out_coff = 0;
+  p.cin = plan.cdim;
+  p.bn = plan.bn;
+  p.K = K;
+  p.k_stride = k_stride;
+  p.m_pad = m_pad;
+  p.num_tiles = num_tiles;
+  p.kflip = kflip;
+  p.stages = 0;
+  p.relu = relu;
+  if (max_ctas <= 0) max_ctas = sm_count();
+  return launch_gather_gemm(p, dtype, plan.n_slabs, max_ctas, S(stream));
+}
+
+int wcn_wgrad(const void* feats, long long in_ld, const void* gout, long long out_ld, float* dw,
+              const int32_t* in_maps, const int32_t* out_maps, const int32_t* offsets, int K,
+              int groups, int cin_g, int cout_g, int dtype, float alpha, int unit_pairs,
+              int max_ctas, void* stream) {
+  if (!feats || !gout || !dw || !offsets) return kErrInvalidArg;
+  if (dtype < 0 || dtype > 2) return kErrUnsupportedDtype;
+  if (groups < 1 || cin_g < 1 || cout_g < 1) return kErrInvalidArg;
+  WgradParams p;
+  p.feats = feats;
+  p.gout = gout;
+  p.dw = dw;
+  p.in_maps = in_maps;
+  p.out_maps = out_maps;
+  p.offsets = offsets;
+  p.in_ld = in_ld;
+  p.out_ld = out_ld;
+  p.in_coff = 0;
+  p.out_coff = 0;
+  p.K = K;
+  p.unit_pairs = unit_pairs;
+  p.stages = 0;
+  p.alpha = alpha;
+  p.dw_k_stride = (long long)groups * cin_g * cout_g;
+  p.dw_g_stride = (long long)cin_g * cout_g;
+  p.dw_ld = cout_g;
+  int y_slabs, z_slabs;
+  if (groups == 1) {
+    y_slabs = (cin_g + 127) / 128;
+    z_slabs = (cout_g + 255) / 256;
+    while (z_slabs <= cout_g && (cout_g % z_slabs != 0 || (cout_g / z_slabs) % 16 != 0)) ++z_slabs;
+    if (z_slabs > cout_g) return kErrUnsupportedShape;
+    p.cin = cin_g < 128 ? cin_g : 128;
+    p.cin_last = cin_g - 128 * (y_slabs - 1);
+    p.cout = cout_g / z_slabs;
+    p.gps = 1;
+    p.cin_g = cin_g;
+    p.cout_g = cout_g;
+    p.in_y_stride = 128;
+    p.out_y_stride = 0;
+    p.out_z_stride = p.cout;
+    p.dw_y_stride = 128LL * cout_g;
+    p.dw_z_stride = p.cout;
+  } else {
+    SlabPlan plan;
+    int st = plan_slabs(groups, cout_g, cin_g, &plan);
+    if (st != kOk) return st;
+    if (plan.gps * cin_g > 128 || plan.gps * cout_g > 256 || cout_g % 8 != 0)
+      return kErrUnsupportedShape;
+    y_slabs = plan.n_slabs;
+    z_slabs = 1;
+    p.gps = plan.gps;
+    p.cin = plan.gps * cin_g;
+    p.cin_last = p.cin;
+    p.cout = plan.gps * cout_g;
+    p.cin_g = cin_g;
+    p.cout_g = cout_g;
+    p.in_y_stride = p.cin;
+    p.out_y_stride = p.cout;
+    p.out_z_stride = 0;
+    p.dw_y_stride = (long long)plan.gps * p.dw_g_stride;
+    p.dw_z_stride = 0;
+    if (plan.gps == 1) {
+      // one (large) group per slab behaves like a dense slab
+      p.dw_ld = cout_g;
+    }
+  }
+  if (max_ctas <= 0) max_ctas = sm_count();
+  return launch_wgrad(p, dtype, y_slabs, z_slabs, max_ctas, S(stream));
+}
+
+}  // extern "C"

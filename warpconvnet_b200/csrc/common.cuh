@@ -1,0 +1,269 @@
+// SPDX-License-Identifier: Apache-2.0
+// Thin inline-PTX layer for sm_100a: mbarrier, cp.async, bulk copy (TMA unit), tcgen05/TMEM.
+// Everything here is hand-written for B200; nothing is borrowed from a template library.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cstdio>
+#include <stdint.h>
+
+namespace wcn {
+
+// ---------------------------------------------------------------------------------------------
+// error codes of the C-ABI (mirrors the reference's "0 = ok, negative = unsupported" convention,
+// reference: warpconvnet/csrc/include/gemm_error_codes.h:7-15)
+// ---------------------------------------------------------------------------------------------
+enum Status : int {
+  kOk = 0,
+  kErrInvalidArg = -1,
+  kErrUnsupportedShape = -2,
+  kErrAlignment = -3,
+  kErrUnsupportedDtype = -4,
+  kErrCuda = -5,
+  kErrWorkspace = -6,
+};
+
+enum DType : int { kBF16 = 0, kF16 = 1, kF32 = 2 };
+
+__host__ __device__ inline int dtype_size(int dt) { return dt == kF32 ? 4 : 2; }
+
+constexpr int kNumSMsB200 = 148;
+
+// ---------------------------------------------------------------------------------------------
+// shared-memory address helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// ---------------------------------------------------------------------------------------------
+// mbarrier
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a trapped kernel (CUDA error on the host), never
+// as a hung GPU. try_wait itself sleeps in hardware, so the bound is generous (seconds).
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 26)) {
+      printf("wcn_b200: mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n",
+             (int)blockIdx.x, (int)threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// cp.async (LDGSTS) 16-byte copies with zero fill, completion tracked by an mbarrier
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src),
+               "r"(src_bytes)
+               : "memory");
+}
+// The arrive fires when all cp.async issued so far by this thread have landed. ".noinc": the
+// arrival is one of the barrier's expected arrivals (counted in mbar_init).
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// bulk asynchronous copy global -> shared through the TMA unit (no tensor map needed)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes,
+                                              uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(dst),
+      "l"(src), "r"(bytes), "r"(bar)
+      : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// tcgen05 / tensor memory
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem),
+               "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]; issued by ONE thread for the whole CTA.
+template <int KIND_TF32>
+__device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                        uint32_t idesc, uint32_t accumulate) {
+  if (KIND_TF32) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+// Arrive on an mbarrier once every tcgen05.mma issued so far by this thread has completed.
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// 32 lanes x 16 consecutive 32-bit columns: thread i of the warp receives lane (base_lane + i).
+__device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7])
+      : "r"(taddr)
+      : "memory");
+}
+
+// Shared-memory matrix descriptor for tcgen05.mma (bit layout as documented for sm_100:
+// [0,14) addr>>4, [16,30) leading-dim byte offset>>4, [32,46) stride-dim byte offset>>4,
+// [46,48) version=1, [61,64) swizzle mode (2 = 128-byte swizzle)).
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr, uint32_t lbo_bytes,
+                                                         uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// Instruction descriptor for kind::f16 / kind::tf32 with fp32 accumulation.
+// fmt: 0 = f16, 1 = bf16, 2 = tf32; a_mn/b_mn: 1 = operand is MN-major in shared memory.
+__host__ __device__ inline uint32_t make_idesc(int fmt, int M, int N, int a_mn, int b_mn) {
+  uint32_t d = 0;
+  d |= 1u << 4;                          // accumulator format: f32
+  d |= (uint32_t)fmt << 7;               // A format
+  d |= (uint32_t)fmt << 10;              // B format
+  d |= (uint32_t)(a_mn & 1) << 15;       // A major
+  d |= (uint32_t)(b_mn & 1) << 16;       // B major
+  d |= (uint32_t)(N >> 3) << 17;         // N / 8
+  d |= (uint32_t)(M >> 4) << 24;         // M / 16
+  return d;
+}
+
+// 128-byte-swizzle position of 16-byte unit `c16` (0..7) of 128-byte row `row`
+// (rows are stored back to back, 8-row / 1024-byte atoms, atom base 1024-byte aligned).
+__device__ __forceinline__ uint32_t sw128_offset(uint32_t row, uint32_t c16) {
+  return row * 128u + ((c16 ^ (row & 7u)) << 4);
+}
+
+template <typename T>
+struct ElemTraits;
+template <>
+struct ElemTraits<__nv_bfloat16> {
+  static constexpr int kFmt = 1;
+  static constexpr int kTF32 = 0;
+  static constexpr int kDType = kBF16;
+};
+template <>
+struct ElemTraits<__half> {
+  static constexpr int kFmt = 0;
+  static constexpr int kTF32 = 0;
+  static constexpr int kDType = kF16;
+};
+template <>
+struct ElemTraits<float> {
+  static constexpr int kFmt = 2;
+  static constexpr int kTF32 = 1;
+  static constexpr int kDType = kF32;
+};
+
+// pack 8 fp32 accumulators (as raw bits) into one 16-byte store of T
+template <typename T>
+__device__ __forceinline__ uint4 pack8(const uint32_t* v);
+template <>
+__device__ __forceinline__ uint4 pack8<__nv_bfloat16>(const uint32_t* v) {
+  uint4 r;
+  __nv_bfloat162 a = __floats2bfloat162_rn(__uint_as_float(v[0]), __uint_as_float(v[1]));
+  __nv_bfloat162 b = __floats2bfloat162_rn(__uint_as_float(v[2]), __uint_as_float(v[3]));
+  __nv_bfloat162 c = __floats2bfloat162_rn(__uint_as_float(v[4]), __uint_as_float(v[5]));
+  __nv_bfloat162 d = __floats2bfloat162_rn(__uint_as_float(v[6]), __uint_as_float(v[7]));
+  r.x = *reinterpret_cast<uint32_t*>(&a);
+  r.y = *reinterpret_cast<uint32_t*>(&b);
+  r.z = *reinterpret_cast<uint32_t*>(&c);
+  r.w = *reinterpret_cast<uint32_t*>(&d);
+  return r;
+}
+template <>
+__device__ __forceinline__ uint4 pack8<__half>(const uint32_t* v) {
+  uint4 r;
+  __half2 a = __floats2half2_rn(__uint_as_float(v[0]), __uint_as_float(v[1]));
+  __half2 b = __floats2half2_rn(__uint_as_float(v[2]), __uint_as_float(v[3]));
+  __half2 c = __floats2half2_rn(__uint_as_float(v[4]), __uint_as_float(v[5]));
+  __half2 d = __floats2half2_rn(__uint_as_float(v[6]), __uint_as_float(v[7]));
+  r.x = *reinterpret_cast<uint32_t*>(&a);
+  r.y = *reinterpret_cast<uint32_t*>(&b);
+  r.z = *reinterpret_cast<uint32_t*>(&c);
+  r.w = *reinterpret_cast<uint32_t*>(&d);
+  return r;
+}
+
+}  // namespace wcn

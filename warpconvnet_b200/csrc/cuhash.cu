@@ -1,0 +1,419 @@
+// SPDX-License-Identifier: Apache-2.0
+// Kernel-map construction for sparse convolution: packed-coordinate hash table, per-offset
+// neighbour probe, deterministic CSR compaction, reverse table, and the mask-sorted tile tables
+// the tensor-core kernels consume. All integer work, HBM/L2-bound; results are bit-exact against
+// oracle/kernel_map.py.
+//
+// Behaviour follows (re-implemented, not copied):
+//   key packing / Splitmix64 / linear probing  warpconvnet/csrc/include/cuhash/hash_functions.cuh:29-84,
+//                                              hash_table.cuh:36-108
+//   offset enumeration k -> (i,j,l)            warpconvnet/csrc/include/cuhash/kernel_map.cuh:34-54
+//   found[K,M] -> counts -> CSR                warpconvnet/csrc/cuhash_kernel_map.cu:93-134,508-599
+//   pair mask / argsort / reverse table        warpconvnet/csrc/mask_data_kernels.cu:23-220
+// Differences by design: one thread owns a query and walks all K offsets (the query row is
+// loaded and packed once instead of K times), per-offset counts are warp-aggregated, and the CSR
+// is emitted in ascending output-row order by a two-pass block scan (the reference reserves slots
+// with atomics, so its row order is non-deterministic).
+#include <cub/device/device_radix_sort.cuh>
+
+#include "common.cuh"
+
+namespace wcn {
+
+constexpr int kMapBlock = 256;  // queries per block in the search / scatter passes
+constexpr uint64_t kValidBit = 1ull << 63;
+constexpr uint64_t kEmptyKey = 0ull;
+
+__host__ __device__ __forceinline__ uint64_t pack_key(int b, int x, int y, int z) {
+  return kValidBit | ((uint64_t)(b & 0x1FF) << 54) | ((uint64_t)(x & 0x3FFFF) << 36) |
+         ((uint64_t)(y & 0x3FFFF) << 18) | (uint64_t)(z & 0x3FFFF);
+}
+
+__device__ __forceinline__ uint32_t splitmix_slot(uint64_t key, uint32_t mask) {
+  key ^= key >> 30;
+  key *= 0xBF58476D1CE4E5B9ull;
+  key ^= key >> 27;
+  key *= 0x94D049BB133111EBull;
+  key ^= key >> 31;
+  return (uint32_t)key & mask;
+}
+
+__device__ __forceinline__ int table_lookup(const uint64_t* __restrict__ keys,
+                                            const int* __restrict__ values, uint64_t key,
+                                            uint32_t mask) {
+  uint32_t slot = splitmix_slot(key, mask);
+  for (uint32_t attempts = 0; attempts <= mask; ++attempts) {
+    const uint64_t k = __ldg(keys + slot);
+    if (k == key) return __ldg(values + slot);
+    if (k == kEmptyKey) return -1;
+    slot = (slot + 1) & mask;
+  }
+  return -1;
+}
+
+// --------------------------------------------------------------------------------------------
+// hash table build
+// --------------------------------------------------------------------------------------------
+__global__ void hash_insert_kernel(uint64_t* __restrict__ keys, int* __restrict__ values,
+                                   const int4* __restrict__ coords, int n, uint32_t mask,
+                                   int* __restrict__ status) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int4 c = __ldg(coords + i);  // (batch, x, y, z): one coalesced 16-byte load
+  if (c.x < 0 || c.x > 511 || c.y < -131072 || c.y > 131071 || c.z < -131072 || c.z > 131071 ||
+      c.w < -131072 || c.w > 131071) {
+    atomicOr(status, 2);  // out-of-range coordinate (the reference raises ValueError on the host)
+    return;
+  }
+  const uint64_t key = pack_key(c.x, c.y, c.z, c.w);
+  uint32_t slot = splitmix_slot(key, mask);
+  for (uint32_t attempts = 0; attempts <= mask; ++attempts) {
+    const unsigned long long prev = atomicCAS(reinterpret_cast<unsigned long long*>(keys + slot),
+                                              (unsigned long long)kEmptyKey, (unsigned long long)key);
+    if (prev == kEmptyKey || prev == key) {
+      // value = insertion index; duplicates keep the SMALLEST index, so the table is
+      // deterministic (the reference keeps whichever thread wins the race). Empty value slots
+      // are pre-filled with 0x7f7f7f7f by hash_prepare, so atomicMin works for both cases.
+      atomicMin(values + slot, i);
+      return;
+    }
+    slot = (slot + 1) & mask;
+  }
+  atomicOr(status, 1);  // table full
+}
+
+__global__ void hash_search_kernel(const uint64_t* __restrict__ keys,
+                                   const int* __restrict__ values,
+                                   const int4* __restrict__ queries, int* __restrict__ results,
+                                   int n, uint32_t mask) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int4 c = __ldg(queries + i);
+  results[i] = table_lookup(keys, values, pack_key(c.x, c.y, c.z, c.w), mask);
+}
+
+// --------------------------------------------------------------------------------------------
+// kernel map: probe all K offsets of every output coordinate
+// --------------------------------------------------------------------------------------------
+// pair_table[k][m] = index of input voxel at out[m]*stride + offset[k], or -1
+// block_counts[k][blockIdx.x] = number of hits of offset k among this block's 256 queries
+// mask_keys[m] = bit k set iff offset k hit (bits folded modulo 64 when K > 64)
+__global__ void __launch_bounds__(kMapBlock)
+kernel_map_search_kernel(const uint64_t* __restrict__ keys, const int* __restrict__ values,
+                         uint32_t mask, const int4* __restrict__ out_coords, int M,
+                         const int* __restrict__ offs, int K, int sx, int sy, int sz,
+                         int* __restrict__ pair_table, int* __restrict__ block_counts,
+                         unsigned long long* __restrict__ mask_keys) {
+  extern __shared__ int s_mem[];  // [K] counts, then [3K] offsets
+  int* s_cnt = s_mem;
+  int* s_off = s_mem + K;
+  for (int i = threadIdx.x; i < K; i += blockDim.x) s_cnt[i] = 0;
+  for (int i = threadIdx.x; i < 3 * K; i += blockDim.x) s_off[i] = offs[i];
+  __syncthreads();
+
+  const int m = blockIdx.x * kMapBlock + threadIdx.x;
+  const bool live = m < M;
+  int4 c = make_int4(0, 0, 0, 0);
+  if (live) c = __ldg(out_coords + m);
+  const int bx = c.y * sx, by = c.z * sy, bz = c.w * sz;
+  unsigned long long bits = 0ull;
+  const int lane = threadIdx.x & 31;
+
+  for (int k0 = 0; k0 < K; k0 += 4) {
+    // four independent probes in flight per thread
+    int res[4];
+    uint32_t slot[4];
+    uint64_t key[4];
+    uint64_t got[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int k = k0 + u;
+      res[u] = -1;
+      if (k < K && live) {
+        key[u] = pack_key(c.x, bx + s_off[3 * k], by + s_off[3 * k + 1], bz + s_off[3 * k + 2]);
+        slot[u] = splitmix_slot(key[u], mask);
+        got[u] = __ldg(keys + slot[u]);
+      } else {
+        key[u] = 1;  // never matches: stored keys have the valid bit set
+        slot[u] = 0;
+        got[u] = kEmptyKey;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      uint32_t attempts = 0;
+      uint64_t g = got[u];
+      uint32_t s = slot[u];
+      while (g != kEmptyKey && attempts <= mask) {
+        if (g == key[u]) {
+          res[u] = __ldg(values + s);
+          break;
+        }
+        s = (s + 1) & mask;
+        g = __ldg(keys + s);
+        ++attempts;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int k = k0 + u;
+      if (k < K) {  // warp-uniform
+        const bool hit = res[u] >= 0;
+        if (live) pair_table[(size_t)k * M + m] = res[u];
+        if (hit) bits ^= 1ull << (k & 63);
+        const unsigned ballot = __ballot_sync(0xffffffffu, hit);
+        if (lane == 0 && ballot) atomicAdd(&s_cnt[k], __popc(ballot));  // warp-aggregated
+      }
+    }
+  }
+  if (live && mask_keys != nullptr) mask_keys[m] = bits;
+  __syncthreads();
+  if (block_counts != nullptr) {
+    for (int i = threadIdx.x; i < K; i += blockDim.x)
+      block_counts[(size_t)i * gridDim.x + blockIdx.x] = s_cnt[i];
+  }
+}
+
+// exclusive scan of block_counts[k][0..nb) in place, total into counts[k]; one block per offset
+__global__ void __launch_bounds__(256)
+block_scan_kernel(int* __restrict__ block_counts, int nb, int* __restrict__ counts) {
+  __shared__ int s_warp[8];
+  __shared__ int s_carry;
+  int* row = block_counts + (size_t)blockIdx.x * nb;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base < nb; base += 256) {
+    const int i = base + threadIdx.x;
+    const int v = i < nb ? row[i] : 0;
+    int incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    int warp_off = 0;
+    for (int w = 0; w < warp; ++w) warp_off += s_warp[w];
+    const int carry = s_carry;
+    if (i < nb) row[i] = carry + warp_off + incl - v;
+    __syncthreads();
+    if (threadIdx.x == 255) s_carry = carry + warp_off + incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) counts[blockIdx.x] = s_carry;
+}
+
+// offsets[0..K] = exclusive scan of counts; single small block
+__global__ void offsets_kernel(const int* __restrict__ counts, int K, int* __restrict__ offsets) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    int acc = 0;
+    for (int k = 0; k < K; ++k) {
+      offsets[k] = acc;
+      acc += counts[k];
+    }
+    offsets[K] = acc;
+  }
+}
+
+// CSR emission in ascending output-row order inside every offset (deterministic)
+__global__ void __launch_bounds__(kMapBlock)
+kernel_map_scatter_kernel(const int* __restrict__ pair_table, const int* __restrict__ block_prefix,
+                          const int* __restrict__ offsets, int* __restrict__ in_maps,
+                          int* __restrict__ out_maps, int K, int M) {
+  __shared__ int s_warp[kMapBlock / 32];
+  const int m = blockIdx.x * kMapBlock + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int k = 0; k < K; ++k) {
+    const int v = m < M ? __ldg(pair_table + (size_t)k * M + m) : -1;
+    const bool hit = v >= 0;
+    const unsigned ballot = __ballot_sync(0xffffffffu, hit);
+    if (lane == 0) s_warp[warp] = __popc(ballot);
+    __syncthreads();
+    if (hit) {
+      int rank = __popc(ballot & ((1u << lane) - 1u));
+      for (int w = 0; w < warp; ++w) rank += s_warp[w];
+      const int pos = offsets[k] + block_prefix[(size_t)k * gridDim.x + blockIdx.x] + rank;
+      in_maps[pos] = v;
+      out_maps[pos] = m;
+    }
+    __syncthreads();
+  }
+}
+
+// rev[k][in] = out  for every valid pair (rev must be pre-filled with -1)
+__global__ void reverse_table_kernel(const int* __restrict__ pair_table, int K, int M,
+                                     int* __restrict__ rev, int n_in) {
+  const long long total = (long long)K * M;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int v = __ldg(pair_table + t);
+    if (v >= 0) {
+      const int k = (int)(t / M);
+      const int m = (int)(t - (long long)k * M);
+      rev[(size_t)k * n_in + v] = m;
+    }
+  }
+}
+
+__global__ void mask_keys_kernel(const int* __restrict__ table, int K, int M,
+                                 unsigned long long* __restrict__ keys) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  unsigned long long bits = 0ull;
+  for (int k = 0; k < K; ++k)
+    if (__ldg(table + (size_t)k * M + m) >= 0) bits ^= 1ull << (k & 63);
+  keys[m] = bits;
+}
+
+__global__ void iota_kernel(int* __restrict__ v, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] = i;
+}
+
+// One block per 128-row tile of the mask-sorted order: permute the table into tile order and
+// list the offsets that are active anywhere in the tile.
+__global__ void __launch_bounds__(128)
+build_tiles_kernel(const int* __restrict__ table, int K, int M, const int* __restrict__ sorted_rows,
+                   int m_pad, int* __restrict__ nbr, int* __restrict__ rows_padded,
+                   uint16_t* __restrict__ tile_ks, int k_stride, int* __restrict__ tile_nk) {
+  __shared__ int s_n;
+  const int tile = blockIdx.x;
+  const int pos = tile * 128 + threadIdx.x;
+  const int row = pos < M ? __ldg(sorted_rows + pos) : -1;
+  rows_padded[pos] = row;
+  if (threadIdx.x == 0) s_n = 0;
+  __syncthreads();
+  for (int k = 0; k < K; ++k) {
+    const int v = row >= 0 ? __ldg(table + (size_t)k * M + row) : -1;
+    nbr[(size_t)k * m_pad + pos] = v;
+    const int any = __syncthreads_or(v >= 0);
+    if (any && threadIdx.x == 0) {
+      tile_ks[(size_t)tile * k_stride + s_n] = (uint16_t)k;
+      ++s_n;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) tile_nk[tile] = s_n;
+}
+
+// --------------------------------------------------------------------------------------------
+// host launchers
+// --------------------------------------------------------------------------------------------
+static inline int cuda_ok() { return cudaGetLastError() == cudaSuccess ? kOk : kErrCuda; }
+static inline bool is_pow2(long long v) { return v > 0 && (v & (v - 1)) == 0; }
+
+int hash_prepare(uint64_t* keys, int* values, int capacity, cudaStream_t s) {
+  if (!is_pow2(capacity)) return kErrInvalidArg;
+  if (cudaMemsetAsync(keys, 0, (size_t)capacity * 8, s) != cudaSuccess) return kErrCuda;
+  if (cudaMemsetAsync(values, 0x7F, (size_t)capacity * 4, s) != cudaSuccess) return kErrCuda;
+  return kOk;
+}
+
+int hash_insert(uint64_t* keys, int* values, const int* coords, int n, int capacity, int* status,
+                cudaStream_t s) {
+  if (!is_pow2(capacity) || n < 0) return kErrInvalidArg;
+  if (n == 0) return kOk;
+  hash_insert_kernel<<<(n + 255) / 256, 256, 0, s>>>(keys, values,
+                                                    reinterpret_cast<const int4*>(coords), n,
+                                                    (uint32_t)(capacity - 1), status);
+  return cuda_ok();
+}
+
+int hash_search(const uint64_t* keys, const int* values, const int* queries, int* results, int n,
+                int capacity, cudaStream_t s) {
+  if (!is_pow2(capacity) || n < 0) return kErrInvalidArg;
+  if (n == 0) return kOk;
+  hash_search_kernel<<<(n + 255) / 256, 256, 0, s>>>(
+      keys, values, reinterpret_cast<const int4*>(queries), results, n, (uint32_t)(capacity - 1));
+  return cuda_ok();
+}
+
+int kernel_map_num_blocks(int M) { return (M + kMapBlock - 1) / kMapBlock; }
+
+int kernel_map_search(const uint64_t* keys, const int* values, int capacity, const int* out_coords,
+                      int M, const int* offsets3, int K, int sx, int sy, int sz, int* pair_table,
+                      int* block_counts, unsigned long long* mask_keys, cudaStream_t s) {
+  if (!is_pow2(capacity) || M < 0 || K < 1 || K > 4096) return kErrInvalidArg;
+  if (M == 0) return kOk;
+  const int nb = kernel_map_num_blocks(M);
+  kernel_map_search_kernel<<<nb, kMapBlock, (size_t)4 * K * sizeof(int), s>>>(
+      keys, values, (uint32_t)(capacity - 1), reinterpret_cast<const int4*>(out_coords), M,
+      offsets3, K, sx, sy, sz, pair_table, block_counts, mask_keys);
+  return cuda_ok();
+}
+
+int kernel_map_count(int* block_counts, int K, int nb, int* counts, int* offsets, cudaStream_t s) {
+  if (K < 1) return kErrInvalidArg;
+  if (nb > 0) {
+    block_scan_kernel<<<K, 256, 0, s>>>(block_counts, nb, counts);
+  } else {
+    if (cudaMemsetAsync(counts, 0, (size_t)K * 4, s) != cudaSuccess) return kErrCuda;
+  }
+  offsets_kernel<<<1, 32, 0, s>>>(counts, K, offsets);
+  return cuda_ok();
+}
+
+int kernel_map_scatter(const int* pair_table, const int* block_prefix, const int* offsets,
+                       int* in_maps, int* out_maps, int K, int M, cudaStream_t s) {
+  if (M == 0) return kOk;
+  kernel_map_scatter_kernel<<<kernel_map_num_blocks(M), kMapBlock, 0, s>>>(
+      pair_table, block_prefix, offsets, in_maps, out_maps, K, M);
+  return cuda_ok();
+}
+
+int reverse_pair_table(const int* pair_table, int K, int M, int* rev, int n_in, cudaStream_t s) {
+  if (cudaMemsetAsync(rev, 0xFF, (size_t)K * n_in * 4, s) != cudaSuccess) return kErrCuda;
+  const long long total = (long long)K * M;
+  if (total == 0) return kOk;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  reverse_table_kernel<<<blocks, 256, 0, s>>>(pair_table, K, M, rev, n_in);
+  return cuda_ok();
+}
+
+int mask_keys_from_table(const int* table, int K, int M, unsigned long long* keys, cudaStream_t s) {
+  if (M == 0) return kOk;
+  mask_keys_kernel<<<(M + 255) / 256, 256, 0, s>>>(table, K, M, keys);
+  return cuda_ok();
+}
+
+// workspace: [keys_out M*8][rows_in M*4][cub temp]
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+size_t sort_workspace_bytes(int M) {
+  size_t temp = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, temp, (const unsigned long long*)nullptr,
+                                  (unsigned long long*)nullptr, (const int*)nullptr, (int*)nullptr,
+                                  M > 0 ? M : 1, 0, 64, (cudaStream_t)0);
+  return align_up((size_t)M * 8, 256) + align_up((size_t)M * 4, 256) + align_up(temp, 256) + 256;
+}
+
+int sort_rows_by_key(const unsigned long long* keys, int M, int K, int* rows_out, void* workspace,
+                     size_t ws_bytes, cudaStream_t s) {
+  if (M == 0) return kOk;
+  if (ws_bytes < sort_workspace_bytes(M)) return kErrWorkspace;
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  unsigned long long* keys_out = reinterpret_cast<unsigned long long*>(ws);
+  int* rows_in = reinterpret_cast<int*>(ws + align_up((size_t)M * 8, 256));
+  void* temp = ws + align_up((size_t)M * 8, 256) + align_up((size_t)M * 4, 256);
+  size_t temp_bytes = ws_bytes - (align_up((size_t)M * 8, 256) + align_up((size_t)M * 4, 256));
+  iota_kernel<<<(M + 255) / 256, 256, 0, s>>>(rows_in, M);
+  const int end_bit = K < 64 ? K : 64;
+  // LSD radix sort is stable: equal masks keep ascending row order (deterministic tiles)
+  cudaError_t e = cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys, keys_out, rows_in,
+                                                  rows_out, M, 0, end_bit, s);
+  return e == cudaSuccess ? cuda_ok() : kErrCuda;
+}
+
+int build_tiles(const int* table, int K, int M, const int* sorted_rows, int m_pad, int* nbr,
+                int* rows_padded, uint16_t* tile_ks, int k_stride, int* tile_nk, cudaStream_t s) {
+  if (m_pad % 128 != 0 || m_pad < M || k_stride < K || K > 65535) return kErrInvalidArg;
+  if (m_pad == 0) return kOk;
+  build_tiles_kernel<<<m_pad / 128, 128, 0, s>>>(table, K, M, sorted_rows, m_pad, nbr, rows_padded,
+                                                tile_ks, k_stride, tile_nk);
+  return cuda_ok();
+}
+
+}  // namespace wcn
