@@ -96,6 +96,11 @@ int wcn_kernel_map_scatter(const int32_t* pair_table, const int32_t* block_prefi
 /* rev[k*n_in + i] = m for every pair_table[k*M + m] = i >= 0, -1 elsewhere. */
 int wcn_reverse_pair_table(const int32_t* pair_table, int K, int M, int32_t* rev, int n_in,
                            void* stream);
+/* Dense table from the CSR lists (replaces csr_to_pair_table, csrc/mask_data_kernels.cu:55-82):
+ * table[k*n_rows + row_maps[j]] = val_maps[j] for every pair j of offset k, -1 elsewhere.
+ * (val=in_maps,row=out_maps) gives the forward pair table, swapped gives the reverse table. */
+int wcn_csr_to_pair_table(const int32_t* val_maps, const int32_t* row_maps, const int32_t* offsets,
+                          int K, int n_rows, int num_pairs, int32_t* table, void* stream);
 int wcn_mask_keys(const int32_t* table, int K, int M, uint64_t* keys, void* stream);
 size_t wcn_sort_workspace_bytes(int M);
 /* rows_out = stable argsort of keys (low min(K,64) bits). */

@@ -1,0 +1,237 @@
+# SPDX-License-Identifier: Apache-2.0
+"""Torch-tensor level wrappers over the C-ABI (device memory and streams only — no math here).
+
+Every function enqueues on ``torch.cuda.current_stream()`` and never synchronises. Tensors are
+allocated by the caller side (here) and handed to the library as raw pointers, the same ownership
+rule the reference uses (detail/mask_gemm.py:723,874,934).
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import check, lib
+
+DTYPE_CODE = {torch.bfloat16: 0, torch.float16: 1, torch.float32: 2}
+TILE_M = 128
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _require_cuda(*tensors: Tensor) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                "warpconvnet_b200 runs on CUDA (sm_100a) only; got a CPU tensor. "
+                "There is no CPU fallback.")
+
+
+def dtype_code(dtype: torch.dtype) -> int:
+    try:
+        return DTYPE_CODE[dtype]
+    except KeyError:
+        raise _lib.WcnError(f"unsupported feature dtype {dtype}; use bf16, fp16 or fp32") from None
+
+
+# ------------------------------------------------------------------------------------------------
+# hash table
+# ------------------------------------------------------------------------------------------------
+def next_power_of_2(n: int) -> int:
+    return 1 if n <= 1 else 1 << (int(n) - 1).bit_length()
+
+
+def hash_prepare(keys: Tensor, values: Tensor) -> None:
+    _require_cuda(keys, values)
+    check(lib.wcn_hash_prepare(_p(keys), _p(values), keys.numel(), _stream()), "hash_prepare")
+
+
+def hash_insert(keys: Tensor, values: Tensor, coords: Tensor, status: Tensor) -> None:
+    _require_cuda(keys, values, coords, status)
+    assert coords.dtype == torch.int32 and coords.is_contiguous() and coords.shape[1] == 4
+    check(lib.wcn_hash_insert(_p(keys), _p(values), _p(coords), coords.shape[0], keys.numel(),
+                              _p(status), _stream()), "hash_insert")
+
+
+def hash_search(keys: Tensor, values: Tensor, queries: Tensor) -> Tensor:
+    _require_cuda(keys, values, queries)
+    assert queries.dtype == torch.int32 and queries.is_contiguous() and queries.shape[1] == 4
+    res = torch.empty(queries.shape[0], dtype=torch.int32, device=queries.device)
+    check(lib.wcn_hash_search(_p(keys), _p(values), _p(queries), _p(res), queries.shape[0],
+                              keys.numel(), _stream()), "hash_search")
+    return res
+
+
+# ------------------------------------------------------------------------------------------------
+# kernel map
+# ------------------------------------------------------------------------------------------------
+def kernel_map_search(keys: Tensor, values: Tensor, out_coords: Tensor, offsets3: Tensor,
+                      stride: Tuple[int, int, int], want_counts: bool = True,
+                      want_mask: bool = True):
+    """Returns (pair_table[K,M], block_counts[K,nb] | None, mask_keys[M] int64 | None)."""
+    _require_cuda(keys, values, out_coords, offsets3)
+    M = out_coords.shape[0]
+    K = offsets3.shape[0]
+    dev = out_coords.device
+    nb = lib.wcn_kernel_map_num_blocks(M)
+    pair_table = torch.empty((K, M), dtype=torch.int32, device=dev)
+    block_counts = torch.empty((K, nb), dtype=torch.int32, device=dev) if want_counts else None
+    mask_keys = torch.empty(M, dtype=torch.int64, device=dev) if want_mask else None
+    check(lib.wcn_kernel_map_search(_p(keys), _p(values), keys.numel(), _p(out_coords), M,
+                                    _p(offsets3), K, int(stride[0]), int(stride[1]),
+                                    int(stride[2]), _p(pair_table), _p(block_counts),
+                                    _p(mask_keys), _stream()), "kernel_map_search")
+    return pair_table, block_counts, mask_keys
+
+
+def kernel_map_count(block_counts: Tensor) -> Tensor:
+    """In-place block scan; returns device offsets[K+1] (int32)."""
+    K, nb = block_counts.shape
+    counts = torch.empty(K, dtype=torch.int32, device=block_counts.device)
+    offsets = torch.empty(K + 1, dtype=torch.int32, device=block_counts.device)
+    check(lib.wcn_kernel_map_count(_p(block_counts), K, nb, _p(counts), _p(offsets), _stream()),
+          "kernel_map_count")
+    return offsets
+
+
+def kernel_map_scatter(pair_table: Tensor, block_prefix: Tensor, offsets_dev: Tensor,
+                       num_pairs: int):
+    K, M = pair_table.shape
+    in_maps = torch.empty(num_pairs, dtype=torch.int32, device=pair_table.device)
+    out_maps = torch.empty(num_pairs, dtype=torch.int32, device=pair_table.device)
+    if num_pairs > 0:
+        check(lib.wcn_kernel_map_scatter(_p(pair_table), _p(block_prefix), _p(offsets_dev),
+                                         _p(in_maps), _p(out_maps), K, M, _stream()),
+              "kernel_map_scatter")
+    return in_maps, out_maps
+
+
+def reverse_pair_table(pair_table: Tensor, n_in: int) -> Tensor:
+    K, M = pair_table.shape
+    rev = torch.empty((K, n_in), dtype=torch.int32, device=pair_table.device)
+    check(lib.wcn_reverse_pair_table(_p(pair_table), K, M, _p(rev), n_in, _stream()),
+          "reverse_pair_table")
+    return rev
+
+
+def csr_to_pair_table(val_maps: Tensor, row_maps: Tensor, offsets_dev: Tensor, n_rows: int):
+    K = offsets_dev.numel() - 1
+    table = torch.empty((K, n_rows), dtype=torch.int32, device=val_maps.device)
+    check(lib.wcn_csr_to_pair_table(_p(val_maps), _p(row_maps), _p(offsets_dev), K, n_rows,
+                                    val_maps.numel(), _p(table), _stream()), "csr_to_pair_table")
+    return table
+
+
+def mask_keys(table: Tensor) -> Tensor:
+    K, M = table.shape
+    keys = torch.empty(M, dtype=torch.int64, device=table.device)
+    check(lib.wcn_mask_keys(_p(table), K, M, _p(keys), _stream()), "mask_keys")
+    return keys
+
+
+@dataclass
+class TilePlan:
+    """Mask-sorted 128-row tiles of one [K, n_rows] neighbour table (see wcn_build_tiles)."""
+    nbr: Tensor        # [K, m_pad] int32
+    rows: Tensor       # [m_pad] int32
+    tile_ks: Tensor    # [num_tiles, k_stride] int16 (uint16 payload)
+    tile_nk: Tensor    # [num_tiles] int32
+    K: int
+    n_rows: int
+    m_pad: int
+    num_tiles: int
+    k_stride: int
+
+
+def build_tile_plan(table: Tensor, keys: Optional[Tensor] = None) -> TilePlan:
+    """Replaces the reference's pair_mask + CUB argsort + per-tile mask OR
+    (detail/mask_gemm.py:127-276)."""
+    _require_cuda(table)
+    K, M = table.shape
+    dev = table.device
+    if keys is None:
+        keys = mask_keys(table)
+    rows_sorted = torch.empty(M, dtype=torch.int32, device=dev)
+    ws_bytes = lib.wcn_sort_workspace_bytes(M)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    check(lib.wcn_sort_rows_by_key(_p(keys), M, K, _p(rows_sorted), _p(ws), ws_bytes, _stream()),
+          "sort_rows_by_key")
+    m_pad = (M + TILE_M - 1) // TILE_M * TILE_M
+    num_tiles = m_pad // TILE_M
+    k_stride = K
+    nbr = torch.empty((K, m_pad), dtype=torch.int32, device=dev)
+    rows = torch.empty(m_pad, dtype=torch.int32, device=dev)
+    tile_ks = torch.empty((max(num_tiles, 1), k_stride), dtype=torch.int16, device=dev)
+    tile_nk = torch.empty(max(num_tiles, 1), dtype=torch.int32, device=dev)
+    check(lib.wcn_build_tiles(_p(table), K, M, _p(rows_sorted), m_pad, _p(nbr), _p(rows),
+                              _p(tile_ks), k_stride, _p(tile_nk), _stream()), "build_tiles")
+    return TilePlan(nbr, rows, tile_ks, tile_nk, K, M, m_pad, num_tiles, k_stride)
+
+
+# ------------------------------------------------------------------------------------------------
+# GEMMs
+# ------------------------------------------------------------------------------------------------
+def weight_image(weight: Tensor, K: int, groups: int, cin_g: int, cout_g: int,
+                 transpose_w: bool) -> Tensor:
+    """weight: contiguous [K, groups, cin_g, cout_g] (or [K, cin, cout] when groups == 1)."""
+    _require_cuda(weight)
+    assert weight.is_contiguous()
+    code = dtype_code(weight.dtype)
+    nbytes = lib.wcn_weight_image_bytes(K, groups, cin_g, cout_g, code, int(transpose_w), None,
+                                        None)
+    if nbytes == 0:
+        raise _lib.WcnError(
+            f"unsupported channel configuration groups={groups} cin/g={cin_g} cout/g={cout_g}")
+    img = torch.empty(nbytes, dtype=torch.uint8, device=weight.device)
+    check(lib.wcn_weight_image(_p(weight), _p(img), K, groups, cin_g, cout_g, code,
+                               int(transpose_w), _stream()), "weight_image")
+    return img
+
+
+def gather_gemm(feats: Tensor, wimg: Tensor, plan: TilePlan, groups: int, cin_g: int,
+                cout_g: int, out: Optional[Tensor] = None, bias: Optional[Tensor] = None,
+                relu: bool = False, kflip: bool = False, max_ctas: int = 0) -> Tensor:
+    """out[plan.rows] = sum_k feats[plan.nbr[k]] @ W_k (forward AB / dgrad ABt gather-scatter).
+
+    Every row of ``out`` (n_rows = plan.n_rows) is written exactly once, so ``out`` may be
+    uninitialised memory (the reference zero-fills, detail/mask_gemm.py:723)."""
+    _require_cuda(feats, wimg)
+    assert feats.dim() == 2 and feats.stride(1) == 1
+    code = dtype_code(feats.dtype)
+    if out is None:
+        out = torch.empty((plan.n_rows, groups * cout_g), dtype=feats.dtype, device=feats.device)
+    assert out.stride(1) == 1 and out.dtype == feats.dtype
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.is_contiguous()
+    check(lib.wcn_gather_gemm(_p(feats), feats.stride(0), _p(wimg), _p(out), out.stride(0),
+                              _p(plan.nbr), _p(plan.rows), _p(plan.tile_ks), plan.k_stride,
+                              _p(plan.tile_nk), plan.num_tiles, plan.m_pad, plan.K, groups, cin_g,
+                              cout_g, code, _p(bias), int(relu), int(kflip), max_ctas, _stream()),
+          "gather_gemm")
+    return out
+
+
+def wgrad(feats: Tensor, gout: Tensor, in_maps: Tensor, out_maps: Tensor, offsets_dev: Tensor,
+          K: int, groups: int, cin_g: int, cout_g: int, dw: Optional[Tensor] = None,
+          alpha: float = 1.0, unit_pairs: int = 0, max_ctas: int = 0) -> Tensor:
+    """dW[K, groups, cin_g, cout_g] (fp32) += X[in_maps]^T @ dY[out_maps] per offset."""
+    _require_cuda(feats, gout, in_maps, out_maps, offsets_dev)
+    assert feats.stride(1) == 1 and gout.stride(1) == 1 and feats.dtype == gout.dtype
+    code = dtype_code(feats.dtype)
+    if dw is None:
+        dw = torch.zeros((K, groups, cin_g, cout_g), dtype=torch.float32, device=feats.device)
+    assert dw.dtype == torch.float32 and dw.is_contiguous()
+    check(lib.wcn_wgrad(_p(feats), feats.stride(0), _p(gout), gout.stride(0), _p(dw), _p(in_maps),
+                        _p(out_maps), _p(offsets_dev), K, groups, cin_g, cout_g, code,
+                        ctypes.c_float(alpha), unit_pairs, max_ctas, _stream()), "wgrad")
+    return dw

@@ -18,6 +18,7 @@ int kernel_map_count(int*, int, int, int*, int*, cudaStream_t);
 int kernel_map_scatter(const int*, const int*, const int*, int*, int*, int, int, cudaStream_t);
 int reverse_pair_table(const int*, int, int, int*, int, cudaStream_t);
 int mask_keys_from_table(const int*, int, int, unsigned long long*, cudaStream_t);
+int csr_to_table(const int*, const int*, const int*, int, int, int, int*, cudaStream_t);
 size_t sort_workspace_bytes(int);
 int sort_rows_by_key(const unsigned long long*, int, int, int*, void*, size_t, cudaStream_t);
 int build_tiles(const int*, int, int, const int*, int, int*, int*, uint16_t*, int, int*,
@@ -133,6 +134,12 @@ int wcn_reverse_pair_table(const int32_t* pair_table, int K, int M, int32_t* rev
                            void* stream) {
   if (K < 1 || M < 0 || n_in < 0 || (n_in > 0 && !rev)) return kErrInvalidArg;
   return reverse_pair_table(pair_table, K, M, rev, n_in, S(stream));
+}
+int wcn_csr_to_pair_table(const int32_t* val_maps, const int32_t* row_maps, const int32_t* offsets,
+                          int K, int n_rows, int num_pairs, int32_t* table, void* stream) {
+  if (K < 1 || n_rows < 0 || (n_rows > 0 && !table) || !offsets) return kErrInvalidArg;
+  if (num_pairs > 0 && (!val_maps || !row_maps)) return kErrInvalidArg;
+  return csr_to_table(val_maps, row_maps, offsets, K, n_rows, num_pairs, table, S(stream));
 }
 int wcn_mask_keys(const int32_t* table, int K, int M, uint64_t* keys, void* stream) {
   if (M > 0 && (!table || !keys)) return kErrInvalidArg;

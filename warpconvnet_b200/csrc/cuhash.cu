@@ -257,6 +257,25 @@ __global__ void reverse_table_kernel(const int* __restrict__ pair_table, int K, 
   }
 }
 
+// table[k][row_maps[j]] = val_maps[j] for every CSR pair j of offset k (table pre-filled with -1)
+__global__ void csr_to_table_kernel(const int* __restrict__ val_maps,
+                                    const int* __restrict__ row_maps,
+                                    const int* __restrict__ offsets, int K, int n_rows,
+                                    int* __restrict__ table) {
+  extern __shared__ int s_offs[];  // [K+1]
+  for (int i = threadIdx.x; i <= K; i += blockDim.x) s_offs[i] = offsets[i];
+  __syncthreads();
+  const int L = s_offs[K];
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < L; j += gridDim.x * blockDim.x) {
+    int lo = 0, hi = K;  // largest k with offsets[k] <= j
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (s_offs[mid] <= j) lo = mid; else hi = mid;
+    }
+    table[(size_t)lo * n_rows + __ldg(row_maps + j)] = __ldg(val_maps + j);
+  }
+}
+
 __global__ void mask_keys_kernel(const int* __restrict__ table, int K, int M,
                                  unsigned long long* __restrict__ keys) {
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
@@ -370,6 +389,17 @@ int reverse_pair_table(const int* pair_table, int K, int M, int* rev, int n_in, 
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 32) blocks = 148 * 32;
   reverse_table_kernel<<<blocks, 256, 0, s>>>(pair_table, K, M, rev, n_in);
+  return cuda_ok();
+}
+
+int csr_to_table(const int* val_maps, const int* row_maps, const int* offsets, int K, int n_rows,
+                 int L_upper, int* table, cudaStream_t s) {
+  if (cudaMemsetAsync(table, 0xFF, (size_t)K * n_rows * 4, s) != cudaSuccess) return kErrCuda;
+  if (L_upper <= 0) return kOk;
+  int blocks = (L_upper + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  csr_to_table_kernel<<<blocks, 256, (size_t)(K + 1) * sizeof(int), s>>>(val_maps, row_maps,
+                                                                        offsets, K, n_rows, table);
   return cuda_ok();
 }
 

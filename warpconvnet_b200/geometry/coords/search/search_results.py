@@ -1,0 +1,166 @@
+# SPDX-License-Identifier: Apache-2.0
+"""Kernel-map and neighbour-search containers.
+
+``IntSearchResult`` keeps the reference's fields and methods
+(warpconvnet/geometry/coords/search/search_results.py:55-202): ``in_maps``, ``out_maps`` on the
+device, ``offsets`` on the CPU, ``identity_map_index``, ``__getitem__`` / ``__len__`` / ``numel`` /
+``clone`` / ``get_batch``. On top of that it lazily caches what the tensor-core kernels need:
+the dense pair table, its reverse, the device copy of ``offsets`` and the mask-sorted tile plans.
+"""
+from __future__ import annotations
+
+from typing import List, Literal, Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from warpconvnet_b200 import _ops
+
+
+class RealSearchResult:
+    """CSR neighbour lists (search_results.py:13-52)."""
+
+    def __init__(self, *args):
+        if len(args) == 2:
+            self.neighbor_indices = args[0].long()
+            self.neighbor_row_splits = args[1].long()
+        elif len(args) == 1:
+            assert isinstance(args[0], Tensor) and args[0].ndim == 2
+            M, K = args[0].shape
+            self.neighbor_indices = args[0].long().reshape(-1)
+            self.neighbor_row_splits = torch.arange(0, M * K + 1, K, device=args[0].device,
+                                                    dtype=torch.long)
+        else:
+            raise ValueError("RealSearchResult must be initialized with 1 or 2 arguments")
+        self.neighbor_distances = None
+
+    def to(self, device):
+        self.neighbor_indices = self.neighbor_indices.to(device)
+        self.neighbor_row_splits = self.neighbor_row_splits.to(device)
+        return self
+
+    def __repr__(self):
+        return (f"{self.__class__.__name__}(neighbor_indices={tuple(self.neighbor_indices.shape)}, "
+                f"neighbor_row_splits={tuple(self.neighbor_row_splits.shape)})")
+
+
+class IntSearchResult:
+    def __init__(self, in_maps: Tensor, out_maps: Tensor, offsets: Tensor,
+                 identity_map_index: Optional[int] = None):
+        offsets_cpu = offsets.cpu()
+        assert len(in_maps) == len(out_maps) == int(offsets_cpu[-1])
+        self.in_maps = in_maps
+        self.out_maps = out_maps
+        self.offsets = offsets_cpu
+        self.identity_map_index = identity_map_index
+        # lazily built device-side state for the sm_100a kernels
+        self._offsets_dev: Optional[Tensor] = offsets if offsets.is_cuda else None
+        self._pair_table: Optional[Tensor] = None      # [K, n_out] -> input row
+        self._rev_pair_table: Optional[Tensor] = None  # [K, n_in]  -> output row
+        self._mask_keys: Optional[Tensor] = None
+        self._fwd_plan: Optional[_ops.TilePlan] = None
+        self._bwd_plan: Optional[_ops.TilePlan] = None
+        self._n_in: Optional[int] = None
+        self._n_out: Optional[int] = None
+        # True when in/out coordinates are the same set and the kernel is odd: then
+        # rev_pair_table[k] == pair_table[K-1-k] and dgrad reuses the forward tile plan.
+        self._symmetric = False
+
+    # ---- reference API ---------------------------------------------------------------------
+    @torch.no_grad()
+    def __getitem__(self, idx: int) -> Tuple[Tensor, Tensor]:
+        start, end = int(self.offsets[idx]), int(self.offsets[idx + 1])
+        return self.in_maps[start:end], self.out_maps[start:end]
+
+    @torch.no_grad()
+    def get_batch(self, start_idx: int, end_idx: int,
+                  out_format: Literal["list", "tensor"] = "list"):
+        in_maps = [self[i][0] for i in range(start_idx, end_idx)]
+        out_maps = [self[i][1] for i in range(start_idx, end_idx)]
+        if out_format == "list":
+            return in_maps, out_maps
+        if out_format == "tensor":
+            width = max(len(m) for m in in_maps)
+            it = torch.full((len(in_maps), width), -1, device=self.in_maps.device, dtype=torch.int64)
+            ot = torch.full((len(in_maps), width), -1, device=self.in_maps.device, dtype=torch.int64)
+            for i, (a, b) in enumerate(zip(in_maps, out_maps)):
+                it[i, : len(a)] = a
+                ot[i, : len(b)] = b
+            return it, ot
+        raise ValueError(f"Invalid output format: {out_format}")
+
+    def __len__(self):
+        return len(self.offsets) - 1
+
+    def __iter__(self):
+        for i in range(len(self)):
+            yield self[i]
+
+    def __repr__(self):
+        return f"{self.__class__.__name__}(len={len(self)}, iden_map={self.identity_map_index})"
+
+    def numel(self, i: int) -> int:
+        return int(self.offsets[i + 1] - self.offsets[i])
+
+    def clone(self):
+        return IntSearchResult(self.in_maps.clone(), self.out_maps.clone(), self.offsets.clone(),
+                               self.identity_map_index)
+
+    @property
+    def device(self):
+        return self.in_maps.device
+
+    @torch.no_grad()
+    def neighbor_count_per_output(self, num_out: int) -> Tensor:
+        counts = torch.zeros(num_out, dtype=torch.long, device=self.out_maps.device)
+        counts.scatter_add_(0, self.out_maps.long(), torch.ones_like(self.out_maps, dtype=torch.long))
+        return counts
+
+    # ---- device-side plans -----------------------------------------------------------------
+    @property
+    def offsets_dev(self) -> Tensor:
+        if self._offsets_dev is None or self._offsets_dev.device != self.in_maps.device:
+            self._offsets_dev = self.offsets.to(device=self.in_maps.device, dtype=torch.int32)
+        if self._offsets_dev.dtype != torch.int32:
+            self._offsets_dev = self._offsets_dev.int()
+        return self._offsets_dev
+
+    @torch.no_grad()
+    def pair_table(self, n_out: int) -> Tensor:
+        if self._pair_table is None:
+            self._pair_table = _ops.csr_to_pair_table(self.in_maps, self.out_maps,
+                                                      self.offsets_dev, n_out)
+        return self._pair_table
+
+    @torch.no_grad()
+    def rev_pair_table(self, n_in: int) -> Tensor:
+        if self._rev_pair_table is None:
+            self._rev_pair_table = _ops.csr_to_pair_table(self.out_maps, self.in_maps,
+                                                          self.offsets_dev, n_in)
+        return self._rev_pair_table
+
+    @torch.no_grad()
+    def fwd_plan(self, n_out: int) -> _ops.TilePlan:
+        """Tile plan of the forward (output-stationary) pass over the n_out output rows."""
+        if self._fwd_plan is None:
+            self._fwd_plan = _ops.build_tile_plan(self.pair_table(n_out), self._mask_keys)
+            self._mask_keys = None
+        return self._fwd_plan
+
+    @torch.no_grad()
+    def bwd_plan(self, n_in: int):
+        """(plan, kflip) of the dgrad pass over the n_in input rows."""
+        if self._symmetric:
+            return self.fwd_plan(n_in), True
+        if self._bwd_plan is None:
+            self._bwd_plan = _ops.build_tile_plan(self.rev_pair_table(n_in))
+        return self._bwd_plan, False
+
+    def transposed_view(self) -> "IntSearchResult":
+        """in/out swapped (helper.py:486-497), sharing every cached table with roles swapped."""
+        t = IntSearchResult(self.out_maps, self.in_maps, self.offsets, None)
+        t._offsets_dev = self._offsets_dev
+        t._pair_table, t._rev_pair_table = self._rev_pair_table, self._pair_table
+        t._fwd_plan, t._bwd_plan = self._bwd_plan, self._fwd_plan
+        t._n_in, t._n_out = self._n_out, self._n_in
+        return t

@@ -1,0 +1,145 @@
+# SPDX-License-Identifier: Apache-2.0
+"""Kernel-map generation for sparse convolution (drop-in for
+warpconvnet/geometry/coords/search/torch_discrete.py:23-57,296-432).
+
+Pipeline (all on the current CUDA stream, ONE host synchronisation per map):
+  hash build -> K-offset probe (pair table + per-block counts + per-row offset mask)
+  -> block scan / offsets -> single D2H of (offsets, status) -> deterministic CSR scatter.
+The reference needs >= 6 host syncs for the same work.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+from torch import Tensor
+
+from warpconvnet_b200 import _ops
+from warpconvnet_b200.utils.ntuple import ntuple
+from .packed_hashmap import PackedHashTable
+from .search_results import IntSearchResult
+
+_OFFSET_CACHE: Dict[tuple, Tensor] = {}
+
+
+@torch.no_grad()
+def kernel_offsets_from_size(kernel_size: Tuple[int, ...], kernel_dilation: Tuple[int, ...],
+                             center_offset: Optional[Tuple[int, ...]] = None,
+                             device: Optional[torch.device] = None) -> Tensor:
+    """[K, D+1] int32 offsets, batch column first (torch_discrete.py:23-57): 'ij' meshgrid order,
+    odd sizes are centred, even sizes start at 0."""
+    assert len(kernel_size) == len(kernel_dilation)
+    ranges = [torch.arange(int(s), dtype=torch.int32) for s in kernel_size]
+    grids = torch.meshgrid(*ranges, indexing="ij")
+    if center_offset is None:
+        center_offset = [(s - 1) // 2 if s % 2 == 1 else 0 for s in kernel_size]
+    assert len(center_offset) == len(kernel_size)
+    cols = [(g.flatten() - int(center_offset[i])) * int(kernel_dilation[i])
+            for i, g in enumerate(grids)]
+    cols = [torch.zeros_like(cols[0])] + cols
+    return torch.stack(cols, dim=1).contiguous().to(device)
+
+
+def _offsets3(kernel_size, kernel_dilation, center_offset, device) -> Tensor:
+    key = (tuple(kernel_size), tuple(kernel_dilation),
+           None if center_offset is None else tuple(center_offset), str(device))
+    t = _OFFSET_CACHE.get(key)
+    if t is None:
+        t = kernel_offsets_from_size(kernel_size, kernel_dilation, center_offset)[:, 1:]
+        t = t.contiguous().to(device)
+        _OFFSET_CACHE[key] = t
+    return t
+
+
+@torch.no_grad()
+def generate_kernel_map(
+    batch_indexed_in_coords: Tensor,
+    batch_indexed_out_coords: Tensor,
+    in_to_out_stride_ratio: Tuple[int, ...],
+    kernel_size: Tuple[int, ...],
+    kernel_dilation: Optional[Tuple[int, ...]] = None,
+    kernel_center_offset: Optional[Tuple[int, ...]] = None,
+    method: str = "size",
+    skip_symmetric_kernel_map: bool = False,
+    same_coords: Optional[bool] = None,
+    **kwargs,
+) -> IntSearchResult:
+    """``coord(in) = stride * coord(out) + offset[k]`` pairs for every kernel offset k.
+
+    Returns an ``IntSearchResult`` whose CSR rows are in ascending output-row order inside each
+    offset (the reference's order is unspecified). ``same_coords=True`` tells the builder that the
+    two coordinate tensors are the same set in the same order (submanifold conv) so the dgrad
+    pass can reuse the forward tables; when None it is inferred from tensor identity.
+    """
+    assert batch_indexed_in_coords.dtype == torch.int32
+    assert batch_indexed_out_coords.dtype == torch.int32
+    dev = batch_indexed_in_coords.device
+    assert dev == batch_indexed_out_coords.device
+    if skip_symmetric_kernel_map:
+        raise NotImplementedError(
+            "skip_symmetric_kernel_map is not supported (the reference's conv path never sets it, "
+            "helper.py:446-455)")
+    if same_coords is None:
+        same_coords = batch_indexed_in_coords is batch_indexed_out_coords or (
+            batch_indexed_in_coords.data_ptr() == batch_indexed_out_coords.data_ptr()
+            and batch_indexed_in_coords.shape == batch_indexed_out_coords.shape)
+
+    in_c, out_c = batch_indexed_in_coords, batch_indexed_out_coords
+    kernel_size = tuple(int(k) for k in kernel_size)
+    stride = tuple(int(s) for s in in_to_out_stride_ratio)
+    if in_c.shape[1] == 3:  # 2-D conv: pad z = 0 (torch_discrete.py:328-342)
+        in_c = torch.nn.functional.pad(in_c, (0, 1), value=0)
+        out_c = in_c if same_coords else torch.nn.functional.pad(out_c, (0, 1), value=0)
+        kernel_size = kernel_size + (1,)
+        stride = stride + (1,)
+        if kernel_dilation is not None:
+            kernel_dilation = tuple(kernel_dilation) + (1,)
+        if kernel_center_offset is not None:
+            kernel_center_offset = tuple(kernel_center_offset) + (0,)
+    assert in_c.shape[1] == 4, f"Expected 4D batch-indexed coords, got {in_c.shape[1]}D"
+    assert len(stride) == 3
+    if kernel_dilation is None:
+        kernel_dilation = (1, 1, 1)
+    kernel_dilation = ntuple(kernel_dilation, ndim=3)
+
+    in_c = in_c.contiguous()
+    out_c = out_c.contiguous()
+    n_in, n_out = in_c.shape[0], out_c.shape[0]
+    K = int(np.prod(kernel_size))
+
+    identity_map_index = None
+    is_odd = all(k % 2 == 1 for k in kernel_size)
+    if is_odd and n_in == n_out:  # by COUNT, exactly like torch_discrete.py:363-370
+        identity_map_index = K // 2
+
+    table = PackedHashTable.from_coords(in_c, check=False)
+    offs3 = _offsets3(kernel_size, kernel_dilation, kernel_center_offset, dev)
+    pair_table, block_counts, mask_keys = _ops.kernel_map_search(
+        table.keys_tensor, table.values_tensor, out_c, offs3, stride)
+    offsets_dev = _ops.kernel_map_count(block_counts)
+    # the only host sync: offsets (needed on the CPU by the IntSearchResult contract) + status
+    host = torch.cat([offsets_dev, table.status_tensor]).cpu()
+    table.raise_if_failed(int(host[-1]))
+    offsets_cpu = host[:-1].clone()
+    num_pairs = int(offsets_cpu[-1])
+    in_maps, out_maps = _ops.kernel_map_scatter(pair_table, block_counts, offsets_dev, num_pairs)
+
+    result = IntSearchResult(in_maps, out_maps, offsets_cpu, identity_map_index=identity_map_index)
+    result._offsets_dev = offsets_dev
+    result._pair_table = pair_table
+    result._mask_keys = mask_keys
+    result._n_in, result._n_out = n_in, n_out
+    result._symmetric = bool(same_coords and is_odd and all(s == 1 for s in stride)
+                             and all(d == 1 for d in kernel_dilation)
+                             and kernel_center_offset is None)
+    result._hashtable = table
+    result._kernel_size = kernel_size
+    return result
+
+
+def _int_sequence_hash(arr: Sequence[int]) -> int:
+    x = hash(arr[0])
+    for i in range(1, len(arr)):
+        x = (x * 31 + hash(arr[i])) & 0xFFFFFFFF
+    return x

@@ -1,0 +1,189 @@
+# SPDX-License-Identifier: Apache-2.0
+"""Autograd function of the sparse convolution
+(drop-in for ``UnifiedSpatiallySparseConvFunction``,
+warpconvnet/nn/functional/sparse_conv/detail/unified.py:143-785).
+
+There is exactly one backend — the hand-written sm_100a kernels behind ``libwcn_b200.so`` — so the
+reference's per-call autotune / benchmark cache / fallback chain is gone by design. The algo-mode
+enums are kept so reference user code keeps working; every value maps to the same kernels.
+
+  forward : Y  = gather_gemm(X,  W image,      fwd tile plan)            AB_gather_scatter
+  dgrad   : dX = gather_gemm(dY, W^T image,    bwd tile plan)            ABt_gather_scatter
+  wgrad   : dW = wgrad(X, dY, CSR pair lists)  fp32, cast to W's dtype   AtB_gather_gather
+"""
+from __future__ import annotations
+
+from enum import Enum
+from typing import Optional
+
+import torch
+from torch import Tensor
+from torch.autograd import Function
+
+from warpconvnet_b200 import _ops
+from warpconvnet_b200.geometry.coords.search.search_results import IntSearchResult
+
+
+class SPARSE_CONV_AB_ALGO_MODE(Enum):
+    EXPLICIT_GEMM = "explicit_gemm"
+    IMPLICIT_GEMM = "implicit_gemm"
+    CUTLASS_IMPLICIT_GEMM = "cutlass_implicit_gemm"
+    CUTE_IMPLICIT_GEMM = "cute_implicit_gemm"
+    EXPLICIT_GEMM_GROUPED = "explicit_gemm_grouped"
+    IMPLICIT_GEMM_GROUPED = "implicit_gemm_grouped"
+    CUTLASS_GROUPED_HYBRID = "cutlass_grouped_hybrid"
+    CUTE_GROUPED = "cute_grouped"
+    MASK_GEMM = "mask_gemm"
+    TCGEN05 = "tcgen05"  # what actually runs
+    AUTO = "auto"
+    ALL = "all"
+    TRIMMED = "trimmed"
+
+
+class SPARSE_CONV_ATB_ALGO_MODE(Enum):
+    EXPLICIT_GEMM = "explicit_gemm"
+    IMPLICIT_GEMM = "implicit_gemm"
+    CUTLASS_IMPLICIT_GEMM = "cutlass_implicit_gemm"
+    CUTE_IMPLICIT_GEMM = "cute_implicit_gemm"
+    EXPLICIT_GEMM_GROUPED = "explicit_gemm_grouped"
+    IMPLICIT_GEMM_GROUPED = "implicit_gemm_grouped"
+    CUTLASS_GROUPED_HYBRID = "cutlass_grouped_hybrid"
+    CUTE_GROUPED = "cute_grouped"
+    MASK_GEMM = "mask_gemm"
+    TCGEN05 = "tcgen05"
+    AUTO = "auto"
+    ALL = "all"
+    TRIMMED = "trimmed"
+
+
+_CH_ALIGN = 16  # channels are padded to a multiple of 16 (one 32-byte MMA K-slice of bf16)
+
+
+def _round_up(v: int, a: int) -> int:
+    return (v + a - 1) // a * a
+
+
+def _pad_cols(t: Tensor, cols: int) -> Tensor:
+    if t.shape[1] == cols and t.stride(1) == 1 and (t.stride(0) * t.element_size()) % 16 == 0 \
+            and t.data_ptr() % 16 == 0:
+        return t
+    out = torch.zeros((t.shape[0], cols), dtype=t.dtype, device=t.device)
+    out[:, : t.shape[1]] = t
+    return out
+
+
+def _canon_weight(weight: Tensor, groups: int):
+    """-> (w4 [K, G, cin_g, cout_g] contiguous, padded), cin_g, cout_g, real cin_g, real cout_g"""
+    if groups == 1:
+        K, cin, cout = weight.shape
+        cin_p, cout_p = _round_up(cin, _CH_ALIGN), _round_up(cout, _CH_ALIGN)
+        if cin_p != cin or cout_p != cout:
+            w = torch.zeros((K, cin_p, cout_p), dtype=weight.dtype, device=weight.device)
+            w[:, :cin, :cout] = weight
+        else:
+            w = weight.contiguous()
+        return w.view(K, 1, cin_p, cout_p), cin_p, cout_p, cin, cout
+    K, G, cin_g, cout_g = weight.shape
+    assert G == groups
+    if cin_g % 8 or cout_g % 8:
+        raise ValueError(
+            f"group conv needs channels-per-group that are multiples of 8, got {cin_g}->{cout_g} "
+            f"(the reference has the same floor: detail/dispatch.py:42-50)")
+    return weight.contiguous(), cin_g, cout_g, cin_g, cout_g
+
+
+def sparse_conv_forward(in_features: Tensor, weight: Tensor, kernel_map: IntSearchResult,
+                        num_out_coords: int, groups: int = 1, bias: Optional[Tensor] = None,
+                        relu: bool = False) -> Tensor:
+    """Y[M, Cout] = sum_k X[in_k] @ W_k  on the tensor cores (no autograd)."""
+    w4, cin_g, cout_g, cin_r, cout_r = _canon_weight(weight, groups)
+    K = w4.shape[0]
+    x = _pad_cols(in_features, groups * cin_g)
+    plan = kernel_map.fwd_plan(num_out_coords)
+    img = _ops.weight_image(w4, K, groups, cin_g, cout_g, transpose_w=False)
+    if bias is not None and cout_g != cout_r:
+        bias = torch.nn.functional.pad(bias.float(), (0, cout_g - cout_r))
+    y = _ops.gather_gemm(x, img, plan, groups, cin_g, cout_g,
+                         bias=None if bias is None else bias.float().contiguous(), relu=relu)
+    return y if cout_g == cout_r else y[:, :cout_r]
+
+
+def sparse_conv_dgrad(grad_output: Tensor, weight: Tensor, kernel_map: IntSearchResult,
+                      num_in_coords: int, groups: int = 1) -> Tensor:
+    """dX[N, Cin] = sum_k dY[out_k] @ W_k^T."""
+    w4, cin_g, cout_g, cin_r, cout_r = _canon_weight(weight, groups)
+    K = w4.shape[0]
+    gy = _pad_cols(grad_output, groups * cout_g)
+    plan, kflip = kernel_map.bwd_plan(num_in_coords)
+    img = _ops.weight_image(w4, K, groups, cin_g, cout_g, transpose_w=True)
+    # roles swap: contraction over cout_g, rows produced = cin_g
+    dx = _ops.gather_gemm(gy, img, plan, groups, cout_g, cin_g, kflip=kflip)
+    return dx if cin_g == cin_r else dx[:, :cin_r]
+
+
+def sparse_conv_wgrad(in_features: Tensor, grad_output: Tensor, weight_shape, kernel_map,
+                      groups: int = 1) -> Tensor:
+    """fp32 dW with the shape of the weight."""
+    if groups == 1:
+        K, cin, cout = weight_shape
+        cin_p, cout_p = _round_up(cin, _CH_ALIGN), _round_up(cout, _CH_ALIGN)
+        x = _pad_cols(in_features, cin_p)
+        gy = _pad_cols(grad_output, cout_p)
+        dw = _ops.wgrad(x, gy, kernel_map.in_maps, kernel_map.out_maps, kernel_map.offsets_dev, K,
+                        1, cin_p, cout_p)
+        dw = dw.view(K, cin_p, cout_p)
+        return dw if (cin_p == cin and cout_p == cout) else dw[:, :cin, :cout]
+    K, G, cin_g, cout_g = weight_shape
+    x = _pad_cols(in_features, G * cin_g)
+    gy = _pad_cols(grad_output, G * cout_g)
+    return _ops.wgrad(x, gy, kernel_map.in_maps, kernel_map.out_maps, kernel_map.offsets_dev, K, G,
+                      cin_g, cout_g)
+
+
+class UnifiedSpatiallySparseConvFunction(Function):
+    """Same positional signature as the reference (unified.py:145-166) so call sites match."""
+
+    @staticmethod
+    def forward(ctx, in_features, weight, kernel_map, num_out_coords, fwd_algo=None,
+                dgrad_algo=None, wgrad_algo=None, compute_dtype=None, fwd_block_size=None,
+                bwd_block_size=None, in_tensor_stride=None, conv_cache_metadata=None, groups=1,
+                use_fp16_accum=False):
+        if not in_features.is_cuda:
+            raise RuntimeError("warpconvnet_b200 sparse conv needs CUDA tensors (no CPU fallback)")
+        out_dtype = in_features.dtype
+        x, w = in_features, weight
+        if compute_dtype is not None:
+            if x.dtype != compute_dtype:
+                x = x.to(compute_dtype)
+            if w.dtype != compute_dtype:
+                w = w.to(compute_dtype)
+        elif w.dtype != x.dtype:
+            w = w.to(x.dtype)
+        y = sparse_conv_forward(x, w, kernel_map, num_out_coords, groups)
+        ctx.save_for_backward(x, w)
+        ctx.kernel_map = kernel_map
+        ctx.groups = groups
+        ctx.in_dtype = in_features.dtype
+        ctx.w_dtype = weight.dtype
+        ctx.num_in = in_features.shape[0]
+        ctx.weight_shape = tuple(weight.shape)
+        return y if compute_dtype is None else y.to(out_dtype)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        x, w = ctx.saved_tensors
+        kernel_map = ctx.kernel_map
+        gy = grad_output
+        if gy.dtype != x.dtype:
+            gy = gy.to(x.dtype)
+        if not gy.is_contiguous():
+            gy = gy.contiguous()
+        grad_in = grad_w = None
+        if ctx.needs_input_grad[0]:
+            grad_in = sparse_conv_dgrad(gy, w, kernel_map, ctx.num_in, ctx.groups).to(ctx.in_dtype)
+        if ctx.needs_input_grad[1]:
+            grad_w = sparse_conv_wgrad(x, gy, ctx.weight_shape, kernel_map, ctx.groups)
+            grad_w = grad_w.to(ctx.w_dtype)
+            if grad_w.shape != ctx.weight_shape:
+                grad_w = grad_w.reshape(ctx.weight_shape)
+        return (grad_in, grad_w) + (None,) * 12

@@ -1,0 +1,249 @@
+# SPDX-License-Identifier: Apache-2.0
+"""``spatially_sparse_conv`` — the functional entry point behind ``SparseConv3d``
+(drop-in for warpconvnet/nn/functional/sparse_conv/helper.py:147-567: same arguments, same
+output-coordinate rules, same kernel-map caching on the ``Voxels`` object, same transposed-map
+reuse)."""
+from __future__ import annotations
+
+from enum import Enum
+from typing import List, Optional, Tuple, Union
+
+import numpy as np
+import torch
+from torch import Tensor
+
+from warpconvnet_b200.geometry.base.geometry import Geometry
+from warpconvnet_b200.geometry.coords.integer import IntCoords
+from warpconvnet_b200.geometry.coords.ops.stride import stride_coords
+from warpconvnet_b200.geometry.coords.search.cache import IntSearchCache, IntSearchCacheKey
+from warpconvnet_b200.geometry.coords.search.search_results import IntSearchResult
+from warpconvnet_b200.geometry.coords.search.torch_discrete import generate_kernel_map
+from warpconvnet_b200.geometry.types.voxels import Voxels
+from warpconvnet_b200.utils.ntuple import ntuple
+
+from .detail.unified import (SPARSE_CONV_AB_ALGO_MODE, SPARSE_CONV_ATB_ALGO_MODE,
+                             UnifiedSpatiallySparseConvFunction)
+
+
+class STRIDED_CONV_MODE(Enum):
+    REDUCE_AND_STRIDE = "reduce_and_stride"
+    STRIDE_ONLY = "stride_only"
+
+
+def _intcoords_from_batch_indexed(reference: IntCoords, bcoords: Tensor, offsets: Tensor):
+    return reference.__class__(bcoords[:, 1:].contiguous(),
+                               offsets.to(device="cpu", dtype=reference.offsets.dtype),
+                               voxel_size=reference.voxel_size,
+                               tensor_stride=reference.tensor_stride)
+
+
+def _apply_generative_policy(input_sparse_tensor: Voxels, kernel_size, kernel_dilation, stride,
+                             stride_mode, transposed):
+    """Output coordinates of a generative conv (helper.py:58-144)."""
+    input_coords = input_sparse_tensor.batched_coordinates
+    bin_coords = input_sparse_tensor.batch_indexed_coordinates
+    if all(s == 1 for s in stride):
+        ex = input_coords.expand(kernel_size, kernel_dilation)
+        return ex.batch_indexed_coordinates, ex.offsets, bin_coords
+    if transposed:
+        st = torch.tensor([1] + list(stride), dtype=bin_coords.dtype, device=bin_coords.device)
+        scaled = bin_coords * st
+        ex = _intcoords_from_batch_indexed(input_coords, scaled, input_sparse_tensor.offsets
+                                           ).expand(kernel_size, kernel_dilation)
+        return ex.batch_indexed_coordinates, ex.offsets, scaled
+    strided, strided_offsets = stride_coords(bin_coords, stride)
+    strided_coords = _intcoords_from_batch_indexed(input_coords, strided, strided_offsets)
+    ex = strided_coords.expand(kernel_size, kernel_dilation)
+    km_in = bin_coords if stride_mode == STRIDED_CONV_MODE.STRIDE_ONLY \
+        else strided_coords.batch_indexed_coordinates
+    return ex.batch_indexed_coordinates, ex.offsets, km_in
+
+
+@torch.compiler.disable
+def spatially_sparse_conv(
+    input_sparse_tensor: Geometry,
+    weight: Tensor,
+    kernel_size: Union[int, List[int], Tuple[int, ...]],
+    stride: Union[int, List[int], Tuple[int, ...]] = 1,
+    kernel_dilation: Union[int, List[int], Tuple[int, ...]] = 1,
+    bias: Optional[Tensor] = None,
+    groups: int = 1,
+    use_fp16_accum: Optional[bool] = None,
+    kernel_matmul_batch_size: int = 2,
+    generative: bool = False,
+    output_spatially_sparse_tensor: Optional[Geometry] = None,
+    transposed: bool = False,
+    fwd_algo=SPARSE_CONV_AB_ALGO_MODE.TCGEN05,
+    dgrad_algo=SPARSE_CONV_AB_ALGO_MODE.TCGEN05,
+    wgrad_algo=SPARSE_CONV_ATB_ALGO_MODE.TCGEN05,
+    stride_mode: STRIDED_CONV_MODE = STRIDED_CONV_MODE.STRIDE_ONLY,
+    stride_reduce: str = "max",
+    order=None,
+    compute_dtype: Optional[torch.dtype] = None,
+    implicit_matmul_fwd_block_size: Optional[int] = 16,
+    implicit_matmul_bwd_block_size: Optional[int] = 16,
+) -> Geometry:
+    if not isinstance(input_sparse_tensor, Voxels):
+        raise TypeError("Native spatially_sparse_conv expects input_sparse_tensor of type Voxels, "
+                        f"got {type(input_sparse_tensor)}")
+    if output_spatially_sparse_tensor is not None and not isinstance(
+            output_spatially_sparse_tensor, Voxels):
+        raise TypeError("Native spatially_sparse_conv expects output_spatially_sparse_tensor of "
+                        f"type Voxels or None, got {type(output_spatially_sparse_tensor)}")
+
+    nd = input_sparse_tensor.num_spatial_dims
+    _kernel_size = ntuple(kernel_size, ndim=nd)
+    _kernel_dilation = ntuple(kernel_dilation, ndim=nd)
+    _stride = ntuple(stride, ndim=nd)
+
+    # 1x1x1 stride-1 shortcut: plain dense matmul, no kernel map (helper.py:206-213)
+    if np.prod(_kernel_size) == 1 and np.prod(_stride) == 1:
+        feats = input_sparse_tensor.feature_tensor
+        w0 = weight[0]
+        if w0.dim() == 3:  # grouped [G, cin_g, cout_g] -> block diagonal
+            w0 = torch.block_diag(*w0.unbind(0))
+        out = feats @ w0.to(feats.dtype)
+        if bias is not None:
+            out = out + bias.to(out.dtype)
+        return input_sparse_tensor.replace(batched_features=out)
+
+    in_tensor_stride = input_sparse_tensor.tensor_stride
+    if in_tensor_stride is None:
+        in_tensor_stride = ntuple(1, ndim=nd)
+    if transposed and not generative:
+        assert output_spatially_sparse_tensor is not None, \
+            "Output spatially sparse tensor is required for transposed convolution without generative"
+
+    if not transposed:
+        out_tensor_stride = tuple(o * s for o, s in zip(_stride, in_tensor_stride))
+    elif generative:
+        out_tensor_stride = tuple(i // s for i, s in zip(in_tensor_stride, _stride))
+    else:
+        if output_spatially_sparse_tensor.tensor_stride is not None:
+            out_tensor_stride = output_spatially_sparse_tensor.tensor_stride
+        else:
+            out_tensor_stride = ntuple(1, ndim=nd)
+        assert any(o < i for o, i in zip(out_tensor_stride, in_tensor_stride)), \
+            "Output stride is larger than input stride"
+
+    if compute_dtype is not None:
+        effective_compute_dtype = compute_dtype
+    elif torch.is_autocast_enabled():
+        effective_compute_dtype = torch.get_autocast_dtype("cuda")
+    else:
+        effective_compute_dtype = input_sparse_tensor.batched_features.dtype
+
+    if stride_mode == STRIDED_CONV_MODE.REDUCE_AND_STRIDE and any(s != 1 for s in _stride):
+        raise NotImplementedError(
+            "stride_mode=REDUCE_AND_STRIDE needs sparse pooling, which is outside the hot path "
+            "(SURVEY.md §2a); use the default STRIDE_ONLY")
+
+    feats = input_sparse_tensor.batched_features.batched_tensor
+    bout, out_offsets, kernel_map = generate_output_coords_and_kernel_map(
+        input_sparse_tensor=input_sparse_tensor, kernel_size=_kernel_size,
+        kernel_dilation=_kernel_dilation, stride=_stride, generative=generative,
+        transposed=transposed, output_spatially_sparse_tensor=output_spatially_sparse_tensor,
+        stride_mode=stride_mode, order=order)
+    num_out = bout.shape[0]
+
+    x, w = feats, weight
+    if x.dtype != effective_compute_dtype:
+        x = x.to(effective_compute_dtype)
+    if w.dtype != effective_compute_dtype:
+        w = w.to(effective_compute_dtype)
+
+    out = UnifiedSpatiallySparseConvFunction.apply(
+        x, w, kernel_map, num_out, fwd_algo, dgrad_algo, wgrad_algo, effective_compute_dtype,
+        implicit_matmul_fwd_block_size, implicit_matmul_bwd_block_size, in_tensor_stride, None,
+        groups, bool(use_fp16_accum))
+    if bias is not None:
+        out = out + bias.to(out.dtype)
+
+    out_offsets_cpu = out_offsets if out_offsets.device.type == "cpu" else out_offsets.cpu()
+    if bout is input_sparse_tensor.batch_indexed_coordinates:
+        # submanifold: same coordinate object -> keep it (and its cached [N,4] view)
+        new_coords = input_sparse_tensor.batched_coordinates
+        if tuple(out_tensor_stride) != tuple(in_tensor_stride):
+            new_coords = IntCoords(new_coords.batched_tensor, offsets=out_offsets_cpu)
+    else:
+        new_coords = IntCoords(bout[:, 1:].contiguous(), offsets=out_offsets_cpu)
+        new_coords._bcoords = bout
+    return input_sparse_tensor.replace(batched_coordinates=new_coords, batched_features=out,
+                                       tensor_stride=out_tensor_stride)
+
+
+@torch.compiler.disable
+def generate_output_coords_and_kernel_map(
+    input_sparse_tensor: Voxels,
+    kernel_size: Tuple[int, ...],
+    kernel_dilation: Tuple[int, ...],
+    stride: Tuple[int, ...],
+    generative: bool = False,
+    transposed: bool = False,
+    output_spatially_sparse_tensor: Optional[Voxels] = None,
+    stride_mode: STRIDED_CONV_MODE = STRIDED_CONV_MODE.STRIDE_ONLY,
+    order=None,
+    kernel_search_batch_size: Optional[int] = None,
+    out_code_backend: Optional[str] = None,
+) -> Tuple[Tensor, Tensor, IntSearchResult]:
+    """helper.py:361-567."""
+    bin_coords = input_sparse_tensor.batch_indexed_coordinates
+    same_coords = False
+    if output_spatially_sparse_tensor is not None:
+        assert not generative, \
+            "Output spatially sparse tensor is not supported with generative convolution"
+        bout = output_spatially_sparse_tensor.batch_indexed_coordinates
+        out_offsets = output_spatially_sparse_tensor.offsets
+    elif generative:
+        bout, out_offsets, bin_coords = _apply_generative_policy(
+            input_sparse_tensor, kernel_size, kernel_dilation, stride, stride_mode, transposed)
+    elif any(s != 1 for s in stride):
+        cache = input_sparse_tensor._extra_attributes.setdefault("_stride_cache", {})
+        key = (tuple(stride), tuple(int(v) for v in input_sparse_tensor.offsets.tolist()))
+        if key not in cache:
+            cache[key] = stride_coords(bin_coords, stride)
+        bout, out_offsets = cache[key]
+    else:
+        bout, out_offsets = bin_coords, input_sparse_tensor.offsets
+        same_coords = True
+
+    key = IntSearchCacheKey(kernel_size=kernel_size, kernel_dilation=kernel_dilation,
+                            transposed=transposed, generative=generative,
+                            stride_mode=str(stride_mode), skip_symmetric_kernel_map=False,
+                            in_offsets=input_sparse_tensor.offsets, out_offsets=out_offsets)
+    if input_sparse_tensor.cache is not None and isinstance(input_sparse_tensor.cache,
+                                                            IntSearchCache):
+        hit = input_sparse_tensor.cache.get(key)
+        if hit is not None:
+            return bout, out_offsets, hit
+
+    if transposed and not generative:
+        fwd_key = IntSearchCacheKey(kernel_size=kernel_size, kernel_dilation=kernel_dilation,
+                                    transposed=False, generative=generative,
+                                    stride_mode=str(stride_mode), skip_symmetric_kernel_map=False,
+                                    in_offsets=out_offsets,
+                                    out_offsets=input_sparse_tensor.offsets)
+        fwd_map = None
+        for src in (input_sparse_tensor, output_spatially_sparse_tensor):
+            if src is not None and isinstance(src.cache, IntSearchCache):
+                fwd_map = src.cache.get(fwd_key)
+                if fwd_map is not None:
+                    break
+        if fwd_map is None:
+            fwd_map = generate_kernel_map(bout, bin_coords, stride, kernel_size, kernel_dilation)
+        kernel_map = fwd_map.transposed_view()
+    elif transposed and generative:
+        kernel_map = generate_kernel_map(
+            bout, bin_coords, ntuple(1, ndim=input_sparse_tensor.num_spatial_dims), kernel_size,
+            kernel_dilation).transposed_view()
+    elif stride_mode == STRIDED_CONV_MODE.STRIDE_ONLY:
+        kernel_map = generate_kernel_map(bin_coords, bout, stride, kernel_size, kernel_dilation,
+                                         same_coords=same_coords)
+    else:
+        raise ValueError(f"Unsupported case. stride_mode: {stride_mode}, generative: {generative}, "
+                         f"transposed: {transposed}")
+
+    if not isinstance(input_sparse_tensor.cache, IntSearchCache):
+        input_sparse_tensor._extra_attributes["_cache"] = IntSearchCache()
+    input_sparse_tensor.cache.put(key, kernel_map)
+    return bout, out_offsets, kernel_map
