@@ -1,0 +1,156 @@
+# SPDX-License-Identifier: Apache-2.0
+"""CPU tests that PIN the oracle: against the committed golden fixtures (brute-force dict
+enumeration + outputs of the reference's own explicit path), against the reference's ones-KAT,
+and — where /root/reference is mounted — against the live reference."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import conv as oconv
+from oracle import kernel_map as okm
+from oracle import ref_adapter
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+def test_golden_fixtures_present():
+    assert len(GOLDEN) >= 6
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_kernel_map_oracle_vs_golden(path):
+    g = np.load(path)
+    km = okm.generate_kernel_map(g["in_bcoords"], g["out_bcoords"], tuple(g["stride"]),
+                                 tuple(g["kernel_size"]))
+    assert np.array_equal(km["offsets"], g["offsets"])
+    assert np.array_equal(km["pair_table"], g["pair_table"])
+    assert np.array_equal(km["in_maps"], g["in_maps"])
+    assert np.array_equal(km["out_maps"], g["out_maps"])
+    # the dict enumeration of the reference's own tests (set of (k, in, out) triples)
+    trip = []
+    for k in range(len(km["offsets"]) - 1):
+        s, e = km["offsets"][k], km["offsets"][k + 1]
+        trip += [(k, int(i), int(o)) for i, o in zip(km["in_maps"][s:e], km["out_maps"][s:e])]
+    assert sorted(trip) == [tuple(t) for t in g["triples"].tolist()]
+    iden = km["identity_map_index"]
+    assert (-1 if iden is None else iden) == int(g["identity_map_index"])
+    # invariant of tests/coords/test_kernel_map_invariants.py:8-12: in = stride*out + offset[k]
+    offs = km["kernel_offsets"]
+    st = g["stride"]
+    for k in range(len(offs)):
+        s, e = km["offsets"][k], km["offsets"][k + 1]
+        i_c = g["in_bcoords"][km["in_maps"][s:e]]
+        o_c = g["out_bcoords"][km["out_maps"][s:e]]
+        assert np.array_equal(i_c[:, 0], o_c[:, 0])
+        assert np.array_equal(i_c[:, 1:], o_c[:, 1:] * st + offs[k])
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_conv_oracle_vs_reference_outputs(path):
+    g = np.load(path)
+    n_out = len(g["out_bcoords"])
+    args = (g["in_maps"], g["out_maps"], g["offsets"])
+    y = oconv.forward(g["x"], g["w"], *args, n_out)
+    dx, dw = oconv.backward(g["gy"], g["x"], g["w"], *args)
+    # fp64 oracle vs the reference run in fp64: summation order only
+    assert oconv.rel_max_err(y, g["y_ref_f64"]) < 1e-12
+    assert oconv.rel_max_err(dx, g["dx_ref_f64"]) < 1e-12
+    assert oconv.rel_max_err(dw, g["dw_ref_f64"]) < 1e-12
+    # and vs the reference run in fp32 (its usual truth, tests/nn/test_kernel_correctness.py:64)
+    assert oconv.rel_max_err(y, g["y_ref_f32"]) < 1e-5
+    assert oconv.rel_max_err(dx, g["dx_ref_f32"]) < 1e-5
+    assert oconv.rel_max_err(dw, g["dw_ref_f32"]) < 1e-5
+
+
+def test_ones_kat():
+    """scripts/validate_tiles_on_device.py:46-96: x = 1, w = 1 => Y[r, :] = Cin * degree(r)."""
+    g = np.load(GOLDEN[0])
+    n_out = len(g["out_bcoords"])
+    cin, cout = 4, 8
+    K = len(g["offsets"]) - 1
+    y = oconv.forward(np.ones((len(g["in_bcoords"]), cin)), np.ones((K, cin, cout)), g["in_maps"],
+                      g["out_maps"], g["offsets"], n_out)
+    deg = oconv.degree(g["out_maps"], n_out)
+    assert np.array_equal(y.numpy(), np.repeat(cin * deg[:, None], cout, axis=1).astype(np.float64))
+
+
+def test_grouped_oracle_matches_block_diagonal_dense():
+    g = np.load(GOLDEN[0])
+    n = len(g["in_bcoords"])
+    K, G, cg, og = 27, 2, 2, 4
+    rng = np.random.RandomState(0)
+    x = rng.randn(n, G * cg)
+    w = rng.randn(K, G, cg, og)
+    gy = rng.randn(n, G * og)
+    args = (g["in_maps"], g["out_maps"], g["offsets"])
+    wd = np.zeros((K, G * cg, G * og))
+    for gi in range(G):
+        wd[:, gi * cg:(gi + 1) * cg, gi * og:(gi + 1) * og] = w[:, gi]
+    y = oconv.forward_grouped(x, w, *args, n)
+    assert oconv.rel_max_err(y, oconv.forward(x, wd, *args, n)) < 1e-13
+    dx, dw = oconv.backward_grouped(gy, x, w, *args)
+    dxd, dwd = oconv.backward(gy, x, wd, *args)
+    assert oconv.rel_max_err(dx, dxd) < 1e-13
+    for gi in range(G):
+        assert oconv.rel_max_err(dw[:, gi], dwd[:, gi * cg:(gi + 1) * cg, gi * og:(gi + 1) * og]) < 1e-13
+
+
+def test_key_range_and_duplicates():
+    with pytest.raises(ValueError):
+        okm.check_range(np.array([[512, 0, 0, 0]]))
+    with pytest.raises(ValueError):
+        okm.check_range(np.array([[0, 131072, 0, 0]]))
+    okm.check_range(np.array([[511, -131072, 131071, 0]]))
+    # duplicates resolve to the smallest index (tests/coords/test_packed_hashmap.py:116-128 accept
+    # any winner; ours is deterministic)
+    c = np.array([[0, 1, 2, 3], [0, 1, 2, 3], [0, 5, 5, 5]], np.int32)
+    t = okm.CoordTable(c)
+    assert t.lookup(c).tolist() == [0, 0, 2]
+    assert t.lookup(np.array([[0, 9, 9, 9]])).tolist() == [-1]
+    # boundary coordinates round-trip (tests/coords/test_packed_hashmap.py:188-240)
+    b = np.array([[511, -131072, 131071, -1], [0, 131071, -131072, 0]], np.int32)
+    assert okm.CoordTable(b).lookup(b).tolist() == [0, 1]
+
+
+def test_empty_inputs():
+    e = np.zeros((0, 4), np.int32)
+    km = okm.generate_kernel_map(e, e, (1, 1, 1), (3, 3, 3))
+    assert km["offsets"].tolist() == [0] * 28 and km["pair_table"].shape == (27, 0)
+    y = oconv.forward(np.zeros((0, 4)), np.zeros((27, 4, 8)), km["in_maps"], km["out_maps"],
+                      km["offsets"], 0)
+    assert tuple(y.shape) == (0, 8)
+
+
+def test_offset_order_matches_reference_enumeration():
+    """kernel_map.cuh:34-54: k -> (k/(kz*ky), (k/kz)%ky, k%kz) - centre; even sizes start at 0."""
+    offs = okm.kernel_offsets((3, 3, 3))
+    for k in range(27):
+        assert offs[k].tolist() == [k // 9 - 1, (k // 3) % 3 - 1, k % 3 - 1]
+    offs = okm.kernel_offsets((2, 2, 2))
+    for k in range(8):
+        assert offs[k].tolist() == [k // 4, (k // 2) % 2, k % 2]
+    assert okm.kernel_offsets((3, 1, 5), dilation=(2, 1, 1))[0].tolist() == [-2, 0, -2]
+
+
+@pytest.mark.skipif(not ref_adapter.available(), reason="reference tree not mounted")
+def test_oracle_vs_live_reference():
+    """Import the reference's explicit path (CPU) and compare on a fresh random case."""
+    fwd, bwd, ISR = ref_adapter.load()
+    rng = np.random.RandomState(7)
+    c = np.unique(rng.randint(0, 12, size=(600, 3)), axis=0).astype(np.int32)
+    bc = okm.batch_indexed([c[: len(c) // 2], c[len(c) // 2:]])
+    km = okm.generate_kernel_map(bc, bc, (1, 1, 1), (3, 3, 3))
+    n = len(bc)
+    x, w, gy = rng.randn(n, 6), rng.randn(27, 6, 10) * 0.1, rng.randn(n, 10)
+    ref_km = ISR(torch.from_numpy(km["in_maps"]).long(), torch.from_numpy(km["out_maps"]).long(),
+                 torch.from_numpy(km["offsets"]).long(), identity_map_index=13)
+    xt, wt, gt = (torch.from_numpy(a) for a in (x, w, gy))
+    y_ref = fwd(xt, wt, ref_km, n)
+    dx_ref, dw_ref = bwd(gt, xt, wt, ref_km)
+    args = (km["in_maps"], km["out_maps"], km["offsets"])
+    assert oconv.rel_max_err(oconv.forward(x, w, *args, n), y_ref) < 1e-12
+    dx, dw = oconv.backward(gy, x, w, *args)
+    assert oconv.rel_max_err(dx, dx_ref) < 1e-12 and oconv.rel_max_err(dw, dw_ref) < 1e-12
