@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+# SPDX-License-Identifier: Apache-2.0
+"""bench.py — SparseConv3d fwd+bwd voxels/sec on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--dist S|R] [--impl ours|reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload): BASELINE config C3 — one SparseConv3d 3^3, 128 -> 128 channels, bf16,
+~200k active voxels per GPU (surface-like distribution S: 448x448 height field = 200 704 voxels;
+--dist R: 200 000 uniformly random voxels at 30 % occupancy). One step = the whole hot path over one
+batch: kernel-map build (hash + 27-offset probe + CSR) + tile plan + forward AB_gather_scatter +
+dgrad ABt_gather_scatter + wgrad AtB_gather_gather (+ one NCCL all-reduce of dW when N > 1).
+
+  value : voxels/s with the inputs already resident in HBM
+  e2e   : the same through the public API (Voxels -> SparseConv3d -> backward) from pinned HOST
+          buffers, H2D and D2H inside the timed region
+  roofline     : forward gather-GEMM kernel alone (CUDA events around its launch in the timed
+                 steps): algorithmic FLOPs 2*L*Cin*Cout / time vs the measured bf16 peak
+  cpu_baseline : the oracle port of the reference's explicit gather-matmul-scatter
+                 (oracle/conv.py, fp32, all host threads) on the same workload, rank 0, N = 1 only
+
+--impl reference runs ONLY that CPU port (the reference is a Python/CUDA library whose CUDA
+extension cannot be built here and /root/reference does not exist on the GPU box).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CIN, COUT, KS = 128, 128, 3
+K = KS ** 3
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic workload
+# ------------------------------------------------------------------------------------------------
+def make_coords(dist: str, seed: int) -> np.ndarray:
+    if dist == "S":
+        rng = np.random.RandomState(seed)
+        a, b = rng.uniform(0, 2 * np.pi, size=2)
+        u, v = np.meshgrid(np.arange(448), np.arange(448), indexing="ij")
+        z = np.rint(12 * np.sin(2 * np.pi * u / 180 + a) + 8 * np.cos(2 * np.pi * v / 130 + b)) + 256
+        return np.stack([u.reshape(-1), v.reshape(-1), z.reshape(-1)], 1).astype(np.int32)
+    n, side = 200000, 88
+    g = torch.Generator().manual_seed(seed)
+    idx = torch.randperm(side ** 3, generator=g)[:n].numpy()
+    return np.stack([idx // (side * side), (idx // side) % side, idx % side], 1).astype(np.int32)
+
+
+def make_tensors(n: int, seed: int):
+    g = torch.Generator().manual_seed(seed + 1)
+    x = torch.randn(n, CIN, generator=g)
+    w = torch.randn(K, CIN, COUT, generator=g) * (K * CIN) ** -0.5
+    gy = torch.randn(n, COUT, generator=g)
+    return x, w, gy
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"tflops": float(p["bf16_tflops_sustained"]), "hbm": float(p["hbm_gbs"]),
+                "which": "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"}
+    return {"tflops": 1400.0, "hbm": 6650.0, "which": "fallback (B200_PROFILING.md, sustained)"}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU port of the reference's explicit path (the oracle) — baseline legs only
+# ------------------------------------------------------------------------------------------------
+def cpu_port_step(coords: np.ndarray, x, w, gy):
+    """One pass of the hot path on the host: kernel map (oracle/kernel_map.py) + explicit
+    gather-matmul-scatter fwd + bwd in fp32 (oracle/conv.py). Returns (seconds, L)."""
+    from oracle import conv as oconv
+    from oracle import kernel_map as okm
+    t0 = time.perf_counter()
+    bc = okm.batch_indexed([coords])
+    km = okm.generate_kernel_map(bc, bc, (1, 1, 1), (KS,) * 3)
+    args = (km["in_maps"], km["out_maps"], km["offsets"])
+    oconv.forward(x, w, *args, len(bc), dtype=torch.float32)
+    oconv.backward(gy, x, w, *args, dtype=torch.float32)
+    return time.perf_counter() - t0, int(km["offsets"][-1])
+
+
+def run_cpu_baseline(dist: str, reps: int, warmup: int, budget_s: float = 40.0):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    coords = make_coords(dist, 0)
+    x, w, gy = make_tensors(len(coords), 0)
+    times = []
+    t_begin = time.perf_counter()
+    for i in range(warmup + reps):
+        t, _ = cpu_port_step(coords, x, w, gy)
+        if i >= warmup:
+            times.append(t)
+        if time.perf_counter() - t_begin > budget_s and times:
+            break
+    t = float(np.mean(times))
+    return {"value": len(coords) / t, "unit": "voxels/s", "cores": cores, "kind": "port",
+            "sample": f"full C3-{dist} workload ({len(coords)} voxels, fp32, kernel map + fwd + "
+                      f"dgrad + wgrad), mean of {len(times)} passes after {warmup} warm-up",
+            "seconds_per_pass": t}, len(coords)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(nm)
+            except (ValueError, IndexError):
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(mx)) if mx else None, "samples": len(sm),
+                "power_w_max": float(max(pw)) if pw else None, "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from warpconvnet_b200 import _ops
+    from warpconvnet_b200._lib import lib
+    from warpconvnet_b200.geometry.coords.search.torch_discrete import generate_kernel_map
+    from warpconvnet_b200.geometry.types.voxels import Voxels
+    from warpconvnet_b200.nn.functional.sparse_conv import sparse_conv_dgrad, sparse_conv_wgrad
+    from warpconvnet_b200.nn.modules.sparse_conv import SparseConv3d
+
+    coords = make_coords(args.dist, seed=rank)  # every rank owns its own scene (weak scaling)
+    n = len(coords)
+    x_h, w_h, gy_h = make_tensors(n, seed=rank)
+    bc = torch.from_numpy(np.concatenate([np.zeros((n, 1), np.int32), coords], 1)).to(dev)
+    x = x_h.to(dev).bfloat16()
+    w = w_h.to(dev).bfloat16()
+    gy = gy_h.to(dev).bfloat16()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    gemm_ev = []
+
+    def step(record: bool):
+        """whole hot path, inputs resident in HBM"""
+        km = generate_kernel_map(bc, bc, (1, 1, 1), (KS,) * 3, same_coords=True)
+        plan = km.fwd_plan(n)
+        img = _ops.weight_image(w.view(K, 1, CIN, COUT), K, 1, CIN, COUT, False)
+        if record:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        y = _ops.gather_gemm(x, img, plan, 1, CIN, COUT)          # forward AB_gather_scatter
+        if record:
+            e1.record()
+            gemm_ev.append((e0, e1))
+        dx = sparse_conv_dgrad(gy, w, km, n)                       # dgrad ABt_gather_scatter
+        dw = sparse_conv_wgrad(x, gy, (K, CIN, COUT), km)          # wgrad AtB_gather_gather
+        if world > 1:
+            dist.all_reduce(dw)
+        return km, y, dx, dw
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn(False)
+        barrier()
+        evs = []
+        l0 = lib.wcn_launch_count()
+        sampler = ClockSampler(local) if rank == 0 else None
+        wall0 = time.perf_counter()
+        for _ in range(steps):
+            flush.fill_(1)  # L2 flush (256 MiB write) before every timed step, outside the events
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            out = fn(True)
+            e.record()
+            evs.append((s, e))
+        barrier()
+        wall = time.perf_counter() - wall0
+        clocks = sampler.stop() if sampler else None
+        launches = lib.wcn_launch_count() - l0
+        ms = sum(s.elapsed_time(e) for s, e in evs) / steps
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), launches, clocks, wall, out
+
+    # ---- device-resident number -------------------------------------------------------------
+    ms, launches, clocks, wall, (km, y, dx, dw) = timed(step, args.steps, args.warmup)
+    L = int(km.offsets[-1])
+    gemm_ms = float(np.mean([a.elapsed_time(b) for a, b in gemm_ev]))
+    gemm_ev.clear()
+    total_vox = torch.tensor([n], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(total_vox)
+    total_vox = float(total_vox.item())
+
+    # ---- per-phase breakdown (untimed for the headline; same step, events between phases) -----
+    def breakdown(reps=5):
+        names = ["kernel_map", "tile_plan", "weight_image", "fwd_gemm", "dgrad", "wgrad"]
+        acc = np.zeros(len(names))
+        for _ in range(reps):
+            flush.fill_(1)
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
+            ev[0].record()
+            km_ = generate_kernel_map(bc, bc, (1, 1, 1), (KS,) * 3, same_coords=True)
+            ev[1].record()
+            plan_ = km_.fwd_plan(n)
+            ev[2].record()
+            img_ = _ops.weight_image(w.view(K, 1, CIN, COUT), K, 1, CIN, COUT, False)
+            ev[3].record()
+            _ops.gather_gemm(x, img_, plan_, 1, CIN, COUT)
+            ev[4].record()
+            sparse_conv_dgrad(gy, w, km_, n)
+            ev[5].record()
+            sparse_conv_wgrad(x, gy, (K, CIN, COUT), km_)
+            ev[6].record()
+            torch.cuda.synchronize()
+            acc += np.array([ev[i].elapsed_time(ev[i + 1]) for i in range(len(names))])
+        return {k: round(float(v / reps), 4) for k, v in zip(names, acc)}
+
+    phases = breakdown()
+
+    # ---- end to end through the public API from pinned host buffers ---------------------------
+    conv = SparseConv3d(CIN, COUT, KS, bias=False).to(dev)
+    with torch.no_grad():
+        conv.weight.copy_(w_h)
+    coords_pin = torch.from_numpy(coords).pin_memory()
+    feats_pin = x_h.bfloat16().pin_memory()
+    dw_pin = torch.empty((K, CIN, COUT), dtype=torch.float32).pin_memory()
+    offsets = torch.tensor([0, n], dtype=torch.int64)
+    h2d = coords_pin.numel() * 4 + feats_pin.numel() * 2
+    d2h = dw_pin.numel() * 4
+
+    def e2e_step(record: bool):
+        c = coords_pin.to(dev, non_blocking=True)
+        f = feats_pin.to(dev, non_blocking=True).requires_grad_(True)
+        vox = Voxels(c, f, offsets=offsets)
+        conv.weight.grad = None
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out = conv(vox)
+        out.feature_tensor.backward(gy)
+        g = conv.weight.grad
+        if world > 1:
+            dist.all_reduce(g)
+        dw_pin.copy_(g, non_blocking=True)
+        return None, None, None, None
+
+    e2e_ms, _, _, _, _ = timed(e2e_step, args.steps, args.warmup)
+    torch.cuda.synchronize()
+
+    peaks = load_peaks()
+    flops = 2.0 * L * CIN * COUT
+    achieved = flops / (gemm_ms * 1e-3) / 1e12
+    out = {
+        "metric": "SparseConv3d fwd+bwd voxels/sec", "value": total_vox / (ms * 1e-3),
+        "unit": "voxels/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {
+            "workload": f"C3-{args.dist}: SparseConv3d 3^3 {CIN}->{COUT} bf16, {n} voxels/GPU "
+                        f"({'surface height field 448^2' if args.dist == 'S' else 'uniform random, 30% occupancy'}), "
+                        "step = kernel-map build + tile plan + fwd AB + dgrad ABt + wgrad AtB"
+                        + (" + NCCL all-reduce(dW)" if world > 1 else ""),
+            "voxels_per_gpu": n, "pairs_L": L, "parallelism": f"scene-sharded dp{world}",
+            "l2": "flushed with a 256 MiB write before every timed step (outside the events)",
+            "timing": "CUDA events per step on the launching stream, mean over steps, max over ranks",
+        },
+        "e2e": {"value": total_vox / (e2e_ms * 1e-3), "unit": "voxels/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "api": "Voxels(pinned host coords+feats) -> SparseConv3d.forward (autocast bf16) -> "
+                       "backward -> weight.grad to pinned host"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"],
+                     "unit": "TFLOP/s", "frac": achieved / peaks["tflops"], "traffic": None,
+                     "kernel": "gather_gemm_kernel<bf16> (forward AB_gather_scatter)",
+                     "kernel_ms": gemm_ms, "flops_per_launch": flops, "peak_source": peaks["which"]},
+        "phases_ms": phases,
+        "wall_s_timed_region": wall,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"], _ = run_cpu_baseline(args.dist, reps=2, warmup=1)
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    base, n = run_cpu_baseline(args.dist, reps=max(1, args.steps), warmup=min(args.warmup, 1),
+                               budget_s=150.0)
+    ms = base["seconds_per_pass"] * 1e3
+    out = {
+        "impl": "reference", "metric": "SparseConv3d fwd+bwd voxels/sec", "value": base["value"],
+        "unit": "voxels/s", "n_gpus": int(os.environ.get("WORLD_SIZE", args.gpus)),
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"C3-{args.dist}: SparseConv3d 3^3 {CIN}->{COUT}, {n} voxels, "
+                               "kernel map + fwd + dgrad + wgrad on the host CPU (port of the "
+                               "reference's explicit gather-matmul-scatter, detail/explicit.py:22-101)"},
+        "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": base["value"], "unit": "voxels/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--dist", choices=["S", "R"], default="S")
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -14,7 +14,9 @@
  *     csrc/include/gemm_error_codes.h:7-15): -1 invalid argument, -2 unsupported shape,
  *     -3 misaligned pointer/stride, -4 unsupported dtype, -5 CUDA launch error,
  *     -6 workspace too small;
- *   - dtype codes: 0 = bf16, 1 = fp16, 2 = fp32 (computed as TF32 on the tensor cores);
+ *   - dtype codes: 0 = bf16, 1 = fp16, 2 = fp32 (computed as TF32 on the tensor cores;
+ *     wcn_wgrad takes 16-bit operands only and returns -4 for fp32 — the host splits fp32 into
+ *     bf16 hi/lo parts);
  *     accumulation is always fp32;
  *   - device-side failures (hash table full, coordinate out of the packed-key range) are reported
  *     through a caller-provided int status word, like the reference's status tensor
@@ -46,6 +48,9 @@ extern "C" {
 const char* wcn_version(void);
 /* 1 when the library was compiled for sm_100a (always, this build has no other target). */
 int wcn_built_for_sm100a(void);
+/* number of CUDA kernels this library has launched so far in this process (bench.py's
+ * `gpu_launches` evidence; library kernels such as the CUB radix sort are not counted). */
+long long wcn_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Packed-coordinate hash table  (replaces _C.cuhash.packed_prepare / packed_insert /        */

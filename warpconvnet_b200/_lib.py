@@ -44,6 +44,7 @@ lib = _load()
 SIGNATURES = {
     "wcn_version": (c_char_p, []),
     "wcn_built_for_sm100a": (c_int, []),
+    "wcn_launch_count": (c_longlong, []),
     "wcn_hash_prepare": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "wcn_hash_insert": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "wcn_hash_search": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),

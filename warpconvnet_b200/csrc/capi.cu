@@ -29,6 +29,9 @@ int launch_weight_image(const WeightPrepParams&, cudaStream_t);
 int launch_gather_gemm(const GatherGemmParams&, int dtype, int n_slabs, int max_ctas, cudaStream_t);
 int launch_wgrad(const WgradParams&, int dtype, int y_slabs, int z_slabs, int max_ctas, cudaStream_t);
 
+static long long g_launches = 0;
+void count_launch() { __atomic_add_fetch(&g_launches, 1, __ATOMIC_RELAXED); }
+
 static int sm_count() {
   static int cached = 0;
   if (cached == 0) {
@@ -90,6 +93,7 @@ extern "C" {
 
 const char* wcn_version(void) { return "wcn_b200 0.1.0 (sm_100a, tcgen05)"; }
 int wcn_built_for_sm100a(void) { return 1; }
+long long wcn_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
 int wcn_hash_prepare(uint64_t* keys, int32_t* values, int capacity, void* stream) {
   if (!keys || !values) return kErrInvalidArg;

@@ -31,6 +31,9 @@ __host__ __device__ inline int dtype_size(int dt) { return dt == kF32 ? 4 : 2; }
 
 constexpr int kNumSMsB200 = 148;
 
+// number of kernels this library has launched in this process (wcn_launch_count in the C-ABI)
+void count_launch();
+
 // ---------------------------------------------------------------------------------------------
 // shared-memory address helpers
 // ---------------------------------------------------------------------------------------------

@@ -255,6 +255,7 @@ static int launch_gather_gemm_t(GatherGemmParams p, int n_slabs, int max_ctas, c
   if (ctas < 1) return kOk;
   dim3 grid(ctas, n_slabs, 1);
   gather_gemm_kernel<T><<<grid, kGemmThreads, smem, stream>>>(p);
+  count_launch();
   return cudaGetLastError() == cudaSuccess ? kOk : kErrCuda;
 }
 

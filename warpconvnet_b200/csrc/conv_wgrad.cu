@@ -296,6 +296,7 @@ static int launch_wgrad_t(WgradParams p, int cin_slabs, int cout_slabs, int max_
   if (per_slab < 1) per_slab = 1;
   dim3 grid(per_slab, cin_slabs, cout_slabs);
   wgrad_kernel<T><<<grid, kWgThreads, smem, stream>>>(p);
+  count_launch();
   return cudaGetLastError() == cudaSuccess ? kOk : kErrCuda;
 }
 
@@ -314,7 +315,8 @@ int launch_wgrad(const WgradParams& p, int dtype, int cin_slabs, int cout_slabs,
   switch (dtype) {
     case kBF16: return launch_wgrad_t<__nv_bfloat16>(p, cin_slabs, cout_slabs, max_ctas, stream);
     case kF16: return launch_wgrad_t<__half>(p, cin_slabs, cout_slabs, max_ctas, stream);
-    case kF32: return launch_wgrad_t<float>(p, cin_slabs, cout_slabs, max_ctas, stream);
+    // fp32 rows as MN-major tf32 operands returned zeros on B200 (bring-up log round 1); the host
+    // side splits fp32 into bf16 hi/lo parts instead (detail/unified.py:_wgrad_call).
     default: return kErrUnsupportedDtype;
   }
 }

@@ -337,6 +337,7 @@ int hash_insert(uint64_t* keys, int* values, const int* coords, int n, int capac
   hash_insert_kernel<<<(n + 255) / 256, 256, 0, s>>>(keys, values,
                                                     reinterpret_cast<const int4*>(coords), n,
                                                     (uint32_t)(capacity - 1), status);
+  count_launch();
   return cuda_ok();
 }
 
@@ -346,6 +347,7 @@ int hash_search(const uint64_t* keys, const int* values, const int* queries, int
   if (n == 0) return kOk;
   hash_search_kernel<<<(n + 255) / 256, 256, 0, s>>>(
       keys, values, reinterpret_cast<const int4*>(queries), results, n, (uint32_t)(capacity - 1));
+  count_launch();
   return cuda_ok();
 }
 
@@ -360,6 +362,7 @@ int kernel_map_search(const uint64_t* keys, const int* values, int capacity, con
   kernel_map_search_kernel<<<nb, kMapBlock, (size_t)4 * K * sizeof(int), s>>>(
       keys, values, (uint32_t)(capacity - 1), reinterpret_cast<const int4*>(out_coords), M,
       offsets3, K, sx, sy, sz, pair_table, block_counts, mask_keys);
+  count_launch();
   return cuda_ok();
 }
 
@@ -367,10 +370,12 @@ int kernel_map_count(int* block_counts, int K, int nb, int* counts, int* offsets
   if (K < 1) return kErrInvalidArg;
   if (nb > 0) {
     block_scan_kernel<<<K, 256, 0, s>>>(block_counts, nb, counts);
+  count_launch();
   } else {
     if (cudaMemsetAsync(counts, 0, (size_t)K * 4, s) != cudaSuccess) return kErrCuda;
   }
   offsets_kernel<<<1, 32, 0, s>>>(counts, K, offsets);
+  count_launch();
   return cuda_ok();
 }
 
@@ -379,6 +384,7 @@ int kernel_map_scatter(const int* pair_table, const int* block_prefix, const int
   if (M == 0) return kOk;
   kernel_map_scatter_kernel<<<kernel_map_num_blocks(M), kMapBlock, 0, s>>>(
       pair_table, block_prefix, offsets, in_maps, out_maps, K, M);
+  count_launch();
   return cuda_ok();
 }
 
@@ -389,6 +395,7 @@ int reverse_pair_table(const int* pair_table, int K, int M, int* rev, int n_in, 
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 32) blocks = 148 * 32;
   reverse_table_kernel<<<blocks, 256, 0, s>>>(pair_table, K, M, rev, n_in);
+  count_launch();
   return cuda_ok();
 }
 
@@ -400,12 +407,14 @@ int csr_to_table(const int* val_maps, const int* row_maps, const int* offsets, i
   if (blocks > 148 * 32) blocks = 148 * 32;
   csr_to_table_kernel<<<blocks, 256, (size_t)(K + 1) * sizeof(int), s>>>(val_maps, row_maps,
                                                                         offsets, K, n_rows, table);
+  count_launch();
   return cuda_ok();
 }
 
 int mask_keys_from_table(const int* table, int K, int M, unsigned long long* keys, cudaStream_t s) {
   if (M == 0) return kOk;
   mask_keys_kernel<<<(M + 255) / 256, 256, 0, s>>>(table, K, M, keys);
+  count_launch();
   return cuda_ok();
 }
 
@@ -430,6 +439,7 @@ int sort_rows_by_key(const unsigned long long* keys, int M, int K, int* rows_out
   void* temp = ws + align_up((size_t)M * 8, 256) + align_up((size_t)M * 4, 256);
   size_t temp_bytes = ws_bytes - (align_up((size_t)M * 8, 256) + align_up((size_t)M * 4, 256));
   iota_kernel<<<(M + 255) / 256, 256, 0, s>>>(rows_in, M);
+  count_launch();
   const int end_bit = K < 64 ? K : 64;
   // LSD radix sort is stable: equal masks keep ascending row order (deterministic tiles)
   cudaError_t e = cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys, keys_out, rows_in,
@@ -443,6 +453,7 @@ int build_tiles(const int* table, int K, int M, const int* sorted_rows, int m_pa
   if (m_pad == 0) return kOk;
   build_tiles_kernel<<<m_pad / 128, 128, 0, s>>>(table, K, M, sorted_rows, m_pad, nbr, rows_padded,
                                                 tile_ks, k_stride, tile_nk);
+  count_launch();
   return cuda_ok();
 }
 

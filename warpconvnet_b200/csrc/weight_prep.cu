@@ -62,6 +62,7 @@ int launch_weight_image(const WeightPrepParams& p, cudaStream_t stream) {
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   weight_image_kernel<<<blocks, 256, 0, stream>>>(p);
+  count_launch();
   return cudaGetLastError() == cudaSuccess ? kOk : kErrCuda;
 }
 

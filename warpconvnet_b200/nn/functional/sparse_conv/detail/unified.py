@@ -121,6 +121,25 @@ def sparse_conv_dgrad(grad_output: Tensor, weight: Tensor, kernel_map: IntSearch
     return dx if cin_g == cin_r else dx[:, :cin_r]
 
 
+def _wgrad_call(x: Tensor, gy: Tensor, kernel_map, K: int, G: int, cin_g: int, cout_g: int) -> Tensor:
+    im, om, od = kernel_map.in_maps, kernel_map.out_maps, kernel_map.offsets_dev
+    if x.dtype != torch.float32:
+        return _ops.wgrad(x, gy, im, om, od, K, G, cin_g, cout_g)
+    # fp32 operands: the contraction runs over gathered rows (MN-major operands), which the
+    # tensor cores take as 16-bit types only, so each operand is split into bf16 hi + lo parts and
+    # three bf16 products (hi*hi + hi*lo + lo*hi, fp32 accumulate) are summed into one dW:
+    # ~16 mantissa bits, tighter than a single TF32 pass. (The reference downcasts fp32 inputs of
+    # its mask_gemm path to fp16 outright, detail/mask_gemm.py:65-103.)
+    xh = x.bfloat16()
+    gh = gy.bfloat16()
+    xl = (x - xh.float()).bfloat16()
+    gl = (gy - gh.float()).bfloat16()
+    dw = _ops.wgrad(xh, gh, im, om, od, K, G, cin_g, cout_g)
+    _ops.wgrad(xh, gl, im, om, od, K, G, cin_g, cout_g, dw=dw)
+    _ops.wgrad(xl, gh, im, om, od, K, G, cin_g, cout_g, dw=dw)
+    return dw
+
+
 def sparse_conv_wgrad(in_features: Tensor, grad_output: Tensor, weight_shape, kernel_map,
                       groups: int = 1) -> Tensor:
     """fp32 dW with the shape of the weight."""
@@ -129,15 +148,12 @@ def sparse_conv_wgrad(in_features: Tensor, grad_output: Tensor, weight_shape, ke
         cin_p, cout_p = _round_up(cin, _CH_ALIGN), _round_up(cout, _CH_ALIGN)
         x = _pad_cols(in_features, cin_p)
         gy = _pad_cols(grad_output, cout_p)
-        dw = _ops.wgrad(x, gy, kernel_map.in_maps, kernel_map.out_maps, kernel_map.offsets_dev, K,
-                        1, cin_p, cout_p)
-        dw = dw.view(K, cin_p, cout_p)
+        dw = _wgrad_call(x, gy, kernel_map, K, 1, cin_p, cout_p).view(K, cin_p, cout_p)
         return dw if (cin_p == cin and cout_p == cout) else dw[:, :cin, :cout]
     K, G, cin_g, cout_g = weight_shape
     x = _pad_cols(in_features, G * cin_g)
     gy = _pad_cols(grad_output, G * cout_g)
-    return _ops.wgrad(x, gy, kernel_map.in_maps, kernel_map.out_maps, kernel_map.offsets_dev, K, G,
-                      cin_g, cout_g)
+    return _wgrad_call(x, gy, kernel_map, K, G, cin_g, cout_g)
 
 
 class UnifiedSpatiallySparseConvFunction(Function):
