@@ -111,13 +111,17 @@ size_t wcn_sort_workspace_bytes(int M);
 /* rows_out = stable argsort of keys (low min(K,64) bits). */
 int wcn_sort_rows_by_key(const uint64_t* keys, int M, int K, int32_t* rows_out, void* workspace,
                          size_t workspace_bytes, void* stream);
-/* Tile tables in mask-sorted order, m_pad = ceil(M/128)*128:
- *   nbr[k*m_pad + p]   = table[k*M + sorted_rows[p]]  (-1 for padding)
- *   rows_padded[p]     = sorted_rows[p]               (-1 for padding)
- *   tile_ks[t*k_stride + i], tile_nk[t] = offsets active in tile t (rows 128t..128t+127). */
-int wcn_build_tiles(const int32_t* table, int K, int M, const int32_t* sorted_rows, int m_pad,
-                    int32_t* nbr, int32_t* rows_padded, uint16_t* tile_ks, int k_stride,
-                    int32_t* tile_nk, void* stream);
+/* Tile plan in mask-sorted order. tile_rows is 128 or 256, m_pad = ceil(M/tile_rows)*tile_rows,
+ * num_tiles = m_pad / tile_rows. For tile t (sorted positions t*tile_rows ...):
+ *   rows_padded[p]                 = sorted_rows[p]  (-1 for padding)
+ *   tile_nk[t]                     = number of kernel offsets active anywhere in the tile (steps)
+ *   step_k[t*K + i]                = kernel offset of step i < tile_nk[t] (ascending)
+ *   step_nbr[(t*K + i)*tile_rows + r] = table[step_k][sorted row r of the tile]  (-1 = none)
+ *   tile_cum[0..num_tiles]         = exclusive prefix sum of tile_nk (work balancing)
+ * step_nbr is sized for the upper bound K*m_pad ints, step_k for K*num_tiles ints. */
+int wcn_build_tiles(const int32_t* table, int K, int M, const int32_t* sorted_rows, int tile_rows,
+                    int m_pad, int32_t* step_nbr, int32_t* step_k, int32_t* rows_padded,
+                    int32_t* tile_nk, int32_t* tile_cum, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Weight image for the gather-GEMM kernel                                                    */
@@ -138,16 +142,18 @@ int wcn_weight_image(const void* weight, void* image, int K, int groups, int cin
 /* forward AB_gather_scatter and dgrad ABt_gather_scatter
  * (replaces _C.mask_gemm.fwd / .dgrad: csrc/bindings/mask_gemm_bindings.cu:993-1750,2071-2116;
  *  semantics detail/explicit.py:22-57,60-101):
- *   out[rows[p], :] = sum_k feats[nbr[k][p], :] @ Wk      (rows not listed are untouched;
- *   every listed row is overwritten, so `out` needs no zero-fill)
- * feats [n_in, in_ld], out [n_out, out_ld]; channels: cin_total = groups*cin_g gathered per row
+ *   out[rows[p], :] = sum over the steps i of p's tile of feats[step_nbr[i][p], :] @ W[step_k[i]]
+ *   (rows not listed are untouched; every listed row is overwritten, so `out` needs no zero-fill)
+ * feats [n_in_rows, in_ld] (16-byte aligned base and pitch), out [n_out, out_ld]; channels: cin_total = groups*cin_g gathered per row
  * (dgrad: pass cout/cin swapped and a transpose_w=1 image); bias (optional fp32[groups*cout_g]);
- * kflip=1 uses weight K-1-k for table row k (dgrad of a submanifold conv on the forward table). */
-int wcn_gather_gemm(const void* feats, long long in_ld, const void* wimg, void* out,
-                    long long out_ld, const int32_t* nbr, const int32_t* rows,
-                    const uint16_t* tile_ks, int k_stride, const int32_t* tile_nk, int num_tiles,
-                    int m_pad, int K, int groups, int cin_g, int cout_g, int dtype,
-                    const float* bias, int relu, int kflip, int max_ctas, void* stream);
+ * kflip=1 uses weight K-1-k for table row k (dgrad of a submanifold conv on the forward table).
+ * The plan arrays come from wcn_build_tiles. */
+int wcn_gather_gemm(const void* feats, int n_in_rows, long long in_ld, const void* wimg, void* out,
+                    long long out_ld, const int32_t* step_nbr, const int32_t* step_k,
+                    const int32_t* rows, const int32_t* tile_nk, const int32_t* tile_cum,
+                    int num_tiles, int tile_rows, int m_pad, int K, int groups, int cin_g,
+                    int cout_g, int dtype, const float* bias, int relu, int kflip, int max_ctas,
+                    void* stream);
 
 /* wgrad AtB_gather_gather
  * (replaces _C.mask_gemm.wgrad: csrc/bindings/mask_gemm_bindings.cu:1755-2040 and

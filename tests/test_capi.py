@@ -65,8 +65,8 @@ def test_argument_errors_without_gpu():
     assert lib.wcn_hash_prepare(None, None, 16, None) == -1
     assert lib.wcn_hash_insert(None, None, None, 4, 16, None, None) == -1
     assert lib.wcn_kernel_map_num_blocks(1000) == 4
-    assert lib.wcn_gather_gemm(None, 0, None, None, 0, None, None, None, 0, None, 0, 0, 27, 1, 64,
-                               64, 0, None, 0, 0, 0, None) == -1
+    assert lib.wcn_gather_gemm(None, 0, 0, None, None, 0, None, None, None, None, None, 4, 128, 512,
+                               27, 1, 64, 64, 0, None, 0, 0, 0, None) == -1
     assert lib.wcn_wgrad(None, 0, None, 0, None, None, None, None, 27, 1, 64, 64, 0, 1.0, 0, 0,
                          None) == -1
     n_slabs, gps = ctypes.c_int(0), ctypes.c_int(0)

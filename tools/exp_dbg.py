@@ -1,0 +1,46 @@
+# SPDX-License-Identifier: Apache-2.0
+"""Per-role wait-cycle counters of the gather-GEMM kernel (bring-up only)."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from conftest import surface_coords  # noqa: E402
+from warpconvnet_b200 import _ops  # noqa: E402
+from warpconvnet_b200.geometry.coords.search.torch_discrete import generate_kernel_map  # noqa: E402
+
+cin = cout = 128
+c = surface_coords(448, 0)
+n = len(c)
+bc = torch.from_numpy(np.concatenate([np.zeros((n, 1), np.int32), c], 1)).cuda()
+km = generate_kernel_map(bc, bc, (1, 1, 1), (3, 3, 3), same_coords=True)
+x = torch.randn(n, cin, device="cuda").bfloat16()
+w = (torch.randn(27, 1, cin, cout, device="cuda") * 0.02).bfloat16()
+img = _ops.weight_image(w, 27, 1, cin, cout, False)
+table = km.pair_table(n)
+dbg = torch.zeros(148 * 8, dtype=torch.int64, device="cuda")
+os.environ["WCN_DEBUG_PTR"] = str(dbg.data_ptr())
+names = ["prod_total", "prod_wait_empty", "mma_total", "mma_wait_full", "mma_wait_accempty",
+         "epi_total", "epi_wait_accfull", "tiles"]
+for tr in (128, 256):
+    plan = _ops.build_tile_plan(table, tile_rows=tr)
+    for flags in (0, 32):
+        os.environ["WCN_DEBUG"] = str(flags)
+        heat = torch.randn(8192, 8192, device="cuda", dtype=torch.bfloat16)
+        for _ in range(20):
+            heat @ heat
+        for _ in range(3):
+            dbg.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            _ops.gather_gemm(x, img, plan, 1, cin, cout)
+            b.record()
+            torch.cuda.synchronize()
+        d = dbg.view(148, 8).cpu().numpy()
+        print(f"tile_rows={tr} dbg={flags} time={a.elapsed_time(b) * 1e3:.1f} us  steps={int(plan.tile_nk.sum())}")
+        for i, nm in enumerate(names):
+            print(f"    {nm:18s} mean={d[:, i].mean():10.0f} min={d[:, i].min():10d} max={d[:, i].max():10d}")

@@ -61,15 +61,16 @@ SIGNATURES = {
     "wcn_sort_workspace_bytes": (c_size_t, [c_int]),
     "wcn_sort_rows_by_key": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t,
                                      c_void_p]),
-    "wcn_build_tiles": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p,
-                                c_void_p, c_int, c_void_p, c_void_p]),
+    "wcn_build_tiles": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p,
+                                c_void_p, c_void_p, c_void_p, c_void_p]),
     "wcn_weight_image_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_int),
                                           POINTER(c_int)]),
     "wcn_weight_image": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                  c_void_p]),
-    "wcn_gather_gemm": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p, c_longlong, c_void_p,
-                                c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int,
-                                c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "wcn_gather_gemm": (c_int, [c_void_p, c_int, c_longlong, c_void_p, c_void_p, c_longlong, c_void_p,
+                                c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int,
+                                c_void_p]),
     "wcn_wgrad": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p,
                           c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_int,
                           c_void_p]),

@@ -141,41 +141,53 @@ def mask_keys(table: Tensor) -> Tensor:
 
 @dataclass
 class TilePlan:
-    """Mask-sorted 128-row tiles of one [K, n_rows] neighbour table (see wcn_build_tiles)."""
-    nbr: Tensor        # [K, m_pad] int32
+    """Mask-sorted tiles of one [K, n_rows] neighbour table with their compact step lists
+    (see wcn_build_tiles)."""
+    step_nbr: Tensor   # [num_tiles, K, tile_rows] int32 (only the first tile_nk[t] steps are valid)
+    step_k: Tensor     # [num_tiles, K] int32
     rows: Tensor       # [m_pad] int32
-    tile_ks: Tensor    # [num_tiles, k_stride] int16 (uint16 payload)
     tile_nk: Tensor    # [num_tiles] int32
+    tile_cum: Tensor   # [num_tiles + 1] int32
     K: int
     n_rows: int
     m_pad: int
     num_tiles: int
-    k_stride: int
+    tile_rows: int
 
 
-def build_tile_plan(table: Tensor, keys: Optional[Tensor] = None) -> TilePlan:
+# 256-row tiles let two 128-row MMA sub-tiles share every weight slice (half the weight traffic);
+# small inputs keep 128-row tiles so the tiles still spread over all SMs.
+_TILE256_MIN_ROWS = 148 * 256
+
+
+def build_tile_plan(table: Tensor, keys: Optional[Tensor] = None,
+                    key_bits: Optional[int] = None, tile_rows: Optional[int] = None) -> TilePlan:
     """Replaces the reference's pair_mask + CUB argsort + per-tile mask OR
     (detail/mask_gemm.py:127-276)."""
     _require_cuda(table)
     K, M = table.shape
     dev = table.device
+    if tile_rows is None:
+        tile_rows = 256 if M >= _TILE256_MIN_ROWS else TILE_M
     if keys is None:
         keys = mask_keys(table)
     rows_sorted = torch.empty(M, dtype=torch.int32, device=dev)
     ws_bytes = lib.wcn_sort_workspace_bytes(M)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    check(lib.wcn_sort_rows_by_key(_p(keys), M, K, _p(rows_sorted), _p(ws), ws_bytes, _stream()),
+    check(lib.wcn_sort_rows_by_key(_p(keys), M, K if key_bits is None else key_bits,
+                                   _p(rows_sorted), _p(ws), ws_bytes, _stream()),
           "sort_rows_by_key")
-    m_pad = (M + TILE_M - 1) // TILE_M * TILE_M
-    num_tiles = m_pad // TILE_M
-    k_stride = K
-    nbr = torch.empty((K, m_pad), dtype=torch.int32, device=dev)
-    rows = torch.empty(m_pad, dtype=torch.int32, device=dev)
-    tile_ks = torch.empty((max(num_tiles, 1), k_stride), dtype=torch.int16, device=dev)
+    m_pad = (M + tile_rows - 1) // tile_rows * tile_rows
+    num_tiles = m_pad // tile_rows
+    step_nbr = torch.empty((max(num_tiles, 1), K, tile_rows), dtype=torch.int32, device=dev)
+    step_k = torch.empty((max(num_tiles, 1), K), dtype=torch.int32, device=dev)
+    rows = torch.empty(max(m_pad, 1), dtype=torch.int32, device=dev)
     tile_nk = torch.empty(max(num_tiles, 1), dtype=torch.int32, device=dev)
-    check(lib.wcn_build_tiles(_p(table), K, M, _p(rows_sorted), m_pad, _p(nbr), _p(rows),
-                              _p(tile_ks), k_stride, _p(tile_nk), _stream()), "build_tiles")
-    return TilePlan(nbr, rows, tile_ks, tile_nk, K, M, m_pad, num_tiles, k_stride)
+    tile_cum = torch.empty(num_tiles + 1, dtype=torch.int32, device=dev)
+    check(lib.wcn_build_tiles(_p(table), K, M, _p(rows_sorted), tile_rows, m_pad, _p(step_nbr),
+                              _p(step_k), _p(rows), _p(tile_nk), _p(tile_cum), _stream()),
+          "build_tiles")
+    return TilePlan(step_nbr, step_k, rows, tile_nk, tile_cum, K, M, m_pad, num_tiles, tile_rows)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -213,10 +225,11 @@ def gather_gemm(feats: Tensor, wimg: Tensor, plan: TilePlan, groups: int, cin_g:
     assert out.stride(1) == 1 and out.dtype == feats.dtype
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.is_contiguous()
-    check(lib.wcn_gather_gemm(_p(feats), feats.stride(0), _p(wimg), _p(out), out.stride(0),
-                              _p(plan.nbr), _p(plan.rows), _p(plan.tile_ks), plan.k_stride,
-                              _p(plan.tile_nk), plan.num_tiles, plan.m_pad, plan.K, groups, cin_g,
-                              cout_g, code, _p(bias), int(relu), int(kflip), max_ctas, _stream()),
+    check(lib.wcn_gather_gemm(_p(feats), feats.shape[0], feats.stride(0), _p(wimg), _p(out), out.stride(0),
+                              _p(plan.step_nbr), _p(plan.step_k), _p(plan.rows), _p(plan.tile_nk),
+                              _p(plan.tile_cum), plan.num_tiles, plan.tile_rows, plan.m_pad,
+                              plan.K, groups, cin_g, cout_g, code, _p(bias), int(relu),
+                              int(kflip), max_ctas, _stream()),
           "gather_gemm")
     return out
 

@@ -3,6 +3,8 @@
 // reference bindings each entry point replaces.
 #include "../../include/wcn_b200.h"
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "conv_gemm.cuh"
 
@@ -21,7 +23,7 @@ int mask_keys_from_table(const int*, int, int, unsigned long long*, cudaStream_t
 int csr_to_table(const int*, const int*, const int*, int, int, int, int*, cudaStream_t);
 size_t sort_workspace_bytes(int);
 int sort_rows_by_key(const unsigned long long*, int, int, int*, void*, size_t, cudaStream_t);
-int build_tiles(const int*, int, int, const int*, int, int*, int*, uint16_t*, int, int*,
+int build_tiles(const int*, int, int, const int*, int, int, int*, int*, int*, int*, int*,
                 cudaStream_t);
 // weight_prep.cu
 int launch_weight_image(const WeightPrepParams&, cudaStream_t);
@@ -31,6 +33,42 @@ int launch_wgrad(const WgradParams&, int dtype, int y_slabs, int z_slabs, int ma
 
 static long long g_launches = 0;
 void count_launch() { __atomic_add_fetch(&g_launches, 1, __ATOMIC_RELAXED); }
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                      const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                      const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TensorMapEncodeFn tensor_map_encoder() {
+  static TensorMapEncodeFn fn = nullptr;
+  if (fn == nullptr) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) ==
+            cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<TensorMapEncodeFn>(sym);
+  }
+  return fn;
+}
+
+// [n_rows, row_elems] row-major matrix with pitch ld elements; box = 128 bytes x 1 row
+static int make_gather_map(CUtensorMap* map, const void* base, long long n_rows, long long ld,
+                           int dtype) {
+  TensorMapEncodeFn enc = tensor_map_encoder();
+  if (enc == nullptr) return kErrCuda;
+  const int es = dtype_size(dtype);
+  const CUtensorMapDataType dt = dtype == kBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                               : dtype == kF16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                                               : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  cuuint64_t gdim[2] = {(cuuint64_t)ld, (cuuint64_t)(n_rows > 0 ? n_rows : 1)};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * es};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / es), 1};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? kOk : kErrInvalidArg;
+}
 
 static int sm_count() {
   static int cached = 0;
@@ -156,13 +194,14 @@ int wcn_sort_rows_by_key(const uint64_t* keys, int M, int K, int32_t* rows_out, 
   return sort_rows_by_key(reinterpret_cast<const unsigned long long*>(keys), M, K, rows_out,
                           workspace, workspace_bytes, S(stream));
 }
-int wcn_build_tiles(const int32_t* table, int K, int M, const int32_t* sorted_rows, int m_pad,
-                    int32_t* nbr, int32_t* rows_padded, uint16_t* tile_ks, int k_stride,
-                    int32_t* tile_nk, void* stream) {
-  if (m_pad > 0 && (!table || !sorted_rows || !nbr || !rows_padded || !tile_ks || !tile_nk))
+int wcn_build_tiles(const int32_t* table, int K, int M, const int32_t* sorted_rows, int tile_rows,
+                    int m_pad, int32_t* step_nbr, int32_t* step_k, int32_t* rows_padded,
+                    int32_t* tile_nk, int32_t* tile_cum, void* stream) {
+  if (!tile_cum || !tile_nk) return kErrInvalidArg;
+  if (m_pad > 0 && (!table || !sorted_rows || !step_nbr || !step_k || !rows_padded))
     return kErrInvalidArg;
-  return build_tiles(table, K, M, sorted_rows, m_pad, nbr, rows_padded, tile_ks, k_stride, tile_nk,
-                     S(stream));
+  return build_tiles(table, K, M, sorted_rows, tile_rows, m_pad, step_nbr, step_k, rows_padded,
+                     tile_nk, tile_cum, S(stream));
 }
 
 size_t wcn_weight_image_bytes(int K, int groups, int cin_g, int cout_g, int dtype, int transpose_w,
@@ -215,25 +254,37 @@ int wcn_weight_image(const void* weight, void* image, int K, int groups, int cin
   return launch_weight_image(p, S(stream));
 }
 
-int wcn_gather_gemm(const void* feats, long long in_ld, const void* wimg, void* out,
-                    long long out_ld, const int32_t* nbr, const int32_t* rows,
-                    const uint16_t* tile_ks, int k_stride, const int32_t* tile_nk, int num_tiles,
-                    int m_pad, int K, int groups, int cin_g, int cout_g, int dtype,
-                    const float* bias, int relu, int kflip, int max_ctas, void* stream) {
-  if (!feats || !wimg || !out || !nbr || !rows || !tile_ks || !tile_nk) return kErrInvalidArg;
+int wcn_gather_gemm(const void* feats, int n_in_rows, long long in_ld, const void* wimg, void* out,
+                    long long out_ld, const int32_t* step_nbr, const int32_t* step_k,
+                    const int32_t* rows, const int32_t* tile_nk, const int32_t* tile_cum,
+                    int num_tiles, int tile_rows, int m_pad, int K, int groups, int cin_g,
+                    int cout_g, int dtype, const float* bias, int relu, int kflip, int max_ctas,
+                    void* stream) {
+  if (num_tiles > 0 && (!feats || !wimg || !out || !step_nbr || !step_k || !rows || !tile_nk ||
+                        !tile_cum))
+    return kErrInvalidArg;
   if (dtype < 0 || dtype > 2) return kErrUnsupportedDtype;
   if (num_tiles == 0) return kOk;
   SlabPlan plan;
   int st = plan_slabs(groups, cout_g, cin_g, &plan);
   if (st != kOk) return st;
   GatherGemmParams p;
+  if (n_in_rows < 0 || (in_ld * dtype_size(dtype)) % 16 != 0 ||
+      (reinterpret_cast<uintptr_t>(feats) & 15))
+    return n_in_rows < 0 ? kErrInvalidArg : kErrAlignment;
+  st = make_gather_map(&p.tmap, feats, n_in_rows, in_ld, dtype);
+  if (st != kOk) return st;
+  p.n_in_rows = n_in_rows;
   p.feats = feats;
   p.wimg = wimg;
   p.out = out;
-  p.nbr = nbr;
+  p.step_nbr = step_nbr;
+  p.step_k = step_k;
   p.rows = rows;
-  p.tile_ks = tile_ks;
   p.tile_nk = tile_nk;
+  p.tile_cum = tile_cum;
+  p.tile_rows = tile_rows;
+  p.halves = 1;
   p.bias = bias;
   p.in_ld = in_ld;
   p.out_ld = out_ld;
@@ -243,12 +294,19 @@ int wcn_gather_gemm(const void* feats, long long in_ld, const void* wimg, void* 
   p.cin = plan.cdim;
   p.bn = plan.bn;
   p.K = K;
-  p.k_stride = k_stride;
   p.m_pad = m_pad;
   p.num_tiles = num_tiles;
   p.kflip = kflip;
   p.stages = 0;
   p.relu = relu;
+  {
+    const char* e = getenv("WCN_DEBUG");
+    p.debug = e ? atoi(e) : 0;
+    const char* dp = getenv("WCN_DEBUG_PTR");
+    p.dbg_out = dp ? reinterpret_cast<long long*>(strtoull(dp, nullptr, 10)) : nullptr;
+    const char* st_env = getenv("WCN_STAGES");
+    if (st_env) p.stages = atoi(st_env);
+  }
   if (max_ctas <= 0) max_ctas = sm_count();
   return launch_gather_gemm(p, dtype, plan.n_slabs, max_ctas, S(stream));
 }

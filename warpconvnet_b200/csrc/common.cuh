@@ -91,6 +91,11 @@ __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint3
                "r"(src_bytes)
                : "memory");
 }
+__device__ __forceinline__ void cp_async_16_ca(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src),
+               "r"(src_bytes)
+               : "memory");
+}
 // The arrive fires when all cp.async issued so far by this thread have landed. ".noinc": the
 // arrival is one of the barrier's expected arrivals (counted in mbar_init).
 __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
@@ -106,6 +111,23 @@ __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uin
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
           "r"(dst),
       "l"(src), "r"(bytes), "r"(bar)
+      : "memory");
+}
+
+// Orders generic-proxy writes to shared memory (cp.async / st.shared, made visible through an
+// mbarrier) before async-proxy reads (tcgen05.mma operand fetch, TMA).
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// TMA gather4: four rows (r0..r3, arbitrary) x one box width of a 2-D tensor map land as four
+// consecutive box rows at dst; rows outside the tensor are zero-filled.
+__device__ __forceinline__ void tma_gather4(uint32_t dst, const void* tmap, int col, int r0, int r1,
+                                            int r2, int r3, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes"
+      ".cta_group::1 [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(dst),
+      "l"(tmap), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(bar)
       : "memory");
 }
 

@@ -5,14 +5,27 @@
 // (Y[out] += X[in] @ W_k over all offsets) and the production kernel family
 // warpconvnet/csrc/mask_gemm/include/MaskGemm_forward_*.h (output-stationary, mma.sync).
 //
-// CTA layout (288 threads, 1 CTA / SM, persistent over tiles):
-//   warps 0-3  gather producers: 8 lanes fetch one 128-byte row segment with cp.async (16 B each,
-//              zero-fill for missing neighbours) straight into the 128B-swizzled K-major A tile
+// Work decomposition: output rows are mask-sorted into tiles of `tile_rows` (128 or 256) rows;
+// a tile owns a compact STEP LIST = the kernel offsets active anywhere in the tile, each step
+// with the `tile_rows` neighbour row indices stored contiguously (see wcn_build_tiles). A CTA
+// takes a contiguous range of tiles balanced by step count, so every role streams through
+// memory sequentially and index loads are prefetched several steps ahead (no dependent-load
+// chain in the steady state).
+//
+// CTA layout (288 threads, 1 CTA / SM, persistent):
+//   warps 0-3  gather producers: cp.async (16 B per lane, zero-fill for missing neighbours)
+//              straight into the 128B-swizzled K-major A tile. A stage covers GC = 2 adjacent
+//              128-byte channel chunks, so 16 lanes fetch 256 CONTIGUOUS bytes of one feature row:
+//              measured on B200 (tools/gather_bench.cu) the L2->SM path serves ~1 gather request
+//              per 8 cycles per SM whatever its size, 16 B/cycle/SM for 128-byte requests and
+//              28 B/cycle/SM for 256-byte ones, identical for LDGSTS, LDG+STS and TMA gather4
+//              (gather4 additionally issues warp-serially). Shared-memory offsets are per-thread
+//              constants. With TM = 2 a stage holds two 128-row A sub-tiles that share one weight
+//              slice. Thread 0 also pulls the per-offset weight slice (a pre-swizzled image in
+//              global memory) through the TMA unit with one cp.async.bulk per stage.
 //   warp  4    lane 0 issues tcgen05.mma (M=128, N=bn, K=32 B per instruction), accumulators in
 //              TMEM, double buffered so the epilogue of tile i overlaps the MMAs of tile i+1
 //   warps 5-8  epilogue: tcgen05.ld -> (+bias, ReLU) -> bf16/fp16/fp32 -> 128-bit global stores
-// The per-offset weight slice is a pre-swizzled image in global memory and is pulled by the TMA
-// unit with one cp.async.bulk per pipeline stage.
 #include "common.cuh"
 #include "conv_gemm.cuh"
 
@@ -22,10 +35,11 @@ constexpr int kTileM = 128;
 constexpr int kProducerThreads = 128;
 constexpr int kMmaWarp = 4;
 constexpr int kGemmThreads = 288;
-constexpr int kAStageBytes = kTileM * 128;  // 16 KB
+constexpr int kAStageBytes = kTileM * 128;  // 16 KB per 128-row sub-tile
 constexpr int kTmemCols = 512;
-constexpr int kAccStride = 256;             // TMEM column offset of the second accumulator
+constexpr int kAccStride = 256;             // TMEM column offset of the second accumulator set
 constexpr int kMaxStages = 8;
+constexpr int kPrefetch = 4;                // steps of index look-ahead in the producers
 
 struct GemmSmemCtrl {
   uint64_t full[kMaxStages];
@@ -33,9 +47,44 @@ struct GemmSmemCtrl {
   uint64_t acc_full[2];
   uint64_t acc_empty[2];
   uint32_t tmem_base;
+  int t_begin;
+  int t_end;
 };
 
-template <typename T>
+// first index t in [0, n] with cum[t] >= target (cum is non-decreasing, cum[n] >= target)
+__device__ __forceinline__ int lower_bound_cum(const int* __restrict__ cum, int n,
+                                               long long target) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if ((long long)__ldg(cum + mid) >= target) hi = mid; else lo = mid + 1;
+  }
+  return lo;
+}
+
+// Walks the (tile, half, step) sequence of this CTA; all members are warp-uniform.
+struct StepCursor {
+  int tile, half, i, nk;
+  __device__ __forceinline__ void seek(const GatherGemmParams& p, int t_end) {
+    // settle on the first existing step at or after (tile, half, i); skips empty tiles
+    while (tile < t_end) {
+      if (nk < 0) nk = __ldg(p.tile_nk + tile);
+      if (i < nk) return;
+      i = 0;
+      if (nk > 0 && ++half < p.halves) continue;
+      half = 0;
+      ++tile;
+      nk = -1;
+    }
+  }
+  __device__ __forceinline__ bool valid(int t_end) const { return tile < t_end; }
+  __device__ __forceinline__ void next(const GatherGemmParams& p, int t_end) {
+    ++i;
+    seek(p, t_end);
+  }
+};
+
+template <typename T, int TM, int GC>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -47,14 +96,19 @@ gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
   const int lane = tid & 31;
   const int slab = blockIdx.y;
 
-  const int b_stage_bytes = p.bn * 128;
-  const int stage_bytes = kAStageBytes + ((b_stage_bytes + 1023) & ~1023);
+  constexpr int kASub = GC * kAStageBytes;  // one 128-row sub-tile: GC slabs of 128 rows x 128 B
+  constexpr int kAStage = TM * kASub;
+  const int b_chunk_bytes = p.bn * 128;     // weight slab of one 128-byte channel chunk
+  const int stage_bytes = kAStage + ((GC * b_chunk_bytes + 1023) & ~1023);
   const int stages = p.stages;
   GemmSmemCtrl* ctrl = reinterpret_cast<GemmSmemCtrl*>(smem_gen + (size_t)stages * stage_bytes);
 
   constexpr int kElem = (int)sizeof(T);
   constexpr int kChunkElems = 128 / kElem;  // channels per 128-byte row segment
   const int n_chunks = (p.cin + kChunkElems - 1) / kChunkElems;
+  const int n_groups = (n_chunks + GC - 1) / GC;  // stages per step
+  const int row_bytes = p.cin * kElem;            // gathered bytes per feature row
+  constexpr int kUnitRows = kTileM * TM;    // rows a CTA processes per step
 
   if (tid == 0) {
     for (int s = 0; s < stages; ++s) {
@@ -66,6 +120,12 @@ gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
       mbar_init(smem_u32(&ctrl->acc_empty[a]), 128);
     }
     fence_mbar_init();
+    // contiguous tile range, balanced by step count
+    const int nt = p.num_tiles;
+    const long long S = __ldg(p.tile_cum + nt);
+    const int G = gridDim.x, b = blockIdx.x;
+    ctrl->t_begin = lower_bound_cum(p.tile_cum, nt, S * b / G);
+    ctrl->t_end = (b == G - 1) ? nt : lower_bound_cum(p.tile_cum, nt, S * (b + 1) / G);
   }
   if (warp == kMmaWarp) {
     tmem_alloc(smem_u32(&ctrl->tmem_base), kTmemCols);
@@ -75,55 +135,114 @@ gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = ctrl->tmem_base;
+  const int t_begin = ctrl->t_begin;
+  const int t_end = ctrl->t_end;
 
   if (warp < 4) {
     // ===================================== gather producers =====================================
-    const uint8_t* feats = reinterpret_cast<const uint8_t*>(p.feats);
-    const long long in_ld_bytes = p.in_ld * kElem;
     const uint8_t* wimg = reinterpret_cast<const uint8_t*>(p.wimg) +
-                          (size_t)slab * p.K * n_chunks * b_stage_bytes;
-    const int c16 = lane & 7;
-    const int sub = lane >> 3;  // which of the 4 rows an instruction covers
+                          (size_t)slab * p.K * n_chunks * b_chunk_bytes;
+    const long long in_ld_bytes = p.in_ld * kElem;
+    // lane -> (row of the instruction, 16-byte unit of the GC*128-byte row segment)
+    constexpr int kLanesPerRow = 8 * GC;
+    constexpr int kRowsPerInstr = 32 / kLanesPerRow;  // 4 (GC = 1) or 2 (GC = 2)
+    constexpr int kInstr = 32 / kRowsPerInstr;        // LDGSTS per thread, sub-tile and stage
+    constexpr int kPar = 8 / kRowsPerInstr;           // distinct (row & 7) phases of a thread
+    const int u = lane % kLanesPerRow;                // 16-byte unit inside the row segment
+    const int sub = lane / kLanesPerRow;              // row of the instruction this lane serves
+    const int ch = u >> 3, c8 = u & 7;
+    // row(q) = warp*32 + kRowsPerInstr*q + sub;  row & 7 only depends on q % kPar:
+    //   off(q) = off_par[q % kPar] + (q / kPar) * 1024
+    uint32_t off_par[kPar];
+#pragma unroll
+    for (int i = 0; i < kPar; ++i) {
+      const int r7 = kRowsPerInstr * i + sub;
+      off_par[i] = (uint32_t)ch * kAStageBytes + (uint32_t)(warp * 32 + r7) * 128u +
+                   (uint32_t)((c8 ^ r7) << 4);
+    }
+    const uint8_t* col_base = reinterpret_cast<const uint8_t*>(p.feats) +
+                              (long long)(p.in_coff + slab * p.in_slab_stride) * kElem + u * 16;
+
+    StepCursor cur{t_begin, 0, 0, -1}, pre{t_begin, 0, 0, -1};
+    cur.seek(p, t_end);
+    pre.seek(p, t_end);
+    int idx_ring[kPrefetch][TM];  // neighbour row of tile row warp*32 + lane, per sub-tile
+    int k_ring[kPrefetch];
+    auto load_step = [&](const StepCursor& c, int (&idx)[TM], int& k) {
+      const size_t step = (size_t)c.tile * p.K + c.i;
+      k = __ldg(p.step_k + step);
+      const int* base = p.step_nbr + step * p.tile_rows + c.half * kUnitRows + warp * 32 + lane;
+#pragma unroll
+      for (int j = 0; j < TM; ++j) idx[j] = __ldg(base + j * kTileM);
+    };
+#pragma unroll
+    for (int d = 0; d < kPrefetch; ++d) {
+      k_ring[d] = 0;
+#pragma unroll
+      for (int j = 0; j < TM; ++j) idx_ring[d][j] = -1;
+      if (pre.valid(t_end)) {
+        load_step(pre, idx_ring[d], k_ring[d]);
+        pre.next(p, t_end);
+      }
+    }
+
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const int nk = p.tile_nk[tile];
-      const uint16_t* ks = p.tile_ks + (size_t)tile * p.k_stride;
-      const int pos = tile * kTileM + warp * 32 + lane;
-      int idx_next = (nk > 0) ? __ldg(p.nbr + (size_t)ks[0] * p.m_pad + pos) : -1;
-      for (int ki = 0; ki < nk; ++ki) {
-        const int k = ks[ki];
-        const int idx_own = idx_next;
-        if (ki + 1 < nk) idx_next = __ldg(p.nbr + (size_t)ks[ki + 1] * p.m_pad + pos);
+    long long w_empty = 0;
+    const long long t_start = clock64();
+    while (cur.valid(t_end)) {
+#pragma unroll
+      for (int d = 0; d < kPrefetch; ++d) {
+        if (!cur.valid(t_end)) break;
+        int idx_own[TM];
+#pragma unroll
+        for (int j = 0; j < TM; ++j) idx_own[j] = idx_ring[d][j];
+        const int k = k_ring[d];
+        if (pre.valid(t_end)) {  // refill this ring slot with the step kPrefetch ahead
+          load_step(pre, idx_ring[d], k_ring[d]);
+          pre.next(p, t_end);
+        }
+        cur.next(p, t_end);
         const int wk = p.kflip ? (p.K - 1 - k) : k;
-        for (int c = 0; c < n_chunks; ++c) {
-          mbar_wait(smem_u32(&ctrl->empty[stage]), phase ^ 1u);
+        for (int g = 0; g < n_groups; ++g) {
+          {
+            const long long t0 = clock64();
+            mbar_wait(smem_u32(&ctrl->empty[stage]), phase ^ 1u);
+            w_empty += clock64() - t0;
+          }
           const uint32_t a_smem = smem_base + stage * stage_bytes;
           const uint32_t full_bar = smem_u32(&ctrl->full[stage]);
           if (tid == 0) {
-            mbar_arrive_expect_tx(full_bar, (uint32_t)b_stage_bytes);
-            bulk_copy_g2s(a_smem + kAStageBytes,
-                          wimg + ((size_t)wk * n_chunks + c) * b_stage_bytes,
-                          (uint32_t)b_stage_bytes, full_bar);
+            const int chunks_here = min(GC, n_chunks - g * GC);
+            const uint32_t b_bytes = (uint32_t)(chunks_here * b_chunk_bytes);
+            mbar_arrive_expect_tx(full_bar, b_bytes);
+            bulk_copy_g2s(a_smem + kAStage,
+                          wimg + ((size_t)wk * n_chunks + g * GC) * b_chunk_bytes, b_bytes,
+                          full_bar);
           }
-          const int chunk_bytes = min(128, (p.cin - c * kChunkElems) * kElem);
-          const long long col_bytes =
-              (long long)(p.in_coff + slab * p.in_slab_stride + c * kChunkElems) * kElem + c16 * 16;
-          const bool lane_active = c16 * 16 < chunk_bytes;
+          const int seg_off = g * GC * 128;  // byte offset of this chunk group inside the row
+          const bool lane_active = seg_off + u * 16 < row_bytes;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int rloc = 4 * j + sub;
-            const int src_idx = __shfl_sync(0xffffffffu, idx_own, rloc);  // warp-uniform call
-            const uint32_t row = warp * 32 + rloc;
-            const uint8_t* src =
-                feats + (long long)(src_idx >= 0 ? src_idx : 0) * in_ld_bytes + col_bytes;
-            if (lane_active)
-              cp_async_16(a_smem + sw128_offset(row, c16), src, src_idx >= 0 ? 16u : 0u);
+          for (int j = 0; j < TM; ++j) {
+#pragma unroll
+            for (int q = 0; q < kInstr; ++q) {
+              // warp-uniform shuffle; only the copy itself is predicated
+              const int src_idx = __shfl_sync(0xffffffffu, idx_own[j], kRowsPerInstr * q + sub);
+              const uint8_t* src =
+                  col_base + (long long)(src_idx >= 0 ? src_idx : 0) * in_ld_bytes + seg_off;
+              const uint32_t dst =
+                  a_smem + j * kASub + off_par[q % kPar] + (uint32_t)(q / kPar) * 1024u;
+              if (lane_active) cp_async_16(dst, src, src_idx >= 0 ? 16u : 0u);
+            }
           }
           cp_async_mbar_arrive_noinc(full_bar);
           if (++stage == stages) { stage = 0; phase ^= 1u; }
         }
       }
+    }
+    if (p.dbg_out != nullptr && tid == 0) {
+      p.dbg_out[blockIdx.x * 8 + 0] = clock64() - t_start;
+      p.dbg_out[blockIdx.x * 8 + 1] = w_empty;
     }
   } else if (warp == kMmaWarp) {
     // ======================================= MMA issuer =========================================
@@ -131,35 +250,64 @@ gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
       const uint32_t idesc = make_idesc(ElemTraits<T>::kFmt, kTileM, p.bn, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
-      uint32_t use = 0;  // number of accumulator uses so far
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int nk = p.tile_nk[tile];
+      uint32_t use = 0;  // number of accumulator-set uses so far
+      int nk_next = (t_begin < t_end) ? __ldg(p.tile_nk + t_begin) : 0;
+      long long w_full = 0, w_acc = 0;
+      const long long t_start = clock64();
+      for (int tile = t_begin; tile < t_end; ++tile) {
+        const int nk = nk_next;
+        if (tile + 1 < t_end) nk_next = __ldg(p.tile_nk + tile + 1);
         if (nk == 0) continue;
-        const uint32_t acc = use & 1u;
-        mbar_wait(smem_u32(&ctrl->acc_empty[acc]), ((use >> 1) & 1u) ^ 1u);
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * kAccStride;
-        uint32_t accumulate = 0;
-        for (int ki = 0; ki < nk; ++ki) {
-          for (int c = 0; c < n_chunks; ++c) {
-            mbar_wait(smem_u32(&ctrl->full[stage]), phase);
-            tc_fence_after();
-            const uint32_t a_smem = smem_base + stage * stage_bytes;
-            const uint32_t b_smem = a_smem + kAStageBytes;
-            const int chunk_bytes = min(128, (p.cin - c * kChunkElems) * kElem);
-            const int n_mma = chunk_bytes >> 5;  // 32 bytes of K per instruction
-            for (int j = 0; j < n_mma; ++j) {
-              const uint64_t adesc = make_smem_desc_sw128(a_smem + j * 32, 16, 1024);
-              const uint64_t bdesc = make_smem_desc_sw128(b_smem + j * 32, 16, 1024);
-              umma_ss<ElemTraits<T>::kTF32>(tmem_d, adesc, bdesc, idesc, accumulate);
-              accumulate = 1;
-            }
-            umma_commit(smem_u32(&ctrl->empty[stage]));
-            if (++stage == stages) { stage = 0; phase ^= 1u; }
+        for (int h = 0; h < p.halves; ++h) {
+          const uint32_t acc = use & 1u;
+          {
+            const long long t0 = clock64();
+            mbar_wait(smem_u32(&ctrl->acc_empty[acc]), ((use >> 1) & 1u) ^ 1u);
+            w_acc += clock64() - t0;
           }
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + acc * kAccStride;
+          uint32_t accumulate = 0;
+          for (int ki = 0; ki < nk; ++ki) {
+            for (int g = 0; g < n_groups; ++g) {
+              {
+                const long long t0 = clock64();
+                mbar_wait(smem_u32(&ctrl->full[stage]), phase);
+                w_full += clock64() - t0;
+              }
+              fence_proxy_async_smem();  // cp.async wrote A through the generic proxy
+              tc_fence_after();
+              const uint32_t a_smem = smem_base + stage * stage_bytes;
+              const uint32_t b_smem = a_smem + kAStage;
+#pragma unroll
+              for (int cc = 0; cc < GC; ++cc) {
+                const int chunk_bytes = min(128, row_bytes - (g * GC + cc) * 128);
+                const int n_mma = chunk_bytes > 0 ? (chunk_bytes >> 5) : 0;  // 32 B of K per MMA
+#pragma unroll
+                for (int j = 0; j < TM; ++j) {
+                  for (int m = 0; m < n_mma; ++m) {
+                    const uint64_t adesc = make_smem_desc_sw128(
+                        a_smem + j * kASub + cc * kAStageBytes + m * 32, 16, 1024);
+                    const uint64_t bdesc =
+                        make_smem_desc_sw128(b_smem + cc * b_chunk_bytes + m * 32, 16, 1024);
+                    umma_ss<ElemTraits<T>::kTF32>(tmem_d + j * p.bn, adesc, bdesc, idesc,
+                                                  (accumulate | (uint32_t)(m + cc)) ? 1u : 0u);
+                  }
+                }
+              }
+              accumulate = 1;
+              umma_commit(smem_u32(&ctrl->empty[stage]));
+              if (++stage == stages) { stage = 0; phase ^= 1u; }
+            }
+          }
+          umma_commit(smem_u32(&ctrl->acc_full[acc]));
+          ++use;
         }
-        umma_commit(smem_u32(&ctrl->acc_full[acc]));
-        ++use;
+      }
+      if (p.dbg_out != nullptr) {
+        p.dbg_out[blockIdx.x * 8 + 2] = clock64() - t_start;
+        p.dbg_out[blockIdx.x * 8 + 3] = w_full;
+        p.dbg_out[blockIdx.x * 8 + 4] = w_acc;
       }
     }
   } else {
@@ -170,52 +318,70 @@ gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
     const long long out_ld_bytes = p.out_ld * kElem;
     const int col_base = p.out_coff + slab * p.bn;
     uint32_t use = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const int nk = p.tile_nk[tile];
-      const int out_row = __ldg(p.rows + tile * kTileM + r);
-      uint32_t acc = 0;
-      if (nk > 0) {
-        acc = use & 1u;
-        mbar_wait(smem_u32(&ctrl->acc_full[acc]), (use >> 1) & 1u);
-        tc_fence_after();
-      }
-      uint8_t* out_ptr = out + (long long)(out_row >= 0 ? out_row : 0) * out_ld_bytes +
-                         (long long)col_base * kElem;
-      for (int col = 0; col < p.bn; col += 16) {
-        uint32_t v[16];
+    long long w_accf = 0;
+    const long long t_start = clock64();
+    for (int tile = t_begin; tile < t_end; ++tile) {
+      const int nk = __ldg(p.tile_nk + tile);
+      for (int h = 0; h < p.halves; ++h) {
+        uint32_t acc = 0;
         if (nk > 0) {
-          tmem_ld_x16(tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccStride + col, v);
-          tmem_ld_wait();
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = 0u;
+          acc = use & 1u;
+          const long long t0 = clock64();
+          mbar_wait(smem_u32(&ctrl->acc_full[acc]), (use >> 1) & 1u);
+          w_accf += clock64() - t0;
+          tc_fence_after();
         }
-        if (p.bias != nullptr) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            v[i] = __float_as_uint(__uint_as_float(v[i]) + __ldg(p.bias + col_base + col + i));
-        }
-        if (p.relu) {
+        for (int j = 0; j < TM; ++j) {
+          const int out_row =
+              __ldg(p.rows + (size_t)tile * p.tile_rows + h * kUnitRows + j * kTileM + r);
+          uint8_t* out_ptr = out + (long long)(out_row >= 0 ? out_row : 0) * out_ld_bytes +
+                             (long long)col_base * kElem;
+          for (int col = 0; col < p.bn; col += 16) {
+            uint32_t v[16];
+            if (nk > 0) {
+              tmem_ld_x16(
+                  tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccStride + j * p.bn + col, v);
+              tmem_ld_wait();
+            } else {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(fmaxf(__uint_as_float(v[i]), 0.f));
-        }
-        if (out_row >= 0) {
-          if constexpr (sizeof(T) == 2) {
-            uint4* dst = reinterpret_cast<uint4*>(out_ptr + col * 2);
-            dst[0] = pack8<T>(v);
-            dst[1] = pack8<T>(v + 8);
-          } else {
-            uint4* dst = reinterpret_cast<uint4*>(out_ptr + col * 4);
+              for (int i = 0; i < 16; ++i) v[i] = 0u;
+            }
+            if (p.bias != nullptr) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) dst[i] = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+              for (int i = 0; i < 16; ++i)
+                v[i] = __float_as_uint(__uint_as_float(v[i]) + __ldg(p.bias + col_base + col + i));
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                v[i] = __float_as_uint(fmaxf(__uint_as_float(v[i]), 0.f));
+            }
+            if (out_row >= 0) {
+              if constexpr (sizeof(T) == 2) {
+                uint4* dst = reinterpret_cast<uint4*>(out_ptr + col * 2);
+                dst[0] = pack8<T>(v);
+                dst[1] = pack8<T>(v + 8);
+              } else {
+                uint4* dst = reinterpret_cast<uint4*>(out_ptr + col * 4);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  dst[i] = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+              }
+            }
           }
         }
+        if (nk > 0) {
+          tc_fence_before();
+          mbar_arrive(smem_u32(&ctrl->acc_empty[acc]));
+          ++use;
+        }
       }
-      if (nk > 0) {
-        tc_fence_before();
-        mbar_arrive(smem_u32(&ctrl->acc_empty[acc]));
-        ++use;
-      }
+    }
+    if (p.dbg_out != nullptr && tid == 5 * 32) {
+      p.dbg_out[blockIdx.x * 8 + 5] = clock64() - t_start;
+      p.dbg_out[blockIdx.x * 8 + 6] = w_accf;
+      p.dbg_out[blockIdx.x * 8 + 7] = t_end - t_begin;
     }
   }
 
@@ -227,26 +393,30 @@ gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
   }
 }
 
-static size_t gemm_smem_bytes(int bn, int stages) {
-  const int stage_bytes = kAStageBytes + ((bn * 128 + 1023) & ~1023);
-  return (size_t)stages * stage_bytes + sizeof(GemmSmemCtrl) + 1024;
+static int stage_bytes_of(int bn, int tm, int gc) {
+  return tm * gc * kAStageBytes + ((gc * bn * 128 + 1023) & ~1023);
 }
 
-int pick_gemm_stages(int bn) {
-  const int stage_bytes = kAStageBytes + ((bn * 128 + 1023) & ~1023);
-  int s = (int)((227 * 1024 - sizeof(GemmSmemCtrl) - 1024) / stage_bytes);
+static size_t gemm_smem_bytes(int bn, int tm, int gc, int stages) {
+  return (size_t)stages * stage_bytes_of(bn, tm, gc) + sizeof(GemmSmemCtrl) + 1024;
+}
+
+static int pick_gemm_stages(int bn, int tm, int gc) {
+  int s = (int)((227 * 1024 - sizeof(GemmSmemCtrl) - 1024) / stage_bytes_of(bn, tm, gc));
   if (s > kMaxStages) s = kMaxStages;
   return s;
 }
 
-template <typename T>
+template <typename T, int TM, int GC>
 static int launch_gather_gemm_t(GatherGemmParams p, int n_slabs, int max_ctas, cudaStream_t stream) {
-  if (p.stages <= 0) p.stages = pick_gemm_stages(p.bn);
+  const int max_stages = pick_gemm_stages(p.bn, TM, GC);
+  if (p.stages <= 0 || p.stages > max_stages) p.stages = max_stages;
   if (p.stages < 2) return kErrUnsupportedShape;
-  const size_t smem = gemm_smem_bytes(p.bn, p.stages);
+  p.halves = p.tile_rows / (kTileM * TM);
+  const size_t smem = gemm_smem_bytes(p.bn, TM, GC, p.stages);
   static int configured_smem = 0;  // per instantiation
   if ((int)smem > configured_smem) {
-    cudaError_t e = cudaFuncSetAttribute(gather_gemm_kernel<T>,
+    cudaError_t e = cudaFuncSetAttribute(gather_gemm_kernel<T, TM, GC>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return kErrCuda;
     configured_smem = (int)smem;
@@ -254,9 +424,25 @@ static int launch_gather_gemm_t(GatherGemmParams p, int n_slabs, int max_ctas, c
   int ctas = p.num_tiles < max_ctas ? p.num_tiles : max_ctas;
   if (ctas < 1) return kOk;
   dim3 grid(ctas, n_slabs, 1);
-  gather_gemm_kernel<T><<<grid, kGemmThreads, smem, stream>>>(p);
+  gather_gemm_kernel<T, TM, GC><<<grid, kGemmThreads, smem, stream>>>(p);
   count_launch();
   return cudaGetLastError() == cudaSuccess ? kOk : kErrCuda;
+}
+
+template <typename T>
+static int launch_gather_gemm_tm(const GatherGemmParams& p, int n_slabs, int max_ctas,
+                                 cudaStream_t stream) {
+  // TM = 2: two 128-row sub-tiles share each weight slice when the plan has 256-row tiles and
+  // both accumulators (double buffered) fit the 512 TMEM columns.
+  // GC = 2: a stage covers two 128-byte channel chunks so gathers are 256-byte requests.
+  const bool tm2 = p.tile_rows == 2 * kTileM && p.bn <= 128 && !(p.debug & 16);  // 16: bring-up
+  const bool gc2 = p.cin * (int)sizeof(T) > 128 && !(p.debug & 32);             // 32: bring-up
+  if (tm2) {
+    return gc2 ? launch_gather_gemm_t<T, 2, 2>(p, n_slabs, max_ctas, stream)
+               : launch_gather_gemm_t<T, 2, 1>(p, n_slabs, max_ctas, stream);
+  }
+  return gc2 ? launch_gather_gemm_t<T, 1, 2>(p, n_slabs, max_ctas, stream)
+             : launch_gather_gemm_t<T, 1, 1>(p, n_slabs, max_ctas, stream);
 }
 
 int launch_gather_gemm(const GatherGemmParams& p, int dtype, int n_slabs, int max_ctas,
@@ -270,11 +456,13 @@ int launch_gather_gemm(const GatherGemmParams& p, int dtype, int n_slabs, int ma
   if ((reinterpret_cast<uintptr_t>(p.feats) & 15) || (reinterpret_cast<uintptr_t>(p.out) & 15) ||
       (reinterpret_cast<uintptr_t>(p.wimg) & 15))
     return kErrAlignment;
-  if (p.m_pad % kTileM != 0 || p.num_tiles * kTileM > p.m_pad) return kErrInvalidArg;
+  if (p.tile_rows != kTileM && p.tile_rows != 2 * kTileM) return kErrInvalidArg;
+  if (p.m_pad % p.tile_rows != 0 || (long long)p.num_tiles * p.tile_rows > p.m_pad)
+    return kErrInvalidArg;
   switch (dtype) {
-    case kBF16: return launch_gather_gemm_t<__nv_bfloat16>(p, n_slabs, max_ctas, stream);
-    case kF16: return launch_gather_gemm_t<__half>(p, n_slabs, max_ctas, stream);
-    case kF32: return launch_gather_gemm_t<float>(p, n_slabs, max_ctas, stream);
+    case kBF16: return launch_gather_gemm_tm<__nv_bfloat16>(p, n_slabs, max_ctas, stream);
+    case kF16: return launch_gather_gemm_tm<__half>(p, n_slabs, max_ctas, stream);
+    case kF32: return launch_gather_gemm_tm<float>(p, n_slabs, max_ctas, stream);
     default: return kErrUnsupportedDtype;
   }
 }

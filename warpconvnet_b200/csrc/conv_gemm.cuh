@@ -1,37 +1,45 @@
 // SPDX-License-Identifier: Apache-2.0
 // Parameter blocks shared by the sparse-conv GEMM kernels and their launchers.
 #pragma once
+#include <cuda.h>
 #include <stdint.h>
 
 namespace wcn {
 
 // Output-stationary fused gather-GEMM (forward AB_gather_scatter and dgrad ABt_gather_scatter).
-// One CTA owns a tile of 128 mask-sorted output rows; for every kernel offset that is active in
-// the tile it gathers the 128 neighbour rows into 128B-swizzled shared memory, streams the
+// One CTA owns a contiguous range of mask-sorted tiles; for every step (= kernel offset active
+// in the tile) it gathers the tile's neighbour rows into 128B-swizzled shared memory, streams the
 // offset's weight slice with a bulk copy and accumulates on the tensor cores into TMEM.
 struct GatherGemmParams {
+  CUtensorMap tmap;         // 2-D map of feats: box = 128 B x 1 row, 128B swizzle (TMA gather4)
   const void* feats;        // [n_in_rows, in_ld] source features (X for fwd, dY for dgrad)
   const void* wimg;         // weight image [n_slabs][K][n_chunks][BN][128 B], see weight_prep.cu
   void* out;                // [n_out_rows, out_ld]
-  const int* nbr;           // [K][m_pad] neighbour row per (offset, sorted position), -1 = none
+  const int* step_nbr;      // [num_tiles][K][tile_rows] neighbour rows of step i of tile t at
+                            // (t*K + i)*tile_rows, -1 = none; only the first tile_nk[t] steps exist
+  const int* step_k;        // [num_tiles][K] kernel offset of each step
   const int* rows;          // [m_pad] output row of each sorted position, -1 = padding
-  const uint16_t* tile_ks;  // [num_tiles][k_stride] active offsets of each tile
-  const int* tile_nk;       // [num_tiles] number of active offsets
+  const int* tile_nk;       // [num_tiles] number of steps (active offsets) of each tile
+  const int* tile_cum;      // [num_tiles + 1] exclusive prefix sum of tile_nk
   const float* bias;        // optional [cout_total] fp32, added in the epilogue
   long long in_ld;          // row strides in elements
   long long out_ld;
+  int n_in_rows;            // rows of feats (row index n_in_rows = "no neighbour", zero-filled)
   int in_coff;              // first input channel used by slab 0
   int in_slab_stride;       // input-channel step between slabs (group conv), 0 = shared input
   int out_coff;             // first output channel written by slab 0
   int cin;                  // contraction length (channels gathered per row)
   int bn;                   // output channels per slab (multiple of 16, <= 256)
   int K;                    // kernel volume
-  int k_stride;             // row pitch of tile_ks
-  int m_pad;                // padded sorted length (multiple of 128)
+  int tile_rows;            // rows per tile of the plan: 128 or 256
+  int halves;               // tile_rows / rows a CTA processes per step (set by the launcher)
+  int m_pad;                // padded sorted length (multiple of tile_rows)
   int num_tiles;
   int kflip;                // weight index = K-1-k (dgrad of a submanifold conv on the fwd table)
   int stages;               // shared-memory pipeline depth
   int relu;                 // fused ReLU in the epilogue (0/1)
+  long long* dbg_out;       // bring-up only: per-CTA wait-cycle counters (env WCN_DEBUG_PTR)
+  int debug;                // bring-up only (env WCN_DEBUG): 16 force TM = 1
 };
 
 // wgrad AtB_gather_gather: per offset k, dW_k[cin, cout] += X[in_maps]^T * dY[out_maps].

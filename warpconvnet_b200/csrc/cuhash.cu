@@ -291,30 +291,58 @@ __global__ void iota_kernel(int* __restrict__ v, int n) {
   if (i < n) v[i] = i;
 }
 
-// One block per 128-row tile of the mask-sorted order: permute the table into tile order and
-// list the offsets that are active anywhere in the tile.
-__global__ void __launch_bounds__(128)
+// One block per tile (tile_rows = 128 or 256 rows) of the mask-sorted order: compacts the offsets
+// that are active anywhere in the tile into the tile's step list and stores each step's
+// neighbour rows contiguously, in the order the GEMM kernel consumes them.
+__global__ void __launch_bounds__(256)
 build_tiles_kernel(const int* __restrict__ table, int K, int M, const int* __restrict__ sorted_rows,
-                   int m_pad, int* __restrict__ nbr, int* __restrict__ rows_padded,
-                   uint16_t* __restrict__ tile_ks, int k_stride, int* __restrict__ tile_nk) {
-  __shared__ int s_n;
+                   int tile_rows, int* __restrict__ step_nbr, int* __restrict__ step_k,
+                   int* __restrict__ rows_padded, int* __restrict__ tile_nk) {
   const int tile = blockIdx.x;
-  const int pos = tile * 128 + threadIdx.x;
+  const int pos = tile * tile_rows + threadIdx.x;  // blockDim.x == tile_rows
   const int row = pos < M ? __ldg(sorted_rows + pos) : -1;
   rows_padded[pos] = row;
-  if (threadIdx.x == 0) s_n = 0;
-  __syncthreads();
+  int n = 0;
   for (int k = 0; k < K; ++k) {
     const int v = row >= 0 ? __ldg(table + (size_t)k * M + row) : -1;
-    nbr[(size_t)k * m_pad + pos] = v;
-    const int any = __syncthreads_or(v >= 0);
-    if (any && threadIdx.x == 0) {
-      tile_ks[(size_t)tile * k_stride + s_n] = (uint16_t)k;
-      ++s_n;
+    if (__syncthreads_or(v >= 0)) {  // block-uniform
+      const size_t step = (size_t)tile * K + n;
+      step_nbr[step * tile_rows + threadIdx.x] = v;
+      if (threadIdx.x == 0) step_k[step] = k;
+      ++n;
     }
   }
+  if (threadIdx.x == 0) tile_nk[tile] = n;
+}
+
+// tile_cum[0..n] = exclusive prefix sum of tile_nk[0..n); single block
+__global__ void __launch_bounds__(1024)
+tile_scan_kernel(const int* __restrict__ tile_nk, int n, int* __restrict__ tile_cum) {
+  __shared__ int s_warp[32];
+  __shared__ int s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
   __syncthreads();
-  if (threadIdx.x == 0) tile_nk[tile] = s_n;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base < n; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int v = i < n ? tile_nk[i] : 0;
+    int incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    int warp_off = 0;
+    for (int w = 0; w < warp; ++w) warp_off += s_warp[w];
+    const int carry = s_carry;
+    if (i < n) tile_cum[i] = carry + warp_off + incl - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) s_carry = carry + warp_off + incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) tile_cum[n] = s_carry;
 }
 
 // --------------------------------------------------------------------------------------------
@@ -447,12 +475,18 @@ int sort_rows_by_key(const unsigned long long* keys, int M, int K, int* rows_out
   return e == cudaSuccess ? cuda_ok() : kErrCuda;
 }
 
-int build_tiles(const int* table, int K, int M, const int* sorted_rows, int m_pad, int* nbr,
-                int* rows_padded, uint16_t* tile_ks, int k_stride, int* tile_nk, cudaStream_t s) {
-  if (m_pad % 128 != 0 || m_pad < M || k_stride < K || K > 65535) return kErrInvalidArg;
-  if (m_pad == 0) return kOk;
-  build_tiles_kernel<<<m_pad / 128, 128, 0, s>>>(table, K, M, sorted_rows, m_pad, nbr, rows_padded,
-                                                tile_ks, k_stride, tile_nk);
+int build_tiles(const int* table, int K, int M, const int* sorted_rows, int tile_rows, int m_pad,
+                int* step_nbr, int* step_k, int* rows_padded, int* tile_nk, int* tile_cum,
+                cudaStream_t s) {
+  if (tile_rows != 128 && tile_rows != 256) return kErrInvalidArg;
+  if (m_pad % tile_rows != 0 || m_pad < M || K < 1) return kErrInvalidArg;
+  const int num_tiles = m_pad / tile_rows;
+  if (num_tiles > 0) {
+    build_tiles_kernel<<<num_tiles, tile_rows, 0, s>>>(table, K, M, sorted_rows, tile_rows,
+                                                      step_nbr, step_k, rows_padded, tile_nk);
+    count_launch();
+  }
+  tile_scan_kernel<<<1, 1024, 0, s>>>(tile_nk, num_tiles, tile_cum);
   count_launch();
   return cuda_ok();
 }

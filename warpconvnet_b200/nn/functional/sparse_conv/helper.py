@@ -146,11 +146,12 @@ def spatially_sparse_conv(
         stride_mode=stride_mode, order=order)
     num_out = bout.shape[0]
 
+    # Features are cast here (like the reference, helper.py:310-320); the weight goes into the
+    # autograd function in its master dtype and is cast inside, so the fp32 wgrad result reaches
+    # weight.grad without a round trip through bf16.
     x, w = feats, weight
     if x.dtype != effective_compute_dtype:
         x = x.to(effective_compute_dtype)
-    if w.dtype != effective_compute_dtype:
-        w = w.to(effective_compute_dtype)
 
     out = UnifiedSpatiallySparseConvFunction.apply(
         x, w, kernel_map, num_out, fwd_algo, dgrad_algo, wgrad_algo, effective_compute_dtype,
