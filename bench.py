@@ -212,6 +212,8 @@ def run_ours(args):
     def timed(fn, steps, warmup):
         for _ in range(warmup):
             fn(False)
+        # NB: no dense-matmul "clock heating" here: sustained tensor load drives a B200 into its
+        # power cap (1.9 -> 1.2 GHz, tools/exp_clock.py), which would distort a short step.
         barrier()
         evs = []
         l0 = lib.wcn_launch_count()

@@ -25,14 +25,11 @@ table = km.pair_table(n)
 dbg = torch.zeros(148 * 8, dtype=torch.int64, device="cuda")
 os.environ["WCN_DEBUG_PTR"] = str(dbg.data_ptr())
 names = ["prod_total", "prod_wait_empty", "mma_total", "mma_wait_full", "mma_wait_accempty",
-         "epi_total", "epi_wait_accfull", "tiles"]
+         "epi_total", "epi_wait_accfull", "prod_ns"]
 for tr in (128, 256):
     plan = _ops.build_tile_plan(table, tile_rows=tr)
     for flags in (0, 32):
         os.environ["WCN_DEBUG"] = str(flags)
-        heat = torch.randn(8192, 8192, device="cuda", dtype=torch.bfloat16)
-        for _ in range(20):
-            heat @ heat
         for _ in range(3):
             dbg.zero_()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -42,5 +39,6 @@ for tr in (128, 256):
             torch.cuda.synchronize()
         d = dbg.view(148, 8).cpu().numpy()
         print(f"tile_rows={tr} dbg={flags} time={a.elapsed_time(b) * 1e3:.1f} us  steps={int(plan.tile_nk.sum())}")
+        print(f"    SM clock (prod cycles / ns): {(d[:, 0] / d[:, 7]).mean():.3f} GHz")
         for i, nm in enumerate(names):
             print(f"    {nm:18s} mean={d[:, i].mean():10.0f} min={d[:, i].min():10d} max={d[:, i].max():10d}")

@@ -34,8 +34,8 @@ def timeit(fn, iters=20):
     if _FLUSH is None:
         _FLUSH = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
         _HEAT = torch.randn(8192, 8192, device="cuda", dtype=torch.bfloat16)
-    for _ in range(20):  # ~0.1-0.2 s of dense work: brings the SM clock up
-        _HEAT @ _HEAT
+    # NOTE: no dense-matmul "heating": sustained tensor load drives this part into its power cap
+    # (1.9 GHz -> 1.2 GHz, tools/exp_clock.py) and it needs > 50 ms to recover.
     for _ in range(5):
         fn()
     evs = []

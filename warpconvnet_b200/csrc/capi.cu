@@ -34,42 +34,6 @@ int launch_wgrad(const WgradParams&, int dtype, int y_slabs, int z_slabs, int ma
 static long long g_launches = 0;
 void count_launch() { __atomic_add_fetch(&g_launches, 1, __ATOMIC_RELAXED); }
 
-// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
-typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
-                                      const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                      const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static TensorMapEncodeFn tensor_map_encoder() {
-  static TensorMapEncodeFn fn = nullptr;
-  if (fn == nullptr) {
-    void* sym = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) ==
-            cudaSuccess && q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<TensorMapEncodeFn>(sym);
-  }
-  return fn;
-}
-
-// [n_rows, row_elems] row-major matrix with pitch ld elements; box = 128 bytes x 1 row
-static int make_gather_map(CUtensorMap* map, const void* base, long long n_rows, long long ld,
-                           int dtype) {
-  TensorMapEncodeFn enc = tensor_map_encoder();
-  if (enc == nullptr) return kErrCuda;
-  const int es = dtype_size(dtype);
-  const CUtensorMapDataType dt = dtype == kBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
-                               : dtype == kF16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
-                                               : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
-  cuuint64_t gdim[2] = {(cuuint64_t)ld, (cuuint64_t)(n_rows > 0 ? n_rows : 1)};
-  cuuint64_t gstride[1] = {(cuuint64_t)ld * es};
-  cuuint32_t box[2] = {(cuuint32_t)(128 / es), 1};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? kOk : kErrInvalidArg;
-}
-
 static int sm_count() {
   static int cached = 0;
   if (cached == 0) {
@@ -272,8 +236,6 @@ int wcn_gather_gemm(const void* feats, int n_in_rows, long long in_ld, const voi
   if (n_in_rows < 0 || (in_ld * dtype_size(dtype)) % 16 != 0 ||
       (reinterpret_cast<uintptr_t>(feats) & 15))
     return n_in_rows < 0 ? kErrInvalidArg : kErrAlignment;
-  st = make_gather_map(&p.tmap, feats, n_in_rows, in_ld, dtype);
-  if (st != kOk) return st;
   p.n_in_rows = n_in_rows;
   p.feats = feats;
   p.wimg = wimg;
@@ -333,6 +295,12 @@ int wcn_wgrad(const void* feats, long long in_ld, const void* gout, long long ou
   p.unit_pairs = unit_pairs;
   p.stages = 0;
   p.alpha = alpha;
+  {
+    const char* e = getenv("WCN_DEBUG");
+    p.debug = e ? atoi(e) : 0;
+    const char* dp = getenv("WCN_DEBUG_PTR");
+    p.dbg_out = dp ? reinterpret_cast<long long*>(strtoull(dp, nullptr, 10)) : nullptr;
+  }
   p.dw_k_stride = (long long)groups * cin_g * cout_g;
   p.dw_g_stride = (long long)cin_g * cout_g;
   p.dw_ld = cout_g;

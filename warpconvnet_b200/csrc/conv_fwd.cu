@@ -190,6 +190,8 @@ gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
     uint32_t phase = 0;
     long long w_empty = 0;
     const long long t_start = clock64();
+    unsigned long long ns_start;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns_start));
     while (cur.valid(t_end)) {
 #pragma unroll
       for (int d = 0; d < kPrefetch; ++d) {
@@ -243,6 +245,9 @@ gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
     if (p.dbg_out != nullptr && tid == 0) {
       p.dbg_out[blockIdx.x * 8 + 0] = clock64() - t_start;
       p.dbg_out[blockIdx.x * 8 + 1] = w_empty;
+      unsigned long long ns_end;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns_end));
+      p.dbg_out[blockIdx.x * 8 + 7] = (long long)(ns_end - ns_start);
     }
   } else if (warp == kMmaWarp) {
     // ======================================= MMA issuer =========================================
@@ -381,7 +386,6 @@ gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
     if (p.dbg_out != nullptr && tid == 5 * 32) {
       p.dbg_out[blockIdx.x * 8 + 5] = clock64() - t_start;
       p.dbg_out[blockIdx.x * 8 + 6] = w_accf;
-      p.dbg_out[blockIdx.x * 8 + 7] = t_end - t_begin;
     }
   }
 

@@ -1,7 +1,6 @@
 // SPDX-License-Identifier: Apache-2.0
 // Parameter blocks shared by the sparse-conv GEMM kernels and their launchers.
 #pragma once
-#include <cuda.h>
 #include <stdint.h>
 
 namespace wcn {
@@ -11,7 +10,6 @@ namespace wcn {
 // in the tile) it gathers the tile's neighbour rows into 128B-swizzled shared memory, streams the
 // offset's weight slice with a bulk copy and accumulates on the tensor cores into TMEM.
 struct GatherGemmParams {
-  CUtensorMap tmap;         // 2-D map of feats: box = 128 B x 1 row, 128B swizzle (TMA gather4)
   const void* feats;        // [n_in_rows, in_ld] source features (X for fwd, dY for dgrad)
   const void* wimg;         // weight image [n_slabs][K][n_chunks][BN][128 B], see weight_prep.cu
   void* out;                // [n_out_rows, out_ld]
@@ -24,7 +22,7 @@ struct GatherGemmParams {
   const float* bias;        // optional [cout_total] fp32, added in the epilogue
   long long in_ld;          // row strides in elements
   long long out_ld;
-  int n_in_rows;            // rows of feats (row index n_in_rows = "no neighbour", zero-filled)
+  int n_in_rows;            // rows of feats (bounds documentation; neighbours are < n_in_rows)
   int in_coff;              // first input channel used by slab 0
   int in_slab_stride;       // input-channel step between slabs (group conv), 0 = shared input
   int out_coff;             // first output channel written by slab 0
@@ -73,6 +71,8 @@ struct WgradParams {
   int unit_pairs;      // pairs per work unit (multiple of the stage depth)
   int stages;
   float alpha;
+  int debug;           // bring-up only (env WCN_DEBUG): 64 skip proxy fence, 128 128-pair stages
+  long long* dbg_out;  // bring-up only: per-CTA cycle counters (env WCN_DEBUG_PTR)
 };
 
 // Weight image builder (weight_prep.cu): see that file for the image layout.

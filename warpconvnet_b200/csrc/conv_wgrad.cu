@@ -23,7 +23,7 @@ constexpr int kWgThreads = 288;
 constexpr int kWgMaxStages = 8;
 constexpr int kWgTmemCols = 512;
 constexpr int kWgAccStride = 256;
-constexpr int kWgMaxK = 1024;  // offsets per kernel map supported by the in-kernel unit table
+constexpr int kWgMaxK = 65535;
 
 struct WgSmemCtrl {
   uint64_t full[kWgMaxStages];
@@ -31,8 +31,9 @@ struct WgSmemCtrl {
   uint64_t acc_full[2];
   uint64_t acc_empty[2];
   uint32_t tmem_base;
-  int total_units;
-  int unit_start[kWgMaxK + 1];
+  int pair_begin;  // this CTA's slice of the concatenated pair lists
+  int pair_end;
+  int k_first;     // offset that contains pair_begin
 };
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
@@ -41,7 +42,7 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
                : "memory");
 }
 
-template <typename T>
+template <typename T, int PAIRS, int NSEGB>
 __global__ void __launch_bounds__(kWgThreads, 1)
 wgrad_kernel(const __grid_constant__ WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -50,7 +51,7 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
 
   constexpr int kElem = (int)sizeof(T);
   constexpr int kBlkElems = 128 / kElem;          // channels per 128-byte MN block
-  constexpr int kPairs = (kElem == 2) ? 64 : 32;  // pairs (K extent) per pipeline stage
+  constexpr int kPairs = PAIRS;                   // pairs (K extent) per pipeline stage
   constexpr int kKPerMma = 32 / kElem;            // 16 (bf16/f16) or 8 (tf32) pairs per MMA
   constexpr int kAStage = (128 / kBlkElems) * kPairs * 128;  // A always spans M = 128 channels
   const int tid = threadIdx.x;
@@ -61,7 +62,7 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
   const int cin_here = (ys == (int)gridDim.y - 1) ? p.cin_last : p.cin;
   const int n_blk_a = (cin_here + kBlkElems - 1) / kBlkElems;
   const int n_blk_b = (p.cout + kBlkElems - 1) / kBlkElems;
-  const int b_stage = n_blk_b * kPairs * 128;
+  const int b_stage = 2 * NSEGB * kPairs * 128;  // whole 256-byte segments (zero-filled tails)
   const int stage_bytes = kAStage + ((b_stage + 1023) & ~1023);
   const int stages = p.stages;
   WgSmemCtrl* ctrl = reinterpret_cast<WgSmemCtrl*>(smem_gen + (size_t)stages * stage_bytes);
@@ -76,14 +77,20 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
       mbar_init(smem_u32(&ctrl->acc_empty[a]), 128);
     }
     fence_mbar_init();
-    int acc = 0;
-    for (int k = 0; k < p.K; ++k) {
-      ctrl->unit_start[k] = acc;
-      const int len = p.offsets[k + 1] - p.offsets[k];
-      acc += (len + p.unit_pairs - 1) / p.unit_pairs;
+    // Balanced split of the concatenated pair lists: CTA b owns pairs [L*b/G, L*(b+1)/G). A work
+    // unit is the intersection of that slice with one offset's list, so every CTA contracts the
+    // same number of pairs (+-1) and issues at most (offsets touched) reductions into dW.
+    const long long L = p.offsets[p.K];
+    const int G = gridDim.x, b = blockIdx.x;
+    const int pb = (int)(L * b / G), pe = (int)(L * (b + 1) / G);
+    int lo = 0, hi = p.K;  // largest k with offsets[k] <= pb
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (p.offsets[mid] <= pb) lo = mid; else hi = mid;
     }
-    ctrl->unit_start[p.K] = acc;
-    ctrl->total_units = acc;
+    ctrl->pair_begin = pb;
+    ctrl->pair_end = pe;
+    ctrl->k_first = lo;
   }
   if (warp == 4) {
     tmem_alloc(smem_u32(&ctrl->tmem_base), kWgTmemCols);
@@ -93,82 +100,137 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = ctrl->tmem_base;
-  const int total_units = ctrl->total_units;
+  const int pair_begin = ctrl->pair_begin;
+  const int pair_end = ctrl->pair_end;
+  const int k_first = ctrl->k_first;
 
-  // unit -> (offset k, first pair, number of pairs); every role evaluates it identically
-  auto locate = [&](int u, int& k, int& first, int& count) {
-    int lo = 0, hi = p.K;  // largest k with unit_start[k] <= u (empty offsets have no units)
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if (ctrl->unit_start[mid] <= u) lo = mid; else hi = mid;
-    }
-    k = lo;
-    const int beg = p.offsets[k], end = p.offsets[k + 1];
-    first = beg + (u - ctrl->unit_start[k]) * p.unit_pairs;
-    count = min(p.unit_pairs, end - first);
+  // unit of offset k: (first pair, number of pairs); count <= 0 when the slice misses offset k.
+  // Every role walks k = k_first, k_first + 1, ... identically and stops at `done`.
+  auto unit_of = [&](int k, int& first, int& count, bool& done) {
+    const int ob = __ldg(p.offsets + k), oe = __ldg(p.offsets + k + 1);
+    done = ob >= pair_end;
+    first = max(ob, pair_begin);
+    count = min(oe, pair_end) - first;
   };
 
   if (warp < 4) {
     // ===================================== gather producers =====================================
+    // 16 lanes fetch 256 contiguous bytes of one gathered row (two 128-byte MN blocks): the
+    // L2->SM path serves about one gather request per 8 cycles per SM whatever its size
+    // (tools/gather_bench.cu), so whole-row requests double the gather rate of 128-byte ones.
     const uint8_t* xs = reinterpret_cast<const uint8_t*>(p.feats);
     const uint8_t* gs = reinterpret_cast<const uint8_t*>(p.gout);
     const long long in_ld_bytes = p.in_ld * kElem;
     const long long out_ld_bytes = p.out_ld * kElem;
-    const int c16 = tid & 7;
-    const int seg0 = tid >> 3;  // 0..15: row segment handled per pass (16 segments per pass)
-    const long long a_col0 = (long long)(p.in_coff + ys * p.in_y_stride) * kElem + c16 * 16;
-    const long long b_col0 =
-        (long long)(p.out_coff + ys * p.out_y_stride + zs * p.out_z_stride) * kElem + c16 * 16;
+    const int u = lane & 15;       // 16-byte unit inside a 256-byte row segment
+    const int blk = u >> 3;        // 128-byte MN block inside the segment
+    const int c16 = u & 7;
+    const int sub = lane >> 4;     // which of the 2 pair rows an instruction covers
+    constexpr int kRowsPerWarp = kPairs / 4;   // pair rows a warp gathers per stage (16 or 32)
+    constexpr int kInstr = kRowsPerWarp / 2;   // cp.async per thread, operand and segment
+    constexpr int kDepth = 4;                  // stages of pair-index look-ahead
+    static_assert(kRowsPerWarp <= 32, "one index per lane");
+    const uint8_t* a_base = xs + (long long)(p.in_coff + ys * p.in_y_stride) * kElem + u * 16;
+    const uint8_t* b_base =
+        gs + (long long)(p.out_coff + ys * p.out_y_stride + zs * p.out_z_stride) * kElem + u * 16;
     const int cin_bytes = cin_here * kElem;
     const int cout_bytes = p.cout * kElem;
-    constexpr int kPass = kPairs / 16;
+    // pair row of instruction q: pr(q) = warp*kRowsPerWarp + 2q + sub; (pr & 7) = (2q + sub) & 7
+    uint32_t off_par[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r7 = 2 * i + sub;
+      off_par[i] = (uint32_t)blk * (kPairs * 128) +
+                   (uint32_t)(warp * kRowsPerWarp + r7) * 128u + (uint32_t)((c16 ^ r7) << 4);
+    }
     int stage = 0;
     uint32_t phase = 0;
-    for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
-      int k, first, count;
-      locate(u, k, first, count);
-      int pi_n[kPass], po_n[kPass];
-#pragma unroll
-      for (int t = 0; t < kPass; ++t) {
-        const int pr = seg0 + 16 * t;
-        pi_n[t] = pr < count ? __ldg(p.in_maps + first + pr) : -1;
-        po_n[t] = pr < count ? __ldg(p.out_maps + first + pr) : -1;
-      }
-      for (int done = 0; done < count; done += kPairs) {
-        int pi[kPass], po[kPass];
-#pragma unroll
-        for (int t = 0; t < kPass; ++t) { pi[t] = pi_n[t]; po[t] = po_n[t]; }
-        if (done + kPairs < count) {  // prefetch the next stage's pair indices
-#pragma unroll
-          for (int t = 0; t < kPass; ++t) {
-            const int pr = done + kPairs + seg0 + 16 * t;
-            pi_n[t] = pr < count ? __ldg(p.in_maps + first + pr) : -1;
-            po_n[t] = pr < count ? __ldg(p.out_maps + first + pr) : -1;
-          }
+    long long w_empty = 0, n_stage = 0, t_issue = 0, t_arrive = 0;
+    const long long t_start = clock64();
+    for (int k = k_first; k < p.K; ++k) {
+      int first, count;
+      bool done;
+      unit_of(k, first, count, done);
+      if (done) break;
+      if (count <= 0) continue;
+      const int n_st = (count + kPairs - 1) / kPairs;
+      // lane l < kRowsPerWarp holds the input row, lane 16 + ... the output row of pair
+      // warp*kRowsPerWarp + l of the stage (kRowsPerWarp = 16: both in one register)
+      auto load_idx = [&](int st, int& vi, int& vo) {
+        const int pr = st * kPairs + warp * kRowsPerWarp + (lane % kRowsPerWarp);
+        const bool ok = pr < count;
+        if (kRowsPerWarp == 16) {
+          const int* src = (lane < 16) ? p.in_maps : p.out_maps;
+          vi = ok ? __ldg(src + first + pr) : -1;
+          vo = vi;
+        } else {
+          vi = ok ? __ldg(p.in_maps + first + pr) : -1;
+          vo = ok ? __ldg(p.out_maps + first + pr) : -1;
         }
-        mbar_wait(smem_u32(&ctrl->empty[stage]), phase ^ 1u);
-        const uint32_t a_smem = smem_base + stage * stage_bytes;
-        const uint32_t b_smem = a_smem + kAStage;
+      };
+      int vi_r[kDepth], vo_r[kDepth];
 #pragma unroll
-        for (int t = 0; t < kPass; ++t) {
-          const int pr = seg0 + 16 * t;
-          const bool valid = pi[t] >= 0;
-          const uint8_t* xrow = xs + (long long)(valid ? pi[t] : 0) * in_ld_bytes + a_col0;
-          const uint8_t* grow = gs + (long long)(valid ? po[t] : 0) * out_ld_bytes + b_col0;
-          const uint32_t sz = valid ? 16u : 0u;
-          const uint32_t soff = sw128_offset(pr, c16);
-          for (int b = 0; b < n_blk_a; ++b) {
-            if (b * 128 + c16 * 16 < cin_bytes)
-              cp_async_16(a_smem + b * (kPairs * 128) + soff, xrow + b * 128, sz);
-          }
-          for (int b = 0; b < n_blk_b; ++b) {
-            if (b * 128 + c16 * 16 < cout_bytes)
-              cp_async_16(b_smem + b * (kPairs * 128) + soff, grow + b * 128, sz);
-          }
-        }
-        cp_async_mbar_arrive_noinc(smem_u32(&ctrl->full[stage]));
-        if (++stage == stages) { stage = 0; phase ^= 1u; }
+      for (int d = 0; d < kDepth; ++d) {
+        vi_r[d] = -1;
+        vo_r[d] = -1;
+        if (d < n_st) load_idx(d, vi_r[d], vo_r[d]);
       }
+      for (int st0 = 0; st0 < n_st; st0 += kDepth) {
+#pragma unroll
+        for (int d = 0; d < kDepth; ++d) {
+          const int st = st0 + d;
+          if (st >= n_st) break;
+          const int vi = vi_r[d], vo = vo_r[d];
+          if (st + kDepth < n_st) load_idx(st + kDepth, vi_r[d], vo_r[d]);
+          {
+            const long long t0 = clock64();
+            mbar_wait(smem_u32(&ctrl->empty[stage]), phase ^ 1u);
+            w_empty += clock64() - t0;
+            ++n_stage;
+          }
+          const uint32_t a_smem = smem_base + stage * stage_bytes;
+          const uint32_t b_smem = a_smem + kAStage;
+          const long long t_i0 = clock64();
+#pragma unroll
+          for (int q = 0; q < kInstr; ++q) {
+            const int row = 2 * q + sub;  // pair row inside this warp's share of the stage
+            int pi, po;
+            if (kRowsPerWarp == 16) {
+              pi = __shfl_sync(0xffffffffu, vi, row);
+              po = __shfl_sync(0xffffffffu, vi, 16 + row);
+            } else {
+              pi = __shfl_sync(0xffffffffu, vi, row);
+              po = __shfl_sync(0xffffffffu, vo, row);
+            }
+            const bool valid = pi >= 0;
+            const uint8_t* xrow = a_base + (long long)(valid ? pi : 0) * in_ld_bytes;
+            const uint8_t* grow = b_base + (long long)(valid ? po : 0) * out_ld_bytes;
+            const uint32_t sz = valid ? 16u : 0u;
+            const uint32_t soff = off_par[q & 3] + (uint32_t)(q >> 2) * 1024u;
+            // branch-free: out-of-range lanes copy 0 source bytes (= zero fill)
+            cp_async_16(a_smem + soff, xrow, (u * 16 < cin_bytes) ? sz : 0u);
+#pragma unroll
+            for (int sgi = 0; sgi < NSEGB; ++sgi)
+              cp_async_16(b_smem + sgi * 2 * (kPairs * 128) + soff, grow + sgi * 256,
+                          (sgi * 256 + u * 16 < cout_bytes) ? sz : 0u);
+          }
+          const long long t_i1 = clock64();
+          cp_async_mbar_arrive_noinc(smem_u32(&ctrl->full[stage]));
+          const long long t_i2 = clock64();
+          t_issue += t_i1 - t_i0;
+          t_arrive += t_i2 - t_i1;
+          if (++stage == stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    if (p.dbg_out != nullptr && tid == 0 && (p.debug & 1024)) {
+      p.dbg_out[blockIdx.x * 8 + 3] = t_issue;
+      p.dbg_out[blockIdx.x * 8 + 4] = t_arrive;
+    }
+    if (p.dbg_out != nullptr && tid == 0) {
+      p.dbg_out[blockIdx.x * 8 + 0] = clock64() - t_start;
+      p.dbg_out[blockIdx.x * 8 + 1] = w_empty;
+      p.dbg_out[blockIdx.x * 8 + 7] = n_stage;
     }
   } else if (warp == 4) {
     // ======================================= MMA issuer =========================================
@@ -177,21 +239,35 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
       int stage = 0;
       uint32_t phase = 0;
       uint32_t use = 0;
-      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
-        int k, first, count;
-        locate(u, k, first, count);
+      long long w_full = 0, w_acc = 0;
+      const long long t_start = clock64();
+      for (int k = k_first; k < p.K; ++k) {
+        int first, count;
+        bool done;
+        unit_of(k, first, count, done);
+        if (done) break;
+        if (count <= 0) continue;
         const uint32_t acc = use & 1u;
-        mbar_wait(smem_u32(&ctrl->acc_empty[acc]), ((use >> 1) & 1u) ^ 1u);
+        {
+          const long long t0 = clock64();
+          mbar_wait(smem_u32(&ctrl->acc_empty[acc]), ((use >> 1) & 1u) ^ 1u);
+          w_acc += clock64() - t0;
+        }
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * kWgAccStride;
         uint32_t accumulate = 0;
         for (int done = 0; done < count; done += kPairs) {
-          mbar_wait(smem_u32(&ctrl->full[stage]), phase);
+          {
+            const long long t0 = clock64();
+            mbar_wait(smem_u32(&ctrl->full[stage]), phase);
+            w_full += clock64() - t0;
+          }
+          if (!(p.debug & 64)) fence_proxy_async_smem();  // cp.async = generic-proxy writes
           tc_fence_after();
           const uint32_t a_smem = smem_base + stage * stage_bytes;
           const uint32_t b_smem = a_smem + kAStage;
 #pragma unroll
-          for (int j = 0; j < kPairs / kKPerMma; ++j) {
+          for (int j = 0; j < kPairs / kKPerMma && !(p.debug & 256); ++j) {
             const uint32_t koff = j * kKPerMma * 128;  // kKPerMma pair rows of 128 bytes
             const uint64_t adesc = make_smem_desc_sw128(a_smem + koff, kPairs * 128, 1024);
             const uint64_t bdesc = make_smem_desc_sw128(b_smem + koff, kPairs * 128, 1024);
@@ -204,6 +280,11 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
         umma_commit(smem_u32(&ctrl->acc_full[acc]));
         ++use;
       }
+      if (p.dbg_out != nullptr && !(p.debug & 1024)) {
+        p.dbg_out[blockIdx.x * 8 + 2] = clock64() - t_start;
+        p.dbg_out[blockIdx.x * 8 + 3] = w_full;
+        p.dbg_out[blockIdx.x * 8 + 4] = w_acc;
+      }
     }
   } else {
     // ======================================== epilogue ==========================================
@@ -211,11 +292,20 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
     const int r = q * 32 + lane;  // input-channel row of the slab handled by this thread
     const int gl = (p.gps > 1) ? r / p.cin_g : 0;
     uint32_t use = 0;
-    for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
-      int k, first, count;
-      locate(u, k, first, count);
+    long long w_accf = 0;
+    const long long t_start = clock64();
+    for (int k = k_first; k < p.K; ++k) {
+      int first, count;
+      bool done;
+      unit_of(k, first, count, done);
+      if (done) break;
+      if (count <= 0) continue;
       const uint32_t acc = use & 1u;
-      mbar_wait(smem_u32(&ctrl->acc_full[acc]), (use >> 1) & 1u);
+      {
+        const long long t0 = clock64();
+        mbar_wait(smem_u32(&ctrl->acc_full[acc]), (use >> 1) & 1u);
+        w_accf += clock64() - t0;
+      }
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kWgAccStride;
       float* base = p.dw + (long long)k * p.dw_k_stride + ys * p.dw_y_stride + zs * p.dw_z_stride;
@@ -258,6 +348,10 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
       mbar_arrive(smem_u32(&ctrl->acc_empty[acc]));
       ++use;
     }
+    if (p.dbg_out != nullptr && tid == 5 * 32) {
+      p.dbg_out[blockIdx.x * 8 + 5] = clock64() - t_start;
+      p.dbg_out[blockIdx.x * 8 + 6] = w_accf;
+    }
   }
 
   tc_fence_before();
@@ -268,26 +362,24 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
   }
 }
 
-template <typename T>
+template <typename T, int PAIRS, int NSEGB>
 static int launch_wgrad_t(WgradParams p, int cin_slabs, int cout_slabs, int max_ctas,
                           cudaStream_t stream) {
   constexpr int kElem = (int)sizeof(T);
   constexpr int kBlkElems = 128 / kElem;
-  constexpr int kPairs = (kElem == 2) ? 64 : 32;
+  constexpr int kPairs = PAIRS;
   const int a_stage = (128 / kBlkElems) * kPairs * 128;
   const int n_blk_b = (p.cout + kBlkElems - 1) / kBlkElems;
-  const int stage_bytes = a_stage + ((n_blk_b * kPairs * 128 + 1023) & ~1023);
+  const int stage_bytes = a_stage + 2 * NSEGB * kPairs * 128;
   if (p.stages <= 0) {
     p.stages = (int)((227 * 1024 - sizeof(WgSmemCtrl) - 1024) / stage_bytes);
     if (p.stages > kWgMaxStages) p.stages = kWgMaxStages;
   }
   if (p.stages < 2) return kErrUnsupportedShape;
-  if (p.unit_pairs <= 0) p.unit_pairs = 4096;
-  p.unit_pairs = ((p.unit_pairs + kPairs - 1) / kPairs) * kPairs;
   const size_t smem = (size_t)p.stages * stage_bytes + sizeof(WgSmemCtrl) + 1024;
   static int configured_smem = 0;
   if ((int)smem > configured_smem) {
-    if (cudaFuncSetAttribute(wgrad_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(wgrad_kernel<T, PAIRS, NSEGB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)smem) != cudaSuccess)
       return kErrCuda;
     configured_smem = (int)smem;
@@ -295,7 +387,7 @@ static int launch_wgrad_t(WgradParams p, int cin_slabs, int cout_slabs, int max_
   int per_slab = max_ctas / (cin_slabs * cout_slabs);
   if (per_slab < 1) per_slab = 1;
   dim3 grid(per_slab, cin_slabs, cout_slabs);
-  wgrad_kernel<T><<<grid, kWgThreads, smem, stream>>>(p);
+  wgrad_kernel<T, PAIRS, NSEGB><<<grid, kWgThreads, smem, stream>>>(p);
   count_launch();
   return cudaGetLastError() == cudaSuccess ? kOk : kErrCuda;
 }
@@ -313,8 +405,12 @@ int launch_wgrad(const WgradParams& p, int dtype, int cin_slabs, int cout_slabs,
   if ((reinterpret_cast<uintptr_t>(p.feats) & 15) || (reinterpret_cast<uintptr_t>(p.gout) & 15))
     return kErrAlignment;
   switch (dtype) {
-    case kBF16: return launch_wgrad_t<__nv_bfloat16>(p, cin_slabs, cout_slabs, max_ctas, stream);
-    case kF16: return launch_wgrad_t<__half>(p, cin_slabs, cout_slabs, max_ctas, stream);
+    case kBF16:
+      return p.cout * es > 256 ? launch_wgrad_t<__nv_bfloat16, 64, 2>(p, cin_slabs, cout_slabs, max_ctas, stream)
+                               : launch_wgrad_t<__nv_bfloat16, 64, 1>(p, cin_slabs, cout_slabs, max_ctas, stream);
+    case kF16:
+      return p.cout * es > 256 ? launch_wgrad_t<__half, 64, 2>(p, cin_slabs, cout_slabs, max_ctas, stream)
+                               : launch_wgrad_t<__half, 64, 1>(p, cin_slabs, cout_slabs, max_ctas, stream);
     // fp32 rows as MN-major tf32 operands returned zeros on B200 (bring-up log round 1); the host
     // side splits fp32 into bf16 hi/lo parts instead (detail/unified.py:_wgrad_call).
     default: return kErrUnsupportedDtype;
