@@ -69,6 +69,7 @@ def load_peaks():
     if os.path.exists(path):
         p = json.load(open(path))
         return {"tflops": float(p["bf16_tflops_sustained"]), "hbm": float(p["hbm_gbs"]),
+                "burst": float(p.get("bf16_tflops", 0)),
                 "which": "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"}
     return {"tflops": 1400.0, "hbm": 6650.0, "which": "fallback (B200_PROFILING.md, sustained)"}
 
@@ -114,43 +115,53 @@ def run_cpu_baseline(dist: str, reps: int, warmup: int, budget_s: float = 40.0):
 # clocks
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """Samples SM clock / power / throttle reasons of one GPU through NVML every 5 ms in a thread
+    (the timed region is tens of milliseconds, too short for an `nvidia-smi -lms` process)."""
 
     def __init__(self, index: int):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        import threading
+        self.rows, self.stop_flag, self.err = [], False, None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "100"],
-                                      stdout=self.f, stderr=subprocess.DEVNULL)
-        except OSError:
-            self.p = None
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        except Exception as e:  # pragma: no cover
+            self.nv, self.err = None, repr(e)
+            return
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+
+    def _run(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                self.rows.append((nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM),
+                                  nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM),
+                                  nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0,
+                                  nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)))
+            except Exception as e:  # pragma: no cover
+                self.err = repr(e)
+                break
+            time.sleep(0.001)
 
     def stop(self):
-        if self.p is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.p.kill()
-        self.f.flush()
-        rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
-        os.unlink(self.f.name)
-        sm, mx, reasons, pw = [], [], set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in rows:
-            try:
-                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
-                for nm, v in zip(names, r[3:7]):
-                    if v.strip().lower().startswith("active"):
-                        reasons.add(nm)
-            except (ValueError, IndexError):
-                continue
+        if self.nv is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"nvml unavailable: {self.err}"]}
+        self.stop_flag = True
+        self.t.join(timeout=2)
+        nv = self.nv
+        names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown,
+                 "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown,
+                 "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+        reasons = sorted(n for n, bit in names.items() if any(r[3] & bit for r in self.rows))
+        sm = [r[0] for r in self.rows]
         return {"sm_mhz": float(np.median(sm)) if sm else None,
-                "sm_max_mhz": float(max(mx)) if mx else None, "samples": len(sm),
-                "power_w_max": float(max(pw)) if pw else None, "reasons": sorted(reasons)}
+                "sm_max_mhz": float(max(r[1] for r in self.rows)) if sm else None,
+                "samples": len(sm),
+                "power_w_max": float(max(r[2] for r in self.rows)) if sm else None,
+                "reasons": reasons}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -189,41 +200,33 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    gemm_ev = []
-
-    def step(record: bool):
-        """whole hot path, inputs resident in HBM"""
+    def step():
+        """whole hot path, inputs resident in HBM; nothing in it synchronises with the host"""
         km = generate_kernel_map(bc, bc, (1, 1, 1), (KS,) * 3, same_coords=True)
         plan = km.fwd_plan(n)
         img = _ops.weight_image(w.view(K, 1, CIN, COUT), K, 1, CIN, COUT, False)
-        if record:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-        y = _ops.gather_gemm(x, img, plan, 1, CIN, COUT)          # forward AB_gather_scatter
-        if record:
-            e1.record()
-            gemm_ev.append((e0, e1))
+        y = _ops.gather_gemm(x, img, plan, 1, CIN, COUT)           # forward AB_gather_scatter
         dx = sparse_conv_dgrad(gy, w, km, n)                       # dgrad ABt_gather_scatter
         dw = sparse_conv_wgrad(x, gy, (K, CIN, COUT), km)          # wgrad AtB_gather_gather
         if world > 1:
             dist.all_reduce(dw)
-        return km, y, dx, dw
+        return km, plan, img, y, dx, dw
 
     def timed(fn, steps, warmup):
+        """W warm-up calls, then K timed calls: L2 flush (outside the events), start event, fn,
+        stop event; barrier + synchronize on both sides; mean over steps, max over ranks."""
         for _ in range(warmup):
-            fn(False)
-        # NB: no dense-matmul "clock heating" here: sustained tensor load drives a B200 into its
-        # power cap (1.9 -> 1.2 GHz, tools/exp_clock.py), which would distort a short step.
+            fn()
         barrier()
         evs = []
         l0 = lib.wcn_launch_count()
         sampler = ClockSampler(local) if rank == 0 else None
         wall0 = time.perf_counter()
         for _ in range(steps):
-            flush.fill_(1)  # L2 flush (256 MiB write) before every timed step, outside the events
+            flush.fill_(1)  # L2 flush (256 MiB write) before every timed step
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
-            out = fn(True)
+            fn()
             e.record()
             evs.append((s, e))
         barrier()
@@ -234,17 +237,39 @@ def run_ours(args):
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), launches, clocks, wall, out
+        return float(t.item()), launches, clocks, wall
 
-    # ---- device-resident number -------------------------------------------------------------
-    ms, launches, clocks, wall, (km, y, dx, dw) = timed(step, args.steps, args.warmup)
+    # ---- device-resident number: the step is captured ONCE into a CUDA graph (no host sync in
+    # the path, so the whole map build + plan + fwd + dgrad + wgrad is capturable) and replayed;
+    # eager launches of the same step are reported next to it ------------------------------------
+    for _ in range(3):
+        km, plan, img, y, dx, dw = step()
+    torch.cuda.synchronize()
     L = int(km.offsets[-1])
-    gemm_ms = float(np.mean([a.elapsed_time(b) for a, b in gemm_ev]))
-    gemm_ev.clear()
+    launches_per_step = None
+    graph = None
+    if not args.no_graph and world == 1:
+        l0 = lib.wcn_launch_count()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, capture_error_mode="relaxed"):
+            g_out = step()
+        launches_per_step = lib.wcn_launch_count() - l0
+        ms, _, clocks, wall = timed(graph.replay, args.steps, args.warmup)
+        launches = launches_per_step * args.steps
+        eager_ms, _, _, _ = timed(step, args.steps, args.warmup)
+    else:
+        ms, launches, clocks, wall = timed(step, args.steps, args.warmup)
+        eager_ms = ms
     total_vox = torch.tensor([n], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(total_vox)
     total_vox = float(total_vox.item())
+
+    # ---- the dominant kernel alone (forward gather-GEMM): same plan / inputs, L2 flushed before
+    # every launch, events on the launching stream; the flush keeps the GPU busy while the host
+    # enqueues, so the events bracket the kernel and not the launch latency ----------------------
+    gemm_ms, _, _, _ = timed(lambda: _ops.gather_gemm(x, img, plan, 1, CIN, COUT, out=y),
+                             args.steps, args.warmup)
 
     # ---- per-phase breakdown (untimed for the headline; same step, events between phases) -----
     def breakdown(reps=5):
@@ -271,6 +296,8 @@ def run_ours(args):
         return {k: round(float(v / reps), 4) for k, v in zip(names, acc)}
 
     phases = breakdown()
+    phases["note"] = ("eager launches with events between phases: each entry is max(host enqueue "
+                      "time, GPU time) of the phase")
 
     # ---- end to end through the public API from pinned host buffers ---------------------------
     conv = SparseConv3d(CIN, COUT, KS, bias=False).to(dev)
@@ -283,7 +310,7 @@ def run_ours(args):
     h2d = coords_pin.numel() * 4 + feats_pin.numel() * 2
     d2h = dw_pin.numel() * 4
 
-    def e2e_step(record: bool):
+    def e2e_step():
         c = coords_pin.to(dev, non_blocking=True)
         f = feats_pin.to(dev, non_blocking=True).requires_grad_(True)
         vox = Voxels(c, f, offsets=offsets)
@@ -295,9 +322,8 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(g)
         dw_pin.copy_(g, non_blocking=True)
-        return None, None, None, None
 
-    e2e_ms, _, _, _, _ = timed(e2e_step, args.steps, args.warmup)
+    e2e_ms, _, _, _ = timed(e2e_step, args.steps, args.warmup)
     torch.cuda.synchronize()
 
     peaks = load_peaks()
@@ -316,6 +342,9 @@ def run_ours(args):
             "voxels_per_gpu": n, "pairs_L": L, "parallelism": f"scene-sharded dp{world}",
             "l2": "flushed with a 256 MiB write before every timed step (outside the events)",
             "timing": "CUDA events per step on the launching stream, mean over steps, max over ranks",
+            "launch": ("one CUDA-graph replay per step (the path has no host sync)" if graph is not None
+                       else "eager launches"),
+            "eager_ms_per_step": eager_ms,
         },
         "e2e": {"value": total_vox / (e2e_ms * 1e-3), "unit": "voxels/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -326,7 +355,8 @@ def run_ours(args):
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"],
                      "unit": "TFLOP/s", "frac": achieved / peaks["tflops"], "traffic": None,
                      "kernel": "gather_gemm_kernel<bf16> (forward AB_gather_scatter)",
-                     "kernel_ms": gemm_ms, "flops_per_launch": flops, "peak_source": peaks["which"]},
+                     "kernel_ms": gemm_ms, "flops_per_launch": flops, "peak_source": peaks["which"],
+                     "frac_of_burst_peak": achieved / float(peaks.get("burst", 0) or 1) if peaks.get("burst") else None},
         "phases_ms": phases,
         "wall_s_timed_region": wall,
     }
@@ -370,6 +400,7 @@ def main():
     ap.add_argument("--dist", choices=["S", "R"], default="S")
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA graph replay")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -28,7 +28,7 @@ names = ["prod_total", "prod_wait_empty", "mma_total", "mma_wait_full", "mma_wai
          "epi_total", "epi_wait_accfull", "prod_ns"]
 for tr in (128, 256):
     plan = _ops.build_tile_plan(table, tile_rows=tr)
-    for flags in (0, 32):
+    for flags in (0,):
         os.environ["WCN_DEBUG"] = str(flags)
         for _ in range(3):
             dbg.zero_()

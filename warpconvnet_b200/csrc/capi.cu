@@ -246,7 +246,6 @@ int wcn_gather_gemm(const void* feats, int n_in_rows, long long in_ld, const voi
   p.tile_nk = tile_nk;
   p.tile_cum = tile_cum;
   p.tile_rows = tile_rows;
-  p.halves = 1;
   p.bias = bias;
   p.in_ld = in_ld;
   p.out_ld = out_ld;

@@ -47,40 +47,64 @@ struct GemmSmemCtrl {
   uint64_t acc_full[2];
   uint64_t acc_empty[2];
   uint32_t tmem_base;
-  int t_begin;
-  int t_end;
+  int u_begin;  // this CTA's range of 128-row units (tile_rows / 128 units per tile)
+  int u_end;
 };
 
-// first index t in [0, n] with cum[t] >= target (cum is non-decreasing, cum[n] >= target)
-__device__ __forceinline__ int lower_bound_cum(const int* __restrict__ cum, int n,
-                                               long long target) {
-  int lo = 0, hi = n;
+// Work is balanced at 128-row UNIT granularity: a tile of the plan has U = tile_rows / 128 units
+// and unit u of tile t starts at cost U * cum[t] + (u - t*U) * nk[t] (cum = tile_cum).
+// Returns the first unit index in [0, U*nt] whose start cost is >= target.
+__device__ __forceinline__ int lower_bound_unit(const int* __restrict__ cum,
+                                                const int* __restrict__ nk, int nt, int U,
+                                                long long target) {
+  int lo = 0, hi = U * nt;
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;
-    if ((long long)__ldg(cum + mid) >= target) hi = mid; else lo = mid + 1;
+    const int t = mid / U;
+    const long long c = (long long)U * __ldg(cum + t) + (long long)(mid - t * U) * __ldg(nk + t);
+    if (c >= target) hi = mid; else lo = mid + 1;
   }
   return lo;
 }
 
-// Walks the (tile, half, step) sequence of this CTA; all members are warp-uniform.
+// Sub-tile span [lo, hi) of `tile` that belongs to the unit range [ub, ue).
+__device__ __forceinline__ void unit_span(int tile, int U, int ub, int ue, int& lo, int& hi) {
+  lo = max(0, ub - tile * U);
+  hi = min(U, ue - tile * U);
+}
+
+// Walks the (tile, pass, step) sequence of this CTA; all members are warp-uniform. With TM == U
+// a tile is one pass over the active sub-tiles [lo, hi); with TM == 1 < U every sub-tile in
+// [lo, hi) is its own pass h.
+template <int TM>
 struct StepCursor {
-  int tile, half, i, nk;
-  __device__ __forceinline__ void seek(const GatherGemmParams& p, int t_end) {
-    // settle on the first existing step at or after (tile, half, i); skips empty tiles
-    while (tile < t_end) {
-      if (nk < 0) nk = __ldg(p.tile_nk + tile);
-      if (i < nk) return;
-      i = 0;
-      if (nk > 0 && ++half < p.halves) continue;
-      half = 0;
+  int tile, h, h1, i, nk, lo, hi;
+  __device__ __forceinline__ void advance_tile(const GatherGemmParams& p, int U, int ub, int ue,
+                                               int t_end) {
+    for (;;) {
       ++tile;
-      nk = -1;
+      if (tile >= t_end) return;
+      nk = __ldg(p.tile_nk + tile);
+      unit_span(tile, U, ub, ue, lo, hi);
+      if (nk > 0 && lo < hi) break;
     }
+    h = (TM == 1) ? lo : 0;
+    h1 = (TM == 1) ? hi : 1;
+    i = 0;
+  }
+  __device__ __forceinline__ void init(const GatherGemmParams& p, int U, int ub, int ue,
+                                       int t_begin, int t_end) {
+    tile = t_begin - 1;
+    h = h1 = i = nk = lo = hi = 0;
+    advance_tile(p, U, ub, ue, t_end);
   }
   __device__ __forceinline__ bool valid(int t_end) const { return tile < t_end; }
-  __device__ __forceinline__ void next(const GatherGemmParams& p, int t_end) {
-    ++i;
-    seek(p, t_end);
+  __device__ __forceinline__ void next(const GatherGemmParams& p, int U, int ub, int ue,
+                                       int t_end) {
+    if (++i < nk) return;
+    i = 0;
+    if (++h < h1) return;
+    advance_tile(p, U, ub, ue, t_end);
   }
 };
 
@@ -120,12 +144,14 @@ gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
       mbar_init(smem_u32(&ctrl->acc_empty[a]), 128);
     }
     fence_mbar_init();
-    // contiguous tile range, balanced by step count
+    // contiguous range of 128-row units, balanced by step count
     const int nt = p.num_tiles;
-    const long long S = __ldg(p.tile_cum + nt);
+    const int U = p.tile_rows / kTileM;
+    const long long S = (long long)U * __ldg(p.tile_cum + nt);
     const int G = gridDim.x, b = blockIdx.x;
-    ctrl->t_begin = lower_bound_cum(p.tile_cum, nt, S * b / G);
-    ctrl->t_end = (b == G - 1) ? nt : lower_bound_cum(p.tile_cum, nt, S * (b + 1) / G);
+    ctrl->u_begin = lower_bound_unit(p.tile_cum, p.tile_nk, nt, U, S * b / G);
+    ctrl->u_end = (b == G - 1) ? U * nt
+                               : lower_bound_unit(p.tile_cum, p.tile_nk, nt, U, S * (b + 1) / G);
   }
   if (warp == kMmaWarp) {
     tmem_alloc(smem_u32(&ctrl->tmem_base), kTmemCols);
@@ -135,8 +161,10 @@ gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = ctrl->tmem_base;
-  const int t_begin = ctrl->t_begin;
-  const int t_end = ctrl->t_end;
+  const int U = p.tile_rows / kTileM;      // 128-row units per tile
+  const int ub = ctrl->u_begin, ue = ctrl->u_end;
+  const int t_begin = ub / U;
+  const int t_end = (ue + U - 1) / U;
 
   if (warp < 4) {
     // ===================================== gather producers =====================================
@@ -163,17 +191,19 @@ gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
     const uint8_t* col_base = reinterpret_cast<const uint8_t*>(p.feats) +
                               (long long)(p.in_coff + slab * p.in_slab_stride) * kElem + u * 16;
 
-    StepCursor cur{t_begin, 0, 0, -1}, pre{t_begin, 0, 0, -1};
-    cur.seek(p, t_end);
-    pre.seek(p, t_end);
+    StepCursor<TM> cur, pre;
+    cur.init(p, U, ub, ue, t_begin, t_end);
+    pre.init(p, U, ub, ue, t_begin, t_end);
     int idx_ring[kPrefetch][TM];  // neighbour row of tile row warp*32 + lane, per sub-tile
     int k_ring[kPrefetch];
-    auto load_step = [&](const StepCursor& c, int (&idx)[TM], int& k) {
+    // idx[j] < -1 marks a sub-tile that is not part of this CTA's range (nothing is gathered)
+    auto load_step = [&](const StepCursor<TM>& c, int (&idx)[TM], int& k) {
       const size_t step = (size_t)c.tile * p.K + c.i;
       k = __ldg(p.step_k + step);
-      const int* base = p.step_nbr + step * p.tile_rows + c.half * kUnitRows + warp * 32 + lane;
+      const int* base = p.step_nbr + step * p.tile_rows + c.h * kUnitRows + warp * 32 + lane;
 #pragma unroll
-      for (int j = 0; j < TM; ++j) idx[j] = __ldg(base + j * kTileM);
+      for (int j = 0; j < TM; ++j)
+        idx[j] = (TM == 1 || (j >= c.lo && j < c.hi)) ? __ldg(base + j * kTileM) : -2;
     };
 #pragma unroll
     for (int d = 0; d < kPrefetch; ++d) {
@@ -182,7 +212,7 @@ gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
       for (int j = 0; j < TM; ++j) idx_ring[d][j] = -1;
       if (pre.valid(t_end)) {
         load_step(pre, idx_ring[d], k_ring[d]);
-        pre.next(p, t_end);
+        pre.next(p, U, ub, ue, t_end);
       }
     }
 
@@ -202,9 +232,9 @@ gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
         const int k = k_ring[d];
         if (pre.valid(t_end)) {  // refill this ring slot with the step kPrefetch ahead
           load_step(pre, idx_ring[d], k_ring[d]);
-          pre.next(p, t_end);
+          pre.next(p, U, ub, ue, t_end);
         }
-        cur.next(p, t_end);
+        cur.next(p, U, ub, ue, t_end);
         const int wk = p.kflip ? (p.K - 1 - k) : k;
         for (int g = 0; g < n_groups; ++g) {
           {
@@ -226,6 +256,7 @@ gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
           const bool lane_active = seg_off + u * 16 < row_bytes;
 #pragma unroll
           for (int j = 0; j < TM; ++j) {
+            if (TM > 1 && idx_own[j] < -1) continue;  // warp-uniform: sub-tile not ours
 #pragma unroll
             for (int q = 0; q < kInstr; ++q) {
               // warp-uniform shuffle; only the copy itself is predicated
@@ -262,8 +293,11 @@ gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
       for (int tile = t_begin; tile < t_end; ++tile) {
         const int nk = nk_next;
         if (tile + 1 < t_end) nk_next = __ldg(p.tile_nk + tile + 1);
-        if (nk == 0) continue;
-        for (int h = 0; h < p.halves; ++h) {
+        int lo, hi;
+        unit_span(tile, U, ub, ue, lo, hi);
+        if (nk == 0 || lo >= hi) continue;
+        const int h0 = (TM == 1) ? lo : 0, h1 = (TM == 1) ? hi : 1;
+        for (int h = h0; h < h1; ++h) {
           const uint32_t acc = use & 1u;
           {
             const long long t0 = clock64();
@@ -290,6 +324,7 @@ gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
                 const int n_mma = chunk_bytes > 0 ? (chunk_bytes >> 5) : 0;  // 32 B of K per MMA
 #pragma unroll
                 for (int j = 0; j < TM; ++j) {
+                  if (TM > 1 && (j < lo || j >= hi)) continue;  // sub-tile not ours
                   for (int m = 0; m < n_mma; ++m) {
                     const uint64_t adesc = make_smem_desc_sw128(
                         a_smem + j * kASub + cc * kAStageBytes + m * 32, 16, 1024);
@@ -327,7 +362,11 @@ gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
     const long long t_start = clock64();
     for (int tile = t_begin; tile < t_end; ++tile) {
       const int nk = __ldg(p.tile_nk + tile);
-      for (int h = 0; h < p.halves; ++h) {
+      int lo, hi;
+      unit_span(tile, U, ub, ue, lo, hi);
+      if (lo >= hi) continue;
+      const int h0 = (TM == 1) ? lo : 0, h1 = (TM == 1) ? hi : 1;
+      for (int h = h0; h < h1; ++h) {
         uint32_t acc = 0;
         if (nk > 0) {
           acc = use & 1u;
@@ -338,6 +377,7 @@ gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
         }
 #pragma unroll
         for (int j = 0; j < TM; ++j) {
+          if (TM > 1 && (j < lo || j >= hi)) continue;  // sub-tile not ours
           const int out_row =
               __ldg(p.rows + (size_t)tile * p.tile_rows + h * kUnitRows + j * kTileM + r);
           uint8_t* out_ptr = out + (long long)(out_row >= 0 ? out_row : 0) * out_ld_bytes +
@@ -362,7 +402,7 @@ gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
               for (int i = 0; i < 16; ++i)
                 v[i] = __float_as_uint(fmaxf(__uint_as_float(v[i]), 0.f));
             }
-            if (out_row >= 0) {
+            if (out_row >= 0 && !(p.debug & 1)) {  // debug 1: skip stores (bring-up)
               if constexpr (sizeof(T) == 2) {
                 uint4* dst = reinterpret_cast<uint4*>(out_ptr + col * 2);
                 dst[0] = pack8<T>(v);
@@ -416,7 +456,6 @@ static int launch_gather_gemm_t(GatherGemmParams p, int n_slabs, int max_ctas, c
   const int max_stages = pick_gemm_stages(p.bn, TM, GC);
   if (p.stages <= 0 || p.stages > max_stages) p.stages = max_stages;
   if (p.stages < 2) return kErrUnsupportedShape;
-  p.halves = p.tile_rows / (kTileM * TM);
   const size_t smem = gemm_smem_bytes(p.bn, TM, GC, p.stages);
   static int configured_smem = 0;  // per instantiation
   if ((int)smem > configured_smem) {
@@ -425,7 +464,8 @@ static int launch_gather_gemm_t(GatherGemmParams p, int n_slabs, int max_ctas, c
     if (e != cudaSuccess) return kErrCuda;
     configured_smem = (int)smem;
   }
-  int ctas = p.num_tiles < max_ctas ? p.num_tiles : max_ctas;
+  const int units = p.num_tiles * (p.tile_rows / kTileM);
+  int ctas = units < max_ctas ? units : max_ctas;
   if (ctas < 1) return kOk;
   dim3 grid(ctas, n_slabs, 1);
   gather_gemm_kernel<T, TM, GC><<<grid, kGemmThreads, smem, stream>>>(p);

@@ -30,7 +30,6 @@ struct GatherGemmParams {
   int bn;                   // output channels per slab (multiple of 16, <= 256)
   int K;                    // kernel volume
   int tile_rows;            // rows per tile of the plan: 128 or 256
-  int halves;               // tile_rows / rows a CTA processes per step (set by the launcher)
   int m_pad;                // padded sorted length (multiple of tile_rows)
   int num_tiles;
   int kflip;                // weight index = K-1-k (dgrad of a submanifold conv on the fwd table)

@@ -45,16 +45,33 @@ class RealSearchResult:
 
 
 class IntSearchResult:
+    """Kernel map in CSR form. Two construction modes:
+
+    * eager (the reference's constructor): ``in_maps``, ``out_maps`` of exact length L and
+      ``offsets`` (copied to the CPU here, like search_results.py:73-76);
+    * deferred (``_from_device``, used by ``generate_kernel_map``): the maps live in upper-bound
+      sized device buffers, ``offsets`` stay on the device and an asynchronous copy to pinned host
+      memory is in flight. Nothing synchronises until ``offsets`` / ``in_maps`` / ``out_maps`` /
+      ``len(in_maps)`` are actually read on the host; the conv kernels only use the raw device
+      buffers, so a whole fwd+bwd step enqueues without a single host sync (the reference needs
+      >= 6 per map).
+    """
+
     def __init__(self, in_maps: Tensor, out_maps: Tensor, offsets: Tensor,
                  identity_map_index: Optional[int] = None):
         offsets_cpu = offsets.cpu()
         assert len(in_maps) == len(out_maps) == int(offsets_cpu[-1])
-        self.in_maps = in_maps
-        self.out_maps = out_maps
-        self.offsets = offsets_cpu
+        self._in_maps: Optional[Tensor] = in_maps
+        self._out_maps: Optional[Tensor] = out_maps
+        self._offsets: Optional[Tensor] = offsets_cpu
+        self._in_buf, self._out_buf = in_maps, out_maps
+        self._pending = None
+        self._init_common(identity_map_index, offsets if offsets.is_cuda else None)
+
+    def _init_common(self, identity_map_index, offsets_dev):
         self.identity_map_index = identity_map_index
         # lazily built device-side state for the sm_100a kernels
-        self._offsets_dev: Optional[Tensor] = offsets if offsets.is_cuda else None
+        self._offsets_dev: Optional[Tensor] = offsets_dev
         self._pair_table: Optional[Tensor] = None      # [K, n_out] -> input row
         self._rev_pair_table: Optional[Tensor] = None  # [K, n_in]  -> output row
         self._mask_keys: Optional[Tensor] = None
@@ -65,6 +82,56 @@ class IntSearchResult:
         # True when in/out coordinates are the same set and the kernel is odd: then
         # rev_pair_table[k] == pair_table[K-1-k] and dgrad reuses the forward tile plan.
         self._symmetric = False
+
+    @classmethod
+    def _from_device(cls, in_buf: Tensor, out_buf: Tensor, offsets_dev: Tensor, host: Tensor,
+                     event, on_ready, identity_map_index: Optional[int]) -> "IntSearchResult":
+        """host: pinned int32 [K + 2] receiving (offsets, status) asynchronously; event: recorded
+        after that copy; on_ready(status): raises the deferred hash-table errors."""
+        self = cls.__new__(cls)
+        self._in_maps = self._out_maps = self._offsets = None
+        self._in_buf, self._out_buf = in_buf, out_buf
+        self._pending = (host, event, on_ready)
+        self._init_common(identity_map_index, offsets_dev)
+        return self
+
+    def _resolve(self) -> None:
+        if self._pending is None:
+            return
+        host, event, on_ready = self._pending
+        self._pending = None
+        if event is not None:
+            event.synchronize()
+        else:
+            # built under CUDA-graph capture: `host` is the device tensor (offsets, status)
+            host = host.cpu()
+        if on_ready is not None:
+            on_ready(int(host[-1]))
+        self._offsets = host[:-1].clone()
+        n = int(self._offsets[-1])
+        self._in_maps = self._in_buf[:n]
+        self._out_maps = self._out_buf[:n]
+
+    @property
+    def in_maps(self) -> Tensor:
+        self._resolve()
+        return self._in_maps
+
+    @property
+    def out_maps(self) -> Tensor:
+        self._resolve()
+        return self._out_maps
+
+    @property
+    def offsets(self) -> Tensor:
+        """CPU offsets[K+1] (synchronises on first access in deferred mode)."""
+        self._resolve()
+        return self._offsets
+
+    def validate(self) -> "IntSearchResult":
+        """Force the deferred checks (out-of-range coordinates, table full) now."""
+        self._resolve()
+        return self
 
     # ---- reference API ---------------------------------------------------------------------
     @torch.no_grad()
@@ -108,7 +175,7 @@ class IntSearchResult:
 
     @property
     def device(self):
-        return self.in_maps.device
+        return self._in_buf.device
 
     @torch.no_grad()
     def neighbor_count_per_output(self, num_out: int) -> Tensor:
@@ -119,8 +186,8 @@ class IntSearchResult:
     # ---- device-side plans -----------------------------------------------------------------
     @property
     def offsets_dev(self) -> Tensor:
-        if self._offsets_dev is None or self._offsets_dev.device != self.in_maps.device:
-            self._offsets_dev = self.offsets.to(device=self.in_maps.device, dtype=torch.int32)
+        if self._offsets_dev is None or self._offsets_dev.device != self._in_buf.device:
+            self._offsets_dev = self.offsets.to(device=self._in_buf.device, dtype=torch.int32)
         if self._offsets_dev.dtype != torch.int32:
             self._offsets_dev = self._offsets_dev.int()
         return self._offsets_dev
@@ -128,14 +195,14 @@ class IntSearchResult:
     @torch.no_grad()
     def pair_table(self, n_out: int) -> Tensor:
         if self._pair_table is None:
-            self._pair_table = _ops.csr_to_pair_table(self.in_maps, self.out_maps,
+            self._pair_table = _ops.csr_to_pair_table(self._in_buf, self._out_buf,
                                                       self.offsets_dev, n_out)
         return self._pair_table
 
     @torch.no_grad()
     def rev_pair_table(self, n_in: int) -> Tensor:
         if self._rev_pair_table is None:
-            self._rev_pair_table = _ops.csr_to_pair_table(self.out_maps, self.in_maps,
+            self._rev_pair_table = _ops.csr_to_pair_table(self._out_buf, self._in_buf,
                                                           self.offsets_dev, n_in)
         return self._rev_pair_table
 
@@ -158,8 +225,11 @@ class IntSearchResult:
 
     def transposed_view(self) -> "IntSearchResult":
         """in/out swapped (helper.py:486-497), sharing every cached table with roles swapped."""
-        t = IntSearchResult(self.out_maps, self.in_maps, self.offsets, None)
-        t._offsets_dev = self._offsets_dev
+        t = IntSearchResult.__new__(IntSearchResult)
+        t._in_maps, t._out_maps, t._offsets = self._out_maps, self._in_maps, self._offsets
+        t._in_buf, t._out_buf = self._out_buf, self._in_buf
+        t._pending = self._pending
+        t._init_common(None, self._offsets_dev)
         t._pair_table, t._rev_pair_table = self._rev_pair_table, self._pair_table
         t._fwd_plan, t._bwd_plan = self._bwd_plan, self._fwd_plan
         t._n_in, t._n_out = self._n_out, self._n_in

@@ -2,10 +2,12 @@
 """Kernel-map generation for sparse convolution (drop-in for
 warpconvnet/geometry/coords/search/torch_discrete.py:23-57,296-432).
 
-Pipeline (all on the current CUDA stream, ONE host synchronisation per map):
+Pipeline (all on the current CUDA stream, NO host synchronisation on the conv path):
   hash build -> K-offset probe (pair table + per-block counts + per-row offset mask)
-  -> block scan / offsets -> single D2H of (offsets, status) -> deterministic CSR scatter.
-The reference needs >= 6 host syncs for the same work.
+  -> block scan / offsets -> async D2H of (offsets, status) -> deterministic CSR scatter.
+The host only waits when `offsets` / `in_maps` / `out_maps` are read on the CPU
+(IntSearchResult._resolve). The reference needs >= 6 host syncs for the same work
+(SURVEY.md §3.1).
 """
 from __future__ import annotations
 
@@ -21,6 +23,11 @@ from .packed_hashmap import PackedHashTable
 from .search_results import IntSearchResult
 
 _OFFSET_CACHE: Dict[tuple, Tensor] = {}
+_DEFERRED_MAX_PAIRS = 1 << 25  # upper-bound CSR buffers of at most 2 x 128 MiB
+
+
+def _pinned_host(n: int) -> Tensor:
+    return torch.empty(n, dtype=torch.int32, pin_memory=True)
 
 
 @torch.no_grad()
@@ -118,14 +125,32 @@ def generate_kernel_map(
     pair_table, block_counts, mask_keys = _ops.kernel_map_search(
         table.keys_tensor, table.values_tensor, out_c, offs3, stride)
     offsets_dev = _ops.kernel_map_count(block_counts)
-    # the only host sync: offsets (needed on the CPU by the IntSearchResult contract) + status
-    host = torch.cat([offsets_dev, table.status_tensor]).cpu()
-    table.raise_if_failed(int(host[-1]))
-    offsets_cpu = host[:-1].clone()
-    num_pairs = int(offsets_cpu[-1])
-    in_maps, out_maps = _ops.kernel_map_scatter(pair_table, block_counts, offsets_dev, num_pairs)
-
-    result = IntSearchResult(in_maps, out_maps, offsets_cpu, identity_map_index=identity_map_index)
+    if K * n_out <= _DEFERRED_MAX_PAIRS:
+        # No host sync: the CSR lists go into upper-bound sized buffers, (offsets, status) travel
+        # to pinned host memory asynchronously and are only waited for when somebody reads
+        # `offsets` / `in_maps` / `out_maps` on the host (IntSearchResult._resolve).
+        meta = torch.cat([offsets_dev, table.status_tensor])
+        if torch.cuda.is_current_stream_capturing():
+            host, event = meta, None  # read back (synchronously) only if somebody asks later
+        else:
+            host = _pinned_host(K + 2)
+            host.copy_(meta, non_blocking=True)
+            event = torch.cuda.Event()
+            event.record()
+        in_maps, out_maps = _ops.kernel_map_scatter(pair_table, block_counts, offsets_dev,
+                                                    K * n_out)
+        result = IntSearchResult._from_device(in_maps, out_maps, offsets_dev, host, event,
+                                              table.raise_if_failed, identity_map_index)
+    else:
+        # very large K * M: allocate the exact length instead (one host sync)
+        host = torch.cat([offsets_dev, table.status_tensor]).cpu()
+        table.raise_if_failed(int(host[-1]))
+        offsets_cpu = host[:-1].clone()
+        num_pairs = int(offsets_cpu[-1])
+        in_maps, out_maps = _ops.kernel_map_scatter(pair_table, block_counts, offsets_dev,
+                                                    num_pairs)
+        result = IntSearchResult(in_maps, out_maps, offsets_cpu,
+                                 identity_map_index=identity_map_index)
     result._offsets_dev = offsets_dev
     result._pair_table = pair_table
     result._mask_keys = mask_keys

@@ -122,7 +122,7 @@ def sparse_conv_dgrad(grad_output: Tensor, weight: Tensor, kernel_map: IntSearch
 
 
 def _wgrad_call(x: Tensor, gy: Tensor, kernel_map, K: int, G: int, cin_g: int, cout_g: int) -> Tensor:
-    im, om, od = kernel_map.in_maps, kernel_map.out_maps, kernel_map.offsets_dev
+    im, om, od = kernel_map._in_buf, kernel_map._out_buf, kernel_map.offsets_dev
     if x.dtype != torch.float32:
         return _ops.wgrad(x, gy, im, om, od, K, G, cin_g, cout_g)
     # fp32 operands: the contraction runs over gathered rows (MN-major operands), which the
