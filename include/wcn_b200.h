@@ -124,6 +124,20 @@ int wcn_build_tiles(const int32_t* table, int K, int M, const int32_t* sorted_ro
                     int32_t* tile_nk, int32_t* tile_cum, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
+/* Batched exact k-nearest-neighbour search for Points / PointConv                            */
+/* (replaces geometry/coords/search/knn.py:10-142: per-batch chunked torch.cdist + topk)      */
+/* ------------------------------------------------------------------------------------------ */
+size_t wcn_knn_workspace_bytes(int n_ref, int n_batches);
+/* ref float32[n_ref][3], query float32[n_query][3]; *_offsets: device int32[n_batches + 1] row
+ * ranges of each batch item; every batch item must hold >= k reference points, 1 <= k <= 64.
+ * out_idx int64[n_query][k]: GLOBAL reference rows, ascending distance (ties: smaller index);
+ * out_dist (optional) float32[n_query][k] Euclidean distances. */
+int wcn_knn_search(const float* ref, int n_ref, const int32_t* ref_offsets, const float* query,
+                   int n_query, const int32_t* query_offsets, int n_batches, int k,
+                   long long* out_idx, float* out_dist, void* workspace, size_t workspace_bytes,
+                   void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
 /* Weight image for the gather-GEMM kernel                                                    */
 /* (replaces weight.transpose(1,2).contiguous(), detail/unified.py:654-671)                   */
 /* ------------------------------------------------------------------------------------------ */

@@ -248,3 +248,27 @@ def wgrad(feats: Tensor, gout: Tensor, in_maps: Tensor, out_maps: Tensor, offset
                         _p(out_maps), _p(offsets_dev), K, groups, cin_g, cout_g, code,
                         ctypes.c_float(alpha), unit_pairs, max_ctas, _stream()), "wgrad")
     return dw
+
+
+# ------------------------------------------------------------------------------------------------
+# k-nearest neighbours
+# ------------------------------------------------------------------------------------------------
+def knn_search(ref: Tensor, ref_offsets: Tensor, query: Tensor, query_offsets: Tensor, k: int,
+               return_distances: bool = False):
+    """int64 [M, k] global reference rows of the k nearest neighbours of every query point,
+    searched inside the query's own batch item (ascending distance)."""
+    _require_cuda(ref, query)
+    assert ref.dtype == torch.float32 and query.dtype == torch.float32
+    ref = ref.contiguous()
+    query = query.contiguous()
+    nb = ref_offsets.numel() - 1
+    ro = ref_offsets.to(device=ref.device, dtype=torch.int32)
+    qo = query_offsets.to(device=ref.device, dtype=torch.int32)
+    out = torch.empty((query.shape[0], k), dtype=torch.int64, device=ref.device)
+    dist = torch.empty((query.shape[0], k), dtype=torch.float32, device=ref.device) \
+        if return_distances else None
+    ws_bytes = lib.wcn_knn_workspace_bytes(ref.shape[0], nb)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=ref.device)
+    check(lib.wcn_knn_search(_p(ref), ref.shape[0], _p(ro), _p(query), query.shape[0], _p(qo), nb,
+                             k, _p(out), _p(dist), _p(ws), ws_bytes, _stream()), "knn_search")
+    return (out, dist) if return_distances else out

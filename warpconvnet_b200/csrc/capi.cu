@@ -25,6 +25,11 @@ size_t sort_workspace_bytes(int);
 int sort_rows_by_key(const unsigned long long*, int, int, int*, void*, size_t, cudaStream_t);
 int build_tiles(const int*, int, int, const int*, int, int, int*, int*, int*, int*, int*,
                 cudaStream_t);
+// knn.cu
+size_t knn_workspace_bytes(int, int, int);
+int knn_dims_for(int, int);
+int knn_search(const float*, int, const int*, const float*, int, const int*, int, int, long long*,
+               float*, void*, size_t, cudaStream_t);
 // weight_prep.cu
 int launch_weight_image(const WeightPrepParams&, cudaStream_t);
 // conv_fwd.cu / conv_wgrad.cu
@@ -166,6 +171,20 @@ int wcn_build_tiles(const int32_t* table, int K, int M, const int32_t* sorted_ro
     return kErrInvalidArg;
   return build_tiles(table, K, M, sorted_rows, tile_rows, m_pad, step_nbr, step_k, rows_padded,
                      tile_nk, tile_cum, S(stream));
+}
+
+size_t wcn_knn_workspace_bytes(int n_ref, int n_batches) {
+  return knn_workspace_bytes(n_ref, n_batches, knn_dims_for(n_ref, n_batches));
+}
+int wcn_knn_search(const float* ref, int n_ref, const int32_t* ref_offsets, const float* query,
+                   int n_query, const int32_t* query_offsets, int n_batches, int k,
+                   long long* out_idx, float* out_dist, void* workspace, size_t workspace_bytes,
+                   void* stream) {
+  if (!ref_offsets || !query_offsets || !workspace || (n_ref > 0 && !ref) ||
+      (n_query > 0 && (!query || !out_idx)))
+    return kErrInvalidArg;
+  return knn_search(ref, n_ref, ref_offsets, query, n_query, query_offsets, n_batches, k, out_idx,
+                    out_dist, workspace, workspace_bytes, S(stream));
 }
 
 size_t wcn_weight_image_bytes(int K, int groups, int cin_g, int cout_g, int dtype, int transpose_w,

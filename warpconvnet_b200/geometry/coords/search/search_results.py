@@ -30,6 +30,7 @@ class RealSearchResult:
             self.neighbor_indices = args[0].long().reshape(-1)
             self.neighbor_row_splits = torch.arange(0, M * K + 1, K, device=args[0].device,
                                                     dtype=torch.long)
+            self.neighbor_row_splits._wcn_uniform_k = K  # fixed row length (kNN): see reductions
         else:
             raise ValueError("RealSearchResult must be initialized with 1 or 2 arguments")
         self.neighbor_distances = None

@@ -1,2 +1,4 @@
 # SPDX-License-Identifier: Apache-2.0
 from .sparse_conv import SparseConv2d, SparseConv3d, SpatiallySparseConv  # noqa: F401
+from .mlp import MLPBlock  # noqa: F401
+from .point_conv import PointConv  # noqa: F401
