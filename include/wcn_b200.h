@@ -60,7 +60,8 @@ long long wcn_launch_count(void);
 /* ------------------------------------------------------------------------------------------ */
 int wcn_hash_prepare(uint64_t* keys, int32_t* values, int capacity, void* stream);
 /* coords: int32[n][4] = (batch, x, y, z). value = insertion index (smallest index wins for
- * duplicates). status (device int, caller-zeroed): bit0 = table full, bit1 = coordinate outside
+ * duplicates). status (device int, caller-zeroed): bit2 = duplicate coordinates seen (not an
+ * error), bit0 = table full, bit1 = coordinate outside
  * batch [0,511] / xyz [-131072,131071] (the reference checks the range on the host,
  * geometry/coords/search/packed_hashmap.py:66-82). */
 int wcn_hash_insert(uint64_t* keys, int32_t* values, const int32_t* coords, int n, int capacity,
@@ -85,6 +86,17 @@ int wcn_kernel_map_search(const uint64_t* keys, const int32_t* values, int capac
                           const int32_t* out_coords, int M, const int32_t* offsets3, int K,
                           int stride_x, int stride_y, int stride_z, int32_t* pair_table,
                           int32_t* block_counts, uint64_t* mask_keys, void* stream);
+/* Submanifold fast path (query coordinates == the table's coordinates, odd kernel, stride 1):
+ * probes only the first K/2 offsets plus the centre and mirrors every hit into offset K-1-k
+ * (same idea as the reference's skip_symmetric_kernel_map, torch_discrete.py:296-432). `status`
+ * is the word wcn_hash_insert wrote; if it reports duplicate coordinates (bit 2) every offset is
+ * probed instead, so the result always equals wcn_kernel_map_search. Fills the whole table. */
+int wcn_kernel_map_search_symmetric(const uint64_t* keys, const int32_t* values, int capacity,
+                                    const int32_t* coords, int M, const int32_t* offsets3, int K,
+                                    const int32_t* status, int32_t* pair_table, void* stream);
+/* block_counts[K][num_blocks] and mask_keys[M] (optional) from a finished pair table. */
+int wcn_kernel_map_stats(const int32_t* pair_table, int K, int M, int32_t* block_counts,
+                         uint64_t* mask_keys, void* stream);
 /* In-place exclusive scan of block_counts per offset; counts[K], offsets[K+1] (exclusive scan of
  * counts, offsets[K] = total pairs L). */
 int wcn_kernel_map_count(int32_t* block_counts, int K, int num_blocks, int32_t* counts,

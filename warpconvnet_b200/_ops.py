@@ -22,7 +22,9 @@ TILE_M = 128
 
 
 def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    # raw cudaStream_t of torch's current stream (torch.cuda.current_stream() costs ~15 us of
+    # Python per call; the ctypes wrappers call this for every launch)
+    return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
 
 
 def _p(t: Optional[Tensor]):
@@ -91,6 +93,25 @@ def kernel_map_search(keys: Tensor, values: Tensor, out_coords: Tensor, offsets3
                                     _p(offsets3), K, int(stride[0]), int(stride[1]),
                                     int(stride[2]), _p(pair_table), _p(block_counts),
                                     _p(mask_keys), _stream()), "kernel_map_search")
+    return pair_table, block_counts, mask_keys
+
+
+def kernel_map_search_symmetric(keys: Tensor, values: Tensor, coords: Tensor, offsets3: Tensor,
+                                status: Tensor):
+    """Submanifold kernel map (in == out coordinates, odd kernel, stride 1): half the probes, hits
+    mirrored. Returns (pair_table[K,M], block_counts[K,nb], mask_keys[M])."""
+    _require_cuda(keys, values, coords, offsets3, status)
+    M, K = coords.shape[0], offsets3.shape[0]
+    dev = coords.device
+    nb = lib.wcn_kernel_map_num_blocks(M)
+    pair_table = torch.empty((K, M), dtype=torch.int32, device=dev)
+    block_counts = torch.empty((K, nb), dtype=torch.int32, device=dev)
+    mask_keys = torch.empty(M, dtype=torch.int64, device=dev)
+    check(lib.wcn_kernel_map_search_symmetric(_p(keys), _p(values), keys.numel(), _p(coords), M,
+                                              _p(offsets3), K, _p(status), _p(pair_table),
+                                              _stream()), "kernel_map_search_symmetric")
+    check(lib.wcn_kernel_map_stats(_p(pair_table), K, M, _p(block_counts), _p(mask_keys),
+                                   _stream()), "kernel_map_stats")
     return pair_table, block_counts, mask_keys
 
 

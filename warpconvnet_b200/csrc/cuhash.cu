@@ -70,6 +70,7 @@ __global__ void hash_insert_kernel(uint64_t* __restrict__ keys, int* __restrict_
   for (uint32_t attempts = 0; attempts <= mask; ++attempts) {
     const unsigned long long prev = atomicCAS(reinterpret_cast<unsigned long long*>(keys + slot),
                                               (unsigned long long)kEmptyKey, (unsigned long long)key);
+    if (prev == key) atomicOr(status, 4);  // duplicate coordinate (informational, see below)
     if (prev == kEmptyKey || prev == key) {
       // value = insertion index; duplicates keep the SMALLEST index, so the table is
       // deterministic (the reference keeps whichever thread wins the race). Empty value slots
@@ -172,6 +173,88 @@ kernel_map_search_kernel(const uint64_t* __restrict__ keys, const int* __restric
     for (int i = threadIdx.x; i < K; i += blockDim.x)
       block_counts[(size_t)i * gridDim.x + blockIdx.x] = s_cnt[i];
   }
+}
+
+// Submanifold variant (in == out coordinates, odd kernel, stride 1): offset K-1-k is the mirror
+// of offset k, so a hit "voxel v sits at m + off_k" also says "voxel m sits at v + off_{K-1-k}".
+// Only the first K/2 offsets (+ the centre) are probed and every hit writes both entries; the
+// table is pre-filled with -1, so misses cost no store. Requires unique coordinates: when the
+// insert kernel flagged a duplicate (status bit 2) every offset is probed instead (no mirrors).
+__global__ void __launch_bounds__(kMapBlock)
+kernel_map_search_sym_kernel(const uint64_t* __restrict__ keys, const int* __restrict__ values,
+                             uint32_t mask, const int4* __restrict__ coords, int M,
+                             const int* __restrict__ offs, int K, const int* __restrict__ status,
+                             int* __restrict__ pair_table) {
+  extern __shared__ int s_off[];  // [3K]
+  for (int i = threadIdx.x; i < 3 * K; i += blockDim.x) s_off[i] = offs[i];
+  __syncthreads();
+  const int m = blockIdx.x * kMapBlock + threadIdx.x;
+  if (m >= M) return;
+  const bool has_dups = (__ldg(status) & 4) != 0;
+  const int k_end = has_dups ? K : K / 2 + 1;
+  const int4 c = __ldg(coords + m);
+  for (int k0 = 0; k0 < k_end; k0 += 4) {
+    uint32_t slot[4];
+    uint64_t key[4], got[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int k = k0 + u;
+      if (k < k_end) {
+        key[u] = pack_key(c.x, c.y + s_off[3 * k], c.z + s_off[3 * k + 1], c.w + s_off[3 * k + 2]);
+        slot[u] = splitmix_slot(key[u], mask);
+        got[u] = __ldg(keys + slot[u]);
+      } else {
+        key[u] = 1;
+        slot[u] = 0;
+        got[u] = kEmptyKey;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int k = k0 + u;
+      uint32_t attempts = 0;
+      uint64_t g = got[u];
+      uint32_t sl = slot[u];
+      while (g != kEmptyKey && attempts <= mask) {
+        if (g == key[u]) {
+          const int v = __ldg(values + sl);
+          pair_table[(size_t)k * M + m] = v;
+          if (!has_dups && k < K / 2) pair_table[(size_t)(K - 1 - k) * M + v] = m;
+          break;
+        }
+        sl = (sl + 1) & mask;
+        g = __ldg(keys + sl);
+        ++attempts;
+      }
+    }
+  }
+}
+
+// block_counts[k][block] = hits of offset k among the block's 256 rows; mask_keys[m] = offset
+// bitmask of row m. One coalesced pass over the pair table.
+__global__ void __launch_bounds__(kMapBlock)
+kernel_map_stats_kernel(const int* __restrict__ pair_table, int K, int M,
+                        int* __restrict__ block_counts,
+                        unsigned long long* __restrict__ mask_keys) {
+  __shared__ int s_warp[kMapBlock / 32];
+  const int m = blockIdx.x * kMapBlock + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned long long bits = 0ull;
+  for (int k = 0; k < K; ++k) {
+    const bool hit = m < M && __ldg(pair_table + (size_t)k * M + m) >= 0;
+    if (hit) bits ^= 1ull << (k & 63);
+    const unsigned ballot = __ballot_sync(0xffffffffu, hit);
+    if (lane == 0) s_warp[warp] = __popc(ballot);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int t = 0;
+#pragma unroll
+      for (int w = 0; w < kMapBlock / 32; ++w) t += s_warp[w];
+      block_counts[(size_t)k * gridDim.x + blockIdx.x] = t;
+    }
+    __syncthreads();
+  }
+  if (m < M && mask_keys != nullptr) mask_keys[m] = bits;
 }
 
 // exclusive scan of block_counts[k][0..nb) in place, total into counts[k]; one block per offset
@@ -390,6 +473,30 @@ int kernel_map_search(const uint64_t* keys, const int* values, int capacity, con
   kernel_map_search_kernel<<<nb, kMapBlock, (size_t)4 * K * sizeof(int), s>>>(
       keys, values, (uint32_t)(capacity - 1), reinterpret_cast<const int4*>(out_coords), M,
       offsets3, K, sx, sy, sz, pair_table, block_counts, mask_keys);
+  count_launch();
+  return cuda_ok();
+}
+
+int kernel_map_search_sym(const uint64_t* keys, const int* values, int capacity, const int* coords,
+                          int M, const int* offsets3, int K, const int* status, int* pair_table,
+                          cudaStream_t s) {
+  if (!is_pow2(capacity) || M < 0 || K < 1 || K > 4096 || (K & 1) == 0) return kErrInvalidArg;
+  if (M == 0) return kOk;
+  if (cudaMemsetAsync(pair_table, 0xFF, (size_t)K * M * 4, s) != cudaSuccess) return kErrCuda;
+  kernel_map_search_sym_kernel<<<kernel_map_num_blocks(M), kMapBlock, (size_t)3 * K * sizeof(int),
+                                 s>>>(keys, values, (uint32_t)(capacity - 1),
+                                      reinterpret_cast<const int4*>(coords), M, offsets3, K, status,
+                                      pair_table);
+  count_launch();
+  return cuda_ok();
+}
+
+int kernel_map_stats(const int* pair_table, int K, int M, int* block_counts,
+                     unsigned long long* mask_keys, cudaStream_t s) {
+  if (K < 1 || M < 0) return kErrInvalidArg;
+  if (M == 0) return kOk;
+  kernel_map_stats_kernel<<<kernel_map_num_blocks(M), kMapBlock, 0, s>>>(pair_table, K, M,
+                                                                        block_counts, mask_keys);
   count_launch();
   return cuda_ok();
 }

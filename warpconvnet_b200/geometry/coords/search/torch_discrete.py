@@ -122,8 +122,14 @@ def generate_kernel_map(
 
     table = PackedHashTable.from_coords(in_c, check=False)
     offs3 = _offsets3(kernel_size, kernel_dilation, kernel_center_offset, dev)
-    pair_table, block_counts, mask_keys = _ops.kernel_map_search(
-        table.keys_tensor, table.values_tensor, out_c, offs3, stride)
+    symmetric = bool(same_coords and is_odd and all(s == 1 for s in stride)
+                     and kernel_center_offset is None)
+    if symmetric and n_out > 0:
+        pair_table, block_counts, mask_keys = _ops.kernel_map_search_symmetric(
+            table.keys_tensor, table.values_tensor, out_c, offs3, table.status_tensor)
+    else:
+        pair_table, block_counts, mask_keys = _ops.kernel_map_search(
+            table.keys_tensor, table.values_tensor, out_c, offs3, stride)
     offsets_dev = _ops.kernel_map_count(block_counts)
     if K * n_out <= _DEFERRED_MAX_PAIRS:
         # No host sync: the CSR lists go into upper-bound sized buffers, (offsets, status) travel
