@@ -53,18 +53,35 @@ struct GemmSmemCtrl {
 
 // Work is balanced at 128-row UNIT granularity: a tile of the plan has U = tile_rows / 128 units
 // and unit u of tile t starts at cost U * cum[t] + (u - t*U) * nk[t] (cum = tile_cum).
-// Returns the first unit index in [0, U*nt] whose start cost is >= target.
+// Returns the first unit index in [0, U*nt] whose start cost is >= target. Warp-cooperative
+// 32-ary search (all 32 lanes must call it): 3 rounds of parallel loads cover 32^3 units, where a
+// scalar binary search would chain ~2*log2(n) dependent L2 round trips in the kernel prologue.
+__device__ __forceinline__ long long unit_cost(const int* __restrict__ cum,
+                                               const int* __restrict__ nk, int U, int u) {
+  const int t = u / U;
+  return (long long)U * __ldg(cum + t) + (long long)(u - t * U) * __ldg(nk + t);
+}
 __device__ __forceinline__ int lower_bound_unit(const int* __restrict__ cum,
                                                 const int* __restrict__ nk, int nt, int U,
-                                                long long target) {
-  int lo = 0, hi = U * nt;
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    const int t = mid / U;
-    const long long c = (long long)U * __ldg(cum + t) + (long long)(mid - t * U) * __ldg(nk + t);
-    if (c >= target) hi = mid; else lo = mid + 1;
+                                                long long target, int lane) {
+  int lo = 0, hi = U * nt;  // answer in [lo, hi]; cost(hi) >= target by construction
+  while (hi - lo > 32) {
+    const int span = hi - lo;
+    // probe points lo + span*(lane+1)/33 (strictly inside (lo, hi))
+    const int u = lo + (int)(((long long)span * (lane + 1)) / 33);
+    const bool ge = unit_cost(cum, nk, U, u) >= target;
+    const unsigned b = __ballot_sync(0xffffffffu, ge);
+    // first probe that is >= target bounds the answer from above, the previous one from below
+    const int first = b ? __ffs(b) - 1 : 32;
+    const int new_hi = first < 32 ? lo + (int)(((long long)span * (first + 1)) / 33) : hi;
+    const int new_lo = first > 0 ? lo + (int)(((long long)span * first) / 33) + 1 : lo;
+    lo = new_lo;
+    hi = new_hi;
   }
-  return lo;
+  const int u = lo + lane;
+  const bool ge = u <= hi && (u == hi || unit_cost(cum, nk, U, u) >= target);
+  const unsigned b = __ballot_sync(0xffffffffu, ge);
+  return b ? lo + __ffs(b) - 1 : hi;
 }
 
 // Sub-tile span [lo, hi) of `tile` that belongs to the unit range [ub, ue).
@@ -144,14 +161,18 @@ gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
       mbar_init(smem_u32(&ctrl->acc_empty[a]), 128);
     }
     fence_mbar_init();
-    // contiguous range of 128-row units, balanced by step count
+  }
+  if (warp < 2) {
+    // contiguous range of 128-row units, balanced by step count (warp 0: begin, warp 1: end)
     const int nt = p.num_tiles;
     const int U = p.tile_rows / kTileM;
     const long long S = (long long)U * __ldg(p.tile_cum + nt);
-    const int G = gridDim.x, b = blockIdx.x;
-    ctrl->u_begin = lower_bound_unit(p.tile_cum, p.tile_nk, nt, U, S * b / G);
-    ctrl->u_end = (b == G - 1) ? U * nt
-                               : lower_bound_unit(p.tile_cum, p.tile_nk, nt, U, S * (b + 1) / G);
+    const int G = gridDim.x, b = blockIdx.x + warp;
+    const int u = (b >= G) ? U * nt
+                           : lower_bound_unit(p.tile_cum, p.tile_nk, nt, U, S * b / G, lane);
+    if (lane == 0) {
+      if (warp == 0) ctrl->u_begin = u; else ctrl->u_end = u;
+    }
   }
   if (warp == kMmaWarp) {
     tmem_alloc(smem_u32(&ctrl->tmem_base), kTmemCols);
