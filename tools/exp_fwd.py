@@ -71,7 +71,7 @@ def main():
             nk = plan.tile_nk.sum().item()
             print(f"[{name}] plan={pname}: tiles={plan.num_tiles} steps={nk} "
                   f"waste={nk * plan.tile_rows / L:.3f}")
-            for dbg, stages in ((0, 0), (1, 0)):
+            for dbg, stages in ((0, 0),):
                 os.environ["WCN_DEBUG"] = str(dbg)
                 if stages:
                     os.environ["WCN_STAGES"] = str(stages)

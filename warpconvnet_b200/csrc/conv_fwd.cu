@@ -25,7 +25,8 @@
 //              global memory) through the TMA unit with one cp.async.bulk per stage.
 //   warp  4    lane 0 issues tcgen05.mma (M=128, N=bn, K=32 B per instruction), accumulators in
 //              TMEM, double buffered so the epilogue of tile i overlaps the MMAs of tile i+1
-//   warps 5-8  epilogue: tcgen05.ld -> (+bias, ReLU) -> bf16/fp16/fp32 -> 128-bit global stores
+//   warps 5-8  epilogue: tcgen05.ld -> (+bias, ReLU) -> bf16/fp16/fp32 -> swizzled smem staging ->
+//              128-bit global stores, 16 lanes per 256 contiguous bytes of an output row
 #include "common.cuh"
 #include "conv_gemm.cuh"
 
@@ -40,6 +41,7 @@ constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;             // TMEM column offset of the second accumulator set
 constexpr int kMaxStages = 8;
 constexpr int kPrefetch = 4;                // steps of index look-ahead in the producers
+constexpr int kEpiStageWarp = 32 * 256;     // epilogue staging: 32 rows x 256 B per warp
 
 struct GemmSmemCtrl {
   uint64_t full[kMaxStages];
@@ -142,7 +144,8 @@ gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
   const int b_chunk_bytes = p.bn * 128;     // weight slab of one 128-byte channel chunk
   const int stage_bytes = kAStage + ((GC * b_chunk_bytes + 1023) & ~1023);
   const int stages = p.stages;
-  GemmSmemCtrl* ctrl = reinterpret_cast<GemmSmemCtrl*>(smem_gen + (size_t)stages * stage_bytes);
+  GemmSmemCtrl* ctrl = reinterpret_cast<GemmSmemCtrl*>(smem_gen + (size_t)stages * stage_bytes +
+                                                       4 * kEpiStageWarp);
 
   constexpr int kElem = (int)sizeof(T);
   constexpr int kChunkElems = 128 / kElem;  // channels per 128-byte row segment
@@ -378,6 +381,9 @@ gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
     uint8_t* out = reinterpret_cast<uint8_t*>(p.out);
     const long long out_ld_bytes = p.out_ld * kElem;
     const int col_base = p.out_coff + slab * p.bn;
+    constexpr int kChunkCols = 256 / kElem;  // output columns per 256-byte staging chunk
+    const uint32_t stage_warp = smem_base + stages * stage_bytes + (uint32_t)q * kEpiStageWarp;
+    const uint32_t stage_row = stage_warp + lane * 256;
     uint32_t use = 0;
     long long w_accf = 0;
     const long long t_start = clock64();
@@ -401,40 +407,57 @@ gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
           if (TM > 1 && (j < lo || j >= hi)) continue;  // sub-tile not ours
           const int out_row =
               __ldg(p.rows + (size_t)tile * p.tile_rows + h * kUnitRows + j * kTileM + r);
-          uint8_t* out_ptr = out + (long long)(out_row >= 0 ? out_row : 0) * out_ld_bytes +
-                             (long long)col_base * kElem;
-          for (int col = 0; col < p.bn; col += 16) {
-            uint32_t v[16];
-            if (nk > 0) {
-              tmem_ld_x16(
-                  tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccStride + j * p.bn + col, v);
-              tmem_ld_wait();
-            } else {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = 0u;
-            }
-            if (p.bias != nullptr) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i)
-                v[i] = __float_as_uint(__uint_as_float(v[i]) + __ldg(p.bias + col_base + col + i));
-            }
-            if (p.relu) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i)
-                v[i] = __float_as_uint(fmaxf(__uint_as_float(v[i]), 0.f));
-            }
-            if (out_row >= 0 && !(p.debug & 1)) {  // debug 1: skip stores (bring-up)
-              if constexpr (sizeof(T) == 2) {
-                uint4* dst = reinterpret_cast<uint4*>(out_ptr + col * 2);
-                dst[0] = pack8<T>(v);
-                dst[1] = pack8<T>(v + 8);
+          // 256-byte column chunks: TMEM -> registers -> (bias, ReLU, convert) -> XOR-swizzled
+          // staging rows in shared memory -> 16 lanes write one output row's 256 contiguous
+          // bytes (two rows per store instruction instead of 32 scattered 16-byte pieces)
+          for (int c0 = 0; c0 < p.bn; c0 += kChunkCols) {
+            const int c1 = min(p.bn, c0 + kChunkCols);
+            for (int col = c0; col < c1; col += 16) {
+              uint32_t v[16];
+              if (nk > 0) {
+                tmem_ld_x16(
+                    tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccStride + j * p.bn + col, v);
+                tmem_ld_wait();
               } else {
-                uint4* dst = reinterpret_cast<uint4*>(out_ptr + col * 4);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = 0u;
+              }
+              if (p.bias != nullptr) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                  v[i] = __float_as_uint(__uint_as_float(v[i]) +
+                                         __ldg(p.bias + col_base + col + i));
+              }
+              if (p.relu) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                  v[i] = __float_as_uint(fmaxf(__uint_as_float(v[i]), 0.f));
+              }
+              const int piece0 = (col - c0) * kElem / 16;  // first 16-byte piece of these columns
+              if constexpr (sizeof(T) == 2) {
+                st_shared_v4(stage_row + (((piece0 + 0) ^ (lane & 15)) << 4), pack8<T>(v));
+                st_shared_v4(stage_row + (((piece0 + 1) ^ (lane & 15)) << 4), pack8<T>(v + 8));
+              } else {
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
-                  dst[i] = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                  st_shared_v4(stage_row + (((piece0 + i) ^ (lane & 15)) << 4),
+                               make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
               }
             }
+            __syncwarp();
+            const int piece = lane & 15;
+            const bool piece_ok = c0 * kElem + piece * 16 < p.bn * kElem;
+#pragma unroll 4
+            for (int rr = 0; rr < 16; ++rr) {
+              const int row = 2 * rr + (lane >> 4);
+              const int orow = __shfl_sync(0xffffffffu, out_row, row);
+              const uint4 val =
+                  ld_shared_v4(stage_warp + row * 256 + ((piece ^ (row & 15)) << 4));
+              if (orow >= 0 && piece_ok && !(p.debug & 1))  // debug 1: skip stores (bring-up)
+                *reinterpret_cast<uint4*>(out + (long long)orow * out_ld_bytes +
+                                          (long long)(col_base + c0) * kElem + piece * 16) = val;
+            }
+            __syncwarp();
           }
         }
         if (nk > 0) {
@@ -463,11 +486,13 @@ static int stage_bytes_of(int bn, int tm, int gc) {
 }
 
 static size_t gemm_smem_bytes(int bn, int tm, int gc, int stages) {
-  return (size_t)stages * stage_bytes_of(bn, tm, gc) + sizeof(GemmSmemCtrl) + 1024;
+  return (size_t)stages * stage_bytes_of(bn, tm, gc) + 4 * kEpiStageWarp + sizeof(GemmSmemCtrl) +
+         1024;
 }
 
 static int pick_gemm_stages(int bn, int tm, int gc) {
-  int s = (int)((227 * 1024 - sizeof(GemmSmemCtrl) - 1024) / stage_bytes_of(bn, tm, gc));
+  int s = (int)((227 * 1024 - 4 * kEpiStageWarp - sizeof(GemmSmemCtrl) - 1024) /
+                stage_bytes_of(bn, tm, gc));
   if (s > kMaxStages) s = kMaxStages;
   return s;
 }
