@@ -30,6 +30,18 @@ def _pinned_host(n: int) -> Tensor:
     return torch.empty(n, dtype=torch.int32, pin_memory=True)
 
 
+_SIDE_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
+
+
+def _side_stream(dev: torch.device) -> "torch.cuda.Stream":
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    s = _SIDE_STREAMS.get(idx)
+    if s is None:
+        s = torch.cuda.Stream(device=idx)
+        _SIDE_STREAMS[idx] = s
+    return s
+
+
 @torch.no_grad()
 def kernel_offsets_from_size(kernel_size: Tuple[int, ...], kernel_dilation: Tuple[int, ...],
                              center_offset: Optional[Tuple[int, ...]] = None,
@@ -70,6 +82,7 @@ def generate_kernel_map(
     method: str = "size",
     skip_symmetric_kernel_map: bool = False,
     same_coords: Optional[bool] = None,
+    build_plan: bool = True,
     **kwargs,
 ) -> IntSearchResult:
     """``coord(in) = stride * coord(out) + offset[k]`` pairs for every kernel offset k.
@@ -78,6 +91,7 @@ def generate_kernel_map(
     offset (the reference's order is unspecified). ``same_coords=True`` tells the builder that the
     two coordinate tensors are the same set in the same order (submanifold conv) so the dgrad
     pass can reuse the forward tables; when None it is inferred from tensor identity.
+    ``build_plan`` also builds the forward tile plan here (overlapped with the CSR emission).
     """
     assert batch_indexed_in_coords.dtype == torch.int32
     assert batch_indexed_out_coords.dtype == torch.int32
@@ -130,33 +144,54 @@ def generate_kernel_map(
     else:
         pair_table, block_counts, mask_keys = _ops.kernel_map_search(
             table.keys_tensor, table.values_tensor, out_c, offs3, stride)
-    offsets_dev = _ops.kernel_map_count(block_counts)
-    if K * n_out <= _DEFERRED_MAX_PAIRS:
-        # No host sync: the CSR lists go into upper-bound sized buffers, (offsets, status) travel
-        # to pinned host memory asynchronously and are only waited for when somebody reads
-        # `offsets` / `in_maps` / `out_maps` on the host (IntSearchResult._resolve).
-        meta = torch.cat([offsets_dev, table.status_tensor])
-        if torch.cuda.is_current_stream_capturing():
-            host, event = meta, None  # read back (synchronously) only if somebody asks later
+    # Fork: the CSR branch (block scan -> offsets -> async D2H of offsets/status -> deterministic
+    # scatter) runs on a side stream while the main stream builds the forward tile plan (radix
+    # sort of the row masks -> step lists); both only read the pair table. Joined before returning,
+    # so callers (and CUDA-graph capture) see one stream.
+    main = torch.cuda.current_stream(dev)
+    side = _side_stream(dev)
+    deferred = K * n_out <= _DEFERRED_MAX_PAIRS
+    fork = torch.cuda.Event()
+    fork.record(main)
+    side.wait_event(fork)
+    with torch.cuda.stream(side):
+        offsets_dev = _ops.kernel_map_count(block_counts)
+        if deferred:
+            # No host sync: the CSR lists go into upper-bound sized buffers, (offsets, status)
+            # travel to pinned host memory asynchronously and are only waited for when somebody
+            # reads `offsets` / `in_maps` / `out_maps` on the host (IntSearchResult._resolve).
+            meta = torch.cat([offsets_dev, table.status_tensor])
+            if torch.cuda.is_current_stream_capturing():
+                host, event = meta, None  # read back (synchronously) only if somebody asks later
+            else:
+                host = _pinned_host(K + 2)
+                host.copy_(meta, non_blocking=True)
+                event = torch.cuda.Event()
+                event.record(side)
+            in_maps, out_maps = _ops.kernel_map_scatter(pair_table, block_counts, offsets_dev,
+                                                        K * n_out)
+            result = IntSearchResult._from_device(in_maps, out_maps, offsets_dev, host, event,
+                                                  table.raise_if_failed, identity_map_index)
         else:
-            host = _pinned_host(K + 2)
-            host.copy_(meta, non_blocking=True)
-            event = torch.cuda.Event()
-            event.record()
-        in_maps, out_maps = _ops.kernel_map_scatter(pair_table, block_counts, offsets_dev,
-                                                    K * n_out)
-        result = IntSearchResult._from_device(in_maps, out_maps, offsets_dev, host, event,
-                                              table.raise_if_failed, identity_map_index)
-    else:
-        # very large K * M: allocate the exact length instead (one host sync)
-        host = torch.cat([offsets_dev, table.status_tensor]).cpu()
-        table.raise_if_failed(int(host[-1]))
-        offsets_cpu = host[:-1].clone()
-        num_pairs = int(offsets_cpu[-1])
-        in_maps, out_maps = _ops.kernel_map_scatter(pair_table, block_counts, offsets_dev,
-                                                    num_pairs)
-        result = IntSearchResult(in_maps, out_maps, offsets_cpu,
-                                 identity_map_index=identity_map_index)
+            # very large K * M: allocate the exact length instead (one host sync)
+            host = torch.cat([offsets_dev, table.status_tensor]).cpu()
+            table.raise_if_failed(int(host[-1]))
+            offsets_cpu = host[:-1].clone()
+            num_pairs = int(offsets_cpu[-1])
+            in_maps, out_maps = _ops.kernel_map_scatter(pair_table, block_counts, offsets_dev,
+                                                        num_pairs)
+            result = IntSearchResult(in_maps, out_maps, offsets_cpu,
+                                     identity_map_index=identity_map_index)
+        join = torch.cuda.Event()
+        join.record(side)
+    for t in (pair_table, block_counts, table.status_tensor):
+        t.record_stream(side)       # allocated on the main stream, read by the side stream
+    for t in (offsets_dev, in_maps, out_maps) + ((host,) if host.is_cuda else ()):
+        t.record_stream(main)       # allocated on the side stream, consumed on the main stream
+    if build_plan and n_out > 0:
+        result._fwd_plan = _ops.build_tile_plan(pair_table, mask_keys)
+        mask_keys = None
+    main.wait_event(join)
     result._offsets_dev = offsets_dev
     result._pair_table = pair_table
     result._mask_keys = mask_keys
