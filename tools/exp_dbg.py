@@ -22,11 +22,11 @@ x = torch.randn(n, cin, device="cuda").bfloat16()
 w = (torch.randn(27, 1, cin, cout, device="cuda") * 0.02).bfloat16()
 img = _ops.weight_image(w, 27, 1, cin, cout, False)
 table = km.pair_table(n)
-dbg = torch.zeros(148 * 8, dtype=torch.int64, device="cuda")
+dbg = torch.zeros(148 * 16, dtype=torch.int64, device="cuda")
 os.environ["WCN_DEBUG_PTR"] = str(dbg.data_ptr())
 names = ["prod_total", "prod_wait_empty", "mma_total", "mma_wait_full", "mma_wait_accempty",
          "epi_total", "epi_wait_accfull", "prod_ns"]
-for tr in (128, 256):
+for tr in (256,):
     plan = _ops.build_tile_plan(table, tile_rows=tr)
     for flags in (0,):
         os.environ["WCN_DEBUG"] = str(flags)
@@ -37,8 +37,21 @@ for tr in (128, 256):
             _ops.gather_gemm(x, img, plan, 1, cin, cout)
             b.record()
             torch.cuda.synchronize()
-        d = dbg.view(148, 8).cpu().numpy()
+        d = dbg.view(148, 16).cpu().numpy()
         print(f"tile_rows={tr} dbg={flags} time={a.elapsed_time(b) * 1e3:.1f} us  steps={int(plan.tile_nk.sum())}")
         print(f"    SM clock (prod cycles / ns): {(d[:, 0] / d[:, 7]).mean():.3f} GHz")
         for i, nm in enumerate(names):
             print(f"    {nm:18s} mean={d[:, i].mean():10.0f} min={d[:, i].min():10d} max={d[:, i].max():10d}")
+        t0 = d[:, 8].min()
+        print(f"    ns since first CTA entry: entry mean={np.mean(d[:, 8] - t0):.0f} max={np.max(d[:, 8] - t0):.0f} | "
+              f"prod start mean={np.mean(d[:, 9] - t0):.0f} max={np.max(d[:, 9] - t0):.0f} | "
+              f"prod end mean={np.mean(d[:, 10] - t0):.0f} max={np.max(d[:, 10] - t0):.0f} | "
+              f"all roles done mean={np.mean(d[:, 11] - t0):.0f} max={np.max(d[:, 11] - t0):.0f}")
+        if flags == 0:
+            np.set_printoptions(linewidth=200)
+            print("    prod_total per CTA (kcycles):")
+            print((d[:, 0] // 1000).reshape(4, 37))
+            print("    prod_wait_empty per CTA (kcycles):")
+            print((d[:, 1] // 1000).reshape(4, 37))
+            print("    mma_wait_full per CTA (kcycles):")
+            print((d[:, 3] // 1000).reshape(4, 37))

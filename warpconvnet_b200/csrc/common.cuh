@@ -138,6 +138,26 @@ __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
   return v;
 }
 
+// one element of T (converted from fp32, round to nearest) to shared memory
+template <typename T>
+__device__ __forceinline__ void st_shared_elem(uint32_t addr, float f);
+template <>
+__device__ __forceinline__ void st_shared_elem<float>(uint32_t addr, float f) {
+  asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(__float_as_uint(f)) : "memory");
+}
+template <>
+__device__ __forceinline__ void st_shared_elem<__nv_bfloat16>(uint32_t addr, float f) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(f);
+  asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(*reinterpret_cast<const uint16_t*>(&h))
+               : "memory");
+}
+template <>
+__device__ __forceinline__ void st_shared_elem<__half>(uint32_t addr, float f) {
+  const __half h = __float2half_rn(f);
+  asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(*reinterpret_cast<const uint16_t*>(&h))
+               : "memory");
+}
+
 // TMA gather4: four rows (r0..r3, arbitrary) x one box width of a 2-D tensor map land as four
 // consecutive box rows at dst; rows outside the tensor are zero-filled.
 __device__ __forceinline__ void tma_gather4(uint32_t dst, const void* tmap, int col, int r0, int r1,

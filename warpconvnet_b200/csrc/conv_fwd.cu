@@ -60,8 +60,14 @@ struct GemmSmemCtrl {
 // scalar binary search would chain ~2*log2(n) dependent L2 round trips in the kernel prologue.
 __device__ __forceinline__ long long unit_cost(const int* __restrict__ cum,
                                                const int* __restrict__ nk, int U, int u) {
+  // nk[t] == cum[t+1] - cum[t]: two INDEPENDENT loads of adjacent words instead of a second
+  // array (cum has nt + 1 entries and u <= U*nt - 1 here, or u == U*nt with u - t*U == 0)
   const int t = u / U;
-  return (long long)U * __ldg(cum + t) + (long long)(u - t * U) * __ldg(nk + t);
+  const int r = u - t * U;
+  const int c0 = __ldg(cum + t);
+  const int c1 = r ? __ldg(cum + t + 1) : c0;
+  (void)nk;
+  return (long long)U * c0 + (long long)r * (c1 - c0);
 }
 __device__ __forceinline__ int lower_bound_unit(const int* __restrict__ cum,
                                                 const int* __restrict__ nk, int nt, int U,
@@ -127,7 +133,14 @@ struct StepCursor {
   }
 };
 
-template <typename T, int TM, int GC>
+// SWAP (bn == 128, TM == 2): the operand roles are exchanged — the weight slice is the M = 128 (Cout)
+// operand and the gathered rows are the N operand, so ONE N = 256 instruction covers both
+// sub-tiles: D^T[cout, voxel] += W_k^T[cout, cin] * Xg^T[cin, voxel]. A 128x128x16 SS instruction
+// reads 8 KB of shared memory for 64 tensor cycles (the shared-memory port, not the tensor pipe,
+// paces it: measured ~150 cycles per instruction); the 128x256x16 form reads 12 KB for twice the
+// work, i.e. the weight slice is fetched once per step instead of once per sub-tile. Both
+// operands are K-major in the same canonical 128B-swizzled layout, so no image changes.
+template <typename T, int TM, int GC, bool SWAP>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -138,9 +151,18 @@ gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
   const int warp = tid >> 5;
   const int lane = tid & 31;
   const int slab = blockIdx.y;
+  if (p.dbg_out != nullptr && tid == 0) {  // bring-up: absolute ns at kernel entry
+    unsigned long long ns;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns));
+    p.dbg_out[blockIdx.x * 16 + 8] = (long long)ns;
+  }
 
   constexpr int kASub = GC * kAStageBytes;  // one 128-row sub-tile: GC slabs of 128 rows x 128 B
   constexpr int kAStage = TM * kASub;
+  // byte strides inside the A part of a stage: [sub-tile][chunk][128 rows] normally,
+  // [chunk][sub-tile][128 rows] when SWAP (the N = 256 operand needs 256 contiguous rows per chunk)
+  constexpr int kChunkStride = SWAP ? TM * kAStageBytes : kAStageBytes;
+  constexpr int kSubStride = SWAP ? kAStageBytes : kASub;
   const int b_chunk_bytes = p.bn * 128;     // weight slab of one 128-byte channel chunk
   const int stage_bytes = kAStage + ((GC * b_chunk_bytes + 1023) & ~1023);
   const int stages = p.stages;
@@ -209,15 +231,20 @@ gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
 #pragma unroll
     for (int i = 0; i < kPar; ++i) {
       const int r7 = kRowsPerInstr * i + sub;
-      off_par[i] = (uint32_t)ch * kAStageBytes + (uint32_t)(warp * 32 + r7) * 128u +
+      off_par[i] = (uint32_t)ch * kChunkStride + (uint32_t)(warp * 32 + r7) * 128u +
                    (uint32_t)((c8 ^ r7) << 4);
     }
     const uint8_t* col_base = reinterpret_cast<const uint8_t*>(p.feats) +
                               (long long)(p.in_coff + slab * p.in_slab_stride) * kElem + u * 16;
+    // row pitch in bytes fits 32 bits (checked by the launcher): the source address of a row is
+    // ONE 32x32->64 multiply-add (IMAD.WIDE.U32) instead of an emulated 64-bit multiply
+    const uint32_t pitch = (uint32_t)in_ld_bytes;
 
     StepCursor<TM> cur, pre;
     cur.init(p, U, ub, ue, t_begin, t_end);
     pre.init(p, U, ub, ue, t_begin, t_end);
+    // ring of prefetched steps, slot 0 = the step issued next (shifted by register moves so the
+    // loop body exists once: the role loops of this kernel must stay small in the instruction cache)
     int idx_ring[kPrefetch][TM];  // neighbour row of tile row warp*32 + lane, per sub-tile
     int k_ring[kPrefetch];
     // idx[j] < -1 marks a sub-tile that is not part of this CTA's range (nothing is gathered)
@@ -246,63 +273,74 @@ gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
     const long long t_start = clock64();
     unsigned long long ns_start;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns_start));
+#pragma unroll 1
     while (cur.valid(t_end)) {
+      int idx_own[TM];
 #pragma unroll
-      for (int d = 0; d < kPrefetch; ++d) {
-        if (!cur.valid(t_end)) break;
-        int idx_own[TM];
+      for (int j = 0; j < TM; ++j) idx_own[j] = idx_ring[0][j];
+      const int k = k_ring[0];
 #pragma unroll
-        for (int j = 0; j < TM; ++j) idx_own[j] = idx_ring[d][j];
-        const int k = k_ring[d];
-        if (pre.valid(t_end)) {  // refill this ring slot with the step kPrefetch ahead
-          load_step(pre, idx_ring[d], k_ring[d]);
-          pre.next(p, U, ub, ue, t_end);
+      for (int d = 0; d + 1 < kPrefetch; ++d) {
+        k_ring[d] = k_ring[d + 1];
+#pragma unroll
+        for (int j = 0; j < TM; ++j) idx_ring[d][j] = idx_ring[d + 1][j];
+      }
+      if (pre.valid(t_end)) {  // refill the last slot with the step kPrefetch ahead
+        load_step(pre, idx_ring[kPrefetch - 1], k_ring[kPrefetch - 1]);
+        pre.next(p, U, ub, ue, t_end);
+      }
+      cur.next(p, U, ub, ue, t_end);
+      const int wk = p.kflip ? (p.K - 1 - k) : k;
+#pragma unroll 1
+      for (int g = 0; g < n_groups; ++g) {
+        {
+          const long long t0 = clock64();
+          mbar_wait(smem_u32(&ctrl->empty[stage]), phase ^ 1u);
+          w_empty += clock64() - t0;
         }
-        cur.next(p, U, ub, ue, t_end);
-        const int wk = p.kflip ? (p.K - 1 - k) : k;
-        for (int g = 0; g < n_groups; ++g) {
-          {
-            const long long t0 = clock64();
-            mbar_wait(smem_u32(&ctrl->empty[stage]), phase ^ 1u);
-            w_empty += clock64() - t0;
-          }
-          const uint32_t a_smem = smem_base + stage * stage_bytes;
-          const uint32_t full_bar = smem_u32(&ctrl->full[stage]);
-          if (tid == 0) {
-            const int chunks_here = min(GC, n_chunks - g * GC);
-            const uint32_t b_bytes = (uint32_t)(chunks_here * b_chunk_bytes);
+        const uint32_t a_smem = smem_base + stage * stage_bytes;
+        const uint32_t full_bar = smem_u32(&ctrl->full[stage]);
+        if (tid == 0) {
+          const int chunks_here = min(GC, n_chunks - g * GC);
+          const uint32_t b_bytes = (uint32_t)(chunks_here * b_chunk_bytes);
+          if (p.debug & 8) {  // bring-up: no weight traffic
+            mbar_arrive(full_bar);
+          } else {
             mbar_arrive_expect_tx(full_bar, b_bytes);
             bulk_copy_g2s(a_smem + kAStage,
                           wimg + ((size_t)wk * n_chunks + g * GC) * b_chunk_bytes, b_bytes,
                           full_bar);
           }
-          const int seg_off = g * GC * 128;  // byte offset of this chunk group inside the row
-          const bool lane_active = seg_off + u * 16 < row_bytes;
-#pragma unroll
-          for (int j = 0; j < TM; ++j) {
-            if (TM > 1 && idx_own[j] < -1) continue;  // warp-uniform: sub-tile not ours
-#pragma unroll
-            for (int q = 0; q < kInstr; ++q) {
-              // warp-uniform shuffle; only the copy itself is predicated
-              const int src_idx = __shfl_sync(0xffffffffu, idx_own[j], kRowsPerInstr * q + sub);
-              const uint8_t* src =
-                  col_base + (long long)(src_idx >= 0 ? src_idx : 0) * in_ld_bytes + seg_off;
-              const uint32_t dst =
-                  a_smem + j * kASub + off_par[q % kPar] + (uint32_t)(q / kPar) * 1024u;
-              if (lane_active) cp_async_16(dst, src, src_idx >= 0 ? 16u : 0u);
-            }
-          }
-          cp_async_mbar_arrive_noinc(full_bar);
-          if (++stage == stages) { stage = 0; phase ^= 1u; }
         }
+        const int seg_off = g * GC * 128;  // byte offset of this chunk group inside the row
+        const bool lane_active = seg_off + u * 16 < row_bytes && !(p.debug & 2);
+        const uint8_t* seg_base = col_base + seg_off;
+#pragma unroll
+        for (int j = 0; j < TM; ++j) {
+          if (TM > 1 && idx_own[j] < -1) continue;  // warp-uniform: sub-tile not ours
+#pragma unroll
+          for (int q = 0; q < kInstr; ++q) {
+            // warp-uniform shuffle; only the copy itself is predicated
+            const int src_idx = __shfl_sync(0xffffffffu, idx_own[j], kRowsPerInstr * q + sub);
+            const uint8_t* src =
+                seg_base + (unsigned long long)(uint32_t)max(src_idx, 0) * pitch;
+            const uint32_t dst =
+                a_smem + j * kSubStride + off_par[q % kPar] + (uint32_t)(q / kPar) * 1024u;
+            if (lane_active) cp_async_16(dst, src, src_idx >= 0 ? 16u : 0u);
+          }
+        }
+        cp_async_mbar_arrive_noinc(full_bar);
+        if (++stage == stages) { stage = 0; phase ^= 1u; }
       }
     }
     if (p.dbg_out != nullptr && tid == 0) {
-      p.dbg_out[blockIdx.x * 8 + 0] = clock64() - t_start;
-      p.dbg_out[blockIdx.x * 8 + 1] = w_empty;
+      p.dbg_out[blockIdx.x * 16 + 0] = clock64() - t_start;
+      p.dbg_out[blockIdx.x * 16 + 1] = w_empty;
       unsigned long long ns_end;
       asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns_end));
-      p.dbg_out[blockIdx.x * 8 + 7] = (long long)(ns_end - ns_start);
+      p.dbg_out[blockIdx.x * 16 + 7] = (long long)(ns_end - ns_start);
+      p.dbg_out[blockIdx.x * 16 + 9] = (long long)ns_start;
+      p.dbg_out[blockIdx.x * 16 + 10] = (long long)ns_end;
     }
   } else if (warp == kMmaWarp) {
     // ======================================= MMA issuer =========================================
@@ -346,16 +384,32 @@ gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
               for (int cc = 0; cc < GC; ++cc) {
                 const int chunk_bytes = min(128, row_bytes - (g * GC + cc) * 128);
                 const int n_mma = chunk_bytes > 0 ? (chunk_bytes >> 5) : 0;  // 32 B of K per MMA
-#pragma unroll
-                for (int j = 0; j < TM; ++j) {
-                  if (TM > 1 && (j < lo || j >= hi)) continue;  // sub-tile not ours
+                if constexpr (SWAP) {
+                  // M = Cout (weight slice), N = the CTA's share of the tile's 256 rows
+                  const uint32_t idesc_sw =
+                      make_idesc(ElemTraits<T>::kFmt, kTileM, (hi - lo) * kTileM, 0, 0);
                   for (int m = 0; m < n_mma; ++m) {
-                    const uint64_t adesc = make_smem_desc_sw128(
-                        a_smem + j * kASub + cc * kAStageBytes + m * 32, 16, 1024);
-                    const uint64_t bdesc =
+                    if (p.debug & 4) continue;  // bring-up: no tensor work
+                    const uint64_t wdesc =
                         make_smem_desc_sw128(b_smem + cc * b_chunk_bytes + m * 32, 16, 1024);
-                    umma_ss<ElemTraits<T>::kTF32>(tmem_d + j * p.bn, adesc, bdesc, idesc,
+                    const uint64_t xdesc = make_smem_desc_sw128(
+                        a_smem + cc * kChunkStride + lo * kAStageBytes + m * 32, 16, 1024);
+                    umma_ss<ElemTraits<T>::kTF32>(tmem_d + lo * kTileM, wdesc, xdesc, idesc_sw,
                                                   (accumulate | (uint32_t)(m + cc)) ? 1u : 0u);
+                  }
+                } else {
+#pragma unroll
+                  for (int j = 0; j < TM; ++j) {
+                    if (TM > 1 && (j < lo || j >= hi)) continue;  // sub-tile not ours
+                    for (int m = 0; m < n_mma; ++m) {
+                      if (p.debug & 4) continue;  // bring-up: no tensor work
+                      const uint64_t adesc = make_smem_desc_sw128(
+                          a_smem + j * kASub + cc * kAStageBytes + m * 32, 16, 1024);
+                      const uint64_t bdesc =
+                          make_smem_desc_sw128(b_smem + cc * b_chunk_bytes + m * 32, 16, 1024);
+                      umma_ss<ElemTraits<T>::kTF32>(tmem_d + j * p.bn, adesc, bdesc, idesc,
+                                                    (accumulate | (uint32_t)(m + cc)) ? 1u : 0u);
+                    }
                   }
                 }
               }
@@ -369,9 +423,9 @@ gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
         }
       }
       if (p.dbg_out != nullptr) {
-        p.dbg_out[blockIdx.x * 8 + 2] = clock64() - t_start;
-        p.dbg_out[blockIdx.x * 8 + 3] = w_full;
-        p.dbg_out[blockIdx.x * 8 + 4] = w_acc;
+        p.dbg_out[blockIdx.x * 16 + 2] = clock64() - t_start;
+        p.dbg_out[blockIdx.x * 16 + 3] = w_full;
+        p.dbg_out[blockIdx.x * 16 + 4] = w_acc;
       }
     }
   } else {
@@ -402,6 +456,52 @@ gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
           w_accf += clock64() - t0;
           tc_fence_after();
         }
+        if constexpr (SWAP) {
+          // TMEM lane = output channel, TMEM column = tile row: every thread owns one channel of
+          // its warp's 32. Batches of 32 rows are transposed through a warp-private staging block
+          // ([row][32 channels]) and leave as 16-byte pieces, 32 * sizeof(T) contiguous bytes of
+          // an output row per warp.
+          constexpr int kRowB = 32 * kElem;           // staging row: this warp's 32 channels
+          constexpr int kPieces = kRowB / 16;         // 4 (16-bit) or 8 (fp32)
+          constexpr int kRowsPerSt = 32 / kPieces;    // rows per store instruction
+          const float bias_c = p.bias != nullptr ? __ldg(p.bias + col_base + q * 32 + lane) : 0.f;
+          const int s_row = lane / kPieces, s_piece = lane % kPieces;
+          for (int j = lo; j < hi; ++j) {
+            for (int vb = 0; vb < kTileM / 32; ++vb) {
+              const int out_row =
+                  __ldg(p.rows + (size_t)tile * p.tile_rows + j * kTileM + vb * 32 + lane);
+              uint32_t v[32];
+              if (nk > 0) {
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccStride +
+                                       j * kTileM + vb * 32;
+                tmem_ld_x16(taddr, v);
+                tmem_ld_x16(taddr + 16, v + 16);
+                tmem_ld_wait();
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = 0u;
+              }
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                float f = __uint_as_float(v[i]) + bias_c;
+                if (p.relu) f = fmaxf(f, 0.f);
+                st_shared_elem<T>(stage_warp + i * kRowB + lane * kElem, f);
+              }
+              __syncwarp();
+#pragma unroll
+              for (int it = 0; it < kPieces; ++it) {
+                const int row = it * kRowsPerSt + s_row;
+                const int orow = __shfl_sync(0xffffffffu, out_row, row);
+                const uint4 val = ld_shared_v4(stage_warp + row * kRowB + s_piece * 16);
+                if (orow >= 0 && !(p.debug & 1))
+                  *reinterpret_cast<uint4*>(out + (long long)orow * out_ld_bytes +
+                                            (long long)(col_base + q * 32) * kElem +
+                                            s_piece * 16) = val;
+              }
+              __syncwarp();
+            }
+          }
+        } else {
 #pragma unroll
         for (int j = 0; j < TM; ++j) {
           if (TM > 1 && (j < lo || j >= hi)) continue;  // sub-tile not ours
@@ -460,6 +560,7 @@ gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
             __syncwarp();
           }
         }
+        }
         if (nk > 0) {
           tc_fence_before();
           mbar_arrive(smem_u32(&ctrl->acc_empty[acc]));
@@ -468,13 +569,18 @@ gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
       }
     }
     if (p.dbg_out != nullptr && tid == 5 * 32) {
-      p.dbg_out[blockIdx.x * 8 + 5] = clock64() - t_start;
-      p.dbg_out[blockIdx.x * 8 + 6] = w_accf;
+      p.dbg_out[blockIdx.x * 16 + 5] = clock64() - t_start;
+      p.dbg_out[blockIdx.x * 16 + 6] = w_accf;
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (p.dbg_out != nullptr && tid == 0) {  // bring-up: absolute ns when every role is done
+    unsigned long long ns;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns));
+    p.dbg_out[blockIdx.x * 16 + 11] = (long long)ns;
+  }
   if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
@@ -497,7 +603,7 @@ static int pick_gemm_stages(int bn, int tm, int gc) {
   return s;
 }
 
-template <typename T, int TM, int GC>
+template <typename T, int TM, int GC, bool SWAP>
 static int launch_gather_gemm_t(GatherGemmParams p, int n_slabs, int max_ctas, cudaStream_t stream) {
   const int max_stages = pick_gemm_stages(p.bn, TM, GC);
   if (p.stages <= 0 || p.stages > max_stages) p.stages = max_stages;
@@ -505,7 +611,7 @@ static int launch_gather_gemm_t(GatherGemmParams p, int n_slabs, int max_ctas, c
   const size_t smem = gemm_smem_bytes(p.bn, TM, GC, p.stages);
   static int configured_smem = 0;  // per instantiation
   if ((int)smem > configured_smem) {
-    cudaError_t e = cudaFuncSetAttribute(gather_gemm_kernel<T, TM, GC>,
+    cudaError_t e = cudaFuncSetAttribute(gather_gemm_kernel<T, TM, GC, SWAP>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return kErrCuda;
     configured_smem = (int)smem;
@@ -514,7 +620,7 @@ static int launch_gather_gemm_t(GatherGemmParams p, int n_slabs, int max_ctas, c
   int ctas = units < max_ctas ? units : max_ctas;
   if (ctas < 1) return kOk;
   dim3 grid(ctas, n_slabs, 1);
-  gather_gemm_kernel<T, TM, GC><<<grid, kGemmThreads, smem, stream>>>(p);
+  gather_gemm_kernel<T, TM, GC, SWAP><<<grid, kGemmThreads, smem, stream>>>(p);
   count_launch();
   return cudaGetLastError() == cudaSuccess ? kOk : kErrCuda;
 }
@@ -527,12 +633,18 @@ static int launch_gather_gemm_tm(const GatherGemmParams& p, int n_slabs, int max
   // GC = 2: a stage covers two 128-byte channel chunks so gathers are 256-byte requests.
   const bool tm2 = p.tile_rows == 2 * kTileM && p.bn <= 128 && !(p.debug & 16);  // 16: bring-up
   const bool gc2 = p.cin * (int)sizeof(T) > 128 && !(p.debug & 32);             // 32: bring-up
-  if (tm2) {
-    return gc2 ? launch_gather_gemm_t<T, 2, 2>(p, n_slabs, max_ctas, stream)
-               : launch_gather_gemm_t<T, 2, 1>(p, n_slabs, max_ctas, stream);
+  // SWAP: Cout is exactly one M = 128 operand and the tile's 256 rows form the N operand
+  const bool swap = tm2 && p.bn == kTileM && !(p.debug & 64);                    // 64: bring-up
+  if (swap) {
+    return gc2 ? launch_gather_gemm_t<T, 2, 2, true>(p, n_slabs, max_ctas, stream)
+               : launch_gather_gemm_t<T, 2, 1, true>(p, n_slabs, max_ctas, stream);
   }
-  return gc2 ? launch_gather_gemm_t<T, 1, 2>(p, n_slabs, max_ctas, stream)
-             : launch_gather_gemm_t<T, 1, 1>(p, n_slabs, max_ctas, stream);
+  if (tm2) {
+    return gc2 ? launch_gather_gemm_t<T, 2, 2, false>(p, n_slabs, max_ctas, stream)
+               : launch_gather_gemm_t<T, 2, 1, false>(p, n_slabs, max_ctas, stream);
+  }
+  return gc2 ? launch_gather_gemm_t<T, 1, 2, false>(p, n_slabs, max_ctas, stream)
+             : launch_gather_gemm_t<T, 1, 1, false>(p, n_slabs, max_ctas, stream);
 }
 
 int launch_gather_gemm(const GatherGemmParams& p, int dtype, int n_slabs, int max_ctas,
@@ -540,6 +652,7 @@ int launch_gather_gemm(const GatherGemmParams& p, int dtype, int n_slabs, int ma
   const int es = dtype_size(dtype);
   if (p.bn < 16 || p.bn > 256 || (p.bn % 16) != 0) return kErrUnsupportedShape;
   if (p.cin <= 0 || (p.cin * es) % 32 != 0) return kErrUnsupportedShape;
+  if (p.in_ld * es >= (1ll << 31)) return kErrUnsupportedShape;  // 32-bit row pitch in the gather
   if ((p.in_ld * es) % 16 != 0 || (p.in_coff * es) % 16 != 0 || (p.in_slab_stride * es) % 16 != 0)
     return kErrAlignment;
   if ((p.out_ld * es) % 16 != 0 || (p.out_coff * es) % 16 != 0) return kErrAlignment;

@@ -120,8 +120,9 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
     // (tools/gather_bench.cu), so whole-row requests double the gather rate of 128-byte ones.
     const uint8_t* xs = reinterpret_cast<const uint8_t*>(p.feats);
     const uint8_t* gs = reinterpret_cast<const uint8_t*>(p.gout);
-    const long long in_ld_bytes = p.in_ld * kElem;
-    const long long out_ld_bytes = p.out_ld * kElem;
+    // row pitches fit 32 bits (checked by the launcher): one IMAD.WIDE.U32 per source address
+    const uint32_t in_ld_bytes = (uint32_t)(p.in_ld * kElem);
+    const uint32_t out_ld_bytes = (uint32_t)(p.out_ld * kElem);
     const int u = lane & 15;       // 16-byte unit inside a 256-byte row segment
     const int blk = u >> 3;        // 128-byte MN block inside the segment
     const int c16 = u & 7;
@@ -203,8 +204,8 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
               po = __shfl_sync(0xffffffffu, vo, row);
             }
             const bool valid = pi >= 0;
-            const uint8_t* xrow = a_base + (long long)(valid ? pi : 0) * in_ld_bytes;
-            const uint8_t* grow = b_base + (long long)(valid ? po : 0) * out_ld_bytes;
+            const uint8_t* xrow = a_base + (unsigned long long)(uint32_t)max(pi, 0) * in_ld_bytes;
+            const uint8_t* grow = b_base + (unsigned long long)(uint32_t)max(po, 0) * out_ld_bytes;
             const uint32_t sz = valid ? 16u : 0u;
             const uint32_t soff = off_par[q & 3] + (uint32_t)(q >> 2) * 1024u;
             // branch-free: out-of-range lanes copy 0 source bytes (= zero fill)
@@ -398,6 +399,7 @@ int launch_wgrad(const WgradParams& p, int dtype, int cin_slabs, int cout_slabs,
   if (p.K > kWgMaxK || p.K < 1) return kErrUnsupportedShape;
   if (p.cout < 16 || p.cout > 256 || p.cout % 16 != 0) return kErrUnsupportedShape;
   if (p.cin < 1 || p.cin > 128 || (p.cin * es) % 16 != 0) return kErrUnsupportedShape;
+  if (p.in_ld * es >= (1ll << 31) || p.out_ld * es >= (1ll << 31)) return kErrUnsupportedShape;
   if ((p.in_ld * es) % 16 != 0 || (p.in_coff * es) % 16 != 0) return kErrAlignment;
   if ((p.out_ld * es) % 16 != 0 || (p.out_coff * es) % 16 != 0) return kErrAlignment;
   if (p.dw_ld % 4 != 0 || p.dw_k_stride % 4 != 0 || (reinterpret_cast<uintptr_t>(p.dw) & 15))
