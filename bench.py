@@ -126,6 +126,7 @@ class ClockSampler:
             pynvml.nvmlInit()
             self.nv = pynvml
             self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
         except Exception as e:  # pragma: no cover
             self.nv, self.err = None, repr(e)
             return
@@ -137,13 +138,13 @@ class ClockSampler:
         while not self.stop_flag:
             try:
                 self.rows.append((nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM),
-                                  nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM),
+                                  self.sm_max,
                                   nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0,
                                   nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)))
             except Exception as e:  # pragma: no cover
                 self.err = repr(e)
                 break
-            time.sleep(0.001)
+            time.sleep(0.0005)
 
     def stop(self):
         if self.nv is None:
@@ -220,7 +221,6 @@ def run_ours(args):
         barrier()
         evs = []
         l0 = lib.wcn_launch_count()
-        sampler = ClockSampler(local) if rank == 0 else None
         wall0 = time.perf_counter()
         for _ in range(steps):
             flush.fill_(1)  # L2 flush (256 MiB write) before every timed step
@@ -231,13 +231,12 @@ def run_ours(args):
             evs.append((s, e))
         barrier()
         wall = time.perf_counter() - wall0
-        clocks = sampler.stop() if sampler else None
         launches = lib.wcn_launch_count() - l0
         ms = sum(s.elapsed_time(e) for s, e in evs) / steps
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), launches, clocks, wall
+        return float(t.item()), launches, wall
 
     # ---- device-resident number: the step is captured ONCE into a CUDA graph (no host sync in
     # the path, so the whole map build + plan + fwd + dgrad + wgrad is capturable) and replayed;
@@ -262,12 +261,15 @@ def run_ours(args):
             graph = None
             graph_note = f"graph capture failed ({type(exc).__name__}), eager launches timed"
             torch.cuda.synchronize()
+    # NVML clock / power / throttle-reason samples are taken from here to the end of the e2e loop:
+    # the headline region alone is ~10 ms, shorter than a handful of NVML round trips
+    sampler = ClockSampler(local) if rank == 0 else None
     if graph is not None:
-        ms, _, clocks, wall = timed(graph.replay, args.steps, args.warmup)
+        ms, _, wall = timed(graph.replay, args.steps, args.warmup)
         launches = launches_per_step * args.steps
-        eager_ms, _, _, _ = timed(step, args.steps, args.warmup)
+        eager_ms, _, _ = timed(step, args.steps, args.warmup)
     else:
-        ms, launches, clocks, wall = timed(step, args.steps, args.warmup)
+        ms, launches, wall = timed(step, args.steps, args.warmup)
         eager_ms = ms
     total_vox = torch.tensor([n], device=dev, dtype=torch.float64)
     if world > 1:
@@ -277,8 +279,8 @@ def run_ours(args):
     # ---- the dominant kernel alone (forward gather-GEMM): same plan / inputs, L2 flushed before
     # every launch, events on the launching stream; the flush keeps the GPU busy while the host
     # enqueues, so the events bracket the kernel and not the launch latency ----------------------
-    gemm_ms, _, _, _ = timed(lambda: _ops.gather_gemm(x, img, plan, 1, CIN, COUT, out=y),
-                             args.steps, args.warmup)
+    gemm_ms, _, _ = timed(lambda: _ops.gather_gemm(x, img, plan, 1, CIN, COUT, out=y),
+                          args.steps, args.warmup)
 
     # ---- per-phase breakdown (untimed for the headline; same step, events between phases) -----
     def breakdown(reps=5):
@@ -370,16 +372,26 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t.item())
+    clocks = sampler.stop() if sampler else None
+    if clocks is not None:
+        clocks["window"] = ("all timed regions of this run (graph steps, eager steps, kernel-only "
+                            "launches, e2e loop)")
 
     peaks = load_peaks()
     steps_total = int(plan.tile_nk.sum().item())
-    xbar_bytes = L * CIN * 2 + steps_total * (CIN * COUT * 2 + plan.tile_rows * 4)
-    l2sm = {"bytes_per_launch_model": xbar_bytes,
-            "achieved_TBps": xbar_bytes / (gemm_ms * 1e-3) / 1e12,
-            "measured_gather_cap_TBps": 7.35,
-            "cap_source": "tools/gather_bench.cu on this pool's B200 (256-byte row gathers, "
-                          "LDGSTS / TMA gather4 alike), profiles/r1b_launches_and_ncu.md",
-            "frac_of_cap": xbar_bytes / (gemm_ms * 1e-3) / 1e12 / 7.35}
+    # Secondary (informational) bound, DESIGN.md 4.3: every gathered row crosses the L2->SM path
+    # through the LSU (cp.async), which tools/l2sm_bench.cu measures at 26.9 B/cycle/SM = 6.1 TB/s
+    # chip-wide for 256-byte row gathers on this pool's B200 (sequential or random rows alike,
+    # TMA gather4 slower). The per-step weight slices (0.88 MB image, hot in L2, cp.async.bulk)
+    # ride on the TMA path and do not compete (same benchmark, "GB" rows).
+    gather_bytes = L * CIN * 2
+    l2sm = {"gathered_bytes_per_launch": gather_bytes,
+            "weight_slice_bytes_per_launch": steps_total * CIN * COUT * 2,
+            "achieved_TBps": gather_bytes / (gemm_ms * 1e-3) / 1e12,
+            "measured_gather_cap_TBps": 6.1,
+            "cap_source": "tools/l2sm_bench.cu, mode G at 148 CTAs (gpurun_out -> "
+                          "profiles/r1c_gather_path.md)",
+            "frac_of_cap": gather_bytes / (gemm_ms * 1e-3) / 1e12 / 6.1}
     flops = 2.0 * L * CIN * COUT
     achieved = flops / (gemm_ms * 1e-3) / 1e12
     out = {
