@@ -435,10 +435,20 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"], _ = run_cpu_baseline(args.dist, reps=2, warmup=1)
     if rank == 0:
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
     if world > 1:
+        # Tear-down: release the captured graph (it holds NCCL work) before the communicator.
+        # ncclCommDestroy has been seen to block forever after a graph-captured all-reduce on this
+        # stack, which would stall the launcher; every rank therefore synchronises, meets at a
+        # barrier and leaves through os._exit(0) once its output is flushed.
+        graph = None
+        g_out = None
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def run_reference(args):
