@@ -194,6 +194,39 @@ int wcn_wgrad(const void* feats, long long in_ld, const void* gout, long long ou
               int groups, int cin_g, int cout_g, int dtype, float alpha, int unit_pairs,
               int max_ctas, void* stream);
 
+/* ------------------------------------------------------------------------------------------ */
+/* Per-channel normalisation + activation + residual on the [n, c] feature matrix             */
+/* (replaces the torch chain nn.BatchNorm1d -> ReLU (-> + identity -> ReLU)  */
+/*  of the reference's ConvBlock / BasicBlock: models/mink_unet.py:31-53,104-140,             */
+/*  nn/modules/normalizations.py:53-67, nn/modules/activations.py:36-53)                      */
+/* All matrices are row-major with a row pitch in elements; dtype as for the GEMMs.           */
+/* ------------------------------------------------------------------------------------------ */
+/* sums[ch] += sum_r x[r][ch], sums[c + ch] += sum_r x[r][ch]^2 (fp64 [2c], caller zero-fills) */
+int wcn_bn_stats(const void* x, long long ld_x, int n, int c, int dtype, double* sums,
+                 void* stream);
+/* From the sums: mean_rstd[2c] (biased variance, like nn.BatchNorm1d), scale = gamma * rstd,
+ * shift = beta - mean * scale, and (optional) running statistics updated with `momentum`
+ * (unbiased variance). gamma / beta may be NULL (1 / 0). */
+int wcn_bn_finalize(const double* sums, int n, int c, const float* gamma, const float* beta,
+                    float eps, float momentum, float* running_mean, float* running_var,
+                    float* scale, float* shift, float* mean_rstd, void* stream);
+/* y = act(x * scale[ch] + shift[ch] (+ res)), act = ReLU when relu != 0; res optional. Also the
+ * eval-mode BatchNorm and the plain bias / affine epilogue. */
+int wcn_scale_shift_act(const void* x, long long ld_x, const void* res, long long ld_res, void* y,
+                        long long ld_y, int n, int c, int dtype, const float* scale,
+                        const float* shift, int relu, void* stream);
+/* dz = dy * (y > 0) (y optional: no activation); sums[ch] += sum dz, sums[c+ch] += sum dz*xhat */
+int wcn_bn_bwd_reduce(const void* dy, long long ld_dy, const void* x, long long ld_x,
+                      const void* y, long long ld_y, int n, int c, int dtype,
+                      const float* mean_rstd, double* sums, void* stream);
+/* training != 0: dx = gamma*rstd*(dz - sums[ch]/n - xhat*sums[c+ch]/n); training == 0:
+ * dx = dz * gamma[ch] (pass gamma * running rstd). dres (optional) receives dz, the gradient
+ * of the residual input. */
+int wcn_bn_bwd_apply(const void* dy, long long ld_dy, const void* x, long long ld_x, const void* y,
+                     long long ld_y, void* dx, long long ld_dx, void* dres, long long ld_dres,
+                     int n, int c, int dtype, const float* gamma, const float* mean_rstd,
+                     const double* sums, int training, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -5,59 +5,49 @@ BASELINE config 4, not part of the package (model zoos are out of scope, SURVEY.
 Same topology as the reference's ``MinkUNetBase(in, out, planes=(32,64,128,256,128,128,96,96),
 layers=(1,)*8)`` (warpconvnet/models/mink_unet.py:259-404): 1x1 stem, four [2^3 stride-2 conv +
 BasicBlock] stages, four [2^3 transposed conv + skip concat + BasicBlock] stages, 1x1 head;
-BatchNorm1d + ReLU on the feature matrix between convs (plain torch, as in the reference)."""
+BatchNorm + ReLU (+ residual add) between convs run as the fused row kernels of csrc/rownorm.cu
+(the reference applies nn.BatchNorm1d / nn.ReLU / add as separate torch passes)."""
 import torch
 import torch.nn as nn
 
 from warpconvnet_b200.geometry.types.voxels import Voxels
+from warpconvnet_b200.nn.modules.normalizations import BatchNorm
 from warpconvnet_b200.nn.modules.sparse_conv import SparseConv3d
 
 
-class _OnFeatures(nn.Module):
-    """Apply a feature-matrix module to a Voxels object (the reference's Sequential does this)."""
-
-    def __init__(self, *mods):
-        super().__init__()
-        self.mods = nn.ModuleList(mods)
-
-    def forward(self, x: Voxels) -> Voxels:
-        f = x.feature_tensor
-        for m in self.mods:
-            f = m(f)
-        return x.replace(batched_features=f)
-
-
 class ConvBlock(nn.Module):
+    """conv -> BatchNorm -> (+ residual) -> ReLU; the norm / add / activation tail is ONE fused
+    row-streaming pass pair (warpconvnet_b200.nn.modules.BatchNorm, csrc/rownorm.cu)."""
+
     def __init__(self, cin, cout, kernel_size=3, stride=1, act=True):
         super().__init__()
         self.conv = SparseConv3d(cin, cout, kernel_size, stride, bias=False)
-        self.post = _OnFeatures(nn.BatchNorm1d(cout), nn.ReLU(inplace=True) if act else nn.Identity())
+        self.bn = BatchNorm(cout, relu=act)
 
-    def forward(self, x):
-        return self.post(self.conv(x))
+    def forward(self, x, residual=None):
+        return self.bn(self.conv(x), residual=residual)
 
 
 class ConvTrBlock(nn.Module):
     def __init__(self, cin, cout):
         super().__init__()
         self.conv_tr = SparseConv3d(cin, cout, 2, 2, transposed=True, bias=False)
-        self.post = _OnFeatures(nn.BatchNorm1d(cout), nn.ReLU(inplace=True))
+        self.bn = BatchNorm(cout, relu=True)
 
     def forward(self, x, target):
-        return self.post(self.conv_tr(x, target))
+        return self.bn(self.conv_tr(x, target))
 
 
 class BasicBlock(nn.Module):
     def __init__(self, cin, cout):
         super().__init__()
         self.conv1 = ConvBlock(cin, cout, 3)
-        self.conv2 = ConvBlock(cout, cout, 3, act=False)
+        self.conv2 = ConvBlock(cout, cout, 3, act=True)   # relu(bn(conv2) + identity)
         self.downsample = ConvBlock(cin, cout, 1, act=False) if cin != cout else None
 
     def forward(self, x):
-        out = self.conv2(self.conv1(x))
         idn = x if self.downsample is None else self.downsample(x)
-        return out.replace(batched_features=torch.relu(out.feature_tensor + idn.feature_tensor))
+        return self.conv2(self.conv1(x), residual=idn)
 
 
 def cat(a: Voxels, b: Voxels) -> Voxels:

@@ -77,6 +77,16 @@ SIGNATURES = {
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                 c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int,
                                 c_void_p]),
+    "wcn_bn_stats": (c_int, [c_void_p, c_longlong, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "wcn_bn_finalize": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_float,
+                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "wcn_scale_shift_act": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong,
+                                    c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),
+    "wcn_bn_bwd_reduce": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong,
+                                  c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "wcn_bn_bwd_apply": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong,
+                                 c_void_p, c_longlong, c_void_p, c_longlong, c_int, c_int, c_int,
+                                 c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "wcn_wgrad": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p,
                           c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_int,
                           c_void_p]),

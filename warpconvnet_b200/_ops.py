@@ -293,3 +293,80 @@ def knn_search(ref: Tensor, ref_offsets: Tensor, query: Tensor, query_offsets: T
     check(lib.wcn_knn_search(_p(ref), ref.shape[0], _p(ro), _p(query), query.shape[0], _p(qo), nb,
                              k, _p(out), _p(dist), _p(ws), ws_bytes, _stream()), "knn_search")
     return (out, dist) if return_distances else out
+
+
+# ------------------------------------------------------------------------------------------------
+# per-channel normalisation / activation passes over the feature matrix (rownorm.cu)
+# ------------------------------------------------------------------------------------------------
+def _rows(t: Tensor):
+    assert t.dim() == 2 and t.stride(1) == 1, "feature matrices are row-major [n, c]"
+    return _p(t), t.stride(0)
+
+
+def bn_stats(x: Tensor) -> Tensor:
+    """fp64 [2, c]: per-channel sum and sum of squares of x [n, c]."""
+    _require_cuda(x)
+    n, c = x.shape
+    sums = torch.zeros((2, c), dtype=torch.float64, device=x.device)
+    px, ldx = _rows(x)
+    check(lib.wcn_bn_stats(px, ldx, n, c, dtype_code(x.dtype), _p(sums), _stream()), "bn_stats")
+    return sums
+
+
+def bn_finalize(sums: Tensor, n: int, gamma: Optional[Tensor], beta: Optional[Tensor], eps: float,
+                momentum: float, running_mean: Optional[Tensor], running_var: Optional[Tensor]):
+    """(scale, shift, mean_rstd[2, c]) from the sums; updates the running statistics in place."""
+    c = sums.shape[1]
+    buf = torch.empty((4, c), dtype=torch.float32, device=sums.device)
+    scale, shift, mean_rstd = buf[0], buf[1], buf[2:]
+    check(lib.wcn_bn_finalize(_p(sums), n, c, _p(gamma), _p(beta), ctypes.c_float(eps),
+                              ctypes.c_float(momentum), _p(running_mean), _p(running_var),
+                              _p(scale), _p(shift), _p(mean_rstd), _stream()), "bn_finalize")
+    return scale, shift, mean_rstd
+
+
+def scale_shift_act(x: Tensor, scale: Tensor, shift: Tensor, residual: Optional[Tensor] = None,
+                    relu: bool = False, out: Optional[Tensor] = None) -> Tensor:
+    """act(x * scale[c] + shift[c] (+ residual))."""
+    _require_cuda(x, scale, shift, residual)
+    n, c = x.shape
+    if out is None:
+        out = torch.empty((n, c), dtype=x.dtype, device=x.device)
+    px, ldx = _rows(x)
+    po, ldo = _rows(out)
+    pr, ldr = _rows(residual) if residual is not None else (None, 0)
+    if residual is not None:
+        assert residual.shape == x.shape and residual.dtype == x.dtype
+    check(lib.wcn_scale_shift_act(px, ldx, pr, ldr, po, ldo, n, c, dtype_code(x.dtype), _p(scale),
+                                  _p(shift), int(relu), _stream()), "scale_shift_act")
+    return out
+
+
+def bn_bwd_reduce(dy: Tensor, x: Tensor, y: Optional[Tensor], mean_rstd: Tensor) -> Tensor:
+    """fp64 [2, c]: sum dz and sum dz * xhat with dz = dy * (y > 0) (y None: dz = dy)."""
+    n, c = x.shape
+    sums = torch.zeros((2, c), dtype=torch.float64, device=x.device)
+    pd, ldd = _rows(dy)
+    px, ldx = _rows(x)
+    py, ldy = _rows(y) if y is not None else (None, 0)
+    check(lib.wcn_bn_bwd_reduce(pd, ldd, px, ldx, py, ldy, n, c, dtype_code(x.dtype),
+                                _p(mean_rstd), _p(sums), _stream()), "bn_bwd_reduce")
+    return sums
+
+
+def bn_bwd_apply(dy: Tensor, x: Optional[Tensor], y: Optional[Tensor], gamma: Tensor,
+                 mean_rstd: Optional[Tensor], sums: Optional[Tensor], training: bool,
+                 want_dres: bool):
+    """(dx, dres | None); see wcn_bn_bwd_apply."""
+    n, c = dy.shape
+    dx = torch.empty((n, c), dtype=dy.dtype, device=dy.device)
+    dres = torch.empty((n, c), dtype=dy.dtype, device=dy.device) if want_dres else None
+    pd, ldd = _rows(dy)
+    px, ldx = _rows(x) if x is not None else (None, 0)
+    py, ldy = _rows(y) if y is not None else (None, 0)
+    pdx, lddx = _rows(dx)
+    pdr, lddr = _rows(dres) if dres is not None else (None, 0)
+    check(lib.wcn_bn_bwd_apply(pd, ldd, px, ldx, py, ldy, pdx, lddx, pdr, lddr, n, c,
+                               dtype_code(dy.dtype), _p(gamma), _p(mean_rstd), _p(sums),
+                               int(training), _stream()), "bn_bwd_apply")
+    return dx, dres

@@ -7,6 +7,7 @@
 
 #include "common.cuh"
 #include "conv_gemm.cuh"
+#include "rownorm.cuh"
 
 namespace wcn {
 // cuhash.cu
@@ -35,6 +36,10 @@ int knn_search(const float*, int, const int*, const float*, int, const int*, int
                float*, void*, size_t, cudaStream_t);
 // weight_prep.cu
 int launch_weight_image(const WeightPrepParams&, cudaStream_t);
+// rownorm.cu
+int rownorm_launch(int which, const RowNormParams&, int dtype, cudaStream_t);
+int bn_finalize(const double*, int, int, const float*, const float*, float, float, float*, float*,
+                float*, float*, float*, cudaStream_t);
 // conv_fwd.cu / conv_wgrad.cu
 int launch_gather_gemm(const GatherGemmParams&, int dtype, int n_slabs, int max_ctas, cudaStream_t);
 int launch_wgrad(const WgradParams&, int dtype, int y_slabs, int z_slabs, int max_ctas, cudaStream_t);
@@ -382,6 +387,64 @@ int wcn_wgrad(const void* feats, long long in_ld, const void* gout, long long ou
   }
   if (max_ctas <= 0) max_ctas = sm_count();
   return launch_wgrad(p, dtype, y_slabs, z_slabs, max_ctas, S(stream));
+}
+
+/* ---- per-channel normalisation / activation passes over the feature matrix (rownorm.cu) ---- */
+static RowNormParams rn_params(int n, int c) {
+  RowNormParams p{};
+  p.n = n;
+  p.c = c;
+  return p;
+}
+
+int wcn_bn_stats(const void* x, long long ld_x, int n, int c, int dtype, double* sums,
+                 void* stream) {
+  if (!x || !sums) return kErrInvalidArg;
+  RowNormParams p = rn_params(n, c);
+  p.x = x; p.ld_x = ld_x; p.sums = sums;
+  return rownorm_launch(0, p, dtype, S(stream));
+}
+
+int wcn_bn_finalize(const double* sums, int n, int c, const float* gamma, const float* beta,
+                    float eps, float momentum, float* running_mean, float* running_var,
+                    float* scale, float* shift, float* mean_rstd, void* stream) {
+  if (!sums || !scale || !shift || !mean_rstd) return kErrInvalidArg;
+  return bn_finalize(sums, n, c, gamma, beta, eps, momentum, running_mean, running_var, scale,
+                     shift, mean_rstd, S(stream));
+}
+
+int wcn_scale_shift_act(const void* x, long long ld_x, const void* res, long long ld_res, void* y,
+                        long long ld_y, int n, int c, int dtype, const float* scale,
+                        const float* shift, int relu, void* stream) {
+  if (!x || !y || !scale || !shift) return kErrInvalidArg;
+  RowNormParams p = rn_params(n, c);
+  p.x = x; p.ld_x = ld_x; p.res = res; p.ld_res = ld_res; p.y = y; p.ld_y = ld_y;
+  p.scale = scale; p.shift = shift; p.relu = relu;
+  return rownorm_launch(1, p, dtype, S(stream));
+}
+
+int wcn_bn_bwd_reduce(const void* dy, long long ld_dy, const void* x, long long ld_x,
+                      const void* y, long long ld_y, int n, int c, int dtype,
+                      const float* mean_rstd, double* sums, void* stream) {
+  if (!dy || !x || !mean_rstd || !sums) return kErrInvalidArg;
+  RowNormParams p = rn_params(n, c);
+  p.dy = dy; p.ld_dy = ld_dy; p.x = x; p.ld_x = ld_x; p.y_in = y; p.ld_yin = ld_y;
+  p.mean_rstd = mean_rstd; p.sums = sums;
+  return rownorm_launch(2, p, dtype, S(stream));
+}
+
+int wcn_bn_bwd_apply(const void* dy, long long ld_dy, const void* x, long long ld_x, const void* y,
+                     long long ld_y, void* dx, long long ld_dx, void* dres, long long ld_dres,
+                     int n, int c, int dtype, const float* gamma, const float* mean_rstd,
+                     const double* sums, int training, void* stream) {
+  if (!dy || !dx || !gamma) return kErrInvalidArg;
+  if (training && (!x || !mean_rstd || !sums)) return kErrInvalidArg;
+  RowNormParams p = rn_params(n, c);
+  p.dy = dy; p.ld_dy = ld_dy; p.x = x; p.ld_x = ld_x; p.y_in = y; p.ld_yin = ld_y;
+  p.y = dx; p.ld_y = ld_dx; p.dres = dres; p.ld_dres = ld_dres;
+  p.scale = gamma; p.mean_rstd = mean_rstd; p.sums = const_cast<double*>(sums);
+  p.training = training;
+  return rownorm_launch(3, p, dtype, S(stream));
 }
 
 }  // extern "C"

@@ -1,0 +1,401 @@
+// SPDX-License-Identifier: Apache-2.0
+// Per-channel normalisation + activation + residual passes over the [N, C] feature matrix that
+// sits between two sparse convolutions. HBM-bound row streaming: every thread
+// owns one 16-byte channel vector and walks rows with a grid stride, so a warp reads whole
+// contiguous rows; per-channel reductions stay in registers, are merged per block through shared
+// memory and leave as one fp64 atomic per channel and block.
+//
+// Replaces (semantics, not code): the feature-matrix chain of the reference's ConvBlock /
+// BasicBlock — nn.BatchNorm1d -> ReLU (-> + identity -> ReLU), warpconvnet/models/mink_unet.py:31-53,
+// 104-140, warpconvnet/nn/modules/normalizations.py:53-67 — which torch runs as 4-6 separate
+// passes (collect statistics, transform, ReLU, add) forward and as many backward.
+#include "common.cuh"
+#include "rownorm.cuh"
+
+namespace wcn {
+
+
+template <typename T>
+struct Vec16 {
+  static constexpr int kElems = 16 / (int)sizeof(T);
+};
+
+template <typename T, int V>
+__device__ __forceinline__ void load_vec(const T* p, float (&f)[V]) {
+  if constexpr (V == 1) {
+    f[0] = (float)p[0];
+  } else {
+    const uint4 raw = *reinterpret_cast<const uint4*>(p);
+    if constexpr (sizeof(T) == 4) {
+      f[0] = __uint_as_float(raw.x); f[1] = __uint_as_float(raw.y);
+      f[2] = __uint_as_float(raw.z); f[3] = __uint_as_float(raw.w);
+    } else {
+      const T* h = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+      for (int i = 0; i < V; ++i) f[i] = (float)h[i];
+    }
+  }
+}
+
+template <typename T, int V>
+__device__ __forceinline__ void store_vec(T* p, const float (&f)[V]) {
+  if constexpr (V == 1) {
+    p[0] = (T)f[0];
+  } else if constexpr (sizeof(T) == 4) {
+    *reinterpret_cast<uint4*>(p) = make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]),
+                                              __float_as_uint(f[2]), __float_as_uint(f[3]));
+  } else {
+    uint4 raw;
+    T* h = reinterpret_cast<T*>(&raw);
+#pragma unroll
+    for (int i = 0; i < V; ++i) h[i] = (T)f[i];
+    *reinterpret_cast<uint4*>(p) = raw;
+  }
+}
+
+constexpr int kRnThreads = 256;
+
+// Thread -> (vector column vc, row lane rl): vecs = ceil(c / V) vectors per row, rpb = threads /
+// vecs rows per block iteration. Threads beyond rpb * vecs idle.
+struct RnMap {
+  int vc, rl, rpb, vecs;
+  bool active;
+};
+template <int V>
+__device__ __forceinline__ RnMap rn_map(int c) {
+  RnMap m;
+  m.vecs = (c + V - 1) / V;
+  m.rpb = kRnThreads / m.vecs;
+  m.vc = threadIdx.x % m.vecs;
+  m.rl = threadIdx.x / m.vecs;
+  m.active = m.rl < m.rpb;
+  return m;
+}
+
+// block-level merge of per-thread partial sums a[V], b[V] into sums[0..c) and sums[c..2c)
+template <int V>
+__device__ __forceinline__ void rn_merge(const RnMap& m, int c, const float (&a)[V],
+                                         const float (&b)[V], double* sums, float* sh) {
+  // sh: [2][c] floats, zeroed
+  for (int i = threadIdx.x; i < 2 * c; i += kRnThreads) sh[i] = 0.f;
+  __syncthreads();
+  if (m.active) {
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const int ch = m.vc * V + i;
+      if (ch < c) {
+        atomicAdd(sh + ch, a[i]);
+        atomicAdd(sh + c + ch, b[i]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * c; i += kRnThreads) atomicAdd(sums + i, (double)sh[i]);
+}
+
+// ---- forward statistics: sums[ch] += sum_r x[r,ch], sums[c+ch] += sum_r x[r,ch]^2 -------------
+template <typename T, int V>
+__global__ void __launch_bounds__(kRnThreads) bn_stats_kernel(const RowNormParams p) {
+  extern __shared__ float sh[];
+  const RnMap m = rn_map<V>(p.c);
+  float s[V], q[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) s[i] = q[i] = 0.f;
+  if (m.active) {
+    const T* x = reinterpret_cast<const T*>(p.x) + m.vc * V;
+    // four independent 16-byte loads in flight per thread (the pass is pure HBM streaming)
+    const long long stride = (long long)gridDim.x * m.rpb;
+    long long r = (long long)blockIdx.x * m.rpb + m.rl;
+    for (; r + 3 * stride < p.n; r += 4 * stride) {
+      float f[4][V];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) load_vec<T, V>(x + (r + u * stride) * p.ld_x, f[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          s[i] += f[u][i];
+          q[i] = fmaf(f[u][i], f[u][i], q[i]);
+        }
+      }
+    }
+    for (; r < p.n; r += stride) {
+      float f[V];
+      load_vec<T, V>(x + r * p.ld_x, f);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        s[i] += f[i];
+        q[i] = fmaf(f[i], f[i], q[i]);
+      }
+    }
+  }
+  rn_merge<V>(m, p.c, s, q, p.sums, sh);
+}
+
+// ---- y = act(x * scale + shift (+ res)) -----------------------------------------------------------
+template <typename T, int V>
+__global__ void __launch_bounds__(kRnThreads) scale_shift_act_kernel(const RowNormParams p) {
+  const RnMap m = rn_map<V>(p.c);
+  if (!m.active) return;
+  float sc[V], sf[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int ch = min(m.vc * V + i, p.c - 1);
+    sc[i] = __ldg(p.scale + ch);
+    sf[i] = __ldg(p.shift + ch);
+  }
+  const T* x = reinterpret_cast<const T*>(p.x) + m.vc * V;
+  const T* res = p.res ? reinterpret_cast<const T*>(p.res) + m.vc * V : nullptr;
+  T* y = reinterpret_cast<T*>(p.y) + m.vc * V;
+  constexpr int U = 2;  // rows in flight per thread
+  const long long stride = (long long)gridDim.x * m.rpb;
+  for (long long r0 = (long long)blockIdx.x * m.rpb + m.rl; r0 < p.n; r0 += U * stride) {
+    float f[U][V], g[U][V];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long r = r0 + u * stride;
+      if (r < p.n) {
+        load_vec<T, V>(x + r * p.ld_x, f[u]);
+        if (res) load_vec<T, V>(res + r * p.ld_res, g[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long r = r0 + u * stride;
+      if (r >= p.n) break;
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        float v = fmaf(f[u][i], sc[i], sf[i]);
+        if (res) v += g[u][i];
+        f[u][i] = p.relu ? fmaxf(v, 0.f) : v;
+      }
+      store_vec<T, V>(y + r * p.ld_y, f[u]);
+    }
+  }
+}
+
+// ---- backward reduce: dz = dy * (y > 0); sums += (sum dz, sum dz * xhat) ---------------------------
+template <typename T, int V>
+__global__ void __launch_bounds__(kRnThreads) bn_bwd_reduce_kernel(const RowNormParams p) {
+  extern __shared__ float sh[];
+  const RnMap m = rn_map<V>(p.c);
+  float s1[V], s2[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) s1[i] = s2[i] = 0.f;
+  if (m.active) {
+    float mu[V], rs[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const int ch = min(m.vc * V + i, p.c - 1);
+      mu[i] = __ldg(p.mean_rstd + ch);
+      rs[i] = __ldg(p.mean_rstd + p.c + ch);
+    }
+    const T* x = reinterpret_cast<const T*>(p.x) + m.vc * V;
+    const T* dy = reinterpret_cast<const T*>(p.dy) + m.vc * V;
+    const T* yin = p.y_in ? reinterpret_cast<const T*>(p.y_in) + m.vc * V : nullptr;
+    constexpr int U = 2;  // rows in flight per thread
+    const long long stride = (long long)gridDim.x * m.rpb;
+    for (long long r0 = (long long)blockIdx.x * m.rpb + m.rl; r0 < p.n; r0 += U * stride) {
+      float fx[U][V], fd[U][V], fy[U][V];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long r = r0 + u * stride;
+        if (r < p.n) {
+          load_vec<T, V>(x + r * p.ld_x, fx[u]);
+          load_vec<T, V>(dy + r * p.ld_dy, fd[u]);
+          if (yin) load_vec<T, V>(yin + r * p.ld_yin, fy[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (r0 + u * stride >= p.n) break;
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          const float d = (yin && !(fy[u][i] > 0.f)) ? 0.f : fd[u][i];
+          s1[i] += d;
+          s2[i] = fmaf(d, (fx[u][i] - mu[i]) * rs[i], s2[i]);
+        }
+      }
+    }
+  }
+  rn_merge<V>(m, p.c, s1, s2, p.sums, sh);
+}
+
+// ---- backward apply: dx = gamma * rstd * (dz - s1/n - xhat * s2/n); dres = dz ----------------------
+template <typename T, int V>
+__global__ void __launch_bounds__(kRnThreads) bn_bwd_apply_kernel(const RowNormParams p) {
+  const RnMap m = rn_map<V>(p.c);
+  if (!m.active) return;
+  float mu[V], rs[V], g[V], m1[V], m2[V];
+  const float inv_n = 1.f / (float)p.n;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int ch = min(m.vc * V + i, p.c - 1);
+    g[i] = __ldg(p.scale + ch);  // gamma (training) or gamma * rstd_running (eval)
+    if (p.training) {
+      mu[i] = __ldg(p.mean_rstd + ch);
+      rs[i] = __ldg(p.mean_rstd + p.c + ch);
+      m1[i] = (float)(p.sums[ch] * (double)inv_n);
+      m2[i] = (float)(p.sums[p.c + ch] * (double)inv_n);
+    } else {
+      mu[i] = 0.f; rs[i] = 1.f; m1[i] = 0.f; m2[i] = 0.f;
+    }
+  }
+  const T* x = reinterpret_cast<const T*>(p.x) + m.vc * V;
+  const T* dy = reinterpret_cast<const T*>(p.dy) + m.vc * V;
+  const T* yin = p.y_in ? reinterpret_cast<const T*>(p.y_in) + m.vc * V : nullptr;
+  T* dx = reinterpret_cast<T*>(p.y) + m.vc * V;
+  T* dres = p.dres ? reinterpret_cast<T*>(p.dres) + m.vc * V : nullptr;
+  constexpr int U = 2;  // rows in flight per thread
+  const long long stride = (long long)gridDim.x * m.rpb;
+  for (long long r0 = (long long)blockIdx.x * m.rpb + m.rl; r0 < p.n; r0 += U * stride) {
+    float fx[U][V], fd[U][V], fy[U][V];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long r = r0 + u * stride;
+      if (r < p.n) {
+        load_vec<T, V>(dy + r * p.ld_dy, fd[u]);
+        if (yin) load_vec<T, V>(yin + r * p.ld_yin, fy[u]);
+        if (p.training) load_vec<T, V>(x + r * p.ld_x, fx[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long r = r0 + u * stride;
+      if (r >= p.n) break;
+      if (yin) {
+#pragma unroll
+        for (int i = 0; i < V; ++i) fd[u][i] = fy[u][i] > 0.f ? fd[u][i] : 0.f;
+      }
+      if (dres) store_vec<T, V>(dres + r * p.ld_dres, fd[u]);
+      if (p.training) {
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          const float xh = (fx[u][i] - mu[i]) * rs[i];
+          fd[u][i] = g[i] * rs[i] * (fd[u][i] - m1[i] - xh * m2[i]);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < V; ++i) fd[u][i] *= g[i];
+      }
+      store_vec<T, V>(dx + r * p.ld_y, fd[u]);
+    }
+  }
+}
+
+// ---- finalize: mean / rstd / scale / shift / running statistics from the fp64 sums ----------------
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, int n, int c,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float eps, float momentum, float* running_mean,
+                                   float* running_var, float* scale, float* shift,
+                                   float* mean_rstd) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  const double mean = sums[ch] / (double)n;
+  double var = sums[c + ch] / (double)n - mean * mean;  // biased (normalisation)
+  if (var < 0.0) var = 0.0;
+  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float g = gamma ? gamma[ch] : 1.f;
+  const float b = beta ? beta[ch] : 0.f;
+  scale[ch] = g * rstd;
+  shift[ch] = b - (float)mean * g * rstd;
+  mean_rstd[ch] = (float)mean;
+  mean_rstd[c + ch] = rstd;
+  if (running_mean) running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * (float)mean;
+  if (running_var) {
+    const double unbiased = n > 1 ? var * (double)n / (double)(n - 1) : var;
+    running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * (float)unbiased;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------
+enum RnKernel { kStats = 0, kApply = 1, kBwdReduce = 2, kBwdApply = 3 };
+
+// One full wave of resident blocks (grid-stride rows): blocks = SMs x occupancy of the kernel,
+// never more than the rows need.
+static int rn_grid(int n, int c, int v, int resident_per_sm, bool reduction) {
+  const int vecs = (c + v - 1) / v;
+  const int rpb = kRnThreads / vecs;
+  // reductions end with 2c fp64 atomics per block: give every block >= 32 row iterations
+  const long long rows_per_block = (long long)rpb * (reduction ? 32 : 1);
+  long long blocks = ((long long)n + rows_per_block - 1) / rows_per_block;
+  const long long cap = (long long)kNumSMsB200 * resident_per_sm;
+  if (blocks > cap) blocks = cap;
+  return blocks < 1 ? 1 : (int)blocks;
+}
+
+template <typename K>
+static int rn_occupancy(K kernel, size_t smem) {
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kRnThreads, smem) != cudaSuccess ||
+      occ < 1)
+    occ = 2;
+  return occ;
+}
+
+template <typename T, int V>
+static int rn_launch_tv(int which, const RowNormParams& p, cudaStream_t s) {
+  const size_t sh = (size_t)2 * p.c * sizeof(float);
+  static int occ[4] = {0, 0, 0, 0};  // per instantiation and kernel
+  if (occ[which] == 0) {
+    switch (which) {
+      case kStats: occ[which] = rn_occupancy(bn_stats_kernel<T, V>, sh); break;
+      case kApply: occ[which] = rn_occupancy(scale_shift_act_kernel<T, V>, 0); break;
+      case kBwdReduce: occ[which] = rn_occupancy(bn_bwd_reduce_kernel<T, V>, sh); break;
+      default: occ[which] = rn_occupancy(bn_bwd_apply_kernel<T, V>, 0); break;
+    }
+  }
+  const int grid = rn_grid(p.n, p.c, V, occ[which], which == kStats || which == kBwdReduce);
+  switch (which) {
+    case kStats: bn_stats_kernel<T, V><<<grid, kRnThreads, sh, s>>>(p); break;
+    case kApply: scale_shift_act_kernel<T, V><<<grid, kRnThreads, 0, s>>>(p); break;
+    case kBwdReduce: bn_bwd_reduce_kernel<T, V><<<grid, kRnThreads, sh, s>>>(p); break;
+    default: bn_bwd_apply_kernel<T, V><<<grid, kRnThreads, 0, s>>>(p); break;
+  }
+  count_launch();
+  return cudaGetLastError() == cudaSuccess ? kOk : kErrCuda;
+}
+
+template <typename T>
+static int rn_launch_t(int which, const RowNormParams& p, bool vec, cudaStream_t s) {
+  constexpr int V = Vec16<T>::kElems;
+  return vec ? rn_launch_tv<T, V>(which, p, s) : rn_launch_tv<T, 1>(which, p, s);
+}
+
+static bool aligned16(const void* ptr, long long ld, int es) {
+  return ptr == nullptr || ((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (ld * es) % 16 == 0);
+}
+
+int rownorm_launch(int which, const RowNormParams& p, int dtype, cudaStream_t s) {
+  if (p.n < 0 || p.c < 1 || p.c > 4096) return kErrInvalidArg;
+  if (p.n == 0) return kOk;
+  const int es = dtype_size(dtype);
+  const int v = 16 / es;
+  // 16-byte channel vectors when every operand allows it, else one element per thread
+  const bool vec = (p.c % v == 0) && p.c / v <= kRnThreads && aligned16(p.x, p.ld_x, es) &&
+                   aligned16(p.res, p.ld_res, es) && aligned16(p.y_in, p.ld_yin, es) &&
+                   aligned16(p.dy, p.ld_dy, es) && aligned16(p.y, p.ld_y, es) &&
+                   aligned16(p.dres, p.ld_dres, es);
+  if (!vec && p.c > kRnThreads) return kErrUnsupportedShape;
+  switch (dtype) {
+    case kBF16: return rn_launch_t<__nv_bfloat16>(which, p, vec, s);
+    case kF16: return rn_launch_t<__half>(which, p, vec, s);
+    case kF32: return rn_launch_t<float>(which, p, vec, s);
+    default: return kErrUnsupportedDtype;
+  }
+}
+
+int bn_finalize(const double* sums, int n, int c, const float* gamma, const float* beta, float eps,
+                float momentum, float* running_mean, float* running_var, float* scale,
+                float* shift, float* mean_rstd, cudaStream_t s) {
+  if (c < 1 || n < 1) return kErrInvalidArg;
+  bn_finalize_kernel<<<(c + 127) / 128, 128, 0, s>>>(sums, n, c, gamma, beta, eps, momentum,
+                                                     running_mean, running_var, scale, shift,
+                                                     mean_rstd);
+  count_launch();
+  return cudaGetLastError() == cudaSuccess ? kOk : kErrCuda;
+}
+
+}  // namespace wcn

@@ -1,0 +1,96 @@
+# SPDX-License-Identifier: Apache-2.0
+"""Fused BatchNorm (+ residual) (+ ReLU) on the feature matrix between two sparse convolutions.
+
+Replaces the torch chain the reference runs per ConvBlock / BasicBlock
+(``nn.BatchNorm1d -> ReLU`` and ``bn(x) + identity -> ReLU``; warpconvnet/models/mink_unet.py:31-53,
+104-140; warpconvnet/nn/modules/normalizations.py:53-67) with the row-streaming kernels of
+``csrc/rownorm.cu``: forward = statistics pass + one normalise/activate pass, backward = one
+reduction pass + one apply pass. Semantics are nn.BatchNorm1d's (biased variance for the
+normalisation, unbiased for ``running_var``, fp32 statistics whatever the feature dtype).
+"""
+from typing import Optional
+
+import torch
+from torch import Tensor
+
+from warpconvnet_b200 import _ops
+
+
+class _BatchNormAct(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x: Tensor, weight: Optional[Tensor], bias: Optional[Tensor],
+                residual: Optional[Tensor], running_mean: Optional[Tensor],
+                running_var: Optional[Tensor], training: bool, momentum: float, eps: float,
+                relu: bool):
+        x = x if x.stride(1) == 1 else x.contiguous()
+        n, c = x.shape
+        gamma = weight.detach().float().contiguous() if weight is not None else None
+        beta = bias.detach().float().contiguous() if bias is not None else None
+        if residual is not None:
+            residual = residual.to(x.dtype)
+            residual = residual if residual.stride(1) == 1 else residual.contiguous()
+        use_batch = training or running_mean is None
+        if use_batch:
+            if n == 0:
+                raise ValueError("BatchNorm in training mode needs at least one row")
+            sums = _ops.bn_stats(x)
+            scale, shift, mean_rstd = _ops.bn_finalize(
+                sums, n, gamma, beta, eps, momentum, running_mean if training else None,
+                running_var if training else None)
+        else:
+            rstd = torch.rsqrt(running_var.float() + eps)
+            scale = rstd if gamma is None else gamma * rstd
+            shift = -running_mean.float() * scale
+            if beta is not None:
+                shift = shift + beta
+            scale, shift, mean_rstd = scale.contiguous(), shift.contiguous(), None
+        y = _ops.scale_shift_act(x, scale, shift, residual, relu)
+        ctx.use_batch = use_batch
+        ctx.relu = relu
+        ctx.has_res = residual is not None
+        ctx.has_w = weight is not None and ctx.needs_input_grad[1]
+        ctx.has_b = bias is not None and ctx.needs_input_grad[2]
+        ctx.w_dtype = weight.dtype if weight is not None else None
+        ctx.b_dtype = bias.dtype if bias is not None else None
+        ctx.save_for_backward(x, y if relu else None, gamma if gamma is not None else None,
+                              mean_rstd, None if use_batch else scale)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy: Tensor):
+        x, y, gamma, mean_rstd, eval_scale = ctx.saved_tensors
+        dy = dy.to(x.dtype)
+        dy = dy if dy.stride(1) == 1 else dy.contiguous()
+        c = x.shape[1]
+        need_res = ctx.has_res and ctx.needs_input_grad[3]
+        if ctx.use_batch:
+            g = gamma if gamma is not None else torch.ones(c, dtype=torch.float32, device=x.device)
+            sums = _ops.bn_bwd_reduce(dy, x, y, mean_rstd)
+            dx, dres = _ops.bn_bwd_apply(dy, x, y, g, mean_rstd, sums, True, need_res)
+            dgamma = sums[1].to(ctx.w_dtype) if ctx.has_w else None
+            dbeta = sums[0].to(ctx.b_dtype) if ctx.has_b else None
+        else:
+            # running statistics: y = x * scale + shift is affine in x
+            dx, dres = _ops.bn_bwd_apply(dy, None, y, eval_scale, None, None, False, need_res)
+            dgamma = dbeta = None
+            if ctx.has_w or ctx.has_b:
+                raise NotImplementedError(
+                    "gradients of BatchNorm affine parameters in eval mode are not on the hot "
+                    "path; call .requires_grad_(False) on them or use training mode")
+        return dx, dgamma, dbeta, dres, None, None, None, None, None, None
+
+
+def batch_norm_act(x: Tensor, weight: Optional[Tensor] = None, bias: Optional[Tensor] = None,
+                   running_mean: Optional[Tensor] = None, running_var: Optional[Tensor] = None,
+                   training: bool = True, momentum: float = 0.1, eps: float = 1e-5,
+                   relu: bool = False, residual: Optional[Tensor] = None) -> Tensor:
+    """``act(batch_norm(x) (+ residual))`` on a CUDA feature matrix ``[n, c]`` (bf16 / fp16 /
+    fp32); same arguments as ``torch.nn.functional.batch_norm`` plus the fused tail."""
+    if not x.is_cuda:
+        raise RuntimeError("warpconvnet_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
+    if x.dim() != 2:
+        raise ValueError(f"expected a feature matrix [n, c], got {tuple(x.shape)}")
+    if not training and (weight is not None and weight.requires_grad and torch.is_grad_enabled()):
+        weight, bias = weight.detach(), (bias.detach() if bias is not None else None)
+    return _BatchNormAct.apply(x, weight, bias, residual, running_mean, running_var, training,
+                               float(momentum), float(eps), bool(relu))

@@ -2,3 +2,5 @@
 from .sparse_conv import SparseConv2d, SparseConv3d, SpatiallySparseConv  # noqa: F401
 from .mlp import MLPBlock  # noqa: F401
 from .point_conv import PointConv  # noqa: F401
+from .normalizations import BatchNorm  # noqa: F401
+from .activations import ReLU  # noqa: F401
