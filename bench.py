@@ -207,10 +207,13 @@ def run_ours(args):
         plan = km.fwd_plan(n)
         img = _ops.weight_image(w.view(K, 1, CIN, COUT), K, 1, CIN, COUT, False)
         y = _ops.gather_gemm(x, img, plan, 1, CIN, COUT)           # forward AB_gather_scatter
-        dx = sparse_conv_dgrad(gy, w, km, n)                       # dgrad ABt_gather_scatter
         dw = sparse_conv_wgrad(x, gy, (K, CIN, COUT), km)          # wgrad AtB_gather_gather
-        if world > 1:
-            dist.all_reduce(dw)
+        # the only collective of the path: all-reduce of dW, issued as soon as wgrad is enqueued
+        # so it overlaps dgrad (what DDP does with the rest of backward)
+        work = dist.all_reduce(dw, async_op=True) if world > 1 else None
+        dx = sparse_conv_dgrad(gy, w, km, n)                       # dgrad ABt_gather_scatter
+        if work is not None:
+            work.wait()
         return km, plan, img, y, dx, dw
 
     def timed(fn, steps, warmup):

@@ -54,7 +54,15 @@ def stride_coords(batch_indexed_coords: Tensor, stride: Tuple[int, ...], order=N
     stride = ntuple(stride, ndim=num_spatial_dims)
     if all(s == 1 for s in stride):
         return batch_indexed_coords, offsets_from_batch_index(batch_indexed_coords[:, 0])
-    st = torch.tensor([1, *stride], dtype=torch.int32, device=batch_indexed_coords.device)
-    discretized = torch.div(batch_indexed_coords, st, rounding_mode="floor").int()
+    # floor division by Python scalars: a torch.tensor(stride, device=cuda) here would be a
+    # synchronous pageable H2D copy, i.e. a host sync in every strided layer
+    discretized = batch_indexed_coords.clone()
+    if len(set(stride)) == 1:
+        discretized[:, 1:] = torch.div(batch_indexed_coords[:, 1:], stride[0],
+                                       rounding_mode="floor")
+    else:
+        for d, s in enumerate(stride):
+            discretized[:, d + 1] = torch.div(batch_indexed_coords[:, d + 1], s,
+                                              rounding_mode="floor")
     unique, _ = unique_coords(discretized)
     return unique.contiguous(), offsets_from_batch_index(unique[:, 0])

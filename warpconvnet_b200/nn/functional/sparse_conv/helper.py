@@ -46,8 +46,9 @@ def _apply_generative_policy(input_sparse_tensor: Voxels, kernel_size, kernel_di
         ex = input_coords.expand(kernel_size, kernel_dilation)
         return ex.batch_indexed_coordinates, ex.offsets, bin_coords
     if transposed:
-        st = torch.tensor([1] + list(stride), dtype=bin_coords.dtype, device=bin_coords.device)
-        scaled = bin_coords * st
+        scaled = bin_coords.clone()  # per-column scalar multiply: no host->device tensor, no sync
+        for d, s_d in enumerate(stride):
+            scaled[:, d + 1] *= int(s_d)
         ex = _intcoords_from_batch_indexed(input_coords, scaled, input_sparse_tensor.offsets
                                            ).expand(kernel_size, kernel_dilation)
         return ex.batch_indexed_coordinates, ex.offsets, scaled
