@@ -55,3 +55,46 @@ for tr in (256,):
             print((d[:, 1] // 1000).reshape(4, 37))
             print("    mma_wait_full per CTA (kcycles):")
             print((d[:, 3] // 1000).reshape(4, 37))
+
+# ---- per-CTA work composition vs measured producer time (static ranges, unit = 128 rows) ---------
+plan = _ops.build_tile_plan(table, tile_rows=256)
+os.environ["WCN_DEBUG"] = "0"
+dbg.zero_()
+_ops.gather_gemm(x, img, plan, 1, cin, cout)
+torch.cuda.synchronize()
+d = dbg.view(148, 16).cpu().numpy()
+nk = plan.tile_nk.cpu().numpy().astype(np.int64)
+cum = plan.tile_cum.cpu().numpy().astype(np.int64)
+nt = plan.num_tiles
+U = 2
+S = U * cum[nt]
+unit_cost = np.zeros(U * nt + 1, np.int64)
+for u in range(U * nt + 1):
+    t = min(u // U, nt - 1) if u < U * nt else nt
+    unit_cost[u] = U * cum[nt] if u == U * nt else U * cum[t] + (u - t * U) * nk[t]
+G = 148
+ub = [int(np.searchsorted(unit_cost, S * b // G, side="left")) for b in range(G + 1)]
+nbr = plan.step_nbr.cpu().numpy().reshape(nt, plan.K, 256)
+valid_per_unit = np.zeros(U * nt, np.int64)
+for t in range(nt):
+    v = (nbr[t, :nk[t]] >= 0)
+    valid_per_unit[2 * t] = v[:, :128].sum()
+    valid_per_unit[2 * t + 1] = v[:, 128:].sum()
+rows = []
+for b in range(G):
+    u0, u1 = ub[b], ub[b + 1]
+    steps = sum(nk[u // U] for u in range(u0, u1))
+    valid = valid_per_unit[u0:u1].sum()
+    partial = (u0 % 2) + (u1 % 2)
+    rows.append((b, u1 - u0, steps, valid, partial, d[b, 0]))
+rows = np.array(rows)
+print("corr(prod_total, unit-steps) =", np.corrcoef(rows[:, 5], rows[:, 2])[0, 1])
+print("corr(prod_total, valid rows) =", np.corrcoef(rows[:, 5], rows[:, 3])[0, 1])
+print("corr(prod_total, partial tiles) =", np.corrcoef(rows[:, 5], rows[:, 4])[0, 1])
+order = np.argsort(-rows[:, 5])
+print("slowest CTAs: (cta, units, unit-steps, valid rows, partial tiles, prod kcycles)")
+for i in order[:8]:
+    print("   ", rows[i, :5].tolist(), rows[i, 5] // 1000)
+print("fastest CTAs:")
+for i in order[-8:]:
+    print("   ", rows[i, :5].tolist(), rows[i, 5] // 1000)

@@ -193,8 +193,15 @@ gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
     const int U = p.tile_rows / kTileM;
     const long long S = (long long)U * __ldg(p.tile_cum + nt);
     const int G = gridDim.x, b = blockIdx.x + warp;
-    const int u = (b >= G) ? U * nt
-                           : lower_bound_unit(p.tile_cum, p.tile_nk, nt, U, S * b / G, lane);
+    const long long target = S * b / G;
+    int u = (b >= G) ? U * nt : lower_bound_unit(p.tile_cum, p.tile_nk, nt, U, target, lane);
+    // round to the NEAREST unit boundary (the lower bound alone biases every range by up to a
+    // whole unit = ~9 steps: 81 .. 114 unit-steps per CTA instead of 98 +- 5, tools/exp_dbg.py)
+    if (b > 0 && b < G && u > 0) {
+      const long long above = unit_cost(p.tile_cum, p.tile_nk, U, u) - target;
+      const long long below = target - unit_cost(p.tile_cum, p.tile_nk, U, u - 1);
+      if (below < above) --u;
+    }
     if (lane == 0) {
       if (warp == 0) ctrl->u_begin = u; else ctrl->u_end = u;
     }
