@@ -188,11 +188,17 @@ int wcn_gather_gemm(const void* feats, int n_in_rows, long long in_ld, const voi
  *   dw[k][g][ci][co] += alpha * sum over pairs j of offset k of feats[in_maps[j], g*cin_g+ci] *
  *                                                     gout[out_maps[j], g*cout_g+co]
  * dw is fp32 [K][groups][cin_g][cout_g], accumulated into (caller zero-fills);
- * offsets: device int32[K+1]. */
+ * offsets: device int32[K+1].
+ * Optional L2-locality order: row_block_prefix = the [K][n_row_blocks] array wcn_kernel_map_count
+ * leaves behind (pairs of offset k whose output row is < 256*b; requires out_maps ascending inside
+ * every offset, which wcn_kernel_map_scatter guarantees). The pair lists are then walked in
+ * `row_parts` row blocks x K offsets, every CTA taking `rounds` round-robin chunks, so a block of
+ * rows sees all K offsets while L2-resident. NULL / (1, 1) = plain offset-major order. */
 int wcn_wgrad(const void* feats, long long in_ld, const void* gout, long long out_ld, float* dw,
               const int32_t* in_maps, const int32_t* out_maps, const int32_t* offsets, int K,
               int groups, int cin_g, int cout_g, int dtype, float alpha, int unit_pairs,
-              int max_ctas, void* stream);
+              int max_ctas, const int32_t* row_block_prefix, int n_row_blocks, int row_parts,
+              int rounds, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Per-channel normalisation + activation + residual on the [n, c] feature matrix             */

@@ -349,3 +349,43 @@ def test_cpu_tensors_are_rejected():
     from warpconvnet_b200 import _ops
     with pytest.raises(RuntimeError):
         _ops.hash_prepare(torch.zeros(16, dtype=torch.int64), torch.zeros(16, dtype=torch.int32))
+
+
+@pytest.mark.parametrize("kind,n,stride,ks", [("S", 160, 1, 3), ("R", 30000, 1, 3), ("R", 40000, 2, 2),
+                                              ("S", 448, 1, 3)])
+@pytest.mark.parametrize("parts,rounds", [(2, 2), (4, 4), (8, 3), (1, 5)])
+def test_wgrad_row_block_major_order(kind, n, stride, ks, parts, rounds):
+    """The L2-locality unit order of wgrad (row blocks x offsets, round-robin chunks) contracts
+    exactly the same pairs as the offset-major order: same dW up to fp32 summation order, and the
+    oracle's dW on the small cases."""
+    from oracle import conv as oconv
+    from warpconvnet_b200 import _ops
+    from warpconvnet_b200.geometry.coords.search.torch_discrete import generate_kernel_map
+    c = surface_coords(n, 1) if kind == "S" else random_coords(n, 0.3, 1)
+    m = len(c)
+    bc = torch.from_numpy(np.concatenate([np.zeros((m, 1), np.int32), c], 1)).cuda()
+    if stride == 1:
+        out_bc = bc
+    else:
+        from warpconvnet_b200.geometry.coords.ops.stride import stride_coords
+        out_bc, _ = stride_coords(bc, (stride,) * 3)
+    km = generate_kernel_map(bc, out_bc, (stride,) * 3, (ks,) * 3, same_coords=stride == 1)
+    K, cin, cout = ks ** 3, 64, 128
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(m, cin, generator=g).bfloat16().cuda()
+    gy = torch.randn(len(out_bc), cout, generator=g).bfloat16().cuda()
+    args = (x, gy, km._in_buf, km._out_buf, km.offsets_dev, K, 1, cin, cout)
+    plain = _ops.wgrad(*args)
+    bp = km._block_prefix
+    assert bp.shape[0] == K
+    if bp.shape[1] < parts:
+        pytest.skip("fewer row blocks than parts")
+    blocked = _ops.wgrad(*args, row_block_prefix=bp, row_parts=parts, rounds=rounds)
+    torch.cuda.synchronize()
+    scale = float(plain.abs().max())
+    assert float((blocked - plain).abs().max()) <= 1e-4 * scale
+    if m <= 60000:
+        ref = oconv.backward(gy.float().cpu(), x.float().cpu(),
+                             torch.zeros(K, cin, cout), km.in_maps.cpu().numpy(),
+                             km.out_maps.cpu().numpy(), km.offsets.numpy())[1]
+        assert oconv.rel_max_err(blocked.view(K, cin, cout), ref) < 1e-4

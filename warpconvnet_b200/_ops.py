@@ -257,8 +257,13 @@ def gather_gemm(feats: Tensor, wimg: Tensor, plan: TilePlan, groups: int, cin_g:
 
 def wgrad(feats: Tensor, gout: Tensor, in_maps: Tensor, out_maps: Tensor, offsets_dev: Tensor,
           K: int, groups: int, cin_g: int, cout_g: int, dw: Optional[Tensor] = None,
-          alpha: float = 1.0, unit_pairs: int = 0, max_ctas: int = 0) -> Tensor:
-    """dW[K, groups, cin_g, cout_g] (fp32) += X[in_maps]^T @ dY[out_maps] per offset."""
+          alpha: float = 1.0, unit_pairs: int = 0, max_ctas: int = 0,
+          row_block_prefix: Optional[Tensor] = None, row_parts: int = 1,
+          rounds: int = 1) -> Tensor:
+    """dW[K, groups, cin_g, cout_g] (fp32) += X[in_maps]^T @ dY[out_maps] per offset.
+
+    ``row_block_prefix`` ([K, n_row_blocks] int32, the scanned block counts of the kernel map)
+    switches on the row-block-major unit order (see wcn_wgrad)."""
     _require_cuda(feats, gout, in_maps, out_maps, offsets_dev)
     assert feats.stride(1) == 1 and gout.stride(1) == 1 and feats.dtype == gout.dtype
     code = dtype_code(feats.dtype)
@@ -267,7 +272,9 @@ def wgrad(feats: Tensor, gout: Tensor, in_maps: Tensor, out_maps: Tensor, offset
     assert dw.dtype == torch.float32 and dw.is_contiguous()
     check(lib.wcn_wgrad(_p(feats), feats.stride(0), _p(gout), gout.stride(0), _p(dw), _p(in_maps),
                         _p(out_maps), _p(offsets_dev), K, groups, cin_g, cout_g, code,
-                        ctypes.c_float(alpha), unit_pairs, max_ctas, _stream()), "wgrad")
+                        ctypes.c_float(alpha), unit_pairs, max_ctas, _p(row_block_prefix),
+                        0 if row_block_prefix is None else row_block_prefix.shape[1],
+                        row_parts, rounds, _stream()), "wgrad")
     return dw
 
 

@@ -316,7 +316,8 @@ int wcn_gather_gemm(const void* feats, int n_in_rows, long long in_ld, const voi
 int wcn_wgrad(const void* feats, long long in_ld, const void* gout, long long out_ld, float* dw,
               const int32_t* in_maps, const int32_t* out_maps, const int32_t* offsets, int K,
               int groups, int cin_g, int cout_g, int dtype, float alpha, int unit_pairs,
-              int max_ctas, void* stream) {
+              int max_ctas, const int32_t* row_block_prefix, int n_row_blocks, int row_parts,
+              int rounds, void* stream) {
   if (!feats || !gout || !dw || !offsets) return kErrInvalidArg;
   if (dtype < 0 || dtype > 2) return kErrUnsupportedDtype;
   if (groups < 1 || cin_g < 1 || cout_g < 1) return kErrInvalidArg;
@@ -335,6 +336,19 @@ int wcn_wgrad(const void* feats, long long in_ld, const void* gout, long long ou
   p.unit_pairs = unit_pairs;
   p.stages = 0;
   p.alpha = alpha;
+  // row-block-major unit order (optional): needs the kernel map's block prefix and a unit table
+  // that fits shared memory; anything else silently keeps the offset-major order
+  p.blk_prefix = nullptr;
+  p.n_row_blocks = 0;
+  p.row_parts = 1;
+  p.rounds = 1;
+  if (row_block_prefix != nullptr && row_parts >= 1 && rounds >= 1 && n_row_blocks >= row_parts &&
+      (long long)row_parts * K <= 1024 && (row_parts > 1 || rounds > 1)) {
+    p.blk_prefix = row_block_prefix;
+    p.n_row_blocks = n_row_blocks;
+    p.row_parts = row_parts;
+    p.rounds = rounds;
+  }
   {
     const char* e = getenv("WCN_DEBUG");
     p.debug = e ? atoi(e) : 0;

@@ -52,6 +52,12 @@ struct WgradParams {
   const int* in_maps;  // [L]
   const int* out_maps; // [L]
   const int* offsets;  // [K+1] device copy of the CSR offsets
+  // optional row-block-major unit order (L2 locality): blk_prefix[k][b] = pairs of offset k whose
+  // output row is < 256*b (the kernel-map block scan, [K][n_row_blocks]); 0 / nullptr = off
+  const int* blk_prefix;
+  int n_row_blocks;
+  int row_parts;       // P: row blocks of the virtual order
+  int rounds;          // R: chunks per CTA (round-robin over the virtual list)
   long long in_ld;
   long long out_ld;
   long long dw_k_stride;  // elements between offsets

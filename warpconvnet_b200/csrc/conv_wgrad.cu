@@ -24,6 +24,8 @@ constexpr int kWgMaxStages = 8;
 constexpr int kWgTmemCols = 512;
 constexpr int kWgAccStride = 256;
 constexpr int kWgMaxK = 65535;
+constexpr int kWgMaxUnits = 1024;  // (row parts) x K units of the row-block-major order
+constexpr int kWgSegTableBytes = (2 * kWgMaxUnits + 2) * 4;
 
 struct WgSmemCtrl {
   uint64_t full[kWgMaxStages];
@@ -34,6 +36,68 @@ struct WgSmemCtrl {
   int pair_begin;  // this CTA's slice of the concatenated pair lists
   int pair_end;
   int k_first;     // offset that contains pair_begin
+};
+
+// Walks this CTA's work segments (offset k, first pair, pair count); every role runs it
+// identically (all state is warp-uniform).
+//  * default order: the CTA owns one contiguous slice of the concatenated (offset-major) pair
+//    lists; a segment is slice ∩ offset.
+//  * row-block-major order (tab != nullptr): the pair lists are re-cut into units (row part p,
+//    offset k) = pairs of offset k whose OUTPUT row lies in part p, laid out p-major as one virtual
+//    list (vstart = prefix sums, ustart = start of each unit in the real lists). The virtual list is
+//    split into G*R equal chunks and CTA b takes chunks b, b+G, b+2G, ...: at any time all CTAs
+//    work inside a window of 1/R of the rows, which sees all K offsets while its X / dY rows are
+//    L2-resident (the offset-major order swept the whole 102 MB working set 27 times: 343 MB of
+//    DRAM reads for 126 MB of algorithmic bytes on C3).
+struct WgSegCursor {
+  const int* offsets;
+  const int* vstart;  // shared memory [U + 1] or nullptr
+  const int* ustart;  // shared memory [U]
+  int K, U, G, R, b;
+  int pair_begin, pair_end, k;  // default order
+  int r, u;                     // row-block-major order
+  long long v0, v1;
+
+  __device__ __forceinline__ bool next(int& k_out, int& first, int& count) {
+    if (vstart == nullptr) {
+      for (; k < K; ++k) {
+        const int ob = __ldg(offsets + k), oe = __ldg(offsets + k + 1);
+        if (ob >= pair_end) return false;
+        first = max(ob, pair_begin);
+        count = min(oe, pair_end) - first;
+        if (count > 0) {
+          k_out = k++;
+          return true;
+        }
+      }
+      return false;
+    }
+    for (;;) {
+      if (r >= R) return false;
+      if (u < 0) {  // open chunk r
+        const long long Lv = vstart[U];
+        const long long j = (long long)b + (long long)r * G;
+        v0 = Lv * j / ((long long)G * R);
+        v1 = Lv * (j + 1) / ((long long)G * R);
+        if (v0 >= v1) { ++r; continue; }
+        int lo = 0, hi = U;  // largest u with vstart[u] <= v0
+        while (hi - lo > 1) {
+          const int mid = (lo + hi) >> 1;
+          if (vstart[mid] <= v0) lo = mid; else hi = mid;
+        }
+        u = lo;
+      }
+      if (u >= U || vstart[u] >= v1) { ++r; u = -1; continue; }
+      const long long s = max(v0, (long long)vstart[u]);
+      const long long e = min(v1, (long long)vstart[u + 1]);
+      const int cu = u++;
+      if (e <= s) continue;
+      k_out = cu % K;
+      first = ustart[cu] + (int)(s - vstart[cu]);
+      count = (int)(e - s);
+      return true;
+    }
+  }
 };
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
@@ -66,6 +130,45 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
   const int stage_bytes = kAStage + ((b_stage + 1023) & ~1023);
   const int stages = p.stages;
   WgSmemCtrl* ctrl = reinterpret_cast<WgSmemCtrl*>(smem_gen + (size_t)stages * stage_bytes);
+  int* seg_vstart = reinterpret_cast<int*>(ctrl + 1);  // [U + 1]
+  int* seg_ustart = seg_vstart + kWgMaxUnits + 1;       // [U]
+  const bool blocked = p.blk_prefix != nullptr;
+  const int n_units = blocked ? p.row_parts * p.K : 0;
+  if (blocked) {
+    // unit (part, k): pairs of offset k with output row in [256*blk(part), 256*blk(part+1))
+    const int nb = p.n_row_blocks, P = p.row_parts;
+    for (int un = tid; un < n_units; un += kWgThreads) {
+      const int part = un / p.K, k = un - part * p.K;
+      const int ob = __ldg(p.offsets + k);
+      const int b0 = (int)((long long)part * nb / P), b1 = (int)((long long)(part + 1) * nb / P);
+      const int lo = ob + (part == 0 ? 0 : __ldg(p.blk_prefix + (size_t)k * nb + b0));
+      const int hi = (part == P - 1) ? __ldg(p.offsets + k + 1)
+                                     : ob + __ldg(p.blk_prefix + (size_t)k * nb + b1);
+      seg_ustart[un] = lo;
+      seg_vstart[un + 1] = hi - lo;  // length; turned into a prefix sum below
+    }
+    __syncthreads();
+    if (warp == 0) {
+      const int per = (n_units + 31) / 32;
+      const int base = lane * per;
+      int sum = 0;
+      for (int i = 0; i < per; ++i)
+        if (base + i < n_units) sum += seg_vstart[base + i + 1];
+      int incl = sum;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+      }
+      int run = incl - sum;
+      for (int i = 0; i < per; ++i)
+        if (base + i < n_units) {
+          run += seg_vstart[base + i + 1];
+          seg_vstart[base + i + 1] = run;
+        }
+      if (lane == 0) seg_vstart[0] = 0;
+    }
+  }
 
   if (tid == 0) {
     for (int s = 0; s < stages; ++s) {
@@ -104,13 +207,15 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
   const int pair_end = ctrl->pair_end;
   const int k_first = ctrl->k_first;
 
-  // unit of offset k: (first pair, number of pairs); count <= 0 when the slice misses offset k.
-  // Every role walks k = k_first, k_first + 1, ... identically and stops at `done`.
-  auto unit_of = [&](int k, int& first, int& count, bool& done) {
-    const int ob = __ldg(p.offsets + k), oe = __ldg(p.offsets + k + 1);
-    done = ob >= pair_end;
-    first = max(ob, pair_begin);
-    count = min(oe, pair_end) - first;
+  auto make_cursor = [&]() {
+    WgSegCursor c;
+    c.offsets = p.offsets;
+    c.vstart = blocked ? seg_vstart : nullptr;
+    c.ustart = seg_ustart;
+    c.K = p.K; c.U = n_units; c.G = gridDim.x; c.R = p.rounds; c.b = blockIdx.x;
+    c.pair_begin = pair_begin; c.pair_end = pair_end; c.k = k_first;
+    c.r = 0; c.u = -1; c.v0 = c.v1 = 0;
+    return c;
   };
 
   if (warp < 4) {
@@ -148,12 +253,9 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
     uint32_t phase = 0;
     long long w_empty = 0, n_stage = 0, t_issue = 0, t_arrive = 0;
     const long long t_start = clock64();
-    for (int k = k_first; k < p.K; ++k) {
-      int first, count;
-      bool done;
-      unit_of(k, first, count, done);
-      if (done) break;
-      if (count <= 0) continue;
+    WgSegCursor seg = make_cursor();
+    int k, first, count;
+    while (seg.next(k, first, count)) {
       const int n_st = (count + kPairs - 1) / kPairs;
       // lane l < kRowsPerWarp holds the input row, lane 16 + ... the output row of pair
       // warp*kRowsPerWarp + l of the stage (kRowsPerWarp = 16: both in one register)
@@ -242,12 +344,9 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
       uint32_t use = 0;
       long long w_full = 0, w_acc = 0;
       const long long t_start = clock64();
-      for (int k = k_first; k < p.K; ++k) {
-        int first, count;
-        bool done;
-        unit_of(k, first, count, done);
-        if (done) break;
-        if (count <= 0) continue;
+      WgSegCursor seg = make_cursor();
+      int k, first, count;
+      while (seg.next(k, first, count)) {
         const uint32_t acc = use & 1u;
         {
           const long long t0 = clock64();
@@ -295,12 +394,9 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
     uint32_t use = 0;
     long long w_accf = 0;
     const long long t_start = clock64();
-    for (int k = k_first; k < p.K; ++k) {
-      int first, count;
-      bool done;
-      unit_of(k, first, count, done);
-      if (done) break;
-      if (count <= 0) continue;
+    WgSegCursor seg = make_cursor();
+    int k, first, count;
+    while (seg.next(k, first, count)) {
       const uint32_t acc = use & 1u;
       {
         const long long t0 = clock64();
@@ -373,11 +469,11 @@ static int launch_wgrad_t(WgradParams p, int cin_slabs, int cout_slabs, int max_
   const int n_blk_b = (p.cout + kBlkElems - 1) / kBlkElems;
   const int stage_bytes = a_stage + 2 * NSEGB * kPairs * 128;
   if (p.stages <= 0) {
-    p.stages = (int)((227 * 1024 - sizeof(WgSmemCtrl) - 1024) / stage_bytes);
+    p.stages = (int)((227 * 1024 - sizeof(WgSmemCtrl) - kWgSegTableBytes - 1024) / stage_bytes);
     if (p.stages > kWgMaxStages) p.stages = kWgMaxStages;
   }
   if (p.stages < 2) return kErrUnsupportedShape;
-  const size_t smem = (size_t)p.stages * stage_bytes + sizeof(WgSmemCtrl) + 1024;
+  const size_t smem = (size_t)p.stages * stage_bytes + sizeof(WgSmemCtrl) + kWgSegTableBytes + 1024;
   static int configured_smem = 0;
   if ((int)smem > configured_smem) {
     if (cudaFuncSetAttribute(wgrad_kernel<T, PAIRS, NSEGB>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -193,6 +193,7 @@ def generate_kernel_map(
         mask_keys = None
     main.wait_event(join)
     result._offsets_dev = offsets_dev
+    result._block_prefix = block_counts  # scanned in place: pairs of offset k with out row < 256*b
     result._pair_table = pair_table
     result._mask_keys = mask_keys
     result._n_in, result._n_out = n_in, n_out
