@@ -233,6 +233,23 @@ int wcn_bn_bwd_apply(const void* dy, long long ld_dy, const void* x, long long l
                      int n, int c, int dtype, const float* gamma, const float* mean_rstd,
                      const double* sums, int training, void* stream);
 
+/* ------------------------------------------------------------------------------------------ */
+/* Depthwise sparse convolution, weight [K][channels] fp32                  */
+/* (replaces nn/functional/sparse_conv_depth.py:227-420, csrc/implicit_fma_kernel.cu,         */
+/*  csrc/implicit_reduction.cu)                                                               */
+/* ------------------------------------------------------------------------------------------ */
+/* out[r][c] = bias[c] + sum_k feats[table[k][r]][c] * weight[kflip ? K-1-k : k][c] for every row
+ * r < n_rows (each row written once, no zero-fill needed); table = int32 [K][n_rows] neighbour
+ * rows, -1 = none (wcn_kernel_map_search / wcn_csr_to_pair_table). dgrad: pass the reverse table
+ * (or the forward table with kflip = 1 for a submanifold map) and the upstream gradient as feats. */
+int wcn_depthwise_conv(const void* feats, long long in_ld, void* out, long long out_ld,
+                       const float* weight, const float* bias, const int32_t* table, int n_rows,
+                       int K, int channels, int dtype, int kflip, int relu, void* stream);
+/* dw[k][c] += sum_r feats[table[k][r]][c] * gout[r][c]; dw fp32 [K][channels], caller zero-fills */
+int wcn_depthwise_wgrad(const void* feats, long long in_ld, const void* gout, long long gout_ld,
+                        float* dw, const int32_t* table, int n_rows, int K, int channels,
+                        int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -118,3 +118,43 @@ def rdiff(a, ref) -> float:
     ref = _t(ref, torch.float64)
     denom = float(ref.abs().mean())
     return float((a - ref).abs().mean()) / (denom if denom > 0 else 1.0)
+
+
+# ------------------------------------------------------------------------------------------------
+# depthwise sparse convolution (weight [K, C]) — restates the reference's explicit path
+# warpconvnet/nn/functional/sparse_conv_depth.py:227-257 (forward), :260-308 (backward).
+# Pinned by tests/golden/dw_*.npz = outputs of the reference's own
+# _explicit_depthwise_forward_logic / _explicit_depthwise_backward_logic (make_golden.py).
+# ------------------------------------------------------------------------------------------------
+def depthwise_forward(x, w, in_maps, out_maps, offsets, n_out: int, dtype=torch.float64):
+    """Y[n_out, C] = sum_k X[in_k] * w[k]."""
+    x = _t(x, dtype)
+    w = _t(w, dtype)
+    im = torch.as_tensor(np.asarray(in_maps)).long()
+    om = torch.as_tensor(np.asarray(out_maps)).long()
+    offs = np.asarray(offsets)
+    y = torch.zeros(n_out, w.shape[-1], dtype=dtype)
+    for k in range(w.shape[0]):
+        s, e = int(offs[k]), int(offs[k + 1])
+        if e > s:
+            y.index_add_(0, om[s:e], x[im[s:e]] * w[k].unsqueeze(0))
+    return y
+
+
+def depthwise_backward(gy, x, w, in_maps, out_maps, offsets, dtype=torch.float64):
+    """(dX[n_in, C], dW[K, C])."""
+    gy = _t(gy, dtype)
+    x = _t(x, dtype)
+    w = _t(w, dtype)
+    im = torch.as_tensor(np.asarray(in_maps)).long()
+    om = torch.as_tensor(np.asarray(out_maps)).long()
+    offs = np.asarray(offsets)
+    dx = torch.zeros_like(x)
+    dw = torch.zeros_like(w)
+    for k in range(w.shape[0]):
+        s, e = int(offs[k]), int(offs[k + 1])
+        if e > s:
+            g = gy[om[s:e]]
+            dx.index_add_(0, im[s:e], g * w[k].unsqueeze(0))
+            dw[k] = (x[im[s:e]] * g).sum(dim=0)
+    return dx, dw

@@ -13,7 +13,8 @@ from oracle import conv as oconv
 from oracle import kernel_map as okm
 from oracle import ref_adapter
 
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
+                if not os.path.basename(p).startswith("dw_"))  # dw_*: depthwise fixtures
 
 
 def test_golden_fixtures_present():

@@ -77,6 +77,10 @@ SIGNATURES = {
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                 c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int,
                                 c_void_p]),
+    "wcn_depthwise_conv": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_void_p,
+                                   c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "wcn_depthwise_wgrad": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_void_p,
+                                    c_int, c_int, c_int, c_int, c_void_p]),
     "wcn_bn_stats": (c_int, [c_void_p, c_longlong, c_int, c_int, c_int, c_void_p, c_void_p]),
     "wcn_bn_finalize": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_float,
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -377,3 +377,37 @@ def bn_bwd_apply(dy: Tensor, x: Optional[Tensor], y: Optional[Tensor], gamma: Te
                                dtype_code(dy.dtype), _p(gamma), _p(mean_rstd), _p(sums),
                                int(training), _stream()), "bn_bwd_apply")
     return dx, dres
+
+
+# ------------------------------------------------------------------------------------------------
+# depthwise sparse convolution (conv_depthwise.cu)
+# ------------------------------------------------------------------------------------------------
+def depthwise_conv(feats: Tensor, weight: Tensor, table: Tensor, bias: Optional[Tensor] = None,
+                   kflip: bool = False, relu: bool = False) -> Tensor:
+    """out[r] = bias + sum_k feats[table[k, r]] * weight[k]; weight fp32 [K, C], table [K, M]."""
+    _require_cuda(feats, weight, table, bias)
+    K, M = table.shape
+    C = weight.shape[1]
+    assert weight.dtype == torch.float32 and weight.is_contiguous() and weight.shape[0] == K
+    assert feats.shape[1] == C and table.dtype == torch.int32 and table.is_contiguous()
+    out = torch.empty((M, C), dtype=feats.dtype, device=feats.device)
+    pf, ldf = _rows(feats)
+    po, ldo = _rows(out)
+    check(lib.wcn_depthwise_conv(pf, ldf, po, ldo, _p(weight), _p(bias), _p(table), M, K, C,
+                                 dtype_code(feats.dtype), int(kflip), int(relu), _stream()),
+          "depthwise_conv")
+    return out
+
+
+def depthwise_wgrad(feats: Tensor, gout: Tensor, table: Tensor) -> Tensor:
+    """fp32 dW[K, C] = sum_r feats[table[k, r]] * gout[r]."""
+    _require_cuda(feats, gout, table)
+    K, M = table.shape
+    C = feats.shape[1]
+    assert gout.shape == (M, C) and gout.dtype == feats.dtype
+    dw = torch.zeros((K, C), dtype=torch.float32, device=feats.device)
+    pf, ldf = _rows(feats)
+    pg, ldg = _rows(gout)
+    check(lib.wcn_depthwise_wgrad(pf, ldf, pg, ldg, _p(dw), _p(table), M, K, C,
+                                  dtype_code(feats.dtype), _stream()), "depthwise_wgrad")
+    return dw

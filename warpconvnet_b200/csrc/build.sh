@@ -6,10 +6,10 @@ NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -diag-suppress 177"
 mkdir -p build
 pids=()
-for f in cuhash conv_fwd conv_wgrad weight_prep knn rownorm capi; do
+for f in cuhash conv_fwd conv_wgrad weight_prep knn rownorm conv_depthwise capi; do
   $NVCC $FLAGS -c $f.cu -o build/$f.o &
   pids+=($!)
 done
 for p in "${pids[@]}"; do wait $p; done
-$NVCC -shared -o libwcn_b200.so build/cuhash.o build/conv_fwd.o build/conv_wgrad.o build/weight_prep.o build/knn.o build/rownorm.o build/capi.o
+$NVCC -shared -o libwcn_b200.so build/cuhash.o build/conv_fwd.o build/conv_wgrad.o build/weight_prep.o build/knn.o build/rownorm.o build/conv_depthwise.o build/capi.o
 echo "built $(pwd)/libwcn_b200.so"

@@ -40,6 +40,11 @@ int launch_weight_image(const WeightPrepParams&, cudaStream_t);
 int rownorm_launch(int which, const RowNormParams&, int dtype, cudaStream_t);
 int bn_finalize(const double*, int, int, const float*, const float*, float, float, float*, float*,
                 float*, float*, float*, cudaStream_t);
+// conv_depthwise.cu
+int depthwise_launch(bool wgrad, const void* x, long long ld_x, const void* dy, long long ld_dy,
+                     void* y, long long ld_y, const float* w, float* dw, const float* bias,
+                     const int* table, int M, int K, int C, int kflip, int relu, int dtype,
+                     cudaStream_t s);
 // conv_fwd.cu / conv_wgrad.cu
 int launch_gather_gemm(const GatherGemmParams&, int dtype, int n_slabs, int max_ctas, cudaStream_t);
 int launch_wgrad(const WgradParams&, int dtype, int y_slabs, int z_slabs, int max_ctas, cudaStream_t);
@@ -459,6 +464,23 @@ int wcn_bn_bwd_apply(const void* dy, long long ld_dy, const void* x, long long l
   p.scale = gamma; p.mean_rstd = mean_rstd; p.sums = const_cast<double*>(sums);
   p.training = training;
   return rownorm_launch(3, p, dtype, S(stream));
+}
+
+/* ---- depthwise sparse convolution (conv_depthwise.cu) ---- */
+int wcn_depthwise_conv(const void* feats, long long in_ld, void* out, long long out_ld,
+                       const float* weight, const float* bias, const int32_t* table, int n_rows,
+                       int K, int channels, int dtype, int kflip, int relu, void* stream) {
+  if (!feats || !out || !weight || !table) return kErrInvalidArg;
+  return depthwise_launch(false, feats, in_ld, nullptr, 0, out, out_ld, weight, nullptr, bias, table,
+                          n_rows, K, channels, kflip, relu, dtype, S(stream));
+}
+
+int wcn_depthwise_wgrad(const void* feats, long long in_ld, const void* gout, long long gout_ld,
+                        float* dw, const int32_t* table, int n_rows, int K, int channels,
+                        int dtype, void* stream) {
+  if (!feats || !gout || !dw || !table) return kErrInvalidArg;
+  return depthwise_launch(true, feats, in_ld, gout, gout_ld, nullptr, 0, nullptr, dw, nullptr, table,
+                          n_rows, K, channels, 0, 0, dtype, S(stream));
 }
 
 }  // extern "C"

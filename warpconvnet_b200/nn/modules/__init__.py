@@ -4,3 +4,5 @@ from .mlp import MLPBlock  # noqa: F401
 from .point_conv import PointConv  # noqa: F401
 from .normalizations import BatchNorm  # noqa: F401
 from .activations import ReLU  # noqa: F401
+from .sparse_conv_depth import (SparseDepthwiseConv2d, SparseDepthwiseConv3d,  # noqa: F401
+                                SpatiallySparseDepthwiseConv)
