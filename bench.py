@@ -424,7 +424,12 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"],
-                     "unit": "TFLOP/s", "frac": achieved / peaks["tflops"], "traffic": None,
+                     "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
+                     # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this workload
+                     # from the committed `ncu --set full` capture (71.4 + 25.0 MB per launch,
+                     # profiles/r1c_launches_ncu_gather_path.md); algorithmic HBM bytes: 111 MB
+                     "traffic": 96.4e6 if args.dist == "S" else None,
+                     "traffic_unit": "bytes per launch (ncu capture C, C3-S)",
                      "kernel": "gather_gemm_kernel<bf16> (forward AB_gather_scatter)",
                      "kernel_ms": gemm_ms, "flops_per_launch": flops, "peak_source": peaks["which"],
                      "frac_of_burst_peak": achieved / float(peaks.get("burst", 0) or 1) if peaks.get("burst") else None,
