@@ -245,6 +245,21 @@ int wcn_bn_bwd_apply(const void* dy, long long ld_dy, const void* x, long long l
 int wcn_depthwise_conv(const void* feats, long long in_ld, void* out, long long out_ld,
                        const float* weight, const float* bias, const int32_t* table, int n_rows,
                        int K, int channels, int dtype, int kflip, int relu, void* stream);
+/* Same result on the mask-sorted tile plan of wcn_build_tiles (the plan the tensor-core kernels
+ * use): only the offsets active in a tile are visited and their neighbour indices are contiguous.
+ * Rows listed in `rows` are written; the preferred entry point when the plan already exists. */
+int wcn_depthwise_conv_plan(const void* feats, long long in_ld, void* out, long long out_ld,
+                            const float* weight, const float* bias, const int32_t* step_nbr,
+                            const int32_t* step_k, const int32_t* rows, const int32_t* tile_nk,
+                            int num_tiles, int tile_rows, int K, int channels, int dtype, int kflip,
+                            int relu, void* stream);
+/* wgrad on the same plan: dw[step_k[i]][c] += sum over tile rows of feats[step_nbr[i][r]][c] *
+ * gout[rows[r]][c]; dw fp32 [K][channels], caller zero-fills */
+int wcn_depthwise_wgrad_plan(const void* feats, long long in_ld, const void* gout,
+                             long long gout_ld, float* dw, const int32_t* step_nbr,
+                             const int32_t* step_k, const int32_t* rows, const int32_t* tile_nk,
+                             int num_tiles, int tile_rows, int K, int channels, int dtype,
+                             void* stream);
 /* dw[k][c] += sum_r feats[table[k][r]][c] * gout[r][c]; dw fp32 [K][channels], caller zero-fills */
 int wcn_depthwise_wgrad(const void* feats, long long in_ld, const void* gout, long long gout_ld,
                         float* dw, const int32_t* table, int n_rows, int K, int channels,

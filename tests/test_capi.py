@@ -72,6 +72,8 @@ def test_argument_errors_without_gpu():
     assert lib.wcn_depthwise_conv(None, 0, None, 0, None, None, None, 8, 27, 64, 0, 0, 0,
                                   None) == -1
     assert lib.wcn_bn_stats(None, 0, 8, 64, 0, None, None) == -1
+    assert lib.wcn_depthwise_conv_plan(None, 0, None, 0, None, None, None, None, None, None, 4, 256,
+                                       27, 64, 0, 0, 0, None) == -1
     n_slabs, gps = ctypes.c_int(0), ctypes.c_int(0)
     nbytes = lib.wcn_weight_image_bytes(27, 1, 64, 128, 0, 0, ctypes.byref(n_slabs),
                                         ctypes.byref(gps))

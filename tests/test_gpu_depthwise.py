@@ -96,3 +96,30 @@ def test_depthwise_rejects_cpu():
         UnifiedSpatiallySparseDepthwiseConvFunction as F)
     with pytest.raises(RuntimeError):
         F.apply(torch.randn(4, 8), torch.randn(27, 8), None, 4, None)
+
+
+@pytest.mark.parametrize("c", [32, 96, 20])
+def test_depthwise_table_and_plan_paths_agree(c):
+    """The dense-table kernel (wcn_depthwise_conv) and the tile-plan kernel
+    (wcn_depthwise_conv_plan) compute the same rows; with kflip both equal the reverse-table dgrad."""
+    from warpconvnet_b200 import _ops
+    from warpconvnet_b200.geometry.coords.search.torch_discrete import generate_kernel_map
+    bc = _bc(random_coords(25000, 0.3, 4))
+    n = len(bc)
+    km = generate_kernel_map(bc, bc, (1, 1, 1), (3, 3, 3), same_coords=True)
+    g = torch.Generator().manual_seed(c)
+    x = torch.randn(n, c, generator=g).bfloat16().cuda()
+    w = (torch.randn(27, c, generator=g) * 0.2).cuda()
+    b = torch.randn(c, generator=g).cuda()
+    table, plan = km.pair_table(n), km.fwd_plan(n)
+    for kflip in (False, True):
+        a = _ops.depthwise_conv(x, w, table, bias=b, kflip=kflip, relu=True)
+        p = _ops.depthwise_conv_plan(x, w, plan, bias=b, kflip=kflip, relu=True)
+        assert float((a.float() - p.float()).abs().max()) <= 2e-2 * float(a.float().abs().max())
+    gy = torch.randn(n, c, generator=g).bfloat16().cuda()
+    dw_t = _ops.depthwise_wgrad(x, gy, table)
+    dw_p = _ops.depthwise_wgrad_plan(x, gy, plan)
+    assert float((dw_t - dw_p).abs().max()) <= 1e-4 * float(dw_t.abs().max())
+    rev = _ops.depthwise_conv(x, w, km.rev_pair_table(n))
+    flip = _ops.depthwise_conv_plan(x, w, plan, kflip=True)
+    assert float((rev.float() - flip.float()).abs().max()) <= 2e-2 * float(rev.float().abs().max())

@@ -39,11 +39,14 @@ for C in (32, 64, 128, 256):
     x = torch.randn(n, C, device="cuda").bfloat16()
     gy = torch.randn(n, C, device="cuda").bfloat16()
     w = torch.randn(27, C, device="cuda") * 0.2
+    plan = km.fwd_plan(n)
+    t_p = timed(lambda: _ops.depthwise_conv_plan(x, w, plan))
     t_f = timed(lambda: _ops.depthwise_conv(x, w, table))
     t_d = timed(lambda: _ops.depthwise_conv(gy, w, table, kflip=True))
     t_w = timed(lambda: _ops.depthwise_wgrad(x, gy, table))
+    t_wp = timed(lambda: _ops.depthwise_wgrad_plan(x, gy, plan))
     gb = L * C * 2
     alg = n * C * 2 * 2 + 27 * n * 4
-    print(f"C={C:4d}: fwd {t_f * 1e6:7.1f} us ({gb / t_f / 1e12:4.2f} TB/s gathered, "
+    print(f"C={C:4d}: plan fwd {t_p * 1e6:7.1f} us ({gb / t_p / 1e12:4.2f} TB/s gathered) | table fwd {t_f * 1e6:7.1f} us ({gb / t_f / 1e12:4.2f} TB/s gathered, "
           f"{alg / t_f / 1e12:4.2f} TB/s algorithmic)  dgrad {t_d * 1e6:7.1f} us  "
-          f"wgrad {t_w * 1e6:7.1f} us ({gb / t_w / 1e12:4.2f} TB/s gathered)")
+          f"wgrad {t_w * 1e6:7.1f} us ({gb / t_w / 1e12:4.2f} TB/s gathered)  plan wgrad {t_wp * 1e6:7.1f} us")

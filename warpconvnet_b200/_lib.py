@@ -79,6 +79,12 @@ SIGNATURES = {
                                 c_void_p]),
     "wcn_depthwise_conv": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_void_p,
                                    c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "wcn_depthwise_conv_plan": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_void_p,
+                                        c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                        c_int, c_int, c_int, c_int, c_void_p]),
+    "wcn_depthwise_wgrad_plan": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p,
+                                         c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                         c_int, c_int, c_void_p]),
     "wcn_depthwise_wgrad": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_void_p,
                                     c_int, c_int, c_int, c_int, c_void_p]),
     "wcn_bn_stats": (c_int, [c_void_p, c_longlong, c_int, c_int, c_int, c_void_p, c_void_p]),

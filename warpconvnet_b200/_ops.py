@@ -399,6 +399,26 @@ def depthwise_conv(feats: Tensor, weight: Tensor, table: Tensor, bias: Optional[
     return out
 
 
+def depthwise_conv_plan(feats: Tensor, weight: Tensor, plan: "TilePlan",
+                        bias: Optional[Tensor] = None, kflip: bool = False,
+                        relu: bool = False) -> Tensor:
+    """depthwise_conv on the mask-sorted tile plan (compact step lists) instead of the dense
+    [K, M] table; every row of the plan is written once."""
+    _require_cuda(feats, weight, bias)
+    K, C = weight.shape
+    assert weight.dtype == torch.float32 and weight.is_contiguous() and K == plan.K
+    assert feats.shape[1] == C
+    out = torch.empty((plan.n_rows, C), dtype=feats.dtype, device=feats.device)
+    pf, ldf = _rows(feats)
+    po, ldo = _rows(out)
+    check(lib.wcn_depthwise_conv_plan(pf, ldf, po, ldo, _p(weight), _p(bias), _p(plan.step_nbr),
+                                      _p(plan.step_k), _p(plan.rows), _p(plan.tile_nk),
+                                      plan.num_tiles, plan.tile_rows, K, C,
+                                      dtype_code(feats.dtype), int(kflip), int(relu), _stream()),
+          "depthwise_conv_plan")
+    return out
+
+
 def depthwise_wgrad(feats: Tensor, gout: Tensor, table: Tensor) -> Tensor:
     """fp32 dW[K, C] = sum_r feats[table[k, r]] * gout[r]."""
     _require_cuda(feats, gout, table)
@@ -410,4 +430,19 @@ def depthwise_wgrad(feats: Tensor, gout: Tensor, table: Tensor) -> Tensor:
     pg, ldg = _rows(gout)
     check(lib.wcn_depthwise_wgrad(pf, ldf, pg, ldg, _p(dw), _p(table), M, K, C,
                                   dtype_code(feats.dtype), _stream()), "depthwise_wgrad")
+    return dw
+
+
+def depthwise_wgrad_plan(feats: Tensor, gout: Tensor, plan: "TilePlan") -> Tensor:
+    """fp32 dW[K, C] on the tile plan (gout rows are indexed through plan.rows)."""
+    _require_cuda(feats, gout)
+    C = feats.shape[1]
+    assert gout.shape[1] == C and gout.dtype == feats.dtype
+    dw = torch.zeros((plan.K, C), dtype=torch.float32, device=feats.device)
+    pf, ldf = _rows(feats)
+    pg, ldg = _rows(gout)
+    check(lib.wcn_depthwise_wgrad_plan(pf, ldf, pg, ldg, _p(dw), _p(plan.step_nbr), _p(plan.step_k),
+                                       _p(plan.rows), _p(plan.tile_nk), plan.num_tiles,
+                                       plan.tile_rows, plan.K, C, dtype_code(feats.dtype),
+                                       _stream()), "depthwise_wgrad_plan")
     return dw

@@ -45,6 +45,14 @@ int depthwise_launch(bool wgrad, const void* x, long long ld_x, const void* dy, 
                      void* y, long long ld_y, const float* w, float* dw, const float* bias,
                      const int* table, int M, int K, int C, int kflip, int relu, int dtype,
                      cudaStream_t s);
+int depthwise_plan_launch(const void* x, long long ld_x, void* y, long long ld_y, const float* w,
+                          const float* bias, const int* step_nbr, const int* step_k,
+                          const int* rows, const int* tile_nk, int num_tiles, int tile_rows, int K,
+                          int C, int kflip, int relu, int dtype, cudaStream_t s);
+int depthwise_plan_wgrad_launch(const void* x, long long ld_x, const void* dy, long long ld_dy,
+                                float* dw, const int* step_nbr, const int* step_k, const int* rows,
+                                const int* tile_nk, int num_tiles, int tile_rows, int K, int C,
+                                int dtype, cudaStream_t s);
 // conv_fwd.cu / conv_wgrad.cu
 int launch_gather_gemm(const GatherGemmParams&, int dtype, int n_slabs, int max_ctas, cudaStream_t);
 int launch_wgrad(const WgradParams&, int dtype, int y_slabs, int z_slabs, int max_ctas, cudaStream_t);
@@ -473,6 +481,27 @@ int wcn_depthwise_conv(const void* feats, long long in_ld, void* out, long long 
   if (!feats || !out || !weight || !table) return kErrInvalidArg;
   return depthwise_launch(false, feats, in_ld, nullptr, 0, out, out_ld, weight, nullptr, bias, table,
                           n_rows, K, channels, kflip, relu, dtype, S(stream));
+}
+
+int wcn_depthwise_conv_plan(const void* feats, long long in_ld, void* out, long long out_ld,
+                            const float* weight, const float* bias, const int32_t* step_nbr,
+                            const int32_t* step_k, const int32_t* rows, const int32_t* tile_nk,
+                            int num_tiles, int tile_rows, int K, int channels, int dtype, int kflip,
+                            int relu, void* stream) {
+  if (!feats || !out || !weight || !step_nbr || !step_k || !rows || !tile_nk) return kErrInvalidArg;
+  return depthwise_plan_launch(feats, in_ld, out, out_ld, weight, bias, step_nbr, step_k, rows,
+                               tile_nk, num_tiles, tile_rows, K, channels, kflip, relu, dtype,
+                               S(stream));
+}
+
+int wcn_depthwise_wgrad_plan(const void* feats, long long in_ld, const void* gout,
+                             long long gout_ld, float* dw, const int32_t* step_nbr,
+                             const int32_t* step_k, const int32_t* rows, const int32_t* tile_nk,
+                             int num_tiles, int tile_rows, int K, int channels, int dtype,
+                             void* stream) {
+  if (!feats || !gout || !dw || !step_nbr || !step_k || !rows || !tile_nk) return kErrInvalidArg;
+  return depthwise_plan_wgrad_launch(feats, in_ld, gout, gout_ld, dw, step_nbr, step_k, rows,
+                                     tile_nk, num_tiles, tile_rows, K, channels, dtype, S(stream));
 }
 
 int wcn_depthwise_wgrad(const void* feats, long long in_ld, const void* gout, long long gout_ld,

@@ -24,6 +24,12 @@ struct DepthwiseParams {
   float* dw;            // wgrad target [K, C] fp32, accumulated into
   const float* bias;    // optional [C]
   const int* table;     // [K, M] neighbour rows (-1 = none)
+  // mask-sorted tile plan (wcn_build_tiles), forward / dgrad only: compact step lists
+  const int* step_nbr;  // [num_tiles][K][tile_rows]
+  const int* step_k;    // [num_tiles][K]
+  const int* rows;      // [num_tiles * tile_rows] output row of each sorted position, -1 = padding
+  const int* tile_nk;   // [num_tiles]
+  int num_tiles, tile_rows;
   long long ld_x, ld_dy, ld_y;
   int M, K, C;
   int kflip;            // weight row K-1-k for table row k
@@ -175,6 +181,80 @@ __global__ void __launch_bounds__(kDwThreads) depthwise_fwd_kernel(const Depthwi
   }
 }
 
+// forward / dgrad on the mask-sorted tile plan the tensor-core kernels use: a tile's rows share one
+// compact list of active offsets (9.2 of 27 on surface data), so the control flow is uniform, no
+// index is loaded for an inactive offset, the step's neighbour indices are contiguous (coalesced)
+// and its weight row is a shared-memory broadcast. One thread = one channel vector of one tile
+// row; work unit = (tile, pass of 256 / vecs rows), grid-stride.
+constexpr int kDwPlanBatch = 5;
+template <typename T, int V>
+__global__ void __launch_bounds__(kDwThreads) depthwise_plan_kernel(const DepthwiseParams p) {
+  extern __shared__ float s_w[];  // [K][C]
+  for (int i = threadIdx.x; i < p.K * p.C; i += kDwThreads) s_w[i] = __ldg(p.w + i);
+  __syncthreads();
+  const int vecs = (p.C + V - 1) / V;
+  const int rpb = kDwThreads / vecs;
+  const int vc = threadIdx.x % vecs, rl = threadIdx.x / vecs;
+  const int passes = (p.tile_rows + rpb - 1) / rpb;
+  const T* x = reinterpret_cast<const T*>(p.x) + vc * V;
+  T* y = reinterpret_cast<T*>(p.y) + vc * V;
+  float bias[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i)
+    bias[i] = (p.bias != nullptr && vc * V + i < p.C) ? __ldg(p.bias + vc * V + i) : 0.f;
+  const long long units = (long long)p.num_tiles * passes;
+  for (long long q = blockIdx.x; q < units; q += gridDim.x) {
+    const int tile = (int)(q / passes);
+    const int row_in_tile = (int)(q - (long long)tile * passes) * rpb + rl;
+    if (rl >= rpb || row_in_tile >= p.tile_rows) continue;
+    const int out_row = __ldg(p.rows + (size_t)tile * p.tile_rows + row_in_tile);
+    if (out_row < 0) continue;
+    const int nk = __ldg(p.tile_nk + tile);
+    const int* nbr = p.step_nbr + (size_t)tile * p.K * p.tile_rows + row_in_tile;
+    const int* sk = p.step_k + (size_t)tile * p.K;
+    float acc[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc[i] = bias[i];
+    for (int i0 = 0; i0 < nk; i0 += kDwPlanBatch) {
+      int idx[kDwPlanBatch], kk[kDwPlanBatch];
+#pragma unroll
+      for (int u = 0; u < kDwPlanBatch; ++u) {
+        const bool live = i0 + u < nk;  // block-uniform
+        idx[u] = live ? __ldg(nbr + (size_t)(i0 + u) * p.tile_rows) : -1;
+        kk[u] = live ? __ldg(sk + i0 + u) : 0;
+      }
+      DwRaw<T, V> raw[kDwPlanBatch];
+#pragma unroll
+      for (int u = 0; u < kDwPlanBatch; ++u)
+        raw[u] = dw_load_raw<T, V>(x + (long long)max(idx[u], 0) * p.ld_x);
+#pragma unroll
+      for (int u = 0; u < kDwPlanBatch; ++u) {
+        if (i0 + u >= nk) break;  // block-uniform
+        const float* wk = s_w + (p.kflip ? p.K - 1 - kk[u] : kk[u]) * p.C + vc * V;
+        float f[V];
+        dw_unpack<T, V>(raw[u], idx[u] >= 0, f);
+        if constexpr (V >= 4) {
+#pragma unroll
+          for (int i = 0; i < V; i += 4) {
+            const float4 w4 = *reinterpret_cast<const float4*>(wk + i);
+            acc[i] = fmaf(f[i], w4.x, acc[i]);
+            acc[i + 1] = fmaf(f[i + 1], w4.y, acc[i + 1]);
+            acc[i + 2] = fmaf(f[i + 2], w4.z, acc[i + 2]);
+            acc[i + 3] = fmaf(f[i + 3], w4.w, acc[i + 3]);
+          }
+        } else {
+          acc[0] = fmaf(f[0], wk[0], acc[0]);
+        }
+      }
+    }
+    if (p.relu) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) acc[i] = fmaxf(acc[i], 0.f);
+    }
+    dw_store<T, V>(y + (long long)out_row * p.ld_y, acc);
+  }
+}
+
 // wgrad: dw[k][c] += sum_r x[table[k][r]][c] * dy[r][c]. blockIdx.y selects a chunk of kDwBatch
 // offsets; a thread owns one channel vector, walks rows with a grid stride and keeps the chunk's
 // kDwBatch x V partial sums in registers (no atomics inside the row loop). Partials are merged per
@@ -232,57 +312,166 @@ __global__ void __launch_bounds__(kDwThreads) depthwise_wgrad_kernel(const Depth
   }
 }
 
+// wgrad on the tile plan: dw[k][c] += sum over the tile rows r of x[nbr_i(r)][c] * dy[row(r)][c] for
+// every step i (offset k = step_k[i]) of every tile. A block walks tiles with a grid stride; a
+// thread owns one channel vector and the tile rows rl, rl + rpb, ...; kDwPlanBatch steps at a time
+// are accumulated in registers over those rows, merged into the block's [K][C] shared-memory
+// accumulator with one atomic per (step, channel, thread) and flushed to dw once per block.
 template <typename T, int V>
-static int dw_launch_tv(bool wgrad, const DepthwiseParams& p, cudaStream_t s) {
+__global__ void __launch_bounds__(kDwThreads) depthwise_plan_wgrad_kernel(const DepthwiseParams p) {
+  extern __shared__ float s_dw[];  // [K][C]
+  for (int i = threadIdx.x; i < p.K * p.C; i += kDwThreads) s_dw[i] = 0.f;
+  __syncthreads();
+  const int vecs = (p.C + V - 1) / V;
+  const int rpb = kDwThreads / vecs;
+  const int vc = threadIdx.x % vecs, rl = threadIdx.x / vecs;
+  if (rl < rpb) {
+    const T* x = reinterpret_cast<const T*>(p.x) + vc * V;
+    const T* dy = reinterpret_cast<const T*>(p.dy) + vc * V;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int nk = __ldg(p.tile_nk + tile);
+      const int* sk = p.step_k + (size_t)tile * p.K;
+      for (int i0 = 0; i0 < nk; i0 += kDwPlanBatch) {
+        float acc[kDwPlanBatch][V];
+#pragma unroll
+        for (int u = 0; u < kDwPlanBatch; ++u)
+#pragma unroll
+          for (int i = 0; i < V; ++i) acc[u][i] = 0.f;
+        for (int row = rl; row < p.tile_rows; row += rpb) {
+          const int out_row = __ldg(p.rows + (size_t)tile * p.tile_rows + row);
+          if (out_row < 0) continue;
+          const int* nbr = p.step_nbr + ((size_t)tile * p.K + i0) * p.tile_rows + row;
+          int idx[kDwPlanBatch];
+#pragma unroll
+          for (int u = 0; u < kDwPlanBatch; ++u)
+            idx[u] = (i0 + u < nk) ? __ldg(nbr + (size_t)u * p.tile_rows) : -1;
+          float g[V];
+          dw_load<T, V>(dy + (long long)out_row * p.ld_dy, g);
+          DwRaw<T, V> raw[kDwPlanBatch];
+#pragma unroll
+          for (int u = 0; u < kDwPlanBatch; ++u)
+            raw[u] = dw_load_raw<T, V>(x + (long long)max(idx[u], 0) * p.ld_x);
+#pragma unroll
+          for (int u = 0; u < kDwPlanBatch; ++u) {
+            float f[V];
+            dw_unpack<T, V>(raw[u], idx[u] >= 0, f);
+#pragma unroll
+            for (int i = 0; i < V; ++i) acc[u][i] = fmaf(f[i], g[i], acc[u][i]);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < kDwPlanBatch; ++u) {
+          if (i0 + u >= nk) break;  // block-uniform
+          float* dst = s_dw + __ldg(sk + i0 + u) * p.C + vc * V;
+#pragma unroll
+          for (int i = 0; i < V; ++i)
+            if (vc * V + i < p.C) atomicAdd(dst + i, acc[u][i]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < p.K * p.C; i += kDwThreads) {
+    const float v = s_dw[i];
+    if (v != 0.f) atomicAdd(p.dw + i, v);
+  }
+}
+
+template <typename T, int V>
+static int dw_launch_tv(int mode, const DepthwiseParams& p, cudaStream_t s) {
+  // mode 0: forward / dgrad on the dense table, 1: wgrad on the table, 2: forward / dgrad on the
+  // tile plan, 3: wgrad on the tile plan
+  const bool wgrad = mode == 1;
   const size_t sh = (size_t)(wgrad ? kDwBatch : p.K) * p.C * sizeof(float);
   const int vecs = (p.C + V - 1) / V;
   const int rpb = kDwThreads / vecs;
-  static int occ[2] = {0, 0};
-  static size_t configured[2] = {0, 0};
-  const int w = wgrad ? 1 : 0;
-  if (sh > 48 * 1024 && sh > configured[w]) {
-    cudaError_t e = wgrad ? cudaFuncSetAttribute(depthwise_wgrad_kernel<T, V>,
-                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh)
-                          : cudaFuncSetAttribute(depthwise_fwd_kernel<T, V>,
-                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
-    if (e != cudaSuccess) return kErrCuda;
-    configured[w] = sh;
-    occ[w] = 0;
+  static int occ[4] = {0, 0, 0, 0};
+  static size_t configured[4] = {0, 0, 0, 0};
+  auto set_attr = [&](int bytes) {
+    switch (mode) {
+      case 0: return cudaFuncSetAttribute(depthwise_fwd_kernel<T, V>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+      case 1: return cudaFuncSetAttribute(depthwise_wgrad_kernel<T, V>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+      case 2: return cudaFuncSetAttribute(depthwise_plan_kernel<T, V>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+      default: return cudaFuncSetAttribute(depthwise_plan_wgrad_kernel<T, V>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    }
+  };
+  auto get_occ = [&](int* o) {
+    switch (mode) {
+      case 0: return cudaOccupancyMaxActiveBlocksPerMultiprocessor(o, depthwise_fwd_kernel<T, V>,
+                                                                   kDwThreads, sh);
+      case 1: return cudaOccupancyMaxActiveBlocksPerMultiprocessor(o, depthwise_wgrad_kernel<T, V>,
+                                                                   kDwThreads, sh);
+      case 2: return cudaOccupancyMaxActiveBlocksPerMultiprocessor(o, depthwise_plan_kernel<T, V>,
+                                                                   kDwThreads, sh);
+      default: return cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+          o, depthwise_plan_wgrad_kernel<T, V>, kDwThreads, sh);
+    }
+  };
+  if (sh > 48 * 1024 && sh > configured[mode]) {
+    if (set_attr((int)sh) != cudaSuccess) return kErrCuda;
+    configured[mode] = sh;
+    occ[mode] = 0;
   }
-  if (occ[w] == 0) {
+  if (occ[mode] == 0) {
     int o = 0;
-    cudaError_t e = wgrad ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-                                &o, depthwise_wgrad_kernel<T, V>, kDwThreads, sh)
-                          : cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-                                &o, depthwise_fwd_kernel<T, V>, kDwThreads, sh);
-    occ[w] = (e == cudaSuccess && o > 0) ? o : 1;
+    occ[mode] = (get_occ(&o) == cudaSuccess && o > 0) ? o : 1;
   }
-  long long blocks = ((long long)p.M + rpb - 1) / rpb;
-  const long long cap = (long long)kNumSMsB200 * occ[w];
-  if (blocks > cap) blocks = cap;
-  if (blocks < 1) blocks = 1;
-  if (wgrad) {
-    // y = offset chunk; the resident wave is shared between the chunks
-    const int chunks = (p.K + kDwBatch - 1) / kDwBatch;
-    long long bx = (cap + chunks - 1) / chunks;
-    if (bx > blocks) bx = blocks;
-    if (bx < 1) bx = 1;
-    depthwise_wgrad_kernel<T, V><<<dim3((unsigned)bx, (unsigned)chunks), kDwThreads, sh, s>>>(p);
+  const long long cap = (long long)kNumSMsB200 * occ[mode];
+  if (mode == 3) {
+    long long blocks = p.num_tiles < cap ? p.num_tiles : cap;
+    if (blocks < 1) blocks = 1;
+    depthwise_plan_wgrad_kernel<T, V><<<(int)blocks, kDwThreads, sh, s>>>(p);
+  } else if (mode == 2) {
+    const long long units = (long long)p.num_tiles * ((p.tile_rows + rpb - 1) / rpb);
+    long long blocks = units < cap ? units : cap;
+    if (blocks < 1) blocks = 1;
+    depthwise_plan_kernel<T, V><<<(int)blocks, kDwThreads, sh, s>>>(p);
+  } else {
+    long long blocks = ((long long)p.M + rpb - 1) / rpb;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    if (wgrad) {
+      // y = offset chunk; the resident wave is shared between the chunks
+      const int chunks = (p.K + kDwBatch - 1) / kDwBatch;
+      long long bx = (cap + chunks - 1) / chunks;
+      if (bx > blocks) bx = blocks;
+      if (bx < 1) bx = 1;
+      depthwise_wgrad_kernel<T, V><<<dim3((unsigned)bx, (unsigned)chunks), kDwThreads, sh, s>>>(p);
+    } else {
+      depthwise_fwd_kernel<T, V><<<(int)blocks, kDwThreads, sh, s>>>(p);
+    }
   }
-  else
-    depthwise_fwd_kernel<T, V><<<(int)blocks, kDwThreads, sh, s>>>(p);
   count_launch();
   return cudaGetLastError() == cudaSuccess ? kOk : kErrCuda;
 }
 
 template <typename T>
-static int dw_launch_t(bool wgrad, const DepthwiseParams& p, bool vec, cudaStream_t s) {
+static int dw_launch_t(int mode, const DepthwiseParams& p, bool vec, cudaStream_t s) {
   constexpr int V = 16 / (int)sizeof(T);
-  return vec ? dw_launch_tv<T, V>(wgrad, p, s) : dw_launch_tv<T, 1>(wgrad, p, s);
+  return vec ? dw_launch_tv<T, V>(mode, p, s) : dw_launch_tv<T, 1>(mode, p, s);
 }
 
 static bool dw_aligned(const void* ptr, long long ld, int es) {
   return ptr == nullptr || ((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (ld * es) % 16 == 0);
+}
+
+static int dw_dispatch(int mode, DepthwiseParams& p, int dtype, cudaStream_t s) {
+  if ((size_t)p.K * p.C * sizeof(float) > 200 * 1024) return kErrUnsupportedShape;
+  const int es = dtype_size(dtype);
+  const int v = 16 / es;
+  const bool vec = (p.C % v == 0) && p.C / v <= kDwThreads && dw_aligned(p.x, p.ld_x, es) &&
+                   dw_aligned(p.dy, p.ld_dy, es) && dw_aligned(p.y, p.ld_y, es);
+  if (!vec && p.C > kDwThreads) return kErrUnsupportedShape;
+  switch (dtype) {
+    case kBF16: return dw_launch_t<__nv_bfloat16>(mode, p, vec, s);
+    case kF16: return dw_launch_t<__half>(mode, p, vec, s);
+    case kF32: return dw_launch_t<float>(mode, p, vec, s);
+    default: return kErrUnsupportedDtype;
+  }
 }
 
 int depthwise_launch(bool wgrad, const void* x, long long ld_x, const void* dy, long long ld_dy,
@@ -290,23 +479,45 @@ int depthwise_launch(bool wgrad, const void* x, long long ld_x, const void* dy, 
                      const int* table, int M, int K, int C, int kflip, int relu, int dtype,
                      cudaStream_t s) {
   if (M < 0 || K < 1 || C < 1) return kErrInvalidArg;
-  if ((size_t)K * C * sizeof(float) > 200 * 1024) return kErrUnsupportedShape;
   if (M == 0) return kOk;
   DepthwiseParams p{};
   p.x = x; p.dy = dy; p.y = y; p.w = w; p.dw = dw; p.bias = bias; p.table = table;
   p.ld_x = ld_x; p.ld_dy = ld_dy; p.ld_y = ld_y;
   p.M = M; p.K = K; p.C = C; p.kflip = kflip; p.relu = relu;
-  const int es = dtype_size(dtype);
-  const int v = 16 / es;
-  const bool vec = (C % v == 0) && C / v <= kDwThreads && dw_aligned(x, ld_x, es) &&
-                   dw_aligned(dy, ld_dy, es) && dw_aligned(y, ld_y, es);
-  if (!vec && C > kDwThreads) return kErrUnsupportedShape;
-  switch (dtype) {
-    case kBF16: return dw_launch_t<__nv_bfloat16>(wgrad, p, vec, s);
-    case kF16: return dw_launch_t<__half>(wgrad, p, vec, s);
-    case kF32: return dw_launch_t<float>(wgrad, p, vec, s);
-    default: return kErrUnsupportedDtype;
-  }
+  return dw_dispatch(wgrad ? 1 : 0, p, dtype, s);
+}
+
+static int depthwise_plan_any(const void* x, long long ld_x, void* y, long long ld_y, const float* w,
+                              const float* bias, const int* step_nbr, const int* step_k,
+                              const int* rows, const int* tile_nk, int num_tiles, int tile_rows,
+                              int K, int C, int kflip, int relu, int dtype, cudaStream_t s,
+                              const void* dy, long long ld_dy, float* dw) {
+  if (num_tiles < 0 || K < 1 || C < 1 || tile_rows < 1) return kErrInvalidArg;
+  if (num_tiles == 0) return kOk;
+  DepthwiseParams p{};
+  p.x = x; p.y = y; p.w = w; p.bias = bias; p.dy = dy; p.ld_dy = ld_dy; p.dw = dw;
+  p.step_nbr = step_nbr; p.step_k = step_k; p.rows = rows; p.tile_nk = tile_nk;
+  p.num_tiles = num_tiles; p.tile_rows = tile_rows;
+  p.ld_x = ld_x; p.ld_y = ld_y;
+  p.K = K; p.C = C; p.kflip = kflip; p.relu = relu;
+  return dw_dispatch(dw != nullptr ? 3 : 2, p, dtype, s);
+}
+
+int depthwise_plan_launch(const void* x, long long ld_x, void* y, long long ld_y, const float* w,
+                          const float* bias, const int* step_nbr, const int* step_k,
+                          const int* rows, const int* tile_nk, int num_tiles, int tile_rows, int K,
+                          int C, int kflip, int relu, int dtype, cudaStream_t s) {
+  return depthwise_plan_any(x, ld_x, y, ld_y, w, bias, step_nbr, step_k, rows, tile_nk, num_tiles,
+                            tile_rows, K, C, kflip, relu, dtype, s, nullptr, 0, nullptr);
+}
+
+int depthwise_plan_wgrad_launch(const void* x, long long ld_x, const void* dy, long long ld_dy,
+                                float* dw, const int* step_nbr, const int* step_k, const int* rows,
+                                const int* tile_nk, int num_tiles, int tile_rows, int K, int C,
+                                int dtype, cudaStream_t s) {
+  if (dw == nullptr || dy == nullptr) return kErrInvalidArg;
+  return depthwise_plan_any(x, ld_x, nullptr, 0, nullptr, nullptr, step_nbr, step_k, rows, tile_nk,
+                            num_tiles, tile_rows, K, C, 0, 0, dtype, s, dy, ld_dy, dw);
 }
 
 }  // namespace wcn

@@ -34,8 +34,8 @@ class UnifiedSpatiallySparseDepthwiseConvFunction(Function):
         x = in_features if compute_dtype is None else in_features.to(compute_dtype)
         x = x if x.stride(1) == 1 else x.contiguous()
         w32 = weight.detach().float().contiguous()
-        table = kernel_map.pair_table(num_out_coords)
-        y = _ops.depthwise_conv(x, w32, table)
+        # the mask-sorted tile plan is shared with the dense convs of the same resolution
+        y = _ops.depthwise_conv_plan(x, w32, kernel_map.fwd_plan(num_out_coords))
         ctx.kernel_map = kernel_map
         ctx.num_in = in_features.shape[0]
         ctx.in_dtype = in_features.dtype
@@ -51,14 +51,20 @@ class UnifiedSpatiallySparseDepthwiseConvFunction(Function):
         gy = gy if gy.stride(1) == 1 else gy.contiguous()
         dx = dw = None
         if ctx.needs_input_grad[0]:
-            if getattr(km, "_symmetric", False):
-                # submanifold map: the reverse table is the forward table with the offset flipped
-                dx = _ops.depthwise_conv(gy, w32, km.pair_table(gy.shape[0]), kflip=True)
-            else:
-                dx = _ops.depthwise_conv(gy, w32, km.rev_pair_table(ctx.num_in))
+            # (plan, kflip): for a submanifold map the reverse plan is the forward plan with the
+            # offset index flipped
+            plan, kflip = km.bwd_plan(ctx.num_in)
+            dx = _ops.depthwise_conv_plan(gy, w32, plan, kflip=kflip)
             dx = dx.to(ctx.in_dtype)
         if ctx.needs_input_grad[1]:
-            dw = _ops.depthwise_wgrad(x, gy, km.pair_table(gy.shape[0])).to(ctx.w_dtype)
+            # tile-plan walk from 64 channels up (206 vs 337 us at 128 channels on C3-S); below,
+            # a thread sees too few rows per tile to amortise its shared-memory merge (184 vs 161 us
+            # at 32 channels) and the dense-table kernel is used
+            if x.shape[1] >= 64:
+                dw = _ops.depthwise_wgrad_plan(x, gy, km.fwd_plan(gy.shape[0]))
+            else:
+                dw = _ops.depthwise_wgrad(x, gy, km.pair_table(gy.shape[0]))
+            dw = dw.to(ctx.w_dtype)
         return dx, dw, None, None, None
 
 
