@@ -603,6 +603,18 @@ size_t sort_workspace_bytes(int M) {
   return align_up((size_t)M * 8, 256) + align_up((size_t)M * 4, 256) + align_up(temp, 256) + 256;
 }
 
+// K <= 32: the offset masks fit 32 bits; sorting (u32 key, row) pairs moves 8 instead of 12 bytes
+// per element and pass. Fused with the row iota.
+__global__ void narrow_keys_iota_kernel(const unsigned long long* __restrict__ keys,
+                                        unsigned* __restrict__ keys32, int* __restrict__ rows,
+                                        int M) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < M) {
+    keys32[i] = (unsigned)keys[i];
+    rows[i] = i;
+  }
+}
+
 int sort_rows_by_key(const unsigned long long* keys, int M, int K, int* rows_out, void* workspace,
                      size_t ws_bytes, cudaStream_t s) {
   if (M == 0) return kOk;
@@ -612,6 +624,17 @@ int sort_rows_by_key(const unsigned long long* keys, int M, int K, int* rows_out
   int* rows_in = reinterpret_cast<int*>(ws + align_up((size_t)M * 8, 256));
   void* temp = ws + align_up((size_t)M * 8, 256) + align_up((size_t)M * 4, 256);
   size_t temp_bytes = ws_bytes - (align_up((size_t)M * 8, 256) + align_up((size_t)M * 4, 256));
+  if (K <= 32) {
+    unsigned* k32_in = reinterpret_cast<unsigned*>(ws);            // the u64 key_out region holds
+    unsigned* k32_out = k32_in + align_up((size_t)M, 32);          // both u32 key buffers
+    if (align_up((size_t)M, 32) * 8 <= align_up((size_t)M * 8, 256)) {
+      narrow_keys_iota_kernel<<<(M + 255) / 256, 256, 0, s>>>(keys, k32_in, rows_in, M);
+      count_launch();
+      cudaError_t e32 = cub::DeviceRadixSort::SortPairs(temp, temp_bytes, k32_in, k32_out, rows_in,
+                                                        rows_out, M, 0, K, s);
+      return e32 == cudaSuccess ? cuda_ok() : kErrCuda;
+    }
+  }
   iota_kernel<<<(M + 255) / 256, 256, 0, s>>>(rows_in, M);
   count_launch();
   const int end_bit = K < 64 ? K : 64;
