@@ -149,6 +149,22 @@ int wcn_knn_search(const float* ref, int n_ref, const int32_t* ref_offsets, cons
                    long long* out_idx, float* out_dist, void* workspace, size_t workspace_bytes,
                    void* stream);
 
+/* Radius search on the same grid (replaces geometry/coords/search/radius.py:16-291,
+ * csrc/radius_search_kernels.cu:17-133). Two passes sharing one workspace of
+ * wcn_knn_workspace_bytes(n_ref, n_batches) bytes that must stay untouched in between:
+ *   wcn_radius_count builds the grid and writes counts[q] = reference points of q's batch item
+ *     within `radius` (Euclidean, <=) of query q;
+ *   the caller turns counts into int64 row_splits[n_query + 1] (exclusive scan) and allocates
+ *     out_idx / out_dist with row_splits[n_query] entries;
+ *   wcn_radius_fill writes the CSR lists: GLOBAL reference rows (order inside a row
+ *     unspecified, as in the reference) and, optionally, their distances. */
+int wcn_radius_count(const float* ref, int n_ref, const int32_t* ref_offsets, const float* query,
+                     int n_query, const int32_t* query_offsets, int n_batches, float radius,
+                     int32_t* counts, void* workspace, size_t workspace_bytes, void* stream);
+int wcn_radius_fill(int n_ref, const float* query, int n_query, const int32_t* query_offsets,
+                    int n_batches, float radius, const long long* row_splits, int32_t* out_idx,
+                    float* out_dist, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------ */
 /* Weight image for the gather-GEMM kernel                                                    */
 /* (replaces weight.transpose(1,2).contiguous(), detail/unified.py:654-671)                   */

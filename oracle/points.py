@@ -60,3 +60,29 @@ def point_conv_forward(in_feats, query_feats, in_coords, query_coords, neighbor_
         else:
             raise ValueError(r)
     return out_mlp(torch.cat(outs, dim=-1))
+
+
+def radius(ref: np.ndarray, ref_offsets, query: np.ndarray, query_offsets, r: float):
+    """Brute-force radius search per batch item in float64 — what the reference's
+    ``batched_radius_search`` computes (geometry/coords/search/radius.py:127-158,228-291:
+    ``cdist`` then ``dists <= radius``). Returns (indices int64 [Q] of global reference rows,
+    ascending inside every row; distances float64 [Q]; row_splits int64 [M + 1]).
+    Pinned by tests/golden/radius_*.npz (outputs of the reference's own ``radius_search``)."""
+    ref = np.asarray(ref, np.float64)
+    query = np.asarray(query, np.float64)
+    idx_parts, d_parts, counts = [], [], []
+    for b in range(len(ref_offsets) - 1):
+        rs, re = int(ref_offsets[b]), int(ref_offsets[b + 1])
+        qs, qe = int(query_offsets[b]), int(query_offsets[b + 1])
+        rr, q = ref[rs:re], query[qs:qe]
+        d = np.sqrt(((q[:, None, :] - rr[None, :, :]) ** 2).sum(-1)) if qe > qs and re > rs \
+            else np.zeros((qe - qs, re - rs))
+        for i in range(qe - qs):
+            nz = np.nonzero(d[i] <= r)[0]
+            idx_parts.append(nz + rs)
+            d_parts.append(d[i, nz])
+            counts.append(len(nz))
+    splits = np.zeros(len(counts) + 1, np.int64)
+    np.cumsum(counts, out=splits[1:])
+    cat = (lambda parts, dt: np.concatenate(parts).astype(dt) if parts else np.zeros(0, dt))
+    return cat(idx_parts, np.int64), cat(d_parts, np.float64), splits

@@ -114,3 +114,76 @@ def test_point_conv_provided_queries_bf16():
         out = conv(pc, qc)
     assert out.feature_tensor.shape == (900, 64)
     assert torch.isfinite(out.feature_tensor.float()).all()
+
+
+def _sorted_rows(idx, dist, splits):
+    idx, splits = np.asarray(idx), np.asarray(splits)
+    dist = np.asarray(dist)
+    out_i, out_d = idx.copy(), dist.copy()
+    for q in range(len(splits) - 1):
+        s, e = splits[q], splits[q + 1]
+        order = np.argsort(idx[s:e], kind="stable")
+        out_i[s:e], out_d[s:e] = idx[s:e][order], dist[s:e][order]
+    return out_i, out_d
+
+
+@pytest.mark.parametrize("name", ["radius_b2", "radius_b1_self"])
+def test_radius_search_vs_reference_golden(name):
+    import os
+    from warpconvnet_b200.geometry.coords.search.radius import batched_radius_search
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", name + ".npz"))
+    idx, dist, splits = batched_radius_search(
+        torch.from_numpy(d["ref"]).cuda(), torch.from_numpy(d["ref_offsets"]),
+        torch.from_numpy(d["query"]).cuda(), torch.from_numpy(d["query_offsets"]),
+        float(d["radius"]))
+    assert idx.dtype == torch.int64 and splits.dtype == torch.int64
+    assert np.array_equal(splits.cpu().numpy(), d["splits"])
+    gi, gd = _sorted_rows(d["idx"], d["dist"], d["splits"])
+    oi, od = _sorted_rows(idx.cpu().numpy(), dist.cpu().numpy(), d["splits"])
+    assert np.array_equal(oi, gi)
+    assert np.allclose(od, gd, atol=1e-3)   # fp32 matmul-cdist error of the reference (up to 7e-4 at d = 0)
+
+
+@pytest.mark.parametrize("sizes,qsizes,r", [((6000, 4000), (2500, 1500), 0.05),
+                                             ((5000,), (200,), 0.5), ((300, 1, 800), (50, 7, 60), 0.2)])
+def test_radius_search_vs_oracle(sizes, qsizes, r):
+    from oracle import points as opts
+    from warpconvnet_b200.geometry.coords.search.radius import batched_radius_search
+    g = torch.Generator().manual_seed(len(sizes) * 7 + 1)
+    ref = torch.rand(sum(sizes), 3, generator=g)
+    query = torch.rand(sum(qsizes), 3, generator=g) * 1.2 - 0.1   # some queries outside the bbox
+    ro = np.concatenate([[0], np.cumsum(sizes)])
+    qo = np.concatenate([[0], np.cumsum(qsizes)])
+    idx, dist, splits = batched_radius_search(ref.cuda(), torch.from_numpy(ro), query.cuda(),
+                                              torch.from_numpy(qo), r)
+    # the oracle works in float64 on the float32 inputs; pairs whose distance is within 1e-6 of
+    # the radius may legitimately differ, so compare through a tolerance band
+    oi, od, osplit = opts.radius(ref.numpy(), ro, query.numpy(), qo, r)
+    lo_i, _, lo_s = opts.radius(ref.numpy(), ro, query.numpy(), qo, r - 1e-5)
+    hi_i, _, hi_s = opts.radius(ref.numpy(), ro, query.numpy(), qo, r + 1e-5)
+    gi = idx.cpu().numpy()
+    gs = splits.cpu().numpy()
+    assert len(gs) == len(osplit)
+    for q in range(len(gs) - 1):
+        got = set(gi[gs[q]:gs[q + 1]].tolist())
+        assert set(lo_i[lo_s[q]:lo_s[q + 1]].tolist()) <= got <= set(hi_i[hi_s[q]:hi_s[q + 1]].tolist())
+        assert len(got) == gs[q + 1] - gs[q]            # no duplicates
+    gd = dist.cpu().numpy()
+    dd = np.linalg.norm(ref.numpy()[gi].astype(np.float64)
+                        - np.repeat(query.numpy().astype(np.float64), np.diff(gs), axis=0), axis=1)
+    assert np.allclose(gd, dd, atol=1e-5)
+
+
+def test_point_conv_radius_mode_runs():
+    from warpconvnet_b200.geometry.coords.search.search_configs import RealSearchConfig
+    from warpconvnet_b200.geometry.types.points import Points
+    from warpconvnet_b200.nn.modules.point_conv import PointConv
+    torch.manual_seed(0)
+    coords = [torch.rand(2000, 3), torch.rand(1500, 3)]
+    feats = [torch.randn(2000, 16), torch.randn(1500, 16)]
+    pc = Points(coords, feats, device="cuda")
+    conv = PointConv(16, 32, neighbor_search_args=RealSearchConfig("radius", radius=0.1)).cuda()
+    out = conv(pc)
+    assert out.feature_tensor.shape == (3500, 32)
+    out.feature_tensor.sum().backward()
+    assert all(p.grad is not None for p in conv.parameters())

@@ -14,7 +14,7 @@ from oracle import kernel_map as okm
 from oracle import ref_adapter
 
 GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
-                if not os.path.basename(p).startswith("dw_"))  # dw_*: depthwise fixtures
+                if os.path.basename(p).startswith(("c1_", "toy_")))  # dw_* / radius_*: other rows
 
 
 def test_golden_fixtures_present():

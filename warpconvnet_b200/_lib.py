@@ -69,6 +69,10 @@ SIGNATURES = {
     "wcn_knn_workspace_bytes": (c_size_t, [c_int, c_int]),
     "wcn_knn_search": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int,
                                c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "wcn_radius_count": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_float,
+                                 c_void_p, c_void_p, c_size_t, c_void_p]),
+    "wcn_radius_fill": (c_int, [c_int, c_void_p, c_int, c_void_p, c_int, c_float, c_void_p, c_void_p,
+                                c_void_p, c_void_p, c_size_t, c_void_p]),
     "wcn_weight_image_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_int),
                                           POINTER(c_int)]),
     "wcn_weight_image": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,

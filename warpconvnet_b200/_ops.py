@@ -302,6 +302,37 @@ def knn_search(ref: Tensor, ref_offsets: Tensor, query: Tensor, query_offsets: T
     return (out, dist) if return_distances else out
 
 
+def radius_search(ref: Tensor, ref_offsets: Tensor, query: Tensor, query_offsets: Tensor,
+                  radius: float, return_distances: bool = True):
+    """CSR neighbour lists of all reference points within ``radius`` of every query (same batch
+    item): (int32 indices [Q] of GLOBAL reference rows, float32 distances [Q] | None, int64
+    row_splits [M + 1]). One host sync (the total count sizes the outputs), like the reference."""
+    _require_cuda(ref, query)
+    assert ref.dtype == torch.float32 and query.dtype == torch.float32
+    ref = ref.contiguous()
+    query = query.contiguous()
+    nb = ref_offsets.numel() - 1
+    m = query.shape[0]
+    ro = ref_offsets.to(device=ref.device, dtype=torch.int32)
+    qo = query_offsets.to(device=ref.device, dtype=torch.int32)
+    ws_bytes = lib.wcn_knn_workspace_bytes(ref.shape[0], nb)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=ref.device)
+    counts = torch.empty(m, dtype=torch.int32, device=ref.device)
+    check(lib.wcn_radius_count(_p(ref), ref.shape[0], _p(ro), _p(query), m, _p(qo), nb,
+                               ctypes.c_float(radius), _p(counts), _p(ws), ws_bytes, _stream()),
+          "radius_count")
+    splits = torch.zeros(m + 1, dtype=torch.int64, device=ref.device)
+    torch.cumsum(counts, dim=0, out=splits[1:])
+    total = int(splits[-1].item()) if m > 0 else 0
+    idx = torch.empty(total, dtype=torch.int32, device=ref.device)
+    dist = torch.empty(total, dtype=torch.float32, device=ref.device) if return_distances else None
+    if total > 0:
+        check(lib.wcn_radius_fill(ref.shape[0], _p(query), m, _p(qo), nb, ctypes.c_float(radius),
+                                  _p(splits), _p(idx), _p(dist), _p(ws), ws_bytes, _stream()),
+              "radius_fill")
+    return idx, dist, splits
+
+
 # ------------------------------------------------------------------------------------------------
 # per-channel normalisation / activation passes over the feature matrix (rownorm.cu)
 # ------------------------------------------------------------------------------------------------

@@ -34,6 +34,10 @@ size_t knn_workspace_bytes(int, int, int);
 int knn_dims_for(int, int);
 int knn_search(const float*, int, const int*, const float*, int, const int*, int, int, long long*,
                float*, void*, size_t, cudaStream_t);
+int radius_count(const float*, int, const int*, const float*, int, const int*, int, float, int*,
+                 void*, size_t, cudaStream_t);
+int radius_fill(int, const float*, int, const int*, int, float, const long long*, int*, float*,
+                void*, size_t, cudaStream_t);
 // weight_prep.cu
 int launch_weight_image(const WeightPrepParams&, cudaStream_t);
 // rownorm.cu
@@ -472,6 +476,26 @@ int wcn_bn_bwd_apply(const void* dy, long long ld_dy, const void* x, long long l
   p.scale = gamma; p.mean_rstd = mean_rstd; p.sums = const_cast<double*>(sums);
   p.training = training;
   return rownorm_launch(3, p, dtype, S(stream));
+}
+
+/* ---- radius search (knn.cu) ---- */
+int wcn_radius_count(const float* ref, int n_ref, const int32_t* ref_offsets, const float* query,
+                     int n_query, const int32_t* query_offsets, int n_batches, float radius,
+                     int32_t* counts, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!ref_offsets || !query_offsets || !workspace || (n_query > 0 && (!query || !counts)) ||
+      (n_ref > 0 && !ref))
+    return kErrInvalidArg;
+  return radius_count(ref, n_ref, ref_offsets, query, n_query, query_offsets, n_batches, radius,
+                      counts, workspace, workspace_bytes, S(stream));
+}
+
+int wcn_radius_fill(int n_ref, const float* query, int n_query, const int32_t* query_offsets,
+                    int n_batches, float radius, const long long* row_splits, int32_t* out_idx,
+                    float* out_dist, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!query_offsets || !workspace || (n_query > 0 && (!query || !row_splits || !out_idx)))
+    return kErrInvalidArg;
+  return radius_fill(n_ref, query, n_query, query_offsets, n_batches, radius, row_splits, out_idx,
+                     out_dist, workspace, workspace_bytes, S(stream));
 }
 
 /* ---- depthwise sparse convolution (conv_depthwise.cu) ---- */

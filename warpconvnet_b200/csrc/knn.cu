@@ -189,6 +189,60 @@ knn_query_kernel(const float* __restrict__ q, int m, const int* __restrict__ q_o
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Radius search on the same grid (replaces warpconvnet/geometry/coords/search/radius.py:16-291 and
+// csrc/radius_search_kernels.cu:17-133): pass 1 counts the reference points within `radius` of
+// every query (same batch item), the caller scans the counts into row splits, pass 2 writes the
+// CSR lists. FILL = false: count only.
+// ---------------------------------------------------------------------------------------------
+template <bool FILL>
+__global__ void __launch_bounds__(128)
+radius_query_kernel(const float* __restrict__ q, int m, const int* __restrict__ q_offsets, int nb,
+                    const KnnGrid* __restrict__ gp, const int* __restrict__ cell_start,
+                    const float4* __restrict__ recs, float radius, int* __restrict__ counts,
+                    const long long* __restrict__ row_splits, int* __restrict__ out_idx,
+                    float* __restrict__ out_dist) {
+  const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (qi >= m) return;
+  const KnnGrid g = *gp;
+  const float x = __ldg(q + 3 * (size_t)qi), y = __ldg(q + 3 * (size_t)qi + 1),
+              z = __ldg(q + 3 * (size_t)qi + 2);
+  const int b = batch_of(q_offsets, nb, qi);
+  const int D = g.dims;
+  // cell range that can hold a point within `radius` (clamped to the grid; queries outside the
+  // reference bounding box are handled by the clamp, the distance test decides)
+  int lo[3], hi[3];
+  const float p3[3] = {x, y, z};
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    lo[a] = min(max((int)floorf((p3[a] - radius - g.origin[a]) * g.inv_cs[a]), 0), D - 1);
+    hi[a] = min(max((int)floorf((p3[a] + radius - g.origin[a]) * g.inv_cs[a]), 0), D - 1);
+  }
+  const float r2 = radius * radius;
+  int n = 0;
+  long long w = FILL ? row_splits[qi] : 0;
+  for (int ux = lo[0]; ux <= hi[0]; ++ux)
+    for (int uy = lo[1]; uy <= hi[1]; ++uy) {
+      // cells (ux, uy, lo..hi) are consecutive in memory: one contiguous record range
+      const int c0 = ((b * D + ux) * D + uy) * D + lo[2];
+      const int s = __ldg(cell_start + c0), e = __ldg(cell_start + c0 + (hi[2] - lo[2]) + 1);
+      for (int pidx = s; pidx < e; ++pidx) {
+        const float4 rec = __ldg(recs + pidx);
+        const float ddx = rec.x - x, ddy = rec.y - y, ddz = rec.z - z;
+        const float d2 = ddx * ddx + ddy * ddy + ddz * ddz;
+        if (d2 <= r2) {
+          if (FILL) {
+            out_idx[w] = __float_as_int(rec.w);
+            if (out_dist != nullptr) out_dist[w] = sqrtf(d2);
+            ++w;
+          }
+          ++n;
+        }
+      }
+    }
+  if (!FILL) counts[qi] = n;
+}
+
 static inline int cuda_ok2() { return cudaGetLastError() == cudaSuccess ? kOk : kErrCuda; }
 
 size_t knn_workspace_bytes(int n_ref, int n_batches, int dims) {
@@ -210,6 +264,103 @@ int knn_dims_for(int n_ref, int n_batches) {
   return d;
 }
 
+struct KnnWorkspace {
+  int* bbox;
+  KnnGrid* grid;
+  int* counts;
+  int* start;
+  int* cursor;
+  int* cell_id;
+  float4* recs;
+  void* scan_tmp;
+  size_t scan_bytes;
+};
+
+static KnnWorkspace knn_carve(void* workspace, size_t ws_bytes, int n_ref, int n_batches, int dims) {
+  const size_t cells = (size_t)n_batches * dims * dims * dims;
+  auto al = [](size_t v) { return (v + 255) / 256 * 256; };
+  uint8_t* w = reinterpret_cast<uint8_t*>(workspace);
+  KnnWorkspace k;
+  k.bbox = reinterpret_cast<int*>(w);
+  k.grid = reinterpret_cast<KnnGrid*>(w + 64);
+  w += al(256);
+  k.counts = reinterpret_cast<int*>(w); w += al((cells + 1) * 4);
+  k.start = reinterpret_cast<int*>(w); w += al((cells + 1) * 4);
+  k.cursor = reinterpret_cast<int*>(w); w += al((cells + 1) * 4);
+  k.cell_id = reinterpret_cast<int*>(w); w += al((size_t)n_ref * 4);
+  k.recs = reinterpret_cast<float4*>(w); w += al((size_t)n_ref * 16);
+  k.scan_tmp = w;
+  k.scan_bytes = ws_bytes - (size_t)(w - reinterpret_cast<uint8_t*>(workspace));
+  return k;
+}
+
+// counting-sorts the reference points into the grid (bbox -> cell ids -> scan -> records)
+static int knn_build_grid(const float* ref, int n_ref, const int* ref_offsets, int n_batches,
+                          int dims, const KnnWorkspace& k, cudaStream_t s) {
+  const size_t cells = (size_t)n_batches * dims * dims * dims;
+  const int h_init[6] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN};
+  if (cudaMemcpyAsync(k.bbox, h_init, sizeof(h_init), cudaMemcpyHostToDevice, s) != cudaSuccess)
+    return kErrCuda;
+  if (cudaMemsetAsync(k.counts, 0, (cells + 1) * 4, s) != cudaSuccess) return kErrCuda;
+  if (cudaMemsetAsync(k.cursor, 0, (cells + 1) * 4, s) != cudaSuccess) return kErrCuda;
+  if (n_ref > 0) {
+    int blocks = (n_ref + 255) / 256;
+    knn_bbox_kernel<<<blocks < 592 ? blocks : 592, 256, 0, s>>>(ref, n_ref, k.bbox);
+    count_launch();
+  }
+  knn_params_kernel<<<1, 32, 0, s>>>(k.bbox, dims, k.grid);
+  count_launch();
+  if (n_ref > 0) {
+    knn_count_kernel<<<(n_ref + 255) / 256, 256, 0, s>>>(ref, n_ref, ref_offsets, n_batches, k.grid,
+                                                        k.cell_id, k.counts);
+    count_launch();
+  }
+  size_t scan_bytes = k.scan_bytes;
+  if (cub::DeviceScan::ExclusiveSum(k.scan_tmp, scan_bytes, k.counts, k.start, (int)(cells + 1),
+                                    s) != cudaSuccess)
+    return kErrCuda;
+  if (n_ref > 0) {
+    knn_fill_kernel<<<(n_ref + 255) / 256, 256, 0, s>>>(ref, n_ref, k.cell_id, k.start, k.cursor,
+                                                       k.recs);
+    count_launch();
+  }
+  return kOk;
+}
+
+// pass 1 of the radius search: builds the grid in `workspace` and writes counts[n_query]
+int radius_count(const float* ref, int n_ref, const int* ref_offsets, const float* query,
+                 int n_query, const int* query_offsets, int n_batches, float radius, int* counts,
+                 void* workspace, size_t ws_bytes, cudaStream_t s) {
+  if (!(radius > 0.f) || n_batches < 1 || n_ref < 0 || n_query < 0) return kErrInvalidArg;
+  const int dims = knn_dims_for(n_ref, n_batches);
+  if (ws_bytes < knn_workspace_bytes(n_ref, n_batches, dims)) return kErrWorkspace;
+  const KnnWorkspace k = knn_carve(workspace, ws_bytes, n_ref, n_batches, dims);
+  const int st = knn_build_grid(ref, n_ref, ref_offsets, n_batches, dims, k, s);
+  if (st != kOk) return st;
+  if (n_query == 0) return kOk;
+  radius_query_kernel<false><<<(n_query + 127) / 128, 128, 0, s>>>(
+      query, n_query, query_offsets, n_batches, k.grid, k.start, k.recs, radius, counts, nullptr,
+      nullptr, nullptr);
+  count_launch();
+  return cuda_ok2();
+}
+
+// pass 2: `workspace` must be the untouched workspace of radius_count for the same reference set
+int radius_fill(int n_ref, const float* query, int n_query, const int* query_offsets,
+                int n_batches, float radius, const long long* row_splits, int* out_idx,
+                float* out_dist, void* workspace, size_t ws_bytes, cudaStream_t s) {
+  if (!(radius > 0.f) || n_batches < 1 || n_query < 0) return kErrInvalidArg;
+  if (n_query == 0) return kOk;
+  const int dims = knn_dims_for(n_ref, n_batches);
+  if (ws_bytes < knn_workspace_bytes(n_ref, n_batches, dims)) return kErrWorkspace;
+  const KnnWorkspace k = knn_carve(workspace, ws_bytes, n_ref, n_batches, dims);
+  radius_query_kernel<true><<<(n_query + 127) / 128, 128, 0, s>>>(
+      query, n_query, query_offsets, n_batches, k.grid, k.start, k.recs, radius, nullptr,
+      row_splits, out_idx, out_dist);
+  count_launch();
+  return cuda_ok2();
+}
+
 int knn_search(const float* ref, int n_ref, const int* ref_offsets, const float* query, int n_query,
                const int* query_offsets, int n_batches, int k, long long* out_idx, float* out_dist,
                void* workspace, size_t ws_bytes, cudaStream_t s) {
@@ -217,44 +368,14 @@ int knn_search(const float* ref, int n_ref, const int* ref_offsets, const float*
   if (n_query == 0) return kOk;
   const int dims = knn_dims_for(n_ref, n_batches);
   if (ws_bytes < knn_workspace_bytes(n_ref, n_batches, dims)) return kErrWorkspace;
-  const size_t cells = (size_t)n_batches * dims * dims * dims;
-  auto al = [](size_t v) { return (v + 255) / 256 * 256; };
-  uint8_t* w = reinterpret_cast<uint8_t*>(workspace);
-  int* bbox = reinterpret_cast<int*>(w);
-  KnnGrid* grid = reinterpret_cast<KnnGrid*>(w + 64);
-  w += al(256);
-  int* counts = reinterpret_cast<int*>(w); w += al((cells + 1) * 4);
-  int* start = reinterpret_cast<int*>(w); w += al((cells + 1) * 4);
-  int* cursor = reinterpret_cast<int*>(w); w += al((cells + 1) * 4);
-  int* cell_id = reinterpret_cast<int*>(w); w += al((size_t)n_ref * 4);
-  float4* recs = reinterpret_cast<float4*>(w); w += al((size_t)n_ref * 16);
-  void* scan_tmp = w;
-  size_t scan_bytes = ws_bytes - (size_t)(w - reinterpret_cast<uint8_t*>(workspace));
-
-  const int h_init[6] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN};
-  if (cudaMemcpyAsync(bbox, h_init, sizeof(h_init), cudaMemcpyHostToDevice, s) != cudaSuccess)
-    return kErrCuda;
-  if (cudaMemsetAsync(counts, 0, (cells + 1) * 4, s) != cudaSuccess) return kErrCuda;
-  if (cudaMemsetAsync(cursor, 0, (cells + 1) * 4, s) != cudaSuccess) return kErrCuda;
-  if (n_ref > 0) {
-    int blocks = (n_ref + 255) / 256;
-    knn_bbox_kernel<<<blocks < 592 ? blocks : 592, 256, 0, s>>>(ref, n_ref, bbox);
-    count_launch();
+  const KnnWorkspace kw = knn_carve(workspace, ws_bytes, n_ref, n_batches, dims);
+  {
+    const int st = knn_build_grid(ref, n_ref, ref_offsets, n_batches, dims, kw, s);
+    if (st != kOk) return st;
   }
-  knn_params_kernel<<<1, 32, 0, s>>>(bbox, dims, grid);
-  count_launch();
-  if (n_ref > 0) {
-    knn_count_kernel<<<(n_ref + 255) / 256, 256, 0, s>>>(ref, n_ref, ref_offsets, n_batches, grid,
-                                                        cell_id, counts);
-    count_launch();
-  }
-  if (cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, counts, start, (int)(cells + 1), s) !=
-      cudaSuccess)
-    return kErrCuda;
-  if (n_ref > 0) {
-    knn_fill_kernel<<<(n_ref + 255) / 256, 256, 0, s>>>(ref, n_ref, cell_id, start, cursor, recs);
-    count_launch();
-  }
+  KnnGrid* grid = kw.grid;
+  int* start = kw.start;
+  float4* recs = kw.recs;
   const int qb = (n_query + 127) / 128;
   if (k <= 8)
     knn_query_kernel<8><<<qb, 128, 0, s>>>(query, n_query, query_offsets, n_batches, grid, start,

@@ -36,5 +36,13 @@ def neighbor_search(ref, ref_offsets, query, query_offsets, cfg: RealSearchConfi
     if cfg.mode == RealSearchMode.KNN:
         return RealSearchResult(batched_knn_search(ref, ref_offsets, query, query_offsets,
                                                    int(cfg.knn_k)))
+    if cfg.mode == RealSearchMode.RADIUS:
+        from .radius import batched_radius_search
+        assert cfg.radius is not None, "RealSearchConfig(mode='radius') needs a radius"
+        idx, dist, splits = batched_radius_search(ref, ref_offsets, query, query_offsets,
+                                                  float(cfg.radius), cfg.grid_dim)
+        res = RealSearchResult(idx, splits)
+        res.neighbor_distances = dist
+        return res
     raise NotImplementedError(f"neighbour search mode {cfg.mode} is not part of the hot path "
-                              "(SURVEY.md §2b: radius search is out of scope)")
+                              "(SURVEY.md §2b: voxel-grid search is out of scope)")
