@@ -34,6 +34,15 @@ constexpr int kNumSMsB200 = 148;
 // number of kernels this library has launched in this process (wcn_launch_count in the C-ABI)
 void count_launch();
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per DEVICE: caches of "already configured"
+// sizes are kept per device ordinal so a process that drives several GPUs stays correct.
+constexpr int kMaxDevices = 64;
+inline int current_device_slot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
+  return dev % kMaxDevices;
+}
+
 // ---------------------------------------------------------------------------------------------
 // shared-memory address helpers
 // ---------------------------------------------------------------------------------------------

@@ -386,7 +386,8 @@ static int dw_launch_tv(int mode, const DepthwiseParams& p, cudaStream_t s) {
   const int vecs = (p.C + V - 1) / V;
   const int rpb = kDwThreads / vecs;
   static int occ[4] = {0, 0, 0, 0};
-  static size_t configured[4] = {0, 0, 0, 0};
+  static size_t configured_dev[kMaxDevices][4] = {};  // per instantiation and device
+  size_t* configured = configured_dev[current_device_slot()];
   auto set_attr = [&](int bytes) {
     switch (mode) {
       case 0: return cudaFuncSetAttribute(depthwise_fwd_kernel<T, V>,

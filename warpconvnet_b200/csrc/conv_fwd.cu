@@ -622,7 +622,8 @@ static int launch_gather_gemm_t(GatherGemmParams p, int n_slabs, int max_ctas, c
   if (p.stages <= 0 || p.stages > max_stages) p.stages = max_stages;
   if (p.stages < 2) return kErrUnsupportedShape;
   const size_t smem = gemm_smem_bytes(p.bn, TM, GC, p.stages);
-  static int configured_smem = 0;  // per instantiation
+  static int configured[kMaxDevices] = {};  // per instantiation and device
+  int& configured_smem = configured[current_device_slot()];
   if ((int)smem > configured_smem) {
     cudaError_t e = cudaFuncSetAttribute(gather_gemm_kernel<T, TM, GC, SWAP>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

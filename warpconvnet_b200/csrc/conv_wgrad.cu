@@ -474,7 +474,8 @@ static int launch_wgrad_t(WgradParams p, int cin_slabs, int cout_slabs, int max_
   }
   if (p.stages < 2) return kErrUnsupportedShape;
   const size_t smem = (size_t)p.stages * stage_bytes + sizeof(WgSmemCtrl) + kWgSegTableBytes + 1024;
-  static int configured_smem = 0;
+  static int configured[kMaxDevices] = {};  // per instantiation and device
+  int& configured_smem = configured[current_device_slot()];
   if ((int)smem > configured_smem) {
     if (cudaFuncSetAttribute(wgrad_kernel<T, PAIRS, NSEGB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)smem) != cudaSuccess)
