@@ -237,17 +237,22 @@ int wcn_bn_finalize(const double* sums, int n, int c, const float* gamma, const 
 int wcn_scale_shift_act(const void* x, long long ld_x, const void* res, long long ld_res, void* y,
                         long long ld_y, int n, int c, int dtype, const float* scale,
                         const float* shift, int relu, void* stream);
-/* dz = dy * (y > 0) (y optional: no activation); sums[ch] += sum dz, sums[c+ch] += sum dz*xhat */
+/* dz = dy * (y > 0) (y optional: no activation); sums[ch] += sum dz, sums[c+ch] += sum dz*xhat.
+ * mask_scale / mask_shift (optional, both or neither): the forward scale / shift of a ReLU layer
+ * WITHOUT residual; the mask is then recomputed as x * mask_scale + mask_shift > 0 and y is not
+ * read (one matrix read less per backward pass). */
 int wcn_bn_bwd_reduce(const void* dy, long long ld_dy, const void* x, long long ld_x,
                       const void* y, long long ld_y, int n, int c, int dtype,
-                      const float* mean_rstd, double* sums, void* stream);
+                      const float* mean_rstd, const float* mask_scale, const float* mask_shift,
+                      double* sums, void* stream);
 /* training != 0: dx = gamma*rstd*(dz - sums[ch]/n - xhat*sums[c+ch]/n); training == 0:
  * dx = dz * gamma[ch] (pass gamma * running rstd). dres (optional) receives dz, the gradient
  * of the residual input. */
 int wcn_bn_bwd_apply(const void* dy, long long ld_dy, const void* x, long long ld_x, const void* y,
                      long long ld_y, void* dx, long long ld_dx, void* dres, long long ld_dres,
                      int n, int c, int dtype, const float* gamma, const float* mean_rstd,
-                     const double* sums, int training, void* stream);
+                     const double* sums, const float* mask_scale, const float* mask_shift,
+                     int training, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Depthwise sparse convolution, weight [K][channels] fp32                  */

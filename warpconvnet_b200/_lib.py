@@ -97,10 +97,12 @@ SIGNATURES = {
     "wcn_scale_shift_act": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong,
                                     c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     "wcn_bn_bwd_reduce": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong,
-                                  c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+                                  c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_void_p]),
     "wcn_bn_bwd_apply": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong,
                                  c_void_p, c_longlong, c_void_p, c_longlong, c_int, c_int, c_int,
-                                 c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                 c_void_p]),
     "wcn_wgrad": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p,
                           c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_int,
                           c_void_p, c_int, c_int, c_int, c_void_p]),

@@ -380,21 +380,26 @@ def scale_shift_act(x: Tensor, scale: Tensor, shift: Tensor, residual: Optional[
     return out
 
 
-def bn_bwd_reduce(dy: Tensor, x: Tensor, y: Optional[Tensor], mean_rstd: Tensor) -> Tensor:
-    """fp64 [2, c]: sum dz and sum dz * xhat with dz = dy * (y > 0) (y None: dz = dy)."""
+def bn_bwd_reduce(dy: Tensor, x: Tensor, y: Optional[Tensor], mean_rstd: Tensor,
+                  mask_scale: Optional[Tensor] = None,
+                  mask_shift: Optional[Tensor] = None) -> Tensor:
+    """fp64 [2, c]: sum dz and sum dz * xhat with dz = dy * (y > 0) (y None: dz = dy);
+    mask_scale / mask_shift: recompute the mask from x instead of reading y."""
     n, c = x.shape
     sums = torch.zeros((2, c), dtype=torch.float64, device=x.device)
     pd, ldd = _rows(dy)
     px, ldx = _rows(x)
     py, ldy = _rows(y) if y is not None else (None, 0)
     check(lib.wcn_bn_bwd_reduce(pd, ldd, px, ldx, py, ldy, n, c, dtype_code(x.dtype),
-                                _p(mean_rstd), _p(sums), _stream()), "bn_bwd_reduce")
+                                _p(mean_rstd), _p(mask_scale), _p(mask_shift), _p(sums),
+                                _stream()), "bn_bwd_reduce")
     return sums
 
 
 def bn_bwd_apply(dy: Tensor, x: Optional[Tensor], y: Optional[Tensor], gamma: Tensor,
                  mean_rstd: Optional[Tensor], sums: Optional[Tensor], training: bool,
-                 want_dres: bool):
+                 want_dres: bool, mask_scale: Optional[Tensor] = None,
+                 mask_shift: Optional[Tensor] = None):
     """(dx, dres | None); see wcn_bn_bwd_apply."""
     n, c = dy.shape
     dx = torch.empty((n, c), dtype=dy.dtype, device=dy.device)
@@ -406,7 +411,8 @@ def bn_bwd_apply(dy: Tensor, x: Optional[Tensor], y: Optional[Tensor], gamma: Te
     pdr, lddr = _rows(dres) if dres is not None else (None, 0)
     check(lib.wcn_bn_bwd_apply(pd, ldd, px, ldx, py, ldy, pdx, lddx, pdr, lddr, n, c,
                                dtype_code(dy.dtype), _p(gamma), _p(mean_rstd), _p(sums),
-                               int(training), _stream()), "bn_bwd_apply")
+                               _p(mask_scale), _p(mask_shift), int(training), _stream()),
+          "bn_bwd_apply")
     return dx, dres
 
 

@@ -456,18 +456,21 @@ int wcn_scale_shift_act(const void* x, long long ld_x, const void* res, long lon
 
 int wcn_bn_bwd_reduce(const void* dy, long long ld_dy, const void* x, long long ld_x,
                       const void* y, long long ld_y, int n, int c, int dtype,
-                      const float* mean_rstd, double* sums, void* stream) {
+                      const float* mean_rstd, const float* mask_scale, const float* mask_shift,
+                      double* sums, void* stream) {
   if (!dy || !x || !mean_rstd || !sums) return kErrInvalidArg;
   RowNormParams p = rn_params(n, c);
   p.dy = dy; p.ld_dy = ld_dy; p.x = x; p.ld_x = ld_x; p.y_in = y; p.ld_yin = ld_y;
   p.mean_rstd = mean_rstd; p.sums = sums;
+  if (mask_scale && mask_shift) { p.mask_scale = mask_scale; p.mask_shift = mask_shift; }
   return rownorm_launch(2, p, dtype, S(stream));
 }
 
 int wcn_bn_bwd_apply(const void* dy, long long ld_dy, const void* x, long long ld_x, const void* y,
                      long long ld_y, void* dx, long long ld_dx, void* dres, long long ld_dres,
                      int n, int c, int dtype, const float* gamma, const float* mean_rstd,
-                     const double* sums, int training, void* stream) {
+                     const double* sums, const float* mask_scale, const float* mask_shift,
+                     int training, void* stream) {
   if (!dy || !dx || !gamma) return kErrInvalidArg;
   if (training && (!x || !mean_rstd || !sums)) return kErrInvalidArg;
   RowNormParams p = rn_params(n, c);
@@ -475,6 +478,7 @@ int wcn_bn_bwd_apply(const void* dy, long long ld_dy, const void* x, long long l
   p.y = dx; p.ld_y = ld_dx; p.dres = dres; p.ld_dres = ld_dres;
   p.scale = gamma; p.mean_rstd = mean_rstd; p.sums = const_cast<double*>(sums);
   p.training = training;
+  if (mask_scale && mask_shift) { p.mask_scale = mask_scale; p.mask_shift = mask_shift; }
   return rownorm_launch(3, p, dtype, S(stream));
 }
 

@@ -176,23 +176,26 @@ __global__ void __launch_bounds__(kRnThreads) scale_shift_act_kernel(const RowNo
 
 // ---- backward reduce: dz = dy * (y > 0); sums += (sum dz, sum dz * xhat) ---------------------------
 template <typename T, int V>
-__global__ void __launch_bounds__(kRnThreads) bn_bwd_reduce_kernel(const RowNormParams p) {
+__global__ void __launch_bounds__(kRnThreads, 2) bn_bwd_reduce_kernel(const RowNormParams p) {
   extern __shared__ float sh[];
   const RnMap m = rn_map<V>(p.c);
   float s1[V], s2[V];
 #pragma unroll
   for (int i = 0; i < V; ++i) s1[i] = s2[i] = 0.f;
   if (m.active) {
-    float mu[V], rs[V];
+    float mu[V], rs[V], msc[V], msh[V];
+    const bool mask_x = p.mask_scale != nullptr;  // recompute the ReLU mask from x
 #pragma unroll
     for (int i = 0; i < V; ++i) {
       const int ch = min(m.vc * V + i, p.c - 1);
       mu[i] = __ldg(p.mean_rstd + ch);
       rs[i] = __ldg(p.mean_rstd + p.c + ch);
+      msc[i] = mask_x ? __ldg(p.mask_scale + ch) : 0.f;
+      msh[i] = mask_x ? __ldg(p.mask_shift + ch) : 1.f;
     }
     const T* x = reinterpret_cast<const T*>(p.x) + m.vc * V;
     const T* dy = reinterpret_cast<const T*>(p.dy) + m.vc * V;
-    const T* yin = p.y_in ? reinterpret_cast<const T*>(p.y_in) + m.vc * V : nullptr;
+    const T* yin = (p.y_in && !mask_x) ? reinterpret_cast<const T*>(p.y_in) + m.vc * V : nullptr;
     constexpr int U = 2;  // rows in flight per thread
     const long long stride = (long long)gridDim.x * m.rpb;
     for (long long r0 = (long long)blockIdx.x * m.rpb + m.rl; r0 < p.n; r0 += U * stride) {
@@ -211,7 +214,9 @@ __global__ void __launch_bounds__(kRnThreads) bn_bwd_reduce_kernel(const RowNorm
         if (r0 + u * stride >= p.n) break;
 #pragma unroll
         for (int i = 0; i < V; ++i) {
-          const float d = (yin && !(fy[u][i] > 0.f)) ? 0.f : fd[u][i];
+          const bool off = yin ? !(fy[u][i] > 0.f)
+                               : (mask_x && !(fmaf(fx[u][i], msc[i], msh[i]) > 0.f));
+          const float d = off ? 0.f : fd[u][i];
           s1[i] += d;
           s2[i] = fmaf(d, (fx[u][i] - mu[i]) * rs[i], s2[i]);
         }
@@ -222,16 +227,20 @@ __global__ void __launch_bounds__(kRnThreads) bn_bwd_reduce_kernel(const RowNorm
 }
 
 // ---- backward apply: dx = gamma * rstd * (dz - s1/n - xhat * s2/n); dres = dz ----------------------
+// (2 resident blocks: 133 registers would leave one block of 256 threads per SM)
 template <typename T, int V>
-__global__ void __launch_bounds__(kRnThreads) bn_bwd_apply_kernel(const RowNormParams p) {
+__global__ void __launch_bounds__(kRnThreads, 2) bn_bwd_apply_kernel(const RowNormParams p) {
   const RnMap m = rn_map<V>(p.c);
   if (!m.active) return;
-  float mu[V], rs[V], g[V], m1[V], m2[V];
+  float mu[V], rs[V], g[V], m1[V], m2[V], msc[V], msh[V];
+  const bool mask_x = p.mask_scale != nullptr && p.training;  // x is only read in training mode
   const float inv_n = 1.f / (float)p.n;
 #pragma unroll
   for (int i = 0; i < V; ++i) {
     const int ch = min(m.vc * V + i, p.c - 1);
     g[i] = __ldg(p.scale + ch);  // gamma (training) or gamma * rstd_running (eval)
+    msc[i] = mask_x ? __ldg(p.mask_scale + ch) : 0.f;
+    msh[i] = mask_x ? __ldg(p.mask_shift + ch) : 1.f;
     if (p.training) {
       mu[i] = __ldg(p.mean_rstd + ch);
       rs[i] = __ldg(p.mean_rstd + p.c + ch);
@@ -243,7 +252,7 @@ __global__ void __launch_bounds__(kRnThreads) bn_bwd_apply_kernel(const RowNormP
   }
   const T* x = reinterpret_cast<const T*>(p.x) + m.vc * V;
   const T* dy = reinterpret_cast<const T*>(p.dy) + m.vc * V;
-  const T* yin = p.y_in ? reinterpret_cast<const T*>(p.y_in) + m.vc * V : nullptr;
+  const T* yin = (p.y_in && !mask_x) ? reinterpret_cast<const T*>(p.y_in) + m.vc * V : nullptr;
   T* dx = reinterpret_cast<T*>(p.y) + m.vc * V;
   T* dres = p.dres ? reinterpret_cast<T*>(p.dres) + m.vc * V : nullptr;
   constexpr int U = 2;  // rows in flight per thread
@@ -266,6 +275,10 @@ __global__ void __launch_bounds__(kRnThreads) bn_bwd_apply_kernel(const RowNormP
       if (yin) {
 #pragma unroll
         for (int i = 0; i < V; ++i) fd[u][i] = fy[u][i] > 0.f ? fd[u][i] : 0.f;
+      } else if (mask_x) {
+#pragma unroll
+        for (int i = 0; i < V; ++i)
+          fd[u][i] = fmaf(fx[u][i], msc[i], msh[i]) > 0.f ? fd[u][i] : 0.f;
       }
       if (dres) store_vec<T, V>(dres + r * p.ld_dres, fd[u]);
       if (p.training) {

@@ -14,6 +14,10 @@ struct RowNormParams {
   const float* scale;    // [c] forward: gamma * rstd; backward: gamma
   const float* shift;    // [c] forward: beta - mean * gamma * rstd
   const float* mean_rstd;  // [2c] saved batch mean, rstd (backward)
+  // backward, optional: forward scale / shift; the ReLU mask is then recomputed as
+  // x * mask_scale + mask_shift > 0 instead of being read from the saved output (one read less)
+  const float* mask_scale;
+  const float* mask_shift;
   double* sums;          // [2c] reduction target (stats: sum x, sum x^2; bwd: sum dz, sum dz*xhat)
   long long ld_x, ld_res, ld_y, ld_dy, ld_yin, ld_dres;  // row pitches in elements
   int n, c;

@@ -52,21 +52,29 @@ class _BatchNormAct(torch.autograd.Function):
         ctx.has_b = bias is not None and ctx.needs_input_grad[2]
         ctx.w_dtype = weight.dtype if weight is not None else None
         ctx.b_dtype = bias.dtype if bias is not None else None
-        ctx.save_for_backward(x, y if relu else None, gamma if gamma is not None else None,
-                              mean_rstd, None if use_batch else scale)
+        # ReLU mask in backward: recomputed from x (x * scale + shift > 0) when there is no residual
+        # and the output dtype keeps fp32's exponent range (bf16 / fp32), so the saved output is
+        # not read again; otherwise taken from the saved output
+        ctx.mask_from_x = bool(relu and use_batch and residual is None
+                               and x.dtype != torch.float16)
+        ctx.save_for_backward(x, y if (relu and not ctx.mask_from_x) else None,
+                              gamma if gamma is not None else None, mean_rstd,
+                              None if use_batch else scale,
+                              scale if ctx.mask_from_x else None,
+                              shift if ctx.mask_from_x else None)
         return y
 
     @staticmethod
     def backward(ctx, dy: Tensor):
-        x, y, gamma, mean_rstd, eval_scale = ctx.saved_tensors
+        x, y, gamma, mean_rstd, eval_scale, msc, msh = ctx.saved_tensors
         dy = dy.to(x.dtype)
         dy = dy if dy.stride(1) == 1 else dy.contiguous()
         c = x.shape[1]
         need_res = ctx.has_res and ctx.needs_input_grad[3]
         if ctx.use_batch:
             g = gamma if gamma is not None else torch.ones(c, dtype=torch.float32, device=x.device)
-            sums = _ops.bn_bwd_reduce(dy, x, y, mean_rstd)
-            dx, dres = _ops.bn_bwd_apply(dy, x, y, g, mean_rstd, sums, True, need_res)
+            sums = _ops.bn_bwd_reduce(dy, x, y, mean_rstd, msc, msh)
+            dx, dres = _ops.bn_bwd_apply(dy, x, y, g, mean_rstd, sums, True, need_res, msc, msh)
             dgamma = sums[1].to(ctx.w_dtype) if ctx.has_w else None
             dbeta = sums[0].to(ctx.b_dtype) if ctx.has_b else None
         else:
