@@ -1,5 +1,6 @@
 # SPDX-License-Identifier: Apache-2.0
-"""Per-role wait-cycle counters of the gather-GEMM kernel (bring-up only)."""
+"""Per-role wait-cycle counters of the gather-GEMM kernel (bring-up only; needs a library built with
+WCN_KERNEL_COUNTERS=1 warpconvnet_b200/csrc/build.sh)."""
 import os
 import sys
 

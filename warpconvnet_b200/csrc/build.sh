@@ -4,6 +4,8 @@ set -euo pipefail
 cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -diag-suppress 177"
+# WCN_KERNEL_COUNTERS=1: compile the per-role cycle counters into the GEMM kernels (bring-up only)
+if [ "${WCN_KERNEL_COUNTERS:-0}" = "1" ]; then FLAGS="$FLAGS -DWCN_KERNEL_COUNTERS"; fi
 mkdir -p build
 pids=()
 for f in cuhash conv_fwd conv_wgrad weight_prep knn rownorm conv_depthwise capi; do

@@ -31,6 +31,15 @@ __host__ __device__ inline int dtype_size(int dt) { return dt == kF32 ? 4 : 2; }
 
 constexpr int kNumSMsB200 = 148;
 
+// Per-role wait-cycle counters of the GEMM kernels (tools/exp_dbg.py, tools/exp_wgrad.py) are a
+// bring-up aid: the clock reads are compiled in only with -DWCN_KERNEL_COUNTERS
+// (WCN_KERNEL_COUNTERS=1 csrc/build.sh); the shipped library carries none of them.
+#ifdef WCN_KERNEL_COUNTERS
+#define WCN_CLOCK() clock64()
+#else
+#define WCN_CLOCK() 0ll
+#endif
+
 // number of kernels this library has launched in this process (wcn_launch_count in the C-ABI)
 void count_launch();
 

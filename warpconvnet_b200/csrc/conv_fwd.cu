@@ -277,7 +277,7 @@ gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
     int stage = 0;
     uint32_t phase = 0;
     long long w_empty = 0;
-    const long long t_start = clock64();
+    const long long t_start = WCN_CLOCK();
     unsigned long long ns_start;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns_start));
 #pragma unroll 1
@@ -301,9 +301,9 @@ gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
 #pragma unroll 1
       for (int g = 0; g < n_groups; ++g) {
         {
-          const long long t0 = clock64();
+          const long long t0 = WCN_CLOCK();
           mbar_wait(smem_u32(&ctrl->empty[stage]), phase ^ 1u);
-          w_empty += clock64() - t0;
+          w_empty += WCN_CLOCK() - t0;
         }
         const uint32_t a_smem = smem_base + stage * stage_bytes;
         const uint32_t full_bar = smem_u32(&ctrl->full[stage]);
@@ -341,7 +341,7 @@ gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
       }
     }
     if (p.dbg_out != nullptr && tid == 0) {
-      p.dbg_out[blockIdx.x * 16 + 0] = clock64() - t_start;
+      p.dbg_out[blockIdx.x * 16 + 0] = WCN_CLOCK() - t_start;
       p.dbg_out[blockIdx.x * 16 + 1] = w_empty;
       unsigned long long ns_end;
       asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns_end));
@@ -358,7 +358,7 @@ gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
       uint32_t use = 0;  // number of accumulator-set uses so far
       int nk_next = (t_begin < t_end) ? __ldg(p.tile_nk + t_begin) : 0;
       long long w_full = 0, w_acc = 0;
-      const long long t_start = clock64();
+      const long long t_start = WCN_CLOCK();
       for (int tile = t_begin; tile < t_end; ++tile) {
         const int nk = nk_next;
         if (tile + 1 < t_end) nk_next = __ldg(p.tile_nk + tile + 1);
@@ -369,9 +369,9 @@ gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
         for (int h = h0; h < h1; ++h) {
           const uint32_t acc = use & 1u;
           {
-            const long long t0 = clock64();
+            const long long t0 = WCN_CLOCK();
             mbar_wait(smem_u32(&ctrl->acc_empty[acc]), ((use >> 1) & 1u) ^ 1u);
-            w_acc += clock64() - t0;
+            w_acc += WCN_CLOCK() - t0;
           }
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + acc * kAccStride;
@@ -379,9 +379,9 @@ gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
           for (int ki = 0; ki < nk; ++ki) {
             for (int g = 0; g < n_groups; ++g) {
               {
-                const long long t0 = clock64();
+                const long long t0 = WCN_CLOCK();
                 mbar_wait(smem_u32(&ctrl->full[stage]), phase);
-                w_full += clock64() - t0;
+                w_full += WCN_CLOCK() - t0;
               }
               fence_proxy_async_smem();  // cp.async wrote A through the generic proxy
               tc_fence_after();
@@ -430,7 +430,7 @@ gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
         }
       }
       if (p.dbg_out != nullptr) {
-        p.dbg_out[blockIdx.x * 16 + 2] = clock64() - t_start;
+        p.dbg_out[blockIdx.x * 16 + 2] = WCN_CLOCK() - t_start;
         p.dbg_out[blockIdx.x * 16 + 3] = w_full;
         p.dbg_out[blockIdx.x * 16 + 4] = w_acc;
       }
@@ -447,7 +447,7 @@ gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
     const uint32_t stage_row = stage_warp + lane * 256;
     uint32_t use = 0;
     long long w_accf = 0;
-    const long long t_start = clock64();
+    const long long t_start = WCN_CLOCK();
     for (int tile = t_begin; tile < t_end; ++tile) {
       const int nk = __ldg(p.tile_nk + tile);
       int lo, hi;
@@ -458,9 +458,9 @@ gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
         uint32_t acc = 0;
         if (nk > 0) {
           acc = use & 1u;
-          const long long t0 = clock64();
+          const long long t0 = WCN_CLOCK();
           mbar_wait(smem_u32(&ctrl->acc_full[acc]), (use >> 1) & 1u);
-          w_accf += clock64() - t0;
+          w_accf += WCN_CLOCK() - t0;
           tc_fence_after();
         }
         if constexpr (SWAP) {
@@ -582,7 +582,7 @@ gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
       }
     }
     if (p.dbg_out != nullptr && tid == 5 * 32) {
-      p.dbg_out[blockIdx.x * 16 + 5] = clock64() - t_start;
+      p.dbg_out[blockIdx.x * 16 + 5] = WCN_CLOCK() - t_start;
       p.dbg_out[blockIdx.x * 16 + 6] = w_accf;
     }
   }

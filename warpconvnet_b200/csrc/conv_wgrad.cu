@@ -252,7 +252,7 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
     int stage = 0;
     uint32_t phase = 0;
     long long w_empty = 0, n_stage = 0, t_issue = 0, t_arrive = 0;
-    const long long t_start = clock64();
+    const long long t_start = WCN_CLOCK();
     WgSegCursor seg = make_cursor();
     int k, first, count;
     while (seg.next(k, first, count)) {
@@ -286,14 +286,14 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
           const int vi = vi_r[d], vo = vo_r[d];
           if (st + kDepth < n_st) load_idx(st + kDepth, vi_r[d], vo_r[d]);
           {
-            const long long t0 = clock64();
+            const long long t0 = WCN_CLOCK();
             mbar_wait(smem_u32(&ctrl->empty[stage]), phase ^ 1u);
-            w_empty += clock64() - t0;
+            w_empty += WCN_CLOCK() - t0;
             ++n_stage;
           }
           const uint32_t a_smem = smem_base + stage * stage_bytes;
           const uint32_t b_smem = a_smem + kAStage;
-          const long long t_i0 = clock64();
+          const long long t_i0 = WCN_CLOCK();
 #pragma unroll
           for (int q = 0; q < kInstr; ++q) {
             const int row = 2 * q + sub;  // pair row inside this warp's share of the stage
@@ -317,9 +317,9 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
               cp_async_16(b_smem + sgi * 2 * (kPairs * 128) + soff, grow + sgi * 256,
                           (sgi * 256 + u * 16 < cout_bytes) ? sz : 0u);
           }
-          const long long t_i1 = clock64();
+          const long long t_i1 = WCN_CLOCK();
           cp_async_mbar_arrive_noinc(smem_u32(&ctrl->full[stage]));
-          const long long t_i2 = clock64();
+          const long long t_i2 = WCN_CLOCK();
           t_issue += t_i1 - t_i0;
           t_arrive += t_i2 - t_i1;
           if (++stage == stages) { stage = 0; phase ^= 1u; }
@@ -331,7 +331,7 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
       p.dbg_out[blockIdx.x * 8 + 4] = t_arrive;
     }
     if (p.dbg_out != nullptr && tid == 0) {
-      p.dbg_out[blockIdx.x * 8 + 0] = clock64() - t_start;
+      p.dbg_out[blockIdx.x * 8 + 0] = WCN_CLOCK() - t_start;
       p.dbg_out[blockIdx.x * 8 + 1] = w_empty;
       p.dbg_out[blockIdx.x * 8 + 7] = n_stage;
     }
@@ -343,24 +343,24 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
       uint32_t phase = 0;
       uint32_t use = 0;
       long long w_full = 0, w_acc = 0;
-      const long long t_start = clock64();
+      const long long t_start = WCN_CLOCK();
       WgSegCursor seg = make_cursor();
       int k, first, count;
       while (seg.next(k, first, count)) {
         const uint32_t acc = use & 1u;
         {
-          const long long t0 = clock64();
+          const long long t0 = WCN_CLOCK();
           mbar_wait(smem_u32(&ctrl->acc_empty[acc]), ((use >> 1) & 1u) ^ 1u);
-          w_acc += clock64() - t0;
+          w_acc += WCN_CLOCK() - t0;
         }
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * kWgAccStride;
         uint32_t accumulate = 0;
         for (int done = 0; done < count; done += kPairs) {
           {
-            const long long t0 = clock64();
+            const long long t0 = WCN_CLOCK();
             mbar_wait(smem_u32(&ctrl->full[stage]), phase);
-            w_full += clock64() - t0;
+            w_full += WCN_CLOCK() - t0;
           }
           if (!(p.debug & 64)) fence_proxy_async_smem();  // cp.async = generic-proxy writes
           tc_fence_after();
@@ -381,7 +381,7 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
         ++use;
       }
       if (p.dbg_out != nullptr && !(p.debug & 1024)) {
-        p.dbg_out[blockIdx.x * 8 + 2] = clock64() - t_start;
+        p.dbg_out[blockIdx.x * 8 + 2] = WCN_CLOCK() - t_start;
         p.dbg_out[blockIdx.x * 8 + 3] = w_full;
         p.dbg_out[blockIdx.x * 8 + 4] = w_acc;
       }
@@ -393,15 +393,15 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
     const int gl = (p.gps > 1) ? r / p.cin_g : 0;
     uint32_t use = 0;
     long long w_accf = 0;
-    const long long t_start = clock64();
+    const long long t_start = WCN_CLOCK();
     WgSegCursor seg = make_cursor();
     int k, first, count;
     while (seg.next(k, first, count)) {
       const uint32_t acc = use & 1u;
       {
-        const long long t0 = clock64();
+        const long long t0 = WCN_CLOCK();
         mbar_wait(smem_u32(&ctrl->acc_full[acc]), (use >> 1) & 1u);
-        w_accf += clock64() - t0;
+        w_accf += WCN_CLOCK() - t0;
       }
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kWgAccStride;
@@ -446,7 +446,7 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
       ++use;
     }
     if (p.dbg_out != nullptr && tid == 5 * 32) {
-      p.dbg_out[blockIdx.x * 8 + 5] = clock64() - t_start;
+      p.dbg_out[blockIdx.x * 8 + 5] = WCN_CLOCK() - t_start;
       p.dbg_out[blockIdx.x * 8 + 6] = w_accf;
     }
   }
