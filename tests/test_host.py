@@ -111,3 +111,52 @@ def test_pointwise_shortcut_on_cpu_and_no_cpu_fallback_for_kernels():
     assert torch.allclose(out.feature_tensor, ref)
     with pytest.raises((RuntimeError, AssertionError)):
         SparseConv3d(3, 5, 3)(v)
+
+
+def test_batchnorm_module_mirrors_reference_names():
+    """BatchNorm keeps the reference's `norm.*` parameter / buffer names
+    (warpconvnet/nn/modules/normalizations.py:53-67) so state dicts interchange with
+    nn.BatchNorm1d wrapped the reference's way."""
+    import torch
+    from warpconvnet_b200.nn.modules.normalizations import BatchNorm
+    bn = BatchNorm(16, eps=1e-4, momentum=0.05, relu=True)
+    keys = set(bn.state_dict().keys())
+    assert keys == {"norm.weight", "norm.bias", "norm.running_mean", "norm.running_var",
+                    "norm.num_batches_tracked"}
+    ref = torch.nn.BatchNorm1d(16, eps=1e-4, momentum=0.05)
+    bn.norm.load_state_dict(ref.state_dict())
+    assert bn.norm.eps == 1e-4 and bn.norm.momentum == 0.05
+    with __import__("pytest").raises(RuntimeError):   # no CPU fallback
+        bn(torch.randn(4, 16))
+
+
+def test_depthwise_module_shapes_and_init_bounds():
+    """SparseDepthwiseConv3d: weight [K, C], bias [C], kaiming-uniform bound of the reference
+    (sparse_conv_depth.py:143-182): sqrt(3) * gain(leaky_relu, sqrt(5)) / sqrt(K)."""
+    import math
+    import torch
+    from warpconvnet_b200.nn.modules.sparse_conv_depth import SparseDepthwiseConv2d, SparseDepthwiseConv3d
+    torch.manual_seed(0)
+    m = SparseDepthwiseConv3d(24, 3)
+    assert tuple(m.weight.shape) == (27, 24) and tuple(m.bias.shape) == (24,)
+    gain = math.sqrt(2.0 / (1 + 5.0))
+    bound = math.sqrt(3) * gain / math.sqrt(27)
+    assert float(m.weight.abs().max()) <= bound + 1e-7
+    assert float(m.bias.abs().max()) <= 1 / math.sqrt(27) + 1e-7
+    m2 = SparseDepthwiseConv2d(8, (3, 5), bias=False)
+    assert tuple(m2.weight.shape) == (15, 8) and m2.bias is None and m2.num_spatial_dims == 2
+    assert "SparseDepthwiseConv3d(channels=24" in repr(m)
+
+
+def test_radius_config_and_wrappers_reject_cpu():
+    import pytest
+    import torch
+    from warpconvnet_b200.geometry.coords.search.radius import batched_radius_search, radius_search
+    from warpconvnet_b200.geometry.coords.search.search_configs import RealSearchConfig, RealSearchMode
+    cfg = RealSearchConfig("radius", radius=0.25)
+    assert cfg.mode == RealSearchMode.RADIUS and cfg.radius == 0.25
+    with pytest.raises(RuntimeError):
+        radius_search(torch.rand(10, 3), torch.rand(4, 3), 0.1)
+    with pytest.raises(RuntimeError):
+        batched_radius_search(torch.rand(10, 3), torch.tensor([0, 10]), torch.rand(4, 3),
+                              torch.tensor([0, 4]), 0.1)
