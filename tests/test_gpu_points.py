@@ -187,3 +187,40 @@ def test_point_conv_radius_mode_runs():
     assert out.feature_tensor.shape == (3500, 32)
     out.feature_tensor.sum().backward()
     assert all(p.grad is not None for p in conv.parameters())
+
+
+@pytest.mark.parametrize("reduction", ["random", "mean", "sum", "max", "min"])
+def test_points_to_voxels_vs_numpy(reduction):
+    """Points.to_voxels: quantise, unique per batch item, reduce features (reference:
+    geometry/types/conversion/to_voxels.py:4-24); checked against a NumPy dictionary build."""
+    from warpconvnet_b200.geometry.types.conversion.to_voxels import points_to_voxels
+    from warpconvnet_b200.geometry.types.points import Points
+    g = torch.Generator().manual_seed(9)
+    coords = [torch.rand(3000, 3, generator=g) * 2 - 0.7, torch.rand(1200, 3, generator=g)]
+    feats = [torch.randn(3000, 5, generator=g), torch.randn(1200, 5, generator=g)]
+    pc = Points(coords, feats, device="cuda")
+    pc.batched_features.batched_tensor.requires_grad_(True)
+    vs = 0.1
+    vox, inv = points_to_voxels(pc, vs, reduction, return_to_unique=True)
+    # oracle
+    cells, rows = {}, []
+    for b, (c, f) in enumerate(zip(coords, feats)):
+        q = np.floor(c.numpy() / np.float32(vs)).astype(np.int64)
+        for i in range(len(q)):
+            cells.setdefault((b, *q[i].tolist()), []).append(f[i].numpy())
+    keys = sorted(cells)
+    red = {"random": lambda a: a[0], "mean": lambda a: np.mean(a, 0), "sum": lambda a: np.sum(a, 0),
+           "max": lambda a: np.max(a, 0), "min": lambda a: np.min(a, 0)}[reduction]
+    ref_feats = np.stack([red(np.stack(cells[k])) for k in keys])
+    ref_bc = np.array(keys, np.int64)
+    assert np.array_equal(vox.batch_indexed_coordinates.cpu().numpy(), ref_bc)
+    assert np.allclose(vox.feature_tensor.detach().cpu().numpy(), ref_feats, atol=1e-5)
+    counts = np.bincount(ref_bc[:, 0], minlength=2)
+    assert vox.offsets.tolist() == [0, counts[0], counts[0] + counts[1]]
+    assert inv.shape == (4200,) and int(inv.max()) == len(keys) - 1
+    vox.feature_tensor.sum().backward()           # features stay differentiable
+    assert pc.batched_features.batched_tensor.grad is not None
+    # the result feeds a sparse conv
+    from warpconvnet_b200.nn.modules.sparse_conv import SparseConv3d
+    out = SparseConv3d(5, 16, 3).cuda()(pc.to_voxels(vs))
+    assert out.feature_tensor.shape == (len(keys), 16)

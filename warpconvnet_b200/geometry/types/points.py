@@ -53,6 +53,11 @@ class Points(Geometry):
         cache.put(search_args, self.offsets, query_coords.offsets, result)
         return result
 
+    def to_voxels(self, voxel_size: float, reduction="mean"):
+        """Quantise to voxels of size ``voxel_size`` (points.py:318-326)."""
+        from warpconvnet_b200.geometry.types.conversion.to_voxels import points_to_voxels
+        return points_to_voxels(self, voxel_size, reduction)
+
     @property
     def voxel_size(self):
         return self._extra_attributes.get("voxel_size", None)
