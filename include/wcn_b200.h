@@ -209,12 +209,19 @@ int wcn_gather_gemm(const void* feats, int n_in_rows, long long in_ld, const voi
  * leaves behind (pairs of offset k whose output row is < 256*b; requires out_maps ascending inside
  * every offset, which wcn_kernel_map_scatter guarantees). The pair lists are then walked in
  * `row_parts` row blocks x K offsets, every CTA taking `rounds` round-robin chunks, so a block of
- * rows sees all K offsets while L2-resident. NULL / (1, 1) = plain offset-major order. */
+ * rows sees all K offsets while L2-resident. NULL / (1, 1) = plain offset-major order.
+ * Optional identity offset: identity_k >= 0 promises that offset identity_k of the map is the
+ * identity (in_maps == out_maps == 0 .. n-1 in order: the centre offset of a submanifold map with
+ * unique coordinates); its contiguous rows are then fetched as 2-D TMA tiles instead of row gathers.
+ * `status` (optional) = the hash table's status word, whose duplicate bit (4) switches the
+ * shortcut off on the device; n_in_rows / n_out_rows = rows of feats / gout (tensor-map bounds).
+ * Pass -1 / NULL / 0 / 0 when unknown. */
 int wcn_wgrad(const void* feats, long long in_ld, const void* gout, long long out_ld, float* dw,
               const int32_t* in_maps, const int32_t* out_maps, const int32_t* offsets, int K,
               int groups, int cin_g, int cout_g, int dtype, float alpha, int unit_pairs,
               int max_ctas, const int32_t* row_block_prefix, int n_row_blocks, int row_parts,
-              int rounds, void* stream);
+              int rounds, int identity_k, const int32_t* status, long long n_in_rows,
+              long long n_out_rows, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Per-channel normalisation + activation + residual on the [n, c] feature matrix             */

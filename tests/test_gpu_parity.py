@@ -385,6 +385,20 @@ def test_wgrad_row_block_major_order(kind, n, stride, ks, parts, rounds):
     torch.cuda.synchronize()
     scale = float(plain.abs().max())
     assert float((blocked - plain).abs().max()) <= 1e-4 * scale
+    if stride == 1:
+        # identity offset through TMA tiles (submanifold map, unique coordinates), alone and
+        # combined with the row-block-major order; fp16 and odd channel counts too
+        st = km._hashtable.status_tensor
+        ident = _ops.wgrad(*args, identity_k=K // 2, status=st)
+        both = _ops.wgrad(*args, row_block_prefix=bp, row_parts=parts, rounds=rounds,
+                          identity_k=K // 2, status=st)
+        assert float((ident - plain).abs().max()) <= 1e-4 * scale
+        assert float((both - plain).abs().max()) <= 1e-4 * scale
+        x2, g2 = x[:, :48].contiguous().half(), gy[:, :96].contiguous().half()
+        a2 = (x2, g2, km._in_buf, km._out_buf, km.offsets_dev, K, 1, 48, 96)
+        p2 = _ops.wgrad(*a2)
+        i2 = _ops.wgrad(*a2, identity_k=K // 2, status=st)
+        assert float((i2 - p2).abs().max()) <= 1e-4 * float(p2.abs().max())
     if m <= 60000:
         ref = oconv.backward(gy.float().cpu(), x.float().cpu(),
                              torch.zeros(K, cin, cout), km.in_maps.cpu().numpy(),

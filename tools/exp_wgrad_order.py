@@ -38,7 +38,10 @@ for name, c in (("S", surface_coords(448, 0)), ("R", random_coords(200000, 0.3, 
     gy = torch.randn(n, 128, device="cuda").bfloat16()
     dw = torch.zeros(27, 1, 128, 128, device="cuda")
     args = (x, gy, km._in_buf, km._out_buf, km.offsets_dev, 27, 1, 128, 128)
-    variants = [("offset-major", {})] + [
+    ident = {"identity_k": 13, "status": km._hashtable.status_tensor}
+    variants = [("offset-major", {}), ("offset-major + identity TMA", dict(ident)),
+                ("parts=2 rounds=2 + identity TMA",
+                 dict(ident, row_block_prefix=km._block_prefix, row_parts=2, rounds=2))] + [
         (f"parts={p} rounds={r}", {"row_block_prefix": km._block_prefix, "row_parts": p, "rounds": r})
         for p, r in ((2, 2), (4, 4), (8, 4), (8, 8), (16, 8), (4, 8))]
     for vname, kw in variants:

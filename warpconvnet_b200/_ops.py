@@ -259,11 +259,12 @@ def wgrad(feats: Tensor, gout: Tensor, in_maps: Tensor, out_maps: Tensor, offset
           K: int, groups: int, cin_g: int, cout_g: int, dw: Optional[Tensor] = None,
           alpha: float = 1.0, unit_pairs: int = 0, max_ctas: int = 0,
           row_block_prefix: Optional[Tensor] = None, row_parts: int = 1,
-          rounds: int = 1) -> Tensor:
+          rounds: int = 1, identity_k: int = -1, status: Optional[Tensor] = None) -> Tensor:
     """dW[K, groups, cin_g, cout_g] (fp32) += X[in_maps]^T @ dY[out_maps] per offset.
 
     ``row_block_prefix`` ([K, n_row_blocks] int32, the scanned block counts of the kernel map)
-    switches on the row-block-major unit order (see wcn_wgrad)."""
+    switches on the row-block-major unit order; ``identity_k`` (+ the hash table's ``status``
+    word) marks the identity offset of a submanifold map, fetched as TMA tiles (see wcn_wgrad)."""
     _require_cuda(feats, gout, in_maps, out_maps, offsets_dev)
     assert feats.stride(1) == 1 and gout.stride(1) == 1 and feats.dtype == gout.dtype
     code = dtype_code(feats.dtype)
@@ -274,7 +275,8 @@ def wgrad(feats: Tensor, gout: Tensor, in_maps: Tensor, out_maps: Tensor, offset
                         _p(out_maps), _p(offsets_dev), K, groups, cin_g, cout_g, code,
                         ctypes.c_float(alpha), unit_pairs, max_ctas, _p(row_block_prefix),
                         0 if row_block_prefix is None else row_block_prefix.shape[1],
-                        row_parts, rounds, _stream()), "wgrad")
+                        row_parts, rounds, identity_k, _p(status), feats.shape[0], gout.shape[0],
+                        _stream()), "wgrad")
     return dw
 
 

@@ -59,7 +59,8 @@ int depthwise_plan_wgrad_launch(const void* x, long long ld_x, const void* dy, l
                                 int dtype, cudaStream_t s);
 // conv_fwd.cu / conv_wgrad.cu
 int launch_gather_gemm(const GatherGemmParams&, int dtype, int n_slabs, int max_ctas, cudaStream_t);
-int launch_wgrad(const WgradParams&, int dtype, int y_slabs, int z_slabs, int max_ctas, cudaStream_t);
+int launch_wgrad(const WgradParams&, int dtype, int y_slabs, int z_slabs, int max_ctas,
+                 long long n_in_rows, long long n_out_rows, cudaStream_t);
 
 static long long g_launches = 0;
 void count_launch() { __atomic_add_fetch(&g_launches, 1, __ATOMIC_RELAXED); }
@@ -334,7 +335,8 @@ int wcn_wgrad(const void* feats, long long in_ld, const void* gout, long long ou
               const int32_t* in_maps, const int32_t* out_maps, const int32_t* offsets, int K,
               int groups, int cin_g, int cout_g, int dtype, float alpha, int unit_pairs,
               int max_ctas, const int32_t* row_block_prefix, int n_row_blocks, int row_parts,
-              int rounds, void* stream) {
+              int rounds, int identity_k, const int32_t* status, long long n_in_rows,
+              long long n_out_rows, void* stream) {
   if (!feats || !gout || !dw || !offsets) return kErrInvalidArg;
   if (dtype < 0 || dtype > 2) return kErrUnsupportedDtype;
   if (groups < 1 || cin_g < 1 || cout_g < 1) return kErrInvalidArg;
@@ -359,6 +361,9 @@ int wcn_wgrad(const void* feats, long long in_ld, const void* gout, long long ou
   p.n_row_blocks = 0;
   p.row_parts = 1;
   p.rounds = 1;
+  p.identity_k = (identity_k >= 0 && identity_k < K && n_in_rows > 0 && n_out_rows > 0) ? identity_k
+                                                                                        : -1;
+  p.status = status;
   if (row_block_prefix != nullptr && row_parts >= 1 && rounds >= 1 && n_row_blocks >= row_parts &&
       (long long)row_parts * K <= 1024 && (row_parts > 1 || rounds > 1)) {
     p.blk_prefix = row_block_prefix;
@@ -417,7 +422,7 @@ int wcn_wgrad(const void* feats, long long in_ld, const void* gout, long long ou
     }
   }
   if (max_ctas <= 0) max_ctas = sm_count();
-  return launch_wgrad(p, dtype, y_slabs, z_slabs, max_ctas, S(stream));
+  return launch_wgrad(p, dtype, y_slabs, z_slabs, max_ctas, n_in_rows, n_out_rows, S(stream));
 }
 
 /* ---- per-channel normalisation / activation passes over the feature matrix (rownorm.cu) ---- */

@@ -176,6 +176,23 @@ __device__ __forceinline__ void st_shared_elem<__half>(uint32_t addr, float f) {
                : "memory");
 }
 
+// adds to the pending transaction count of the current phase without arriving
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+
+// TMA tiled 2-D load: box (c0 = innermost coordinate, c1 = row) of the tensor map lands densely
+// (with the map's swizzle) at dst; out-of-range elements are zero-filled and still counted.
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, int c0, int c1,
+                                            uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cta.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(tmap), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+
 // TMA gather4: four rows (r0..r3, arbitrary) x one box width of a 2-D tensor map land as four
 // consecutive box rows at dst; rows outside the tensor are zero-filled.
 __device__ __forceinline__ void tma_gather4(uint32_t dst, const void* tmap, int col, int r0, int r1,

@@ -58,6 +58,12 @@ struct WgradParams {
   int n_row_blocks;
   int row_parts;       // P: row blocks of the virtual order
   int rounds;          // R: chunks per CTA (round-robin over the virtual list)
+  // identity offset of a submanifold map (in_maps == out_maps == 0..n-1 for offset identity_k):
+  // its rows are contiguous, so full stages are fetched by the TMA unit as 2-D tiles instead of
+  // 2 x 64 row gathers. -1 = off. `status` = the hash table's status word (bit 2: duplicate
+  // coordinates were seen, the identity property does not hold then).
+  int identity_k;
+  const int* status;
   long long in_ld;
   long long out_ld;
   long long dw_k_stride;  // elements between offsets

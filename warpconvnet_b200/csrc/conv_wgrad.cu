@@ -14,6 +14,10 @@
 //
 // CTA layout identical to the forward kernel: warps 0-3 gather, warp 4 issues MMAs, warps 5-8
 // drain TMEM (double buffered).
+#include <cuda.h>
+
+#include <cstring>
+
 #include "common.cuh"
 #include "conv_gemm.cuh"
 
@@ -108,7 +112,8 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 
 template <typename T, int PAIRS, int NSEGB>
 __global__ void __launch_bounds__(kWgThreads, 1)
-wgrad_kernel(const __grid_constant__ WgradParams p) {
+wgrad_kernel(const __grid_constant__ WgradParams p, const __grid_constant__ CUtensorMap tmap_x,
+             const __grid_constant__ CUtensorMap tmap_dy) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -253,10 +258,15 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
     uint32_t phase = 0;
     long long w_empty = 0, n_stage = 0, t_issue = 0, t_arrive = 0;
     const long long t_start = WCN_CLOCK();
+    // identity offset through the TMA unit (dense slab, one 128-byte-block pair per operand)
+    const bool tma_ok = NSEGB == 1 && kPairs == 64 && p.identity_k >= 0 &&
+                        (p.status == nullptr || (__ldg(p.status) & 4) == 0);
     WgSegCursor seg = make_cursor();
     int k, first, count;
     while (seg.next(k, first, count)) {
       const int n_st = (count + kPairs - 1) / kPairs;
+      const bool ident = tma_ok && k == p.identity_k;
+      const int ident_row0 = ident ? first - __ldg(p.offsets + k) : 0;
       // lane l < kRowsPerWarp holds the input row, lane 16 + ... the output row of pair
       // warp*kRowsPerWarp + l of the stage (kRowsPerWarp = 16: both in one register)
       auto load_idx = [&](int st, int& vi, int& vo) {
@@ -294,6 +304,22 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
           const uint32_t a_smem = smem_base + stage * stage_bytes;
           const uint32_t b_smem = a_smem + kAStage;
           const long long t_i0 = WCN_CLOCK();
+          if (ident && (st + 1) * kPairs <= count) {
+            // pairs (r, r) for r = ident_row0 + st*64 ...: four 64-row x 128-byte boxes, swizzled
+            // by the TMA unit exactly like the gathered layout ([block][pair row][128 B])
+            if (tid == 0) {
+              const uint32_t bar = smem_u32(&ctrl->full[stage]);
+              const int r = ident_row0 + st * kPairs;
+              mbar_expect_tx(bar, 4u * kPairs * 128u);
+              tma_load_2d(a_smem, &tmap_x, 0, r, bar);
+              tma_load_2d(a_smem + kPairs * 128, &tmap_x, kBlkElems, r, bar);
+              tma_load_2d(b_smem, &tmap_dy, 0, r, bar);
+              tma_load_2d(b_smem + kPairs * 128, &tmap_dy, kBlkElems, r, bar);
+            }
+            cp_async_mbar_arrive_noinc(smem_u32(&ctrl->full[stage]));
+            if (++stage == stages) { stage = 0; phase ^= 1u; }
+            continue;
+          }
 #pragma unroll
           for (int q = 0; q < kInstr; ++q) {
             const int row = 2 * q + sub;  // pair row inside this warp's share of the stage
@@ -459,9 +485,49 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
   }
 }
 
+typedef CUresult (*WcnEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                     const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static WcnEncodeTiledFn encode_tiled_fn() {
+  static WcnEncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) ==
+            cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<WcnEncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+// [n_rows, channels] row-major matrix as a 2-D tensor map with a (64-row x 128-byte) box and the
+// 128-byte swizzle of the MN-major operand layout. Returns false when the matrix cannot be mapped.
+static bool make_row_tile_map(CUtensorMap* map, const void* base, long long ld_elems, int channels,
+                              long long n_rows, int es, int box_rows, bool is_half) {
+  WcnEncodeTiledFn fn = encode_tiled_fn();
+  if (fn == nullptr || n_rows < 1 || (ld_elems * es) % 16 != 0 ||
+      (reinterpret_cast<uintptr_t>(base) & 15) != 0)
+    return false;
+  const cuuint64_t gdim[2] = {(cuuint64_t)channels, (cuuint64_t)n_rows};
+  const cuuint64_t gstr[1] = {(cuuint64_t)(ld_elems * es)};
+  const cuuint32_t box[2] = {(cuuint32_t)(128 / es), (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapDataType dt = es == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                 : (is_half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                                            : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+  return fn(map, dt, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <typename T, int PAIRS, int NSEGB>
 static int launch_wgrad_t(WgradParams p, int cin_slabs, int cout_slabs, int max_ctas,
-                          cudaStream_t stream) {
+                          long long n_in_rows, long long n_out_rows, cudaStream_t stream) {
   constexpr int kElem = (int)sizeof(T);
   constexpr int kBlkElems = 128 / kElem;
   constexpr int kPairs = PAIRS;
@@ -473,6 +539,23 @@ static int launch_wgrad_t(WgradParams p, int cin_slabs, int cout_slabs, int max_
     if (p.stages > kWgMaxStages) p.stages = kWgMaxStages;
   }
   if (p.stages < 2) return kErrUnsupportedShape;
+  (void)n_blk_b;
+  // TMA tiles for the identity offset: single dense slab, 16-bit operands, both matrices mappable
+  CUtensorMap tmap_x, tmap_dy;
+  memset(&tmap_x, 0, sizeof(tmap_x));
+  memset(&tmap_dy, 0, sizeof(tmap_dy));
+  if (p.identity_k >= 0) {
+    const bool ok = NSEGB == 1 && kPairs == 64 && kElem == 2 && cin_slabs == 1 && cout_slabs == 1 &&
+                    p.gps == 1 && p.in_coff == 0 && p.out_coff == 0 && p.identity_k < p.K &&
+                    make_row_tile_map(&tmap_x, p.feats, p.in_ld, p.cin, n_in_rows, kElem, kPairs,
+                                      ElemTraits<T>::kFmt == 0) &&
+                    make_row_tile_map(&tmap_dy, p.gout, p.out_ld, p.cout, n_out_rows, kElem, kPairs,
+                                      ElemTraits<T>::kFmt == 0);
+    if (p.debug & 2048)  // bring-up: WCN_DEBUG=2048 reports whether the TMA identity path is on
+      fprintf(stderr, "wcn wgrad: identity_k=%d tma_tiles=%d (encode fn %p)\n", p.identity_k, (int)ok,
+              (void*)encode_tiled_fn());
+    if (!ok) p.identity_k = -1;
+  }
   const size_t smem = (size_t)p.stages * stage_bytes + sizeof(WgSmemCtrl) + kWgSegTableBytes + 1024;
   static int configured[kMaxDevices] = {};  // per instantiation and device
   int& configured_smem = configured[current_device_slot()];
@@ -485,13 +568,13 @@ static int launch_wgrad_t(WgradParams p, int cin_slabs, int cout_slabs, int max_
   int per_slab = max_ctas / (cin_slabs * cout_slabs);
   if (per_slab < 1) per_slab = 1;
   dim3 grid(per_slab, cin_slabs, cout_slabs);
-  wgrad_kernel<T, PAIRS, NSEGB><<<grid, kWgThreads, smem, stream>>>(p);
+  wgrad_kernel<T, PAIRS, NSEGB><<<grid, kWgThreads, smem, stream>>>(p, tmap_x, tmap_dy);
   count_launch();
   return cudaGetLastError() == cudaSuccess ? kOk : kErrCuda;
 }
 
 int launch_wgrad(const WgradParams& p, int dtype, int cin_slabs, int cout_slabs, int max_ctas,
-                 cudaStream_t stream) {
+                 long long n_in_rows, long long n_out_rows, cudaStream_t stream) {
   const int es = dtype_size(dtype);
   if (p.K > kWgMaxK || p.K < 1) return kErrUnsupportedShape;
   if (p.cout < 16 || p.cout > 256 || p.cout % 16 != 0) return kErrUnsupportedShape;
@@ -505,11 +588,11 @@ int launch_wgrad(const WgradParams& p, int dtype, int cin_slabs, int cout_slabs,
     return kErrAlignment;
   switch (dtype) {
     case kBF16:
-      return p.cout * es > 256 ? launch_wgrad_t<__nv_bfloat16, 64, 2>(p, cin_slabs, cout_slabs, max_ctas, stream)
-                               : launch_wgrad_t<__nv_bfloat16, 64, 1>(p, cin_slabs, cout_slabs, max_ctas, stream);
+      return p.cout * es > 256 ? launch_wgrad_t<__nv_bfloat16, 64, 2>(p, cin_slabs, cout_slabs, max_ctas, n_in_rows, n_out_rows, stream)
+                               : launch_wgrad_t<__nv_bfloat16, 64, 1>(p, cin_slabs, cout_slabs, max_ctas, n_in_rows, n_out_rows, stream);
     case kF16:
-      return p.cout * es > 256 ? launch_wgrad_t<__half, 64, 2>(p, cin_slabs, cout_slabs, max_ctas, stream)
-                               : launch_wgrad_t<__half, 64, 1>(p, cin_slabs, cout_slabs, max_ctas, stream);
+      return p.cout * es > 256 ? launch_wgrad_t<__half, 64, 2>(p, cin_slabs, cout_slabs, max_ctas, n_in_rows, n_out_rows, stream)
+                               : launch_wgrad_t<__half, 64, 1>(p, cin_slabs, cout_slabs, max_ctas, n_in_rows, n_out_rows, stream);
     // fp32 rows as MN-major tf32 operands returned zeros on B200 (bring-up log round 1); the host
     // side splits fp32 into bf16 hi/lo parts instead (detail/unified.py:_wgrad_call).
     default: return kErrUnsupportedDtype;

@@ -133,6 +133,24 @@ _WGRAD_LOCALITY_BYTES = 48 << 20
 _WGRAD_ROUNDS = int(os.environ.get("WCN_WGRAD_ROUNDS", "2"))
 
 
+# Measured on C3-S: fetching the identity offset's rows (11 % of the pairs) as TMA tiles leaves the
+# kernel time unchanged (132.1 vs 132.6 us) — the CTAs that own those pairs finish early but the
+# static pair-count partition does not hand them more work, and a TMA-fed stage is still paced by
+# its four 128x128x16 MMAs (~600 of the 1 140 cycles of a gathered stage). Kept behind the C-ABI,
+# off by default (the two tensor-map encodes also cost host time per call).
+_WGRAD_IDENTITY_TMA = os.environ.get("WCN_WGRAD_IDENTITY_TMA", "0") == "1"
+
+
+def _wgrad_identity(kernel_map, K: int):
+    """The centre offset of a submanifold map (same coordinates, odd kernel, stride 1) pairs every
+    row with itself, in order: wgrad can fetch those rows as TMA tiles. The hash table's status
+    word tells the kernel when duplicate coordinates break that property."""
+    if not _WGRAD_IDENTITY_TMA or not getattr(kernel_map, "_symmetric", False) or K % 2 == 0:
+        return {}
+    table = getattr(kernel_map, "_hashtable", None)
+    return {"identity_k": K // 2, "status": None if table is None else table.status_tensor}
+
+
 def _wgrad_order(x: Tensor, gy: Tensor, kernel_map, K: int):
     bp = getattr(kernel_map, "_block_prefix", None)
     work = x.numel() * x.element_size() + gy.numel() * gy.element_size()
@@ -144,7 +162,7 @@ def _wgrad_order(x: Tensor, gy: Tensor, kernel_map, K: int):
 
 def _wgrad_call(x: Tensor, gy: Tensor, kernel_map, K: int, G: int, cin_g: int, cout_g: int) -> Tensor:
     im, om, od = kernel_map._in_buf, kernel_map._out_buf, kernel_map.offsets_dev
-    order = _wgrad_order(x, gy, kernel_map, K)
+    order = dict(_wgrad_order(x, gy, kernel_map, K), **_wgrad_identity(kernel_map, K))
     if x.dtype != torch.float32:
         return _ops.wgrad(x, gy, im, om, od, K, G, cin_g, cout_g, **order)
     # fp32 operands: the contraction runs over gathered rows (MN-major operands), which the
