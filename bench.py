@@ -121,6 +121,7 @@ class ClockSampler:
     def __init__(self, index: int):
         import threading
         self.rows, self.stop_flag, self.err = [], False, None
+        self.period = 0.0005  # seconds between NVML samples (raised for the host-paced e2e loop)
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -144,7 +145,7 @@ class ClockSampler:
             except Exception as e:  # pragma: no cover
                 self.err = repr(e)
                 break
-            time.sleep(0.0005)
+            time.sleep(self.period)
 
     def stop(self):
         if self.nv is None:
@@ -370,6 +371,10 @@ def run_ours(args):
     # untimed warm-up of the e2e loop: on a freshly booted box the first process sees ~1.5x slower
     # host->device copies for its first few dozen steps (link / host clocks ramping up; a second
     # process on the same box does not), so the loop is run for 50 steps before the K timed ones
+    if sampler is not None:
+        # the e2e loop is paced by the host thread: sample clocks every 20 ms there so the sampler
+        # thread does not compete with it for the interpreter lock
+        sampler.period = 0.02
     e2e_run(max(args.warmup, 50))
     barrier()
     s_ev, e_ev = e2e_run(args.steps)
