@@ -420,19 +420,41 @@ __global__ void __launch_bounds__(256)
 build_tiles_kernel(const int* __restrict__ table, int K, int M, const int* __restrict__ sorted_rows,
                    int tile_rows, int* __restrict__ step_nbr, int* __restrict__ step_k,
                    int* __restrict__ rows_padded, int* __restrict__ tile_nk) {
+  // 32 offsets per chunk: the 32 table loads of a thread are independent (one round trip instead
+  // of a dependent chain with a block barrier per offset: 20.4 us on C3), the tile's union mask of
+  // the chunk is ONE shared-memory OR, and every thread then writes its neighbours of the active
+  // offsets at their compacted step positions.
+  __shared__ unsigned s_union;
   const int tile = blockIdx.x;
   const int pos = tile * tile_rows + threadIdx.x;  // blockDim.x == tile_rows
   const int row = pos < M ? __ldg(sorted_rows + pos) : -1;
   rows_padded[pos] = row;
   int n = 0;
-  for (int k = 0; k < K; ++k) {
-    const int v = row >= 0 ? __ldg(table + (size_t)k * M + row) : -1;
-    if (__syncthreads_or(v >= 0)) {  // block-uniform
-      const size_t step = (size_t)tile * K + n;
-      step_nbr[step * tile_rows + threadIdx.x] = v;
-      if (threadIdx.x == 0) step_k[step] = k;
-      ++n;
+  for (int k0 = 0; k0 < K; k0 += 32) {
+    const int kc = min(32, K - k0);
+    if (threadIdx.x == 0) s_union = 0u;
+    __syncthreads();
+    int v[32];
+    unsigned hits = 0u;
+#pragma unroll
+    for (int kk = 0; kk < 32; ++kk) {
+      v[kk] = (kk < kc && row >= 0) ? __ldg(table + (size_t)(k0 + kk) * M + row) : -1;
+      hits |= (v[kk] >= 0 ? 1u : 0u) << kk;
     }
+    const unsigned warp_or = __reduce_or_sync(0xffffffffu, hits);
+    if ((threadIdx.x & 31) == 0 && warp_or) atomicOr(&s_union, warp_or);
+    __syncthreads();
+    const unsigned uni = s_union;
+#pragma unroll
+    for (int kk = 0; kk < 32; ++kk) {
+      if ((uni >> kk) & 1u) {  // block-uniform
+        const size_t step = (size_t)tile * K + n + __popc(uni & ((1u << kk) - 1u));
+        step_nbr[step * tile_rows + threadIdx.x] = v[kk];
+        if (threadIdx.x == 0) step_k[step] = k0 + kk;
+      }
+    }
+    n += __popc(uni);
+    __syncthreads();  // s_union is reset by the next chunk
   }
   if (threadIdx.x == 0) tile_nk[tile] = n;
 }
