@@ -206,13 +206,15 @@ def run_ours(args):
         """whole hot path, inputs resident in HBM; nothing in it synchronises with the host"""
         km = generate_kernel_map(bc, bc, (1, 1, 1), (KS,) * 3, same_coords=True)
         plan = km.fwd_plan(n)
-        img = _ops.weight_image(w.view(K, 1, CIN, COUT), K, 1, CIN, COUT, False)
+        # forward + dgrad weight images in one launch (what SparseConv3d's autograd function does)
+        img, img_t = _ops.weight_image_pair(w.view(K, 1, CIN, COUT), K, 1, CIN, COUT, w.dtype)
         y = _ops.gather_gemm(x, img, plan, 1, CIN, COUT)           # forward AB_gather_scatter
         dw = sparse_conv_wgrad(x, gy, (K, CIN, COUT), km)          # wgrad AtB_gather_gather
         # the only collective of the path: all-reduce of dW, issued as soon as wgrad is enqueued
         # so it overlaps dgrad (what DDP does with the rest of backward)
         work = dist.all_reduce(dw, async_op=True) if world > 1 else None
-        dx = sparse_conv_dgrad(gy, w, km, n)                       # dgrad ABt_gather_scatter
+        bplan, kflip = km.bwd_plan(n)                              # submanifold: fwd plan, k flipped
+        dx = _ops.gather_gemm(gy, img_t, bplan, 1, COUT, CIN, kflip=kflip)  # dgrad ABt_gather_scatter
         if work is not None:
             work.wait()
         return km, plan, img, y, dx, dw

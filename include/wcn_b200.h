@@ -177,6 +177,12 @@ size_t wcn_weight_image_bytes(int K, int groups, int cin_g, int cout_g, int dtyp
  * transpose_w = 1: dgrad image (rows = input channels, contraction over output channels). */
 int wcn_weight_image(const void* weight, void* image, int K, int groups, int cin_g, int cout_g,
                      int dtype, int transpose_w, void* stream);
+/* One launch for a layer's step: the forward image and (image_t != NULL) the dgrad image of the
+ * same weights. src_dtype is the dtype of `weight`: equal to `dtype`, or fp32 master weights
+ * converted (round to nearest even) to a 16-bit image dtype on the way
+ * (replaces weight.to(compute_dtype) + the two calls above). */
+int wcn_weight_image_pair(const void* weight, int src_dtype, void* image_fwd, void* image_t, int K,
+                          int groups, int cin_g, int cout_g, int dtype, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* The three sparse-conv GEMMs                                                                */

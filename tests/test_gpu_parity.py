@@ -404,3 +404,22 @@ def test_wgrad_row_block_major_order(kind, n, stride, ks, parts, rounds):
                              torch.zeros(K, cin, cout), km.in_maps.cpu().numpy(),
                              km.out_maps.cpu().numpy(), km.offsets.numpy())[1]
         assert oconv.rel_max_err(blocked.view(K, cin, cout), ref) < 1e-4
+
+
+@pytest.mark.parametrize("groups,cin,cout", [(1, 64, 128), (1, 48, 16), (4, 32, 64)])
+@pytest.mark.parametrize("src,dst", [(torch.float32, torch.bfloat16), (torch.float32, torch.float16),
+                                     (torch.bfloat16, torch.bfloat16), (torch.float32, torch.float32)])
+def test_weight_image_pair_equals_two_single_images(groups, cin, cout, src, dst):
+    """wcn_weight_image_pair (one launch, optional fp32 -> 16-bit conversion) produces byte-identical
+    images to cast + two wcn_weight_image calls."""
+    from warpconvnet_b200 import _ops
+    K = 27
+    g = torch.Generator().manual_seed(3)
+    w = torch.randn(K, groups, cin // groups, cout // groups, generator=g).to(src).cuda()
+    cg, og = cin // groups, cout // groups
+    a, b = _ops.weight_image_pair(w, K, groups, cg, og, dst)
+    wc = w.to(dst).contiguous()
+    assert torch.equal(a, _ops.weight_image(wc, K, groups, cg, og, transpose_w=False))
+    assert torch.equal(b, _ops.weight_image(wc, K, groups, cg, og, transpose_w=True))
+    only, none = _ops.weight_image_pair(w, K, groups, cg, og, dst, want_transposed=False)
+    assert none is None and torch.equal(only, a)

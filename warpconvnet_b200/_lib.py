@@ -77,6 +77,8 @@ SIGNATURES = {
                                           POINTER(c_int)]),
     "wcn_weight_image": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                  c_void_p]),
+    "wcn_weight_image_pair": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                      c_int, c_void_p]),
     "wcn_gather_gemm": (c_int, [c_void_p, c_int, c_longlong, c_void_p, c_void_p, c_longlong, c_void_p,
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                 c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int,

@@ -231,6 +231,26 @@ def weight_image(weight: Tensor, K: int, groups: int, cin_g: int, cout_g: int,
     return img
 
 
+def weight_image_pair(weight: Tensor, K: int, groups: int, cin_g: int, cout_g: int,
+                      image_dtype: torch.dtype, want_transposed: bool = True):
+    """(forward image, dgrad image | None) of contiguous weights [K, groups, cin_g, cout_g] in ONE
+    launch; fp32 weights are converted to a 16-bit ``image_dtype`` inside the kernel."""
+    _require_cuda(weight)
+    assert weight.is_contiguous()
+    code = dtype_code(image_dtype)
+    src = dtype_code(weight.dtype)
+    nb_f = lib.wcn_weight_image_bytes(K, groups, cin_g, cout_g, code, 0, None, None)
+    nb_t = lib.wcn_weight_image_bytes(K, groups, cin_g, cout_g, code, 1, None, None)
+    if nb_f == 0 or (want_transposed and nb_t == 0):
+        raise _lib.WcnError(
+            f"unsupported channel configuration groups={groups} cin/g={cin_g} cout/g={cout_g}")
+    img = torch.empty(nb_f, dtype=torch.uint8, device=weight.device)
+    img_t = torch.empty(nb_t, dtype=torch.uint8, device=weight.device) if want_transposed else None
+    check(lib.wcn_weight_image_pair(_p(weight), src, _p(img), _p(img_t), K, groups, cin_g, cout_g,
+                                    code, _stream()), "weight_image_pair")
+    return img, img_t
+
+
 def gather_gemm(feats: Tensor, wimg: Tensor, plan: TilePlan, groups: int, cin_g: int,
                 cout_g: int, out: Optional[Tensor] = None, bias: Optional[Tensor] = None,
                 relu: bool = False, kflip: bool = False, max_ctas: int = 0) -> Tensor:

@@ -39,7 +39,7 @@ int radius_count(const float*, int, const int*, const float*, int, const int*, i
 int radius_fill(int, const float*, int, const int*, int, float, const long long*, int*, float*,
                 void*, size_t, cudaStream_t);
 // weight_prep.cu
-int launch_weight_image(const WeightPrepParams&, cudaStream_t);
+int launch_weight_image(const WeightPrepParams&, const WeightPrepParams*, cudaStream_t);
 // rownorm.cu
 int rownorm_launch(int which, const RowNormParams&, int dtype, cudaStream_t);
 int bn_finalize(const double*, int, int, const float*, const float*, float, float, float*, float*,
@@ -240,10 +240,13 @@ size_t wcn_weight_image_bytes(int K, int groups, int cin_g, int cout_g, int dtyp
   return (size_t)plan.n_slabs * K * n_chunks * plan.bn * 128;
 }
 
-int wcn_weight_image(const void* weight, void* image, int K, int groups, int cin_g, int cout_g,
-                     int dtype, int transpose_w, void* stream) {
+// fills the parameter block of one image; src_dtype may be fp32 with a 16-bit image dtype
+static int weight_image_params(const void* weight, void* image, int K, int groups, int cin_g,
+                               int cout_g, int dtype, int src_dtype, int transpose_w,
+                               WeightPrepParams* out) {
   if (!weight || !image || K < 1) return kErrInvalidArg;
-  if (dtype < 0 || dtype > 2) return kErrUnsupportedDtype;
+  if (dtype < 0 || dtype > 2 || src_dtype < 0 || src_dtype > 2) return kErrUnsupportedDtype;
+  if (src_dtype != dtype && !(src_dtype == kF32 && dtype != kF32)) return kErrUnsupportedDtype;
   const int rg = transpose_w ? cin_g : cout_g;
   const int cg = transpose_w ? cout_g : cin_g;
   SlabPlan plan;
@@ -253,6 +256,8 @@ int wcn_weight_image(const void* weight, void* image, int K, int groups, int cin
   p.w = weight;
   p.img = image;
   p.es = dtype_size(dtype);
+  p.src_es = dtype_size(src_dtype);
+  p.cvt = src_dtype == dtype ? 0 : (dtype == kBF16 ? 1 : 2);
   p.K = K;
   p.n_slabs = plan.n_slabs;
   p.gps = plan.gps;
@@ -274,7 +279,28 @@ int wcn_weight_image(const void* weight, void* image, int K, int groups, int cin
   }
   const int ce = 128 / p.es;
   p.n_chunks = (plan.cdim + ce - 1) / ce;
-  return launch_weight_image(p, S(stream));
+  *out = p;
+  return kOk;
+}
+
+int wcn_weight_image(const void* weight, void* image, int K, int groups, int cin_g, int cout_g,
+                     int dtype, int transpose_w, void* stream) {
+  WeightPrepParams p;
+  const int st = weight_image_params(weight, image, K, groups, cin_g, cout_g, dtype, dtype,
+                                     transpose_w, &p);
+  if (st != kOk) return st;
+  return launch_weight_image(p, nullptr, S(stream));
+}
+
+int wcn_weight_image_pair(const void* weight, int src_dtype, void* image_fwd, void* image_t, int K,
+                          int groups, int cin_g, int cout_g, int dtype, void* stream) {
+  WeightPrepParams a, b;
+  int st = weight_image_params(weight, image_fwd, K, groups, cin_g, cout_g, dtype, src_dtype, 0, &a);
+  if (st != kOk) return st;
+  if (image_t == nullptr) return launch_weight_image(a, nullptr, S(stream));
+  st = weight_image_params(weight, image_t, K, groups, cin_g, cout_g, dtype, src_dtype, 1, &b);
+  if (st != kOk) return st;
+  return launch_weight_image(a, &b, S(stream));
 }
 
 int wcn_gather_gemm(const void* feats, int n_in_rows, long long in_ld, const void* wimg, void* out,

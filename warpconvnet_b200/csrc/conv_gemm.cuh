@@ -94,7 +94,9 @@ struct WeightPrepParams {
   int K, n_slabs, gps;  // gps = groups per slab
   int rg, cg;           // rows / contraction channels per group
   int n_chunks;
-  int es;               // element size in bytes
+  int es;               // element size of the IMAGE in bytes
+  int src_es;           // element size of the source weights (== es, or 4 with a 16-bit image)
+  int cvt;              // 0: copy bits, 1: fp32 -> bf16, 2: fp32 -> fp16 (round to nearest even)
 };
 
 }  // namespace wcn

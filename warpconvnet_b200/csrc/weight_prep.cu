@@ -16,7 +16,11 @@
 
 namespace wcn {
 
-__global__ void weight_image_kernel(const WeightPrepParams p) {
+// blockIdx.y selects the parameter block: one launch builds the forward image and the transposed
+// (dgrad) image of the same weights, optionally converting fp32 master weights to the 16-bit
+// compute type on the way (replaces weight.to(bf16) + two image launches per layer and step).
+__global__ void weight_image_kernel(const WeightPrepParams pa, const WeightPrepParams pb) {
+  const WeightPrepParams& p = blockIdx.y == 0 ? pa : pb;
   const int bn = p.gps * p.rg;
   const int cdim = p.gps * p.cg;
   const long long total = (long long)p.n_slabs * p.K * p.n_chunks * bn * 8;
@@ -41,7 +45,13 @@ __global__ void weight_image_kernel(const WeightPrepParams p) {
         const long long src = (long long)k * p.w_k_stride +
                               (long long)(s * p.gps + gl_row) * p.w_g_stride +
                               (long long)r * p.w_r_stride + (long long)cc * p.w_c_stride;
-        if (p.es == 2) {
+        if (p.cvt == 1) {
+          const __nv_bfloat16 h = __float2bfloat16_rn(reinterpret_cast<const float*>(p.w)[src]);
+          reinterpret_cast<uint16_t*>(vb)[e] = *reinterpret_cast<const uint16_t*>(&h);
+        } else if (p.cvt == 2) {
+          const __half h = __float2half_rn(reinterpret_cast<const float*>(p.w)[src]);
+          reinterpret_cast<uint16_t*>(vb)[e] = *reinterpret_cast<const uint16_t*>(&h);
+        } else if (p.es == 2) {
           reinterpret_cast<uint16_t*>(vb)[e] = reinterpret_cast<const uint16_t*>(p.w)[src];
         } else {
           reinterpret_cast<uint32_t*>(vb)[e] = reinterpret_cast<const uint32_t*>(p.w)[src];
@@ -54,14 +64,24 @@ __global__ void weight_image_kernel(const WeightPrepParams p) {
   }
 }
 
-int launch_weight_image(const WeightPrepParams& p, cudaStream_t stream) {
-  const int bn = p.gps * p.rg;
-  if (bn % 16 != 0 || bn > 256 || bn < 16) return kErrUnsupportedShape;
-  const long long total = (long long)p.n_slabs * p.K * p.n_chunks * bn * 8;
+static long long image_units(const WeightPrepParams& p) {
+  return (long long)p.n_slabs * p.K * p.n_chunks * (p.gps * p.rg) * 8;
+}
+
+// second == nullptr: one image
+int launch_weight_image(const WeightPrepParams& p, const WeightPrepParams* second,
+                        cudaStream_t stream) {
+  for (const WeightPrepParams* q : {&p, second}) {
+    if (q == nullptr) continue;
+    const int bn = q->gps * q->rg;
+    if (bn % 16 != 0 || bn > 256 || bn < 16) return kErrUnsupportedShape;
+  }
+  long long total = image_units(p);
+  if (second != nullptr && image_units(*second) > total) total = image_units(*second);
   if (total == 0) return kOk;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  weight_image_kernel<<<blocks, 256, 0, stream>>>(p);
+  weight_image_kernel<<<dim3(blocks, second ? 2 : 1), 256, 0, stream>>>(p, second ? *second : p);
   count_launch();
   return cudaGetLastError() == cudaSuccess ? kOk : kErrCuda;
 }

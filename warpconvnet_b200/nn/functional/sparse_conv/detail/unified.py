@@ -94,6 +94,27 @@ def _canon_weight(weight: Tensor, groups: int):
     return weight.contiguous(), cin_g, cout_g, cin_g, cout_g
 
 
+def _fusable_weight(weight: Tensor, compute_dtype: torch.dtype, groups: int):
+    """(K, G, cin_g, cout_g) when the weight can go through wcn_weight_image_pair as it is: no
+    channel padding, master dtype equal to the compute dtype or fp32 above a 16-bit one."""
+    if weight.dtype != compute_dtype and not (weight.dtype == torch.float32
+                                              and compute_dtype in (torch.bfloat16, torch.float16)):
+        return None
+    if groups == 1:
+        if weight.dim() != 3:
+            return None
+        K, cin, cout = weight.shape
+        if cin % _CH_ALIGN or cout % _CH_ALIGN:
+            return None
+        return K, 1, cin, cout
+    if weight.dim() != 4 or weight.shape[1] != groups:
+        return None
+    K, G, cin_g, cout_g = weight.shape
+    if cin_g % 8 or cout_g % 8:
+        return None
+    return K, G, cin_g, cout_g
+
+
 def sparse_conv_forward(in_features: Tensor, weight: Tensor, kernel_map: IntSearchResult,
                         num_out_coords: int, groups: int = 1, bias: Optional[Tensor] = None,
                         relu: bool = False) -> Tensor:
@@ -207,16 +228,27 @@ class UnifiedSpatiallySparseConvFunction(Function):
         if not in_features.is_cuda:
             raise RuntimeError("warpconvnet_b200 sparse conv needs CUDA tensors (no CPU fallback)")
         out_dtype = in_features.dtype
-        x, w = in_features, weight
-        if compute_dtype is not None:
-            if x.dtype != compute_dtype:
-                x = x.to(compute_dtype)
-            if w.dtype != compute_dtype:
-                w = w.to(compute_dtype)
-        elif w.dtype != x.dtype:
-            w = w.to(x.dtype)
-        y = sparse_conv_forward(x, w, kernel_map, num_out_coords, groups)
-        ctx.save_for_backward(x, w)
+        x = in_features
+        if compute_dtype is not None and x.dtype != compute_dtype:
+            x = x.to(compute_dtype)
+        # One launch prepares the forward AND the dgrad weight image straight from the master
+        # weights (fp32 -> compute dtype inside the kernel): no weight.to(bf16) copy, no second
+        # image launch in backward. Needs channel counts that take no padding.
+        fused = _fusable_weight(weight, x.dtype, groups)
+        if fused:
+            K, G, cin_g, cout_g = fused
+            w4 = weight.detach().contiguous().view(K, G, cin_g, cout_g)
+            img, img_t = _ops.weight_image_pair(w4, K, G, cin_g, cout_g, x.dtype,
+                                                want_transposed=bool(ctx.needs_input_grad[0]))
+            xp = _pad_cols(x, G * cin_g)
+            y = _ops.gather_gemm(xp, img, kernel_map.fwd_plan(num_out_coords), G, cin_g, cout_g)
+            ctx.save_for_backward(x, img_t)
+            ctx.fused_dims = (G, cin_g, cout_g)
+        else:
+            w = weight if weight.dtype == x.dtype else weight.to(x.dtype)
+            y = sparse_conv_forward(x, w, kernel_map, num_out_coords, groups)
+            ctx.save_for_backward(x, w)
+            ctx.fused_dims = None
         ctx.kernel_map = kernel_map
         ctx.groups = groups
         ctx.in_dtype = in_features.dtype
@@ -227,7 +259,7 @@ class UnifiedSpatiallySparseConvFunction(Function):
 
     @staticmethod
     def backward(ctx, grad_output):
-        x, w = ctx.saved_tensors
+        x, w = ctx.saved_tensors   # fused path: w is the dgrad weight image (or None)
         kernel_map = ctx.kernel_map
         gy = grad_output
         if gy.dtype != x.dtype:
@@ -235,7 +267,12 @@ class UnifiedSpatiallySparseConvFunction(Function):
         if not gy.is_contiguous():
             gy = gy.contiguous()
         grad_in = grad_w = None
-        if ctx.needs_input_grad[0]:
+        if ctx.needs_input_grad[0] and ctx.fused_dims is not None:
+            G, cin_g, cout_g = ctx.fused_dims
+            plan, kflip = kernel_map.bwd_plan(ctx.num_in)
+            grad_in = _ops.gather_gemm(_pad_cols(gy, G * cout_g), w, plan, G, cout_g, cin_g,
+                                       kflip=kflip).to(ctx.in_dtype)
+        elif ctx.needs_input_grad[0]:
             grad_in = sparse_conv_dgrad(gy, w, kernel_map, ctx.num_in, ctx.groups).to(ctx.in_dtype)
         if ctx.needs_input_grad[1]:
             grad_w = sparse_conv_wgrad(x, gy, ctx.weight_shape, kernel_map, ctx.groups)
