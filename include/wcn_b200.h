@@ -299,6 +299,18 @@ int wcn_depthwise_wgrad(const void* feats, long long in_ld, const void* gout, lo
                         float* dw, const int32_t* table, int n_rows, int K, int channels,
                         int dtype, void* stream);
 
+/* Training-mode BatchNorm (+ residual) (+ ReLU) of one layer in one call each way: zero-fill of
+ * `sums` (fp64 [2c]), statistics, finalize and apply (forward); zero-fill, reduction and apply
+ * (backward). scale_shift_mean_rstd is fp32 [4c]: scale, shift, mean, rstd (kept for backward). */
+int wcn_bn_forward(const void* x, long long ld_x, const void* res, long long ld_res, void* y,
+                   long long ld_y, int n, int c, int dtype, const float* gamma, const float* beta,
+                   float eps, float momentum, float* running_mean, float* running_var,
+                   double* sums, float* scale_shift_mean_rstd, int relu, void* stream);
+int wcn_bn_backward(const void* dy, long long ld_dy, const void* x, long long ld_x, const void* y,
+                    long long ld_y, void* dx, long long ld_dx, void* dres, long long ld_dres, int n,
+                    int c, int dtype, const float* gamma, const float* mean_rstd,
+                    const float* mask_scale, const float* mask_shift, double* sums, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -83,6 +83,12 @@ SIGNATURES = {
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                 c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int,
                                 c_void_p]),
+    "wcn_bn_forward": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong, c_int,
+                               c_int, c_int, c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p,
+                               c_void_p, c_void_p, c_int, c_void_p]),
+    "wcn_bn_backward": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong,
+                                c_void_p, c_longlong, c_void_p, c_longlong, c_int, c_int, c_int,
+                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "wcn_depthwise_conv": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_void_p,
                                    c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "wcn_depthwise_conv_plan": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_void_p,

@@ -505,3 +505,41 @@ def depthwise_wgrad_plan(feats: Tensor, gout: Tensor, plan: "TilePlan") -> Tenso
                                        plan.tile_rows, plan.K, C, dtype_code(feats.dtype),
                                        _stream()), "depthwise_wgrad_plan")
     return dw
+
+
+def bn_forward(x: Tensor, gamma: Optional[Tensor], beta: Optional[Tensor], eps: float,
+               momentum: float, running_mean: Optional[Tensor], running_var: Optional[Tensor],
+               residual: Optional[Tensor], relu: bool):
+    """Training-mode BatchNorm (+ residual) (+ ReLU) in one native call.
+    Returns (y, scale, shift, mean_rstd[2, c])."""
+    _require_cuda(x, residual)
+    n, c = x.shape
+    y = torch.empty((n, c), dtype=x.dtype, device=x.device)
+    sums = torch.empty((2, c), dtype=torch.float64, device=x.device)
+    buf = torch.empty((4, c), dtype=torch.float32, device=x.device)
+    px, ldx = _rows(x)
+    py, ldy = _rows(y)
+    pr, ldr = _rows(residual) if residual is not None else (None, 0)
+    check(lib.wcn_bn_forward(px, ldx, pr, ldr, py, ldy, n, c, dtype_code(x.dtype), _p(gamma),
+                             _p(beta), ctypes.c_float(eps), ctypes.c_float(momentum),
+                             _p(running_mean), _p(running_var), _p(sums), _p(buf), int(relu),
+                             _stream()), "bn_forward")
+    return y, buf[0], buf[1], buf[2:]
+
+
+def bn_backward(dy: Tensor, x: Tensor, y: Optional[Tensor], gamma: Tensor, mean_rstd: Tensor,
+                mask_scale: Optional[Tensor], mask_shift: Optional[Tensor], want_dres: bool):
+    """(dx, dres | None, sums fp64 [2, c]: d beta, d gamma) of training-mode BatchNorm in one call."""
+    n, c = x.shape
+    dx = torch.empty((n, c), dtype=dy.dtype, device=dy.device)
+    dres = torch.empty((n, c), dtype=dy.dtype, device=dy.device) if want_dres else None
+    sums = torch.empty((2, c), dtype=torch.float64, device=x.device)
+    pd, ldd = _rows(dy)
+    px, ldx = _rows(x)
+    py, ldy = _rows(y) if y is not None else (None, 0)
+    pdx, lddx = _rows(dx)
+    pdr, lddr = _rows(dres) if dres is not None else (None, 0)
+    check(lib.wcn_bn_backward(pd, ldd, px, ldx, py, ldy, pdx, lddx, pdr, lddr, n, c,
+                              dtype_code(dy.dtype), _p(gamma), _p(mean_rstd), _p(mask_scale),
+                              _p(mask_shift), _p(sums), _stream()), "bn_backward")
+    return dx, dres, sums

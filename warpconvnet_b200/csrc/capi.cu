@@ -513,6 +513,39 @@ int wcn_bn_bwd_apply(const void* dy, long long ld_dy, const void* x, long long l
   return rownorm_launch(3, p, dtype, S(stream));
 }
 
+/* One call per layer and direction: fewer host round trips for the host-paced small levels. */
+int wcn_bn_forward(const void* x, long long ld_x, const void* res, long long ld_res, void* y,
+                   long long ld_y, int n, int c, int dtype, const float* gamma, const float* beta,
+                   float eps, float momentum, float* running_mean, float* running_var,
+                   double* sums, float* scale_shift_mean_rstd, int relu, void* stream) {
+  if (!x || !y || !sums || !scale_shift_mean_rstd || n < 1 || c < 1) return kErrInvalidArg;
+  if (cudaMemsetAsync(sums, 0, (size_t)2 * c * sizeof(double), S(stream)) != cudaSuccess)
+    return kErrCuda;
+  float* scale = scale_shift_mean_rstd;
+  float* shift = scale + c;
+  float* mean_rstd = scale + 2 * c;
+  int st = wcn_bn_stats(x, ld_x, n, c, dtype, sums, stream);
+  if (st != kOk) return st;
+  st = wcn_bn_finalize(sums, n, c, gamma, beta, eps, momentum, running_mean, running_var, scale,
+                       shift, mean_rstd, stream);
+  if (st != kOk) return st;
+  return wcn_scale_shift_act(x, ld_x, res, ld_res, y, ld_y, n, c, dtype, scale, shift, relu, stream);
+}
+
+int wcn_bn_backward(const void* dy, long long ld_dy, const void* x, long long ld_x, const void* y,
+                    long long ld_y, void* dx, long long ld_dx, void* dres, long long ld_dres, int n,
+                    int c, int dtype, const float* gamma, const float* mean_rstd,
+                    const float* mask_scale, const float* mask_shift, double* sums, void* stream) {
+  if (!dy || !x || !dx || !gamma || !mean_rstd || !sums || n < 1 || c < 1) return kErrInvalidArg;
+  if (cudaMemsetAsync(sums, 0, (size_t)2 * c * sizeof(double), S(stream)) != cudaSuccess)
+    return kErrCuda;
+  int st = wcn_bn_bwd_reduce(dy, ld_dy, x, ld_x, y, ld_y, n, c, dtype, mean_rstd, mask_scale,
+                             mask_shift, sums, stream);
+  if (st != kOk) return st;
+  return wcn_bn_bwd_apply(dy, ld_dy, x, ld_x, y, ld_y, dx, ld_dx, dres, ld_dres, n, c, dtype, gamma,
+                          mean_rstd, sums, mask_scale, mask_shift, 1, stream);
+}
+
 /* ---- radius search (knn.cu) ---- */
 int wcn_radius_count(const float* ref, int n_ref, const int32_t* ref_offsets, const float* query,
                      int n_query, const int32_t* query_offsets, int n_batches, float radius,

@@ -33,10 +33,9 @@ class _BatchNormAct(torch.autograd.Function):
         if use_batch:
             if n == 0:
                 raise ValueError("BatchNorm in training mode needs at least one row")
-            sums = _ops.bn_stats(x)
-            scale, shift, mean_rstd = _ops.bn_finalize(
-                sums, n, gamma, beta, eps, momentum, running_mean if training else None,
-                running_var if training else None)
+            y, scale, shift, mean_rstd = _ops.bn_forward(
+                x, gamma, beta, eps, momentum, running_mean if training else None,
+                running_var if training else None, residual, relu)
         else:
             rstd = torch.rsqrt(running_var.float() + eps)
             scale = rstd if gamma is None else gamma * rstd
@@ -44,7 +43,7 @@ class _BatchNormAct(torch.autograd.Function):
             if beta is not None:
                 shift = shift + beta
             scale, shift, mean_rstd = scale.contiguous(), shift.contiguous(), None
-        y = _ops.scale_shift_act(x, scale, shift, residual, relu)
+            y = _ops.scale_shift_act(x, scale, shift, residual, relu)
         ctx.use_batch = use_batch
         ctx.relu = relu
         ctx.has_res = residual is not None
@@ -73,8 +72,7 @@ class _BatchNormAct(torch.autograd.Function):
         need_res = ctx.has_res and ctx.needs_input_grad[3]
         if ctx.use_batch:
             g = gamma if gamma is not None else torch.ones(c, dtype=torch.float32, device=x.device)
-            sums = _ops.bn_bwd_reduce(dy, x, y, mean_rstd, msc, msh)
-            dx, dres = _ops.bn_bwd_apply(dy, x, y, g, mean_rstd, sums, True, need_res, msc, msh)
+            dx, dres, sums = _ops.bn_backward(dy, x, y, g, mean_rstd, msc, msh, need_res)
             dgamma = sums[1].to(ctx.w_dtype) if ctx.has_w else None
             dbeta = sums[0].to(ctx.b_dtype) if ctx.has_b else None
         else:
