@@ -16,15 +16,17 @@
 //   warps 0-3  gather producers: cp.async (16 B per lane, zero-fill for missing neighbours)
 //              straight into the 128B-swizzled K-major A tile. A stage covers GC = 2 adjacent
 //              128-byte channel chunks, so 16 lanes fetch 256 CONTIGUOUS bytes of one feature row:
-//              measured on B200 (tools/gather_bench.cu) the L2->SM path serves ~1 gather request
-//              per 8 cycles per SM whatever its size, 16 B/cycle/SM for 128-byte requests and
-//              28 B/cycle/SM for 256-byte ones, identical for LDGSTS, LDG+STS and TMA gather4
-//              (gather4 additionally issues warp-serially). Shared-memory offsets are per-thread
-//              constants. With TM = 2 a stage holds two 128-row A sub-tiles that share one weight
-//              slice. Thread 0 also pulls the per-offset weight slice (a pre-swizzled image in
-//              global memory) through the TMA unit with one cp.async.bulk per stage.
-//   warp  4    lane 0 issues tcgen05.mma (M=128, N=bn, K=32 B per instruction), accumulators in
-//              TMEM, double buffered so the epilogue of tile i overlaps the MMAs of tile i+1
+//              measured on B200 (tools/l2sm_bench.cu, tools/hybrid_bench.cu) the LSU path serves
+//              about one gathered row per 8-9 cycles per SM whatever its length up to 256 bytes
+//              (16 B/cycle/SM for 128-byte rows, 27-35 for 256-byte rows; sequential = random), TMA
+//              tile::gather4 is request-rate bound below that (7.8 B/cycle/SM) and does not add to
+//              it, while large cp.async.bulk copies ride on a separate, much faster path. Shared-
+//              memory offsets are per-thread constants. With TM = 2 a stage holds two 128-row A
+//              sub-tiles that share one weight slice. Thread 0 also pulls the per-offset weight
+//              slice (a pre-swizzled image in global memory) with one cp.async.bulk per stage.
+//   warp  4    lane 0 issues tcgen05.mma (K = 32 B per instruction; swap-AB form: M = 128 output
+//              channels x N = 256 tile rows, else M = 128 rows x N = bn), accumulators in TMEM,
+//              double buffered so the epilogue of tile i overlaps the MMAs of tile i+1
 //   warps 5-8  epilogue: tcgen05.ld -> (+bias, ReLU) -> bf16/fp16/fp32 -> swizzled smem staging ->
 //              128-bit global stores, 16 lanes per 256 contiguous bytes of an output row
 #include "common.cuh"
