@@ -61,29 +61,16 @@ def _apply_generative_policy(input_sparse_tensor: Voxels, kernel_size, kernel_di
 
 
 @torch.compiler.disable
-def spatially_sparse_conv(
-    input_sparse_tensor: Geometry,
-    weight: Tensor,
-    kernel_size: Union[int, List[int], Tuple[int, ...]],
-    stride: Union[int, List[int], Tuple[int, ...]] = 1,
-    kernel_dilation: Union[int, List[int], Tuple[int, ...]] = 1,
-    bias: Optional[Tensor] = None,
-    groups: int = 1,
-    use_fp16_accum: Optional[bool] = None,
-    kernel_matmul_batch_size: int = 2,
-    generative: bool = False,
-    output_spatially_sparse_tensor: Optional[Geometry] = None,
-    transposed: bool = False,
-    fwd_algo=SPARSE_CONV_AB_ALGO_MODE.TCGEN05,
-    dgrad_algo=SPARSE_CONV_AB_ALGO_MODE.TCGEN05,
-    wgrad_algo=SPARSE_CONV_ATB_ALGO_MODE.TCGEN05,
-    stride_mode: STRIDED_CONV_MODE = STRIDED_CONV_MODE.STRIDE_ONLY,
-    stride_reduce: str = "max",
-    order=None,
-    compute_dtype: Optional[torch.dtype] = None,
-    implicit_matmul_fwd_block_size: Optional[int] = 16,
-    implicit_matmul_bwd_block_size: Optional[int] = 16,
-) -> Geometry:
+def spatially_sparse_conv(input_sparse_tensor, weight, kernel_size, stride=1, kernel_dilation=1,
+                          bias=None, groups=1, use_fp16_accum=None, kernel_matmul_batch_size=2,
+                          generative=False, output_spatially_sparse_tensor=None, transposed=False,
+                          fwd_algo=SPARSE_CONV_AB_ALGO_MODE.TCGEN05,
+                          dgrad_algo=SPARSE_CONV_AB_ALGO_MODE.TCGEN05,
+                          wgrad_algo=SPARSE_CONV_ATB_ALGO_MODE.TCGEN05,
+                          stride_mode=STRIDED_CONV_MODE.STRIDE_ONLY, stride_reduce="max", order=None,
+                          compute_dtype=None, implicit_matmul_fwd_block_size=16,
+                          implicit_matmul_bwd_block_size=16) -> Geometry:
+    """Functional sparse convolution (same keywords as the reference's, helper.py:147-358)."""
     if not isinstance(input_sparse_tensor, Voxels):
         raise TypeError("Native spatially_sparse_conv expects input_sparse_tensor of type Voxels, "
                         f"got {type(input_sparse_tensor)}")
@@ -127,12 +114,10 @@ def spatially_sparse_conv(
         assert any(o < i for o, i in zip(out_tensor_stride, in_tensor_stride)), \
             "Output stride is larger than input stride"
 
-    if compute_dtype is not None:
-        effective_compute_dtype = compute_dtype
-    elif torch.is_autocast_enabled():
-        effective_compute_dtype = torch.get_autocast_dtype("cuda")
-    else:
-        effective_compute_dtype = input_sparse_tensor.batched_features.dtype
+    effective_compute_dtype = compute_dtype
+    if effective_compute_dtype is None:
+        effective_compute_dtype = (torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled()
+                                   else input_sparse_tensor.batched_features.dtype)
 
     if stride_mode == STRIDED_CONV_MODE.REDUCE_AND_STRIDE and any(s != 1 for s in _stride):
         raise NotImplementedError(
@@ -175,20 +160,14 @@ def spatially_sparse_conv(
 
 
 @torch.compiler.disable
-def generate_output_coords_and_kernel_map(
-    input_sparse_tensor: Voxels,
-    kernel_size: Tuple[int, ...],
-    kernel_dilation: Tuple[int, ...],
-    stride: Tuple[int, ...],
-    generative: bool = False,
-    transposed: bool = False,
-    output_spatially_sparse_tensor: Optional[Voxels] = None,
-    stride_mode: STRIDED_CONV_MODE = STRIDED_CONV_MODE.STRIDE_ONLY,
-    order=None,
-    kernel_search_batch_size: Optional[int] = None,
-    out_code_backend: Optional[str] = None,
-) -> Tuple[Tensor, Tensor, IntSearchResult]:
-    """helper.py:361-567."""
+def generate_output_coords_and_kernel_map(input_sparse_tensor, kernel_size, kernel_dilation, stride,
+                                          generative=False, transposed=False,
+                                          output_spatially_sparse_tensor=None,
+                                          stride_mode=STRIDED_CONV_MODE.STRIDE_ONLY, order=None,
+                                          kernel_search_batch_size=None, out_code_backend=None):
+    """(batch-indexed output coordinates, output offsets, kernel map) for one conv; kernel maps are
+    cached on the input ``Voxels`` and transposed convs reuse the encoder's map with in / out
+    swapped (same rules as the reference, helper.py:361-567)."""
     bin_coords = input_sparse_tensor.batch_indexed_coordinates
     same_coords = False
     if output_spatially_sparse_tensor is not None:
