@@ -130,10 +130,15 @@ int wcn_sort_rows_by_key(const uint64_t* keys, int M, int K, int32_t* rows_out, 
  *   step_k[t*K + i]                = kernel offset of step i < tile_nk[t] (ascending)
  *   step_nbr[(t*K + i)*tile_rows + r] = table[step_k][sorted row r of the tile]  (-1 = none)
  *   tile_cum[0..num_tiles]         = exclusive prefix sum of tile_nk (work balancing)
+ *   cta_units[0..n_range_ctas]     = (optional, n_range_ctas > 0) first 128-row unit of each of
+ *                                    n_range_ctas CTAs of wcn_gather_gemm, balanced by step count;
+ *                                    pass the same array and count to wcn_gather_gemm, whose
+ *                                    prologue then skips its own search when its grid matches
  * step_nbr is sized for the upper bound K*m_pad ints, step_k for K*num_tiles ints. */
 int wcn_build_tiles(const int32_t* table, int K, int M, const int32_t* sorted_rows, int tile_rows,
                     int m_pad, int32_t* step_nbr, int32_t* step_k, int32_t* rows_padded,
-                    int32_t* tile_nk, int32_t* tile_cum, void* stream);
+                    int32_t* tile_nk, int32_t* tile_cum, int n_range_ctas, int32_t* cta_units,
+                    void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Batched exact k-nearest-neighbour search for Points / PointConv                            */
@@ -201,7 +206,7 @@ int wcn_gather_gemm(const void* feats, int n_in_rows, long long in_ld, const voi
                     const int32_t* rows, const int32_t* tile_nk, const int32_t* tile_cum,
                     int num_tiles, int tile_rows, int m_pad, int K, int groups, int cin_g,
                     int cout_g, int dtype, const float* bias, int relu, int kflip, int max_ctas,
-                    void* stream);
+                    const int32_t* cta_units, int n_range_ctas, void* stream);
 
 /* wgrad AtB_gather_gather
  * (replaces _C.mask_gemm.wgrad: csrc/bindings/mask_gemm_bindings.cu:1755-2040 and

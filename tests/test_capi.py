@@ -66,7 +66,7 @@ def test_argument_errors_without_gpu():
     assert lib.wcn_hash_insert(None, None, None, 4, 16, None, None) == -1
     assert lib.wcn_kernel_map_num_blocks(1000) == 4
     assert lib.wcn_gather_gemm(None, 0, 0, None, None, 0, None, None, None, None, None, 4, 128, 512,
-                               27, 1, 64, 64, 0, None, 0, 0, 0, None) == -1
+                               27, 1, 64, 64, 0, None, 0, 0, 0, None, 0, None) == -1
     assert lib.wcn_wgrad(None, 0, None, 0, None, None, None, None, 27, 1, 64, 64, 0, 1.0, 0, 0,
                          None, 0, 1, 1, -1, None, 0, 0, None) == -1
     assert lib.wcn_depthwise_conv(None, 0, None, 0, None, None, None, 8, 27, 64, 0, 0, 0,
@@ -98,3 +98,21 @@ def test_missing_library_fails_loudly(tmp_path):
                         f"import sys; sys.path.insert(0, {str(tmp_path)!r}); import pkg._lib"],
                        capture_output=True, text=True)
     assert r.returncode != 0 and "native library not found" in r.stderr
+
+
+def test_ctypes_signatures_match_header_argument_counts():
+    """Every ctypes signature lists exactly as many arguments as the prototype in
+    include/wcn_b200.h (a short argtypes list makes ctypes pass the surplus pointers as 32-bit
+    ints: a truncated stream / device pointer, i.e. a crash that depends on address bits)."""
+    import os
+    import re
+    from warpconvnet_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "wcn_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    for name, (_, args) in _lib.SIGNATURES.items():
+        m = re.search(r"\b" + name + r"\s*\((.*?)\)\s*;", hdr, flags=re.S)
+        assert m is not None, f"{name} is bound but not declared in the header"
+        body = m.group(1).strip()
+        n = 0 if body in ("", "void") else body.count(",") + 1
+        assert n == len(args), f"{name}: header has {n} parameters, ctypes lists {len(args)}"

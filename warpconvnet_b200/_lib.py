@@ -65,7 +65,7 @@ SIGNATURES = {
     "wcn_sort_rows_by_key": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t,
                                      c_void_p]),
     "wcn_build_tiles": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p,
-                                c_void_p, c_void_p, c_void_p, c_void_p]),
+                                c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "wcn_knn_workspace_bytes": (c_size_t, [c_int, c_int]),
     "wcn_knn_search": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int,
                                c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
@@ -82,7 +82,7 @@ SIGNATURES = {
     "wcn_gather_gemm": (c_int, [c_void_p, c_int, c_longlong, c_void_p, c_void_p, c_longlong, c_void_p,
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                 c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int,
-                                c_void_p]),
+                                c_void_p, c_int, c_void_p]),
     "wcn_bn_forward": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong, c_int,
                                c_int, c_int, c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p,
                                c_void_p, c_void_p, c_int, c_void_p]),

@@ -27,6 +27,17 @@ def _stream() -> int:
     return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
 
 
+_SM_COUNT = {}
+
+
+def _sm_count(dev) -> int:
+    idx = torch.device(dev).index
+    idx = torch.cuda.current_device() if idx is None else idx
+    if idx not in _SM_COUNT:
+        _SM_COUNT[idx] = torch.cuda.get_device_properties(idx).multi_processor_count
+    return _SM_COUNT[idx]
+
+
 def _p(t: Optional[Tensor]):
     return None if t is None else t.data_ptr()
 
@@ -174,6 +185,8 @@ class TilePlan:
     m_pad: int
     num_tiles: int
     tile_rows: int
+    cta_units: Optional[Tensor] = None  # [n_range_ctas + 1] unit range of every GEMM CTA
+    n_range_ctas: int = 0
 
 
 # 256-row tiles let two 128-row MMA sub-tiles share every weight slice (half the weight traffic);
@@ -205,10 +218,16 @@ def build_tile_plan(table: Tensor, keys: Optional[Tensor] = None,
     rows = torch.empty(max(m_pad, 1), dtype=torch.int32, device=dev)
     tile_nk = torch.empty(max(num_tiles, 1), dtype=torch.int32, device=dev)
     tile_cum = torch.empty(num_tiles + 1, dtype=torch.int32, device=dev)
+    # per-CTA unit ranges of the gather-GEMM kernel for its default grid (one CTA per SM, never
+    # more than 128-row units): computed by the plan's scan kernel, read by the GEMM prologue
+    n_range = min(_sm_count(dev), num_tiles * (tile_rows // TILE_M))
+    cta_units = torch.empty(n_range + 1, dtype=torch.int32, device=dev) if n_range > 0 else None
     check(lib.wcn_build_tiles(_p(table), K, M, _p(rows_sorted), tile_rows, m_pad, _p(step_nbr),
-                              _p(step_k), _p(rows), _p(tile_nk), _p(tile_cum), _stream()),
+                              _p(step_k), _p(rows), _p(tile_nk), _p(tile_cum), n_range,
+                              _p(cta_units), _stream()),
           "build_tiles")
-    return TilePlan(step_nbr, step_k, rows, tile_nk, tile_cum, K, M, m_pad, num_tiles, tile_rows)
+    return TilePlan(step_nbr, step_k, rows, tile_nk, tile_cum, K, M, m_pad, num_tiles, tile_rows,
+                    cta_units, n_range)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -270,7 +289,8 @@ def gather_gemm(feats: Tensor, wimg: Tensor, plan: TilePlan, groups: int, cin_g:
                               _p(plan.step_nbr), _p(plan.step_k), _p(plan.rows), _p(plan.tile_nk),
                               _p(plan.tile_cum), plan.num_tiles, plan.tile_rows, plan.m_pad,
                               plan.K, groups, cin_g, cout_g, code, _p(bias), int(relu),
-                              int(kflip), max_ctas, _stream()),
+                              int(kflip), max_ctas, _p(plan.cta_units), plan.n_range_ctas,
+                              _stream()),
           "gather_gemm")
     return out
 

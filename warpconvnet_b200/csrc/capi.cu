@@ -27,7 +27,7 @@ int mask_keys_from_table(const int*, int, int, unsigned long long*, cudaStream_t
 int csr_to_table(const int*, const int*, const int*, int, int, int, int*, cudaStream_t);
 size_t sort_workspace_bytes(int);
 int sort_rows_by_key(const unsigned long long*, int, int, int*, void*, size_t, cudaStream_t);
-int build_tiles(const int*, int, int, const int*, int, int, int*, int*, int*, int*, int*,
+int build_tiles(const int*, int, int, const int*, int, int, int*, int*, int*, int*, int*, int, int*,
                 cudaStream_t);
 // knn.cu
 size_t knn_workspace_bytes(int, int, int);
@@ -58,7 +58,8 @@ int depthwise_plan_wgrad_launch(const void* x, long long ld_x, const void* dy, l
                                 const int* tile_nk, int num_tiles, int tile_rows, int K, int C,
                                 int dtype, cudaStream_t s);
 // conv_fwd.cu / conv_wgrad.cu
-int launch_gather_gemm(const GatherGemmParams&, int dtype, int n_slabs, int max_ctas, cudaStream_t);
+int launch_gather_gemm(const GatherGemmParams&, int dtype, int n_slabs, int max_ctas,
+                       int n_range_ctas, cudaStream_t);
 int launch_wgrad(const WgradParams&, int dtype, int y_slabs, int z_slabs, int max_ctas,
                  long long n_in_rows, long long n_out_rows, cudaStream_t);
 
@@ -205,12 +206,14 @@ int wcn_sort_rows_by_key(const uint64_t* keys, int M, int K, int32_t* rows_out, 
 }
 int wcn_build_tiles(const int32_t* table, int K, int M, const int32_t* sorted_rows, int tile_rows,
                     int m_pad, int32_t* step_nbr, int32_t* step_k, int32_t* rows_padded,
-                    int32_t* tile_nk, int32_t* tile_cum, void* stream) {
+                    int32_t* tile_nk, int32_t* tile_cum, int n_range_ctas, int32_t* cta_units,
+                    void* stream) {
   if (!tile_cum || !tile_nk) return kErrInvalidArg;
   if (m_pad > 0 && (!table || !sorted_rows || !step_nbr || !step_k || !rows_padded))
     return kErrInvalidArg;
+  if (n_range_ctas < 0 || (n_range_ctas > 0 && !cta_units)) return kErrInvalidArg;
   return build_tiles(table, K, M, sorted_rows, tile_rows, m_pad, step_nbr, step_k, rows_padded,
-                     tile_nk, tile_cum, S(stream));
+                     tile_nk, tile_cum, n_range_ctas, cta_units, S(stream));
 }
 
 size_t wcn_knn_workspace_bytes(int n_ref, int n_batches) {
@@ -308,7 +311,7 @@ int wcn_gather_gemm(const void* feats, int n_in_rows, long long in_ld, const voi
                     const int32_t* rows, const int32_t* tile_nk, const int32_t* tile_cum,
                     int num_tiles, int tile_rows, int m_pad, int K, int groups, int cin_g,
                     int cout_g, int dtype, const float* bias, int relu, int kflip, int max_ctas,
-                    void* stream) {
+                    const int32_t* cta_units, int n_range_ctas, void* stream) {
   if (num_tiles > 0 && (!feats || !wimg || !out || !step_nbr || !step_k || !rows || !tile_nk ||
                         !tile_cum))
     return kErrInvalidArg;
@@ -330,6 +333,7 @@ int wcn_gather_gemm(const void* feats, int n_in_rows, long long in_ld, const voi
   p.rows = rows;
   p.tile_nk = tile_nk;
   p.tile_cum = tile_cum;
+  p.cta_units = (cta_units != nullptr && n_range_ctas > 0) ? cta_units : nullptr;
   p.tile_rows = tile_rows;
   p.bias = bias;
   p.in_ld = in_ld;
@@ -354,7 +358,7 @@ int wcn_gather_gemm(const void* feats, int n_in_rows, long long in_ld, const voi
     if (st_env) p.stages = atoi(st_env);
   }
   if (max_ctas <= 0) max_ctas = sm_count();
-  return launch_gather_gemm(p, dtype, plan.n_slabs, max_ctas, S(stream));
+  return launch_gather_gemm(p, dtype, plan.n_slabs, max_ctas, n_range_ctas, S(stream));
 }
 
 int wcn_wgrad(const void* feats, long long in_ld, const void* gout, long long out_ld, float* dw,

@@ -196,13 +196,18 @@ gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
     const long long S = (long long)U * __ldg(p.tile_cum + nt);
     const int G = gridDim.x, b = blockIdx.x + warp;
     const long long target = S * b / G;
-    int u = (b >= G) ? U * nt : lower_bound_unit(p.tile_cum, p.tile_nk, nt, U, target, lane);
-    // round to the NEAREST unit boundary (the lower bound alone biases every range by up to a
-    // whole unit = ~9 steps: 81 .. 114 unit-steps per CTA instead of 98 +- 5, tools/exp_dbg.py)
-    if (b > 0 && b < G && u > 0) {
-      const long long above = unit_cost(p.tile_cum, p.tile_nk, U, u) - target;
-      const long long below = target - unit_cost(p.tile_cum, p.tile_nk, U, u - 1);
-      if (below < above) --u;
+    int u;
+    if (p.cta_units != nullptr) {
+      u = __ldg(p.cta_units + b);  // computed with the plan (tile_scan_kernel), same rule
+    } else {
+      u = (b >= G) ? U * nt : lower_bound_unit(p.tile_cum, p.tile_nk, nt, U, target, lane);
+      // round to the NEAREST unit boundary (the lower bound alone biases every range by up to a
+      // whole unit = ~9 steps: 81 .. 114 unit-steps per CTA instead of 98 +- 5, tools/exp_dbg.py)
+      if (b > 0 && b < G && u > 0) {
+        const long long above = unit_cost(p.tile_cum, p.tile_nk, U, u) - target;
+        const long long below = target - unit_cost(p.tile_cum, p.tile_nk, U, u - 1);
+        if (below < above) --u;
+      }
     }
     if (lane == 0) {
       if (warp == 0) ctrl->u_begin = u; else ctrl->u_end = u;
@@ -619,7 +624,8 @@ static int pick_gemm_stages(int bn, int tm, int gc) {
 }
 
 template <typename T, int TM, int GC, bool SWAP>
-static int launch_gather_gemm_t(GatherGemmParams p, int n_slabs, int max_ctas, cudaStream_t stream) {
+static int launch_gather_gemm_t(GatherGemmParams p, int n_slabs, int max_ctas, int n_range_ctas,
+                                cudaStream_t stream) {
   const int max_stages = pick_gemm_stages(p.bn, TM, GC);
   if (p.stages <= 0 || p.stages > max_stages) p.stages = max_stages;
   if (p.stages < 2) return kErrUnsupportedShape;
@@ -635,6 +641,7 @@ static int launch_gather_gemm_t(GatherGemmParams p, int n_slabs, int max_ctas, c
   const int units = p.num_tiles * (p.tile_rows / kTileM);
   int ctas = units < max_ctas ? units : max_ctas;
   if (ctas < 1) return kOk;
+  if (p.cta_units != nullptr && ctas != n_range_ctas) p.cta_units = nullptr;  // other grid: search
   dim3 grid(ctas, n_slabs, 1);
   gather_gemm_kernel<T, TM, GC, SWAP><<<grid, kGemmThreads, smem, stream>>>(p);
   count_launch();
@@ -643,7 +650,7 @@ static int launch_gather_gemm_t(GatherGemmParams p, int n_slabs, int max_ctas, c
 
 template <typename T>
 static int launch_gather_gemm_tm(const GatherGemmParams& p, int n_slabs, int max_ctas,
-                                 cudaStream_t stream) {
+                                 int n_range_ctas, cudaStream_t stream) {
   // TM = 2: two 128-row sub-tiles share each weight slice when the plan has 256-row tiles and
   // both accumulators (double buffered) fit the 512 TMEM columns.
   // GC = 2: a stage covers two 128-byte channel chunks so gathers are 256-byte requests.
@@ -655,19 +662,19 @@ static int launch_gather_gemm_tm(const GatherGemmParams& p, int n_slabs, int max
   // 117 us at 32/64 — so it is only taken where the padding is small)
   const bool swap = tm2 && p.bn > 96 && p.bn <= kTileM && !(p.debug & 64);       // 64: bring-up
   if (swap) {
-    return gc2 ? launch_gather_gemm_t<T, 2, 2, true>(p, n_slabs, max_ctas, stream)
-               : launch_gather_gemm_t<T, 2, 1, true>(p, n_slabs, max_ctas, stream);
+    return gc2 ? launch_gather_gemm_t<T, 2, 2, true>(p, n_slabs, max_ctas, n_range_ctas, stream)
+               : launch_gather_gemm_t<T, 2, 1, true>(p, n_slabs, max_ctas, n_range_ctas, stream);
   }
   if (tm2) {
-    return gc2 ? launch_gather_gemm_t<T, 2, 2, false>(p, n_slabs, max_ctas, stream)
-               : launch_gather_gemm_t<T, 2, 1, false>(p, n_slabs, max_ctas, stream);
+    return gc2 ? launch_gather_gemm_t<T, 2, 2, false>(p, n_slabs, max_ctas, n_range_ctas, stream)
+               : launch_gather_gemm_t<T, 2, 1, false>(p, n_slabs, max_ctas, n_range_ctas, stream);
   }
-  return gc2 ? launch_gather_gemm_t<T, 1, 2, false>(p, n_slabs, max_ctas, stream)
-             : launch_gather_gemm_t<T, 1, 1, false>(p, n_slabs, max_ctas, stream);
+  return gc2 ? launch_gather_gemm_t<T, 1, 2, false>(p, n_slabs, max_ctas, n_range_ctas, stream)
+             : launch_gather_gemm_t<T, 1, 1, false>(p, n_slabs, max_ctas, n_range_ctas, stream);
 }
 
 int launch_gather_gemm(const GatherGemmParams& p, int dtype, int n_slabs, int max_ctas,
-                       cudaStream_t stream) {
+                       int n_range_ctas, cudaStream_t stream) {
   const int es = dtype_size(dtype);
   if (p.bn < 16 || p.bn > 256 || (p.bn % 16) != 0) return kErrUnsupportedShape;
   if (p.cin <= 0 || (p.cin * es) % 32 != 0) return kErrUnsupportedShape;
@@ -682,9 +689,9 @@ int launch_gather_gemm(const GatherGemmParams& p, int dtype, int n_slabs, int ma
   if (p.m_pad % p.tile_rows != 0 || (long long)p.num_tiles * p.tile_rows > p.m_pad)
     return kErrInvalidArg;
   switch (dtype) {
-    case kBF16: return launch_gather_gemm_tm<__nv_bfloat16>(p, n_slabs, max_ctas, stream);
-    case kF16: return launch_gather_gemm_tm<__half>(p, n_slabs, max_ctas, stream);
-    case kF32: return launch_gather_gemm_tm<float>(p, n_slabs, max_ctas, stream);
+    case kBF16: return launch_gather_gemm_tm<__nv_bfloat16>(p, n_slabs, max_ctas, n_range_ctas, stream);
+    case kF16: return launch_gather_gemm_tm<__half>(p, n_slabs, max_ctas, n_range_ctas, stream);
+    case kF32: return launch_gather_gemm_tm<float>(p, n_slabs, max_ctas, n_range_ctas, stream);
     default: return kErrUnsupportedDtype;
   }
 }

@@ -19,6 +19,7 @@ struct GatherGemmParams {
   const int* rows;          // [m_pad] output row of each sorted position, -1 = padding
   const int* tile_nk;       // [num_tiles] number of steps (active offsets) of each tile
   const int* tile_cum;      // [num_tiles + 1] exclusive prefix sum of tile_nk
+  const int* cta_units;     // optional [gridDim.x + 1] precomputed unit range of every CTA
   const float* bias;        // optional [cout_total] fp32, added in the epilogue
   long long in_ld;          // row strides in elements
   long long out_ld;

@@ -461,7 +461,8 @@ build_tiles_kernel(const int* __restrict__ table, int K, int M, const int* __res
 
 // tile_cum[0..n] = exclusive prefix sum of tile_nk[0..n); single block
 __global__ void __launch_bounds__(1024)
-tile_scan_kernel(const int* __restrict__ tile_nk, int n, int* __restrict__ tile_cum) {
+tile_scan_kernel(const int* __restrict__ tile_nk, int n, int* __restrict__ tile_cum, int U,
+                 int n_ctas, int* __restrict__ cta_units) {
   __shared__ int s_warp[32];
   __shared__ int s_carry;
   if (threadIdx.x == 0) s_carry = 0;
@@ -487,6 +488,33 @@ tile_scan_kernel(const int* __restrict__ tile_nk, int n, int* __restrict__ tile_
     __syncthreads();
   }
   if (threadIdx.x == 0) tile_cum[n] = s_carry;
+  // Optional: the gather-GEMM kernel's per-CTA unit ranges (unit = 128 rows, U per tile; cost of
+  // a unit = its tile's step count), so its prologue reads two words instead of running a
+  // 3-round search over tile_cum. Same rule as conv_fwd.cu: first unit whose start cost reaches
+  // S*b/G, moved one down when that boundary is nearer.
+  if (cta_units == nullptr || n_ctas < 1) return;
+  __syncthreads();  // tile_cum written by this block is visible to all its threads
+  const long long S = (long long)U * s_carry;
+  const int total_units = U * n;
+  auto cost = [&](int u) {
+    const int t = u / U, r = u - t * U;
+    const int c0 = tile_cum[t];
+    return (long long)U * c0 + (r ? (long long)r * (tile_cum[t + 1] - c0) : 0ll);
+  };
+  for (int b = threadIdx.x; b <= n_ctas; b += blockDim.x) {
+    int u = total_units;
+    if (b < n_ctas) {
+      const long long target = S * b / n_ctas;
+      int lo = 0, hi = total_units;  // first u in [0, total] with cost(u) >= target
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (cost(mid) >= target) hi = mid; else lo = mid + 1;
+      }
+      u = lo;
+      if (b > 0 && u > 0 && target - cost(u - 1) < cost(u) - target) --u;
+    }
+    cta_units[b] = u;
+  }
 }
 
 // --------------------------------------------------------------------------------------------
@@ -668,7 +696,7 @@ int sort_rows_by_key(const unsigned long long* keys, int M, int K, int* rows_out
 
 int build_tiles(const int* table, int K, int M, const int* sorted_rows, int tile_rows, int m_pad,
                 int* step_nbr, int* step_k, int* rows_padded, int* tile_nk, int* tile_cum,
-                cudaStream_t s) {
+                int n_range_ctas, int* cta_units, cudaStream_t s) {
   if (tile_rows != 128 && tile_rows != 256) return kErrInvalidArg;
   if (m_pad % tile_rows != 0 || m_pad < M || K < 1) return kErrInvalidArg;
   const int num_tiles = m_pad / tile_rows;
@@ -677,7 +705,8 @@ int build_tiles(const int* table, int K, int M, const int* sorted_rows, int tile
                                                       step_nbr, step_k, rows_padded, tile_nk);
     count_launch();
   }
-  tile_scan_kernel<<<1, 1024, 0, s>>>(tile_nk, num_tiles, tile_cum);
+  tile_scan_kernel<<<1, 1024, 0, s>>>(tile_nk, num_tiles, tile_cum, tile_rows / 128, n_range_ctas,
+                                      cta_units);
   count_launch();
   return cuda_ok();
 }
