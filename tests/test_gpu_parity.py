@@ -325,6 +325,66 @@ def test_strided_and_transposed_modules():
     assert oconv.rel_max_err(u.feature_tensor, ru) < 1e-2
 
 
+def _pool_oracle(bc, x, stride, how):
+    """Dictionary pooling over stride-sized windows (reference sparse_pool.py:25-117 semantics)."""
+    out_bc, offs = okm.stride_coords(bc, stride)
+    row = {tuple(c): i for i, c in enumerate(out_bc.tolist())}
+    cells = bc.copy()
+    cells[:, 1:] = np.floor_divide(bc[:, 1:], np.asarray(stride))
+    owner = np.array([row[tuple(c)] for c in cells.tolist()])
+    pooled = np.zeros((len(out_bc), x.shape[1]), np.float64)
+    for m in range(len(out_bc)):
+        sel = x[owner == m]
+        pooled[m] = {"max": sel.max(0), "mean": sel.mean(0), "sum": sel.sum(0),
+                     "min": sel.min(0)}[how]
+    return out_bc, offs, pooled
+
+
+@pytest.mark.parametrize("how", ["max", "mean", "sum", "min"])
+def test_sparse_reduce_matches_dictionary_pooling(how):
+    from warpconvnet_b200.nn.functional.sparse_pool import sparse_reduce
+    v, coords, feats = _voxels(cin=16, seed=3)
+    pooled = sparse_reduce(v, 2, 2, reduction=how)
+    bc = okm.batch_indexed([c.numpy() for c in coords])
+    x = torch.cat(feats).double().numpy()
+    out_bc, offs, ref = _pool_oracle(bc, x, (2, 2, 2), how)
+    assert pooled.tensor_stride == (2, 2, 2)
+    assert np.array_equal(pooled.batch_indexed_coordinates.cpu().numpy(), out_bc)
+    assert pooled.offsets.tolist() == offs.tolist()
+    assert np.abs(pooled.feature_tensor.double().cpu().numpy() - ref).max() < 1e-5
+    # var goes through to_csr + row reductions like the reference
+    var = sparse_reduce(v, 2, 2, reduction="var").feature_tensor.double().cpu().numpy()
+    mean = _pool_oracle(bc, x, (2, 2, 2), "mean")[2]
+    assert np.abs(var - (_pool_oracle(bc, x * x, (2, 2, 2), "mean")[2] - mean ** 2)).max() < 1e-4
+
+
+def test_reduce_and_stride_mode():
+    """stride_mode=REDUCE_AND_STRIDE = max-pool over the stride window, then the conv at stride 1
+    on the pooled voxels (reference helper.py:275-288, 539-548)."""
+    from warpconvnet_b200.nn.functional.sparse_conv import STRIDED_CONV_MODE
+    from warpconvnet_b200.nn.modules.sparse_conv import SparseConv3d
+    torch.manual_seed(2)
+    v, coords, feats = _voxels(cin=32, seed=5)
+    v.batched_features.batched_tensor.requires_grad_(True)
+    conv = SparseConv3d(32, 64, 3, stride=2, bias=False,
+                        stride_mode=STRIDED_CONV_MODE.REDUCE_AND_STRIDE).cuda()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out = conv(v)
+    out.feature_tensor.float().sum().backward()
+    bc = okm.batch_indexed([c.numpy() for c in coords])
+    out_bc, offs, pooled = _pool_oracle(bc, torch.cat(feats).double().numpy(), (2, 2, 2), "max")
+    assert out.tensor_stride == (2, 2, 2)
+    assert np.array_equal(out.batch_indexed_coordinates.cpu().numpy(), out_bc)
+    km = okm.generate_kernel_map(out_bc, out_bc, (1, 1, 1), (3, 3, 3))
+    xp = torch.from_numpy(pooled).bfloat16().float()
+    w = conv.weight.detach().cpu().bfloat16().float()
+    ref = oconv.forward(xp, w, km["in_maps"], km["out_maps"], km["offsets"], len(out_bc))
+    assert oconv.rel_max_err(out.feature_tensor, ref) < 1e-2
+    g = v.batched_features.batched_tensor.grad
+    assert g is not None and g.shape == (5500, 32) and bool(torch.isfinite(g).all())
+    assert conv.weight.grad is not None and float(conv.weight.grad.abs().sum()) > 0
+
+
 @pytest.mark.parametrize("cin,cout,groups", [(64, 64, 8), (128, 256, 4), (512, 512, 64), (32, 32, 2)])
 def test_group_conv(cin, cout, groups):
     """Group conv vs per-group explicit oracle (reference tests/nn/test_sparse_conv.py:742-776,

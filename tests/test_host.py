@@ -160,3 +160,103 @@ def test_radius_config_and_wrappers_reject_cpu():
     with pytest.raises(RuntimeError):
         batched_radius_search(torch.rand(10, 3), torch.tensor([0, 10]), torch.rand(4, 3),
                               torch.tensor([0, 4]), 0.1)
+
+
+def test_to_csr_and_pair_table_reduction_on_cpu():
+    """IntSearchResult.to_csr (search_results.py:147-174) and the pair-table pooling walk are plain
+    torch: checked on the CPU against a hand-built map."""
+    from warpconvnet_b200.geometry.coords.search.search_results import IntSearchResult
+    from warpconvnet_b200.nn.functional.sparse_pool import reduce_over_pair_table
+    from warpconvnet_b200.ops.reductions import REDUCTIONS
+    # offset 0: (in 0 -> out 1), (in 2 -> out 0); offset 1: (in 1 -> out 1), (in 3 -> out 3)
+    km = IntSearchResult(torch.tensor([0, 2, 1, 3], dtype=torch.int32),
+                         torch.tensor([1, 0, 1, 3], dtype=torch.int32),
+                         torch.tensor([0, 2, 4], dtype=torch.int32))
+    in_rows, out_rows, offs = km.to_csr()
+    assert in_rows.tolist() == [2, 0, 1, 3] and out_rows.tolist() == [0, 1, 3]
+    assert offs.tolist() == [0, 1, 3, 4]
+    table = torch.tensor([[2, 0, -1, -1], [-1, 1, -1, 3]], dtype=torch.int32)
+    x = torch.tensor([[1., -2.], [3., 4.], [-5., 6.], [7., 8.]])
+    assert reduce_over_pair_table(x, table, REDUCTIONS.MAX).tolist() == \
+        [[-5., 6.], [3., 4.], [0., 0.], [7., 8.]]
+    assert reduce_over_pair_table(x, table, REDUCTIONS.MIN)[1].tolist() == [1., -2.]
+    assert reduce_over_pair_table(x, table, REDUCTIONS.SUM)[1].tolist() == [4., 2.]
+    assert reduce_over_pair_table(x, table, REDUCTIONS.MEAN)[1].tolist() == [2., 1.]
+    x.requires_grad_(True)
+    reduce_over_pair_table(x, table, REDUCTIONS.MAX).sum().backward()
+    assert x.grad.tolist() == [[0., 0.], [1., 1.], [1., 1.], [1., 1.]]
+
+
+def test_geometry_container_api_matches_reference_surface():
+    """Members of Geometry / BatchedTensor / Voxels / Points that the reference exposes
+    (geometry/base/geometry.py:37-388, base/batched.py:14-270, types/voxels.py, types/points.py):
+    arithmetic, aliases, nested / padded views, dense round trip, z-order sort, downsampling."""
+    from warpconvnet_b200.geometry.base.batched import CatFeatures, PadFeatures
+    from warpconvnet_b200.geometry.coords.ops.serialization import POINT_ORDERING, morton_code
+    from warpconvnet_b200.geometry.types.points import Points
+    from warpconvnet_b200.geometry.types.voxels import Voxels
+    g = torch.Generator().manual_seed(0)
+    coords = [torch.randint(0, 8, (n, 3), generator=g, dtype=torch.int32) for n in (20, 12)]
+    feats = [torch.randn(n, 4, generator=g) for n in (20, 12)]
+    v = Voxels(coords, feats).unique()
+    n = v.coordinate_tensor.shape[0]
+    assert len(v) == n and v.coords.shape == (n, 4) and v.coordinates.shape == (n, 3)
+    assert torch.equal(v.feats, v.features) and str(v).startswith("Voxels(feature_shape=")
+    # arithmetic: geometry, scalar, reflected, per-channel tensor
+    assert torch.allclose((v + v).feature_tensor, 2 * v.feature_tensor)
+    assert torch.allclose((1 - v).feature_tensor, 1 - v.feature_tensor)
+    assert torch.allclose((2 / (v * v + 1)).feature_tensor, 2 / (v.feature_tensor ** 2 + 1))
+    assert torch.allclose((v ** 2).feature_tensor, v.feature_tensor ** 2)
+    assert torch.allclose((v * torch.arange(4.)).feature_tensor, v.feature_tensor * torch.arange(4.))
+    assert v.equal_shape(v * 2)
+    with pytest.raises(AssertionError):
+        v + Voxels(coords[:1], feats[:1])  # different batch layout
+    # batched tensors
+    f = v.batched_features
+    assert f == f * 2 and f.equal_rigorous(f + 0) and not f.equal_rigorous(f + 1)
+    assert len(f) == n and (f - f).batched_tensor.abs().max() == 0
+    nested = v.nested_features
+    assert nested.is_nested and CatFeatures.from_nested(nested).equal_rigorous(f)
+    pad = v.padded_features
+    assert isinstance(pad, PadFeatures) and pad.shape[0] == 2 and pad.to_cat().equal_rigorous(f)
+    assert v.to_pad(8).batched_features.shape[1] % 8 == 0 and v.to_pad(8).to_cat().to_cat() is not None
+    # dense round trip (from_dense lists cells in (b, x, y, z) order = unique()'s order)
+    dense = v.to_dense(channel_dim=1, spatial_shape=(8, 8, 8), min_coords=(0, 0, 0))
+    back = Voxels.from_dense(dense)
+    keep = v.feature_tensor.abs().sum(1) > 0
+    assert torch.equal(back.batch_indexed_coordinates, v.batch_indexed_coordinates[keep])
+    assert torch.equal(back.feature_tensor, v.feature_tensor[keep])
+    assert torch.equal(Voxels.from_dense(dense, target_spatial_sparse_tensor=v).feature_tensor,
+                       v.feature_tensor)
+    # z-order: code definition (first axis in the lowest bit) and per-scene sortedness
+    assert morton_code(torch.tensor([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1], [3, 0, 0]])
+                       ).tolist() == [0, 1, 2, 4, 9]
+    s = v.sort()
+    assert s.ordering == POINT_ORDERING.MORTON_XYZ and s.offsets.tolist() == v.offsets.tolist()
+    codes = morton_code(s.coordinate_tensor)    # normalised by the minimum over the whole batch
+    for b in range(2):
+        lo, hi = int(s.offsets[b]), int(s.offsets[b + 1])
+        code = codes[lo:hi]
+        assert bool((code[1:] >= code[:-1]).all())
+        assert sorted(map(tuple, s.coordinate_tensor[lo:hi].tolist())) == \
+            sorted(map(tuple, v.coordinate_tensor[lo:hi].tolist()))
+    # points
+    p = v.to_point(voxel_size=0.5)
+    assert isinstance(p, Points) and torch.equal(p.coordinate_tensor, v.coordinate_tensor * 0.5)
+    pts = Points([torch.rand(50, 3, generator=g), torch.rand(30, 3, generator=g)],
+                 [torch.randn(50, 4, generator=g), torch.randn(30, 4, generator=g)])
+    down = pts.voxel_downsample(0.25, reduction="mean")
+    cells = torch.floor(pts.coordinate_tensor / 0.25)
+    first = cells[:50]
+    m0 = len({tuple(c) for c in first.tolist()})
+    assert down.offsets[1] == m0 and down.voxel_size == 0.25
+    c0 = torch.floor(down.coordinate_tensor[0] / 0.25)
+    members = (first == c0).all(1)
+    assert torch.allclose(down.feature_tensor[0], pts.feature_tensor[:50][members].mean(0), atol=1e-6)
+    assert pts.voxel_downsample(0.25).feature_tensor.shape == down.feature_tensor.shape
+    rs = pts.random_downsample(10)
+    assert rs.offsets.tolist() == [0, 10, 20]
+    assert pts.sort(0.25).coordinate_tensor.shape == (80, 3) and pts.contiguous() is pts
+    enc = Points.from_list_of_coordinates([torch.rand(5, 3), torch.rand(7, 3)], encoding_channels=4,
+                                          encoding_range=1.0)
+    assert enc.feature_tensor.shape == (12, 12)

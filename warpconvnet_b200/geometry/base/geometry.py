@@ -53,7 +53,20 @@ class Geometry:
         return self.batched_coordinates.batched_tensor
 
     coordinates = coordinate_tensor
-    coords = coordinate_tensor
+
+    @property
+    def batch_indexed_coordinates(self) -> Tensor:
+        from warpconvnet_b200.geometry.coords.ops.batch_index import batch_indexed_coordinates
+        return batch_indexed_coordinates(self.coordinate_tensor, self.offsets)
+
+    @property
+    def coords(self) -> Tensor:
+        """``[N, 1 + D]`` with the batch index in column 0 (geometry.py ``coords`` alias)."""
+        return self.batch_indexed_coordinates
+
+    @property
+    def nested_coordinates(self) -> Tensor:
+        return self.batched_coordinates.to_nested()
 
     @property
     def feature_tensor(self) -> Tensor:
@@ -68,6 +81,27 @@ class Geometry:
 
     features = feature_tensor
     feats = feature_tensor
+
+    @property
+    def nested_features(self) -> Tensor:
+        return self.batched_features.to_nested()
+
+    @property
+    def padded_features(self):
+        return self.batched_features.to_pad()
+
+    def to_pad(self, pad_multiple: Optional[int] = None) -> "Geometry":
+        f = self.batched_features
+        if f.is_pad and f.pad_multiple == pad_multiple:
+            return self
+        return self.replace(batched_features=f.to_pad(pad_multiple))
+
+    def to_cat(self) -> "Geometry":
+        return self if self.batched_features.is_cat else \
+            self.replace(batched_features=self.batched_features.to_cat())
+
+    def sort(self, *args, **kwargs):
+        raise NotImplementedError
 
     def replace_features(self, new_features) -> "Geometry":
         return self.replace(batched_features=new_features)
@@ -99,6 +133,9 @@ class Geometry:
     def _apply(self, fn):
         return self.replace(batched_features=fn(self.batched_features.batched_tensor))
 
+    def _apply_feature_transform(self, feature_transform_fn):
+        return self.replace(batched_features=feature_transform_fn(self.feature_tensor))
+
     def half(self):
         return self._apply(lambda t: t.half())
 
@@ -109,9 +146,28 @@ class Geometry:
         return self._apply(lambda t: t.double())
 
     def binary_op(self, value, op: str) -> "Geometry":
+        """Feature-wise arithmetic with a same-shape geometry, a scalar / one-element tensor or a
+        feature-shaped tensor (geometry.py ``binary_op``)."""
         a = self.batched_features.batched_tensor
-        b = value.batched_features.batched_tensor if isinstance(value, Geometry) else value
+        if isinstance(value, Geometry):
+            assert self.equal_shape(value), f"Shapes do not match. {self} != {value}"
+            b = value.batched_features.batched_tensor
+        elif isinstance(value, (int, float)) or (torch.is_tensor(value) and value.numel() == 1):
+            b = value
+        elif isinstance(value, Tensor):
+            assert value.shape == a.shape or value.shape == a.shape[-1:], \
+                f"tensor operand {tuple(value.shape)} does not match features {tuple(a.shape)}"
+            b = value
+        else:
+            raise NotImplementedError(f"unsupported operand {type(value)}")
         return self.replace(batched_features=getattr(a, op)(b))
+
+    def equal_shape(self, value) -> bool:
+        return (self.batched_coordinates.equal_shape(value.batched_coordinates)
+                and self.batched_features.equal_shape(value.batched_features))
+
+    def equal_rigorous(self, value) -> bool:
+        raise NotImplementedError
 
     def __add__(self, v):
         return self.binary_op(v, "__add__")
@@ -125,11 +181,26 @@ class Geometry:
     def __truediv__(self, v):
         return self.binary_op(v, "__truediv__")
 
+    def __floordiv__(self, v):
+        return self.binary_op(v, "__floordiv__")
+
+    def __mod__(self, v):
+        return self.binary_op(v, "__mod__")
+
+    def __pow__(self, v):
+        return self.binary_op(v, "__pow__")
+
     __radd__ = __add__
     __rmul__ = __mul__
 
+    def __rsub__(self, v):
+        return self._apply(lambda t: -t).binary_op(v, "__add__")
+
+    def __rtruediv__(self, v):
+        return self._apply(lambda t: t.reciprocal()).binary_op(v, "__mul__")
+
     def __len__(self) -> int:
-        return self.batch_size
+        return len(self.batched_coordinates)  # rows, like the reference (geometry.py ``__len__``)
 
     def numel(self):
         return int(self.offsets[-1]) * self.num_channels
@@ -140,7 +211,9 @@ class Geometry:
                 f"coords_shape={tuple(self.batched_coordinates.shape)}, device={self.device}, "
                 f"dtype={self.batched_features.dtype})")
 
-    __str__ = __repr__
+    def __str__(self) -> str:
+        return (f"{self.__class__.__name__}(feature_shape={tuple(self.batched_features.shape)}, "
+                f"coords_shape={tuple(self.batched_coordinates.shape)})")
 
     @property
     def extra_attributes(self):

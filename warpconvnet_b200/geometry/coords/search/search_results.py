@@ -174,6 +174,17 @@ class IntSearchResult:
         return IntSearchResult(self.in_maps.clone(), self.out_maps.clone(), self.offsets.clone(),
                                self.identity_map_index)
 
+    @torch.no_grad()
+    def to_csr(self) -> Tuple[Tensor, Tensor, Tensor]:
+        """(in rows grouped by output row, the output rows that have pairs, CPU row offsets) —
+        search_results.py:147-174. A stable sort keeps the offset order inside every row, so the
+        result is deterministic (the reference's ``torch.sort`` is not stable)."""
+        out_sorted, perm = torch.sort(self.out_maps.long(), stable=True)
+        rows, counts = torch.unique_consecutive(out_sorted, return_counts=True)
+        offsets = torch.zeros(len(rows) + 1, dtype=torch.int64)
+        offsets[1:] = torch.cumsum(counts.cpu(), dim=0)
+        return self.in_maps[perm], rows, offsets
+
     @property
     def device(self):
         return self._in_buf.device

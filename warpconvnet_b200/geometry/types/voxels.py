@@ -42,6 +42,65 @@ class Voxels(Geometry):
                                                    device=device)
         Geometry.__init__(self, batched_coordinates, batched_features, **kwargs)
 
+    @classmethod
+    def from_dense(cls, dense_tensor: Tensor, dense_tensor_channel_dim: int = 1,
+                   target_spatial_sparse_tensor: Optional["Voxels"] = None,
+                   dense_max_coords=None, **kwargs) -> "Voxels":
+        """Voxels of the non-zero cells of a dense ``[B, C, *spatial]`` tensor, or — with a target —
+        the dense values at the target's coordinates (voxels.py:50-106)."""
+        if dense_tensor_channel_dim != -1 and dense_tensor_channel_dim != dense_tensor.ndim - 1:
+            dense_tensor = dense_tensor.moveaxis(dense_tensor_channel_dim, -1)
+        flat = dense_tensor.flatten(0, -2)
+        dims = dense_tensor.shape[:-1]
+
+        def ravel(bc: Tensor) -> Tensor:
+            idx = bc[:, 0].long()
+            for d in range(1, len(dims)):
+                idx = idx * dims[d] + bc[:, d].long()
+            return idx
+
+        if target_spatial_sparse_tensor is None:
+            cells = torch.nonzero(dense_tensor.abs().sum(dim=-1)).int()   # sorted by (b, x, y, z)
+            offs = offsets_from_batch_index(cells[:, 0], dense_tensor.shape[0])
+            return cls(cells[:, 1:].contiguous(), flat[ravel(cells)], offsets=offs, **kwargs)
+        target = target_spatial_sparse_tensor
+        assert target.num_spatial_dims == dense_tensor.ndim - 2
+        assert target.batch_size == dense_tensor.shape[0]
+        bc = target.batch_indexed_coordinates
+        if dense_max_coords is not None:
+            assert bool((bc[:, 1:].max(dim=0).values.cpu() <= torch.as_tensor(dense_max_coords)).all())
+        return target.replace(batched_features=flat[ravel(bc)])
+
+    def to_point(self, voxel_size: Optional[float] = None):
+        """Points at ``coordinate * voxel_size (* tensor_stride)`` (voxels.py:230-246)."""
+        from warpconvnet_b200.geometry.coords.integer import RealCoords
+        from warpconvnet_b200.geometry.types.points import Points
+        if voxel_size is None:
+            assert self.voxel_size is not None, \
+                "Voxel size must be provided or the object must have been initialized with one"
+            voxel_size = self.voxel_size
+        scale = self.coordinate_tensor.new_tensor(
+            [voxel_size * s for s in (self.tensor_stride or (1,) * self.num_spatial_dims)],
+            dtype=torch.float32)
+        return Points(RealCoords(self.coordinate_tensor.float() * scale, self.offsets),
+                      self.batched_features)
+
+    def sort(self, ordering=None) -> "Voxels":
+        """Rows of every batch item in z-order (voxels.py:248-270)."""
+        from warpconvnet_b200.geometry.coords.ops.serialization import POINT_ORDERING, encode
+        ordering = POINT_ORDERING.MORTON_XYZ if ordering is None else ordering
+        if ordering == self.ordering:
+            return self
+        res = encode(self.coordinate_tensor, batch_offsets=self.offsets, order=ordering,
+                     return_perm=True)
+        attrs = {k: v for k, v in self._extra_attributes.items() if k != "_cache"}
+        attrs.update(ordering=ordering, code=res.codes)
+        coords = IntCoords(self.coordinate_tensor[res.perm], self.offsets,
+                           voxel_size=self.batched_coordinates.voxel_size,
+                           tensor_stride=self.tensor_stride)
+        feats = CatFeatures(self.batched_features.batched_tensor[res.perm], self.offsets)
+        return self.__class__(coords, feats, **attrs)
+
     def unique(self) -> "Voxels":
         """One voxel per distinct coordinate (voxels.py:271-278); keeps the first occurrence,
         rows sorted by (batch, x, y, z)."""

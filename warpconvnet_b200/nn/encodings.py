@@ -13,7 +13,16 @@ def get_freqs(num_freqs: int, data_range: float = 2.0, device=None) -> Tensor:
     return (2 * math.pi / data_range) * freqs
 
 
-def sinusoidal_encoding(x: Tensor, freqs: Tensor, concat_input: bool = False) -> Tensor:
+def sinusoidal_encoding(x: Tensor, num_channels=None, data_range=None, encoding_axis: int = -1,
+                        freqs: Tensor = None, concat_input: bool = False) -> Tensor:
+    """``[..., D] -> [..., D * num_channels (+ D)]`` (nn/functional/encodings.py:28-80, same
+    keywords: either ``freqs`` or ``num_channels`` + ``data_range``)."""
+    assert encoding_axis == -1, "Only encoding_axis=-1 is supported at the moment"
+    if freqs is None:
+        assert num_channels is not None and data_range is not None, \
+            "num_channels and data_range must be provided if freqs are not given"
+        assert num_channels % 2 == 0, f"num_channels must be even for sin/cos, got {num_channels}"
+        freqs = get_freqs(num_channels // 2, data_range, device=x.device)
     x = x.unsqueeze(-1)
     fx = x * freqs.reshape((1,) * (x.dim() - 1) + freqs.shape)
     parts = [fx.cos(), fx.sin()] + ([x] if concat_input else [])
@@ -29,4 +38,4 @@ class SinusoidalEncoding(nn.Module):
         self.register_buffer("freqs", get_freqs(num_channels // 2, data_range))
 
     def forward(self, x: Tensor) -> Tensor:
-        return sinusoidal_encoding(x, self.freqs, self.concat_input)
+        return sinusoidal_encoding(x, freqs=self.freqs, concat_input=self.concat_input)

@@ -120,9 +120,12 @@ def spatially_sparse_conv(input_sparse_tensor, weight, kernel_size, stride=1, ke
                                    else input_sparse_tensor.batched_features.dtype)
 
     if stride_mode == STRIDED_CONV_MODE.REDUCE_AND_STRIDE and any(s != 1 for s in _stride):
-        raise NotImplementedError(
-            "stride_mode=REDUCE_AND_STRIDE needs sparse pooling, which is outside the hot path "
-            "(SURVEY.md §2a); use the default STRIDE_ONLY")
+        # pool the input over stride-sized windows, then convolve the pooled voxels at stride 1
+        # (helper.py:275-288); the kernel map below indexes the pooled rows
+        from warpconvnet_b200.nn.functional.sparse_pool import sparse_reduce
+        input_sparse_tensor = sparse_reduce(input_sparse_tensor, kernel_size=_stride,
+                                            stride=_stride, reduction=stride_reduce)
+        _stride = ntuple(1, ndim=nd)
 
     feats = input_sparse_tensor.batched_features.batched_tensor
     bout, out_offsets, kernel_map = generate_output_coords_and_kernel_map(
@@ -217,7 +220,9 @@ def generate_output_coords_and_kernel_map(input_sparse_tensor, kernel_size, kern
         kernel_map = generate_kernel_map(
             bout, bin_coords, ntuple(1, ndim=input_sparse_tensor.num_spatial_dims), kernel_size,
             kernel_dilation).transposed_view()
-    elif stride_mode == STRIDED_CONV_MODE.STRIDE_ONLY:
+    elif stride_mode == STRIDED_CONV_MODE.STRIDE_ONLY or all(s == 1 for s in stride):
+        # REDUCE_AND_STRIDE arrives here with the pooled voxels and stride 1 (helper.py:539-558:
+        # out-to-out map, or in-to-expanded map when generative)
         kernel_map = generate_kernel_map(bin_coords, bout, stride, kernel_size, kernel_dilation,
                                          same_coords=same_coords)
     else:
