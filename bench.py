@@ -64,6 +64,13 @@ def make_tensors(n: int, seed: int):
     return x, w, gy
 
 
+def workload_name(dist: str, n: int, world: int) -> str:
+    shape = "surface height field 448^2" if dist == "S" else "uniform random, 30% occupancy"
+    return (f"C3-{dist}: SparseConv3d 3^3 {CIN}->{COUT} bf16, {n} voxels/GPU ({shape}), "
+            "step = kernel-map build + tile plan + fwd AB + dgrad ABt + wgrad AtB"
+            + (" + NCCL all-reduce(dW)" if world > 1 else ""))
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -419,10 +426,7 @@ def run_ours(args):
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
         "config": {
-            "workload": f"C3-{args.dist}: SparseConv3d 3^3 {CIN}->{COUT} bf16, {n} voxels/GPU "
-                        f"({'surface height field 448^2' if args.dist == 'S' else 'uniform random, 30% occupancy'}), "
-                        "step = kernel-map build + tile plan + fwd AB + dgrad ABt + wgrad AtB"
-                        + (" + NCCL all-reduce(dW)" if world > 1 else ""),
+            "workload": workload_name(args.dist, n, world),
             "voxels_per_gpu": n, "pairs_L": L, "parallelism": f"scene-sharded dp{world}",
             "l2": "flushed with a 256 MiB write before every timed step (outside the events)",
             "timing": "CUDA events per step on the launching stream, mean over steps, max over ranks",
@@ -488,9 +492,11 @@ def run_reference(args):
         "unit": "voxels/s", "n_gpus": int(os.environ.get("WORLD_SIZE", args.gpus)),
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"C3-{args.dist}: SparseConv3d 3^3 {CIN}->{COUT}, {n} voxels, "
-                               "kernel map + fwd + dgrad + wgrad on the host CPU (port of the "
-                               "reference's explicit gather-matmul-scatter, detail/explicit.py:22-101)"},
+        # same workload name as our arm's line; what differs is said in `arm`
+        "config": {"workload": workload_name(args.dist, n, int(os.environ.get("WORLD_SIZE", 1))),
+                   "voxels_per_gpu": n,
+                   "arm": "host CPU, fp32: oracle kernel map + port of the reference's explicit "
+                          "gather-matmul-scatter (detail/explicit.py:22-101), rank 0 only"},
         "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": base["value"], "unit": "voxels/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
