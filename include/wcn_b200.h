@@ -120,7 +120,11 @@ int wcn_csr_to_pair_table(const int32_t* val_maps, const int32_t* row_maps, cons
                           int K, int n_rows, int num_pairs, int32_t* table, void* stream);
 int wcn_mask_keys(const int32_t* table, int K, int M, uint64_t* keys, void* stream);
 size_t wcn_sort_workspace_bytes(int M);
-/* rows_out = stable argsort of keys (low min(K,64) bits). */
+/* rows_out = stable argsort of the row masks: rows with equal masks stay adjacent in ascending row
+ * order, similar masks close. K <= 24 and K > 32: numeric order of the low min(K,64) bits;
+ * 24 < K <= 32: order of a 24-bit compression of the mask (three radix passes instead of four; the
+ * centre bit of an odd K is dropped, the lowest bits are folded in — see cuhash.cu);
+ * WCN_FOLD_MASK_KEYS=0 in the environment keeps the numeric order. Any order is a valid plan. */
 int wcn_sort_rows_by_key(const uint64_t* keys, int M, int K, int32_t* rows_out, void* workspace,
                          size_t workspace_bytes, void* stream);
 /* Tile plan in mask-sorted order. tile_rows is 128 or 256, m_pad = ceil(M/tile_rows)*tile_rows,

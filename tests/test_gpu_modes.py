@@ -161,3 +161,78 @@ def test_kernel_map_shape_sweep():
         assert np.array_equal(km.out_maps.cpu().numpy(), ref["out_maps"]), tag
         iden = ref["identity_map_index"]
         assert km.identity_map_index == iden, tag
+
+
+def test_explicit_output_coordinates_non_transposed():
+    """``forward(x, output_spatially_sparse_tensor=target)``: the conv is evaluated at the
+    target's coordinates (helper.py:421-428); here a 3^3 stride-1 conv sampled on another set."""
+    from warpconvnet_b200.geometry.types.voxels import Voxels
+    from warpconvnet_b200.nn.modules.sparse_conv import SparseConv3d
+    torch.manual_seed(5)
+    v, bc, x = _scenes((2000, 1000), 16, seed=8)
+    tcoords = [torch.from_numpy(random_coords(n, 0.3, 20 + i)) for i, n in enumerate((1500, 1200))]
+    target = Voxels(tcoords, [torch.zeros(len(c), 1) for c in tcoords], device="cuda")
+    conv = SparseConv3d(16, 32, 3, bias=False).cuda()
+    out = conv(v, target)
+    out_bc = okm.batch_indexed([c.numpy() for c in tcoords])
+    km = okm.generate_kernel_map(bc, out_bc, (1, 1, 1), (3, 3, 3))
+    assert out.offsets.tolist() == target.offsets.tolist()
+    _check(conv, v, out, x, km["in_maps"], km["out_maps"], km["offsets"], out_bc)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_compute_dtype_argument_and_grouped_strided(dtype):
+    """``compute_dtype`` without autocast (fp32 features cast on entry, helper.py:310-320) on a
+    grouped, strided conv; oracle on the rounded operands, per-group loops."""
+    from warpconvnet_b200.nn.modules.sparse_conv import SparseConv3d
+    torch.manual_seed(6)
+    v, bc, x = _scenes((3000,), 32, seed=10)
+    conv = SparseConv3d(32, 64, 2, stride=2, groups=4, bias=False, compute_dtype=dtype).cuda()
+    out = conv(v)
+    assert out.feature_tensor.dtype == dtype and conv.weight.shape == (8, 4, 8, 16)
+    out_bc, _ = okm.stride_coords(bc, (2, 2, 2))
+    km = okm.generate_kernel_map(bc, out_bc, (2, 2, 2), (2, 2, 2))
+    xr = x.to(dtype).float()
+    wr = conv.weight.detach().cpu().to(dtype).float()
+    ref = oconv.forward_grouped(xr, wr, km["in_maps"], km["out_maps"], km["offsets"], len(out_bc))
+    assert np.array_equal(out.batch_indexed_coordinates.cpu().numpy(), out_bc)
+    assert oconv.rel_max_err(out.feature_tensor, ref) < 1e-2
+    g = torch.Generator().manual_seed(11)
+    gy = torch.randn(len(out_bc), 64, generator=g).to(dtype)
+    out.feature_tensor.backward(gy.cuda())
+    dx_ref, dw_ref = oconv.backward_grouped(gy.float(), xr, wr, km["in_maps"], km["out_maps"],
+                                            km["offsets"])
+    assert oconv.rel_max_err(v.batched_features.batched_tensor.grad, dx_ref) < 1e-2
+    assert oconv.rel_max_err(conv.weight.grad, dw_ref) < 1e-3
+
+
+def test_tile_plan_is_a_row_permutation_and_close_to_the_full_width_sort():
+    """The 24-bit compressed mask keys (cuhash.cu, three radix passes instead of four) may order
+    the rows differently from a numeric sort of the 27-bit masks; the plan must still list every
+    row exactly once, give every tile exactly the offsets its rows use, and need at most 1 % more
+    steps than the full-width order on surface data."""
+    from conftest import surface_coords
+    from warpconvnet_b200.geometry.coords.search.torch_discrete import generate_kernel_map
+    bc = okm.batch_indexed([surface_coords(300, 1)])
+    t = torch.from_numpy(bc).cuda()
+    n = len(bc)
+    km = generate_kernel_map(t, t, (1, 1, 1), (3, 3, 3), same_coords=True)
+    plan = km.fwd_plan(n)
+    rows = plan.rows.cpu().numpy()
+    assert np.array_equal(np.sort(rows[rows >= 0]), np.arange(n))
+    pt = km._pair_table.cpu().numpy()
+    masks = np.zeros(n, np.uint32)
+    for k in range(27):
+        masks |= (pt[k] >= 0).astype(np.uint32) << np.uint32(k)
+    tr = plan.tile_rows
+
+    def union_steps(order):
+        m = np.concatenate([masks[order], np.zeros((-n) % tr, np.uint32)]).reshape(-1, tr)
+        return np.array([bin(int(u)).count("1") for u in np.bitwise_or.reduce(m, axis=1)])
+
+    nk = plan.tile_nk.cpu().numpy()[:plan.num_tiles]
+    padded = np.where(rows >= 0, rows, 0)
+    mine = np.where(rows >= 0, masks[padded], 0).astype(np.uint32).reshape(-1, tr)
+    assert np.array_equal(nk, [bin(int(u)).count("1") for u in np.bitwise_or.reduce(mine, axis=1)])
+    full = union_steps(np.argsort(masks, kind="stable")).sum()
+    assert nk.sum() <= 1.01 * full, (int(nk.sum()), int(full))
