@@ -260,3 +260,36 @@ def test_geometry_container_api_matches_reference_surface():
     enc = Points.from_list_of_coordinates([torch.rand(5, 3), torch.rand(7, 3)], encoding_channels=4,
                                           encoding_range=1.0)
     assert enc.feature_tensor.shape == (12, 12)
+
+
+def test_sparse_ops_cat_prune_and_pool_modules():
+    """cat / prune of sparse tensors (nn/functional/sparse_ops.py:13-66), IntCoords.prune / sort and
+    the pooling module surface (nn/modules/sparse_pool.py:20-92) — host logic only."""
+    from warpconvnet_b200.geometry.types.voxels import Voxels
+    from warpconvnet_b200.nn.functional.sparse_ops import (cat_spatially_sparse_tensors,
+                                                           prune_spatially_sparse_tensor)
+    from warpconvnet_b200.nn.modules import SparseAvgPool, SparseMaxPool, SparseMinPool, SparsePool
+    g = torch.Generator().manual_seed(1)
+    coords = [torch.randint(0, 16, (n, 3), generator=g, dtype=torch.int32) for n in (9, 6)]
+    a = Voxels(coords, [torch.randn(n, 3, generator=g) for n in (9, 6)])
+    b = a.replace(batched_features=torch.randn(15, 5, generator=g))
+    c = cat_spatially_sparse_tensors(a, b)
+    assert c.feature_tensor.shape == (15, 8)
+    assert torch.equal(c.feature_tensor[:, :3], a.feature_tensor)
+    assert torch.equal(c.coordinate_tensor, a.coordinate_tensor)
+    with pytest.raises(ValueError):
+        cat_spatially_sparse_tensors(a, Voxels(coords[:1], [torch.randn(9, 2)]))
+    mask = torch.zeros(15, dtype=torch.bool)
+    mask[[0, 3, 8, 9, 14]] = True
+    p = prune_spatially_sparse_tensor(a, mask)
+    assert p.offsets.tolist() == [0, 3, 5] and p.cache is None
+    assert torch.equal(p.coordinate_tensor, a.coordinate_tensor[mask])
+    assert torch.equal(p.feature_tensor, a.feature_tensor[mask])
+    with pytest.raises(ValueError):
+        prune_spatially_sparse_tensor(a, mask[:5])
+    srt = a.batched_coordinates.sort()
+    assert srt.offsets.tolist() == a.offsets.tolist()
+    assert sorted(map(tuple, srt.batched_tensor[:9].tolist())) == sorted(map(tuple, coords[0].tolist()))
+    assert repr(SparseMaxPool(2, 2)) == "SparseMaxPool(kernel_size=2, stride=2, reduce=max)"
+    assert SparseMinPool(2, 2).reduce == "min" and SparseAvgPool(3, 2).reduce == "mean"
+    assert SparsePool(2, 2, "sum").stride == 2

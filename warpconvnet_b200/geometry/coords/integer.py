@@ -60,6 +60,27 @@ class IntCoords(Coords):
         return self.__class__(uniq[:, 1:].contiguous(), offsets_from_batch_index(uniq[:, 0]),
                               voxel_size=self.voxel_size, tensor_stride=self.tensor_stride)
 
+    def prune(self, mask: Tensor) -> "IntCoords":
+        """Rows where ``mask`` is true, offsets recomputed per batch item (integer.py:99-134)."""
+        assert mask.shape[0] == self.batched_tensor.shape[0], "Mask must match tensor shape"
+        mask = mask.to(self.batched_tensor.device)
+        if mask.dtype != torch.bool:
+            mask = mask.bool()
+        from warpconvnet_b200.geometry.coords.ops.batch_index import batch_index_from_offset
+        bidx = batch_index_from_offset(self.offsets, device=self.batched_tensor.device)
+        offsets = offsets_from_batch_index(bidx[mask], len(self.offsets) - 1)
+        return self.__class__(self.batched_tensor[mask], offsets.to(self.offsets.dtype),
+                              voxel_size=self.voxel_size, tensor_stride=self.tensor_stride)
+
+    def sort(self, ordering=None) -> "IntCoords":
+        """Rows of every batch item in z-order (integer.py ``sort``)."""
+        from warpconvnet_b200.geometry.coords.ops.serialization import POINT_ORDERING, encode
+        res = encode(self.batched_tensor, batch_offsets=self.offsets,
+                     order=POINT_ORDERING.MORTON_XYZ if ordering is None else ordering,
+                     return_perm=True)
+        return self.__class__(self.batched_tensor[res.perm], self.offsets,
+                              voxel_size=self.voxel_size, tensor_stride=self.tensor_stride)
+
     def expand(self, kernel_size, dilation=1) -> "IntCoords":
         from warpconvnet_b200.geometry.coords.ops.expand import expand_coords
         nd = self.num_spatial_dims

@@ -6,3 +6,4 @@ from .normalizations import BatchNorm  # noqa: F401
 from .activations import ReLU  # noqa: F401
 from .sparse_conv_depth import (SparseDepthwiseConv2d, SparseDepthwiseConv3d,  # noqa: F401
                                 SpatiallySparseDepthwiseConv)
+from .sparse_pool import SparseAvgPool, SparseMaxPool, SparseMinPool, SparsePool  # noqa: F401
