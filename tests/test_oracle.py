@@ -155,3 +155,36 @@ def test_oracle_vs_live_reference():
     assert oconv.rel_max_err(oconv.forward(x, w, *args, n), y_ref) < 1e-12
     dx, dw = oconv.backward(gy, x, w, *args)
     assert oconv.rel_max_err(dx, dx_ref) < 1e-12 and oconv.rel_max_err(dw, dw_ref) < 1e-12
+
+
+def test_reference_backend_registration_against_the_live_reference():
+    """INTEGRATION.md seam A as code: the adapters land in the reference's own registries and the
+    name passes its strict pool filter (detail/algo_params.py:1104-1129). Registration only —
+    the adapters call CUDA kernels. Skipped where the reference tree is not mounted."""
+    from oracle import ref_adapter
+    if not ref_adapter.available():
+        pytest.skip("reference tree not mounted")
+    ref_adapter.load()
+    import importlib
+    try:
+        backends = importlib.import_module("warpconvnet.nn.functional.sparse_conv.detail.backends")
+        algo_params = importlib.import_module(
+            "warpconvnet.nn.functional.sparse_conv.detail.algo_params")
+    except Exception as exc:  # the stubbed extension may not satisfy every import-time probe
+        pytest.skip(f"reference dispatcher does not import on CPU: {type(exc).__name__}: {exc}")
+    from warpconvnet_b200.integration import reference_backend as rb
+    name = rb.register()
+    assert rb.register() == name                      # idempotent
+    assert backends.FORWARD_BACKENDS[name] is rb.forward_adapter
+    assert backends.BACKWARD_BACKENDS[name] is rb.backward_adapter
+    assert sum(1 for tag, _ in algo_params._ALL_AB_PARAMS if str(tag) == name) == 1
+    assert sum(1 for tag, _ in algo_params._ALL_ATB_PARAMS if str(tag) == name) == 1
+    # the reference's kernel-map container wraps into ours without touching the GPU
+    _, _, RefResult = ref_adapter.load()
+    import torch
+    ref_map = RefResult(torch.tensor([0, 2, 1], dtype=torch.int32),
+                        torch.tensor([1, 0, 1], dtype=torch.int32),
+                        torch.tensor([0, 2, 3], dtype=torch.int32))
+    own = rb.wrap_kernel_map(ref_map)
+    assert rb.wrap_kernel_map(ref_map) is own
+    assert own.offsets.tolist() == [0, 2, 3] and own.in_maps.tolist() == [0, 2, 1]
