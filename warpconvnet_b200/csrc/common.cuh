@@ -113,6 +113,12 @@ __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint3
                "r"(src_bytes)
                : "memory");
 }
+__device__ __forceinline__ void st_shared_zero_16(uint32_t dst) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0) : "memory");
+}
+__device__ __forceinline__ void fence_acq_rel_cta() {
+  asm volatile("fence.acq_rel.cta;" ::: "memory");
+}
 __device__ __forceinline__ void cp_async_16_ca(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src),
                "r"(src_bytes)

@@ -340,9 +340,38 @@ gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
                 seg_base + (unsigned long long)(uint32_t)max(src_idx, 0) * pitch;
             const uint32_t dst =
                 a_smem + j * kSubStride + off_par[q % kPar] + (uint32_t)(q / kPar) * 1024u;
+#ifdef WCN_ZERO_ROWS_SECOND_PASS
+            if (lane_active && src_idx >= 0) cp_async_16(dst, src, 16u);
+#else
             if (lane_active) cp_async_16(dst, src, src_idx >= 0 ? 16u : 0u);
+#endif
           }
         }
+#ifdef WCN_ZERO_ROWS_SECOND_PASS
+        // EXPERIMENT (not compiled by default, not yet measured; profiles/r1i): a zero-size
+        // cp.async still takes a slot of the global-load path, so missing neighbours are written
+        // with st.shared in a second pass, after all copies of the stage are in flight. The
+        // stores are generic-proxy writes like the cp.async data; they are performed before this
+        // thread's arrival can fire, and the consumer's fence.proxy.async covers both.
+        {
+          bool stored_zero = false;
+#pragma unroll
+          for (int j = 0; j < TM; ++j) {
+            if (TM > 1 && idx_own[j] < -1) continue;
+#pragma unroll
+            for (int q = 0; q < kInstr; ++q) {
+              const int src_idx = __shfl_sync(0xffffffffu, idx_own[j], kRowsPerInstr * q + sub);
+              const uint32_t dst =
+                  a_smem + j * kSubStride + off_par[q % kPar] + (uint32_t)(q / kPar) * 1024u;
+              if (lane_active && src_idx == -1) {
+                st_shared_zero_16(dst);
+                stored_zero = true;
+              }
+            }
+          }
+          if (stored_zero) fence_acq_rel_cta();
+        }
+#endif
         cp_async_mbar_arrive_noinc(full_bar);
         if (++stage == stages) { stage = 0; phase ^= 1u; }
       }
