@@ -1,5 +1,7 @@
 # SPDX-License-Identifier: Apache-2.0
-"""Bandwidth experiments on the forward gather-GEMM (bring-up only; WCN_DEBUG flags)."""
+"""Bandwidth experiments on the forward gather-GEMM (bring-up only; the WCN_DEBUG / WCN_STAGES
+switches need a library built with `WCN_BRINGUP=1 warpconvnet_b200/csrc/build.sh` — the default
+build ignores them and this script then times the default configuration only)."""
 import os
 import sys
 

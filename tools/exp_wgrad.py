@@ -1,5 +1,6 @@
 # SPDX-License-Identifier: Apache-2.0
-"""wgrad kernel variants (bring-up only; WCN_DEBUG flags 64 / 128)."""
+"""wgrad kernel variants (bring-up only; WCN_DEBUG flags 64 / 128, honoured only by a library
+built with `WCN_BRINGUP=1 warpconvnet_b200/csrc/build.sh`)."""
 import os
 import sys
 

@@ -4,8 +4,11 @@ set -euo pipefail
 cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -diag-suppress 177"
+# WCN_BRINGUP=1: the library honours the experiment switches of tools/exp_*.py (environment
+# variables WCN_DEBUG / WCN_DEBUG_PTR / WCN_STAGES). The default build ignores them.
+if [ "${WCN_BRINGUP:-0}" = "1" ]; then FLAGS="$FLAGS -DWCN_BRINGUP"; fi
 # WCN_KERNEL_COUNTERS=1: compile the per-role cycle counters into the GEMM kernels (bring-up only)
-if [ "${WCN_KERNEL_COUNTERS:-0}" = "1" ]; then FLAGS="$FLAGS -DWCN_KERNEL_COUNTERS"; fi
+if [ "${WCN_KERNEL_COUNTERS:-0}" = "1" ]; then FLAGS="$FLAGS -DWCN_KERNEL_COUNTERS -DWCN_BRINGUP"; fi
 # WCN_ZERO_ROWS_SECOND_PASS=1: EXPERIMENT, off by default and not yet measured (profiles/r1i):
 # missing neighbours of a gather stage are written with st.shared after the copies are issued
 if [ "${WCN_ZERO_ROWS_SECOND_PASS:-0}" = "1" ]; then FLAGS="$FLAGS -DWCN_ZERO_ROWS_SECOND_PASS"; fi

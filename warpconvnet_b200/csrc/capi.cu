@@ -349,6 +349,9 @@ int wcn_gather_gemm(const void* feats, int n_in_rows, long long in_ld, const voi
   p.kflip = kflip;
   p.stages = 0;
   p.relu = relu;
+  p.debug = 0;
+  p.dbg_out = nullptr;
+#ifdef WCN_BRINGUP  // bring-up builds only (WCN_BRINGUP=1 build.sh): experiment switches of tools/exp_*.py
   {
     const char* e = getenv("WCN_DEBUG");
     p.debug = e ? atoi(e) : 0;
@@ -357,6 +360,7 @@ int wcn_gather_gemm(const void* feats, int n_in_rows, long long in_ld, const voi
     const char* st_env = getenv("WCN_STAGES");
     if (st_env) p.stages = atoi(st_env);
   }
+#endif
   if (max_ctas <= 0) max_ctas = sm_count();
   return launch_gather_gemm(p, dtype, plan.n_slabs, max_ctas, n_range_ctas, S(stream));
 }
@@ -401,12 +405,16 @@ int wcn_wgrad(const void* feats, long long in_ld, const void* gout, long long ou
     p.row_parts = row_parts;
     p.rounds = rounds;
   }
+  p.debug = 0;
+  p.dbg_out = nullptr;
+#ifdef WCN_BRINGUP  // bring-up builds only: experiment switches of tools/exp_wgrad*.py
   {
     const char* e = getenv("WCN_DEBUG");
     p.debug = e ? atoi(e) : 0;
     const char* dp = getenv("WCN_DEBUG_PTR");
     p.dbg_out = dp ? reinterpret_cast<long long*>(strtoull(dp, nullptr, 10)) : nullptr;
   }
+#endif
   p.dw_k_stride = (long long)groups * cin_g * cout_g;
   p.dw_g_stride = (long long)cin_g * cout_g;
   p.dw_ld = cout_g;
