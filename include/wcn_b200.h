@@ -123,8 +123,8 @@ size_t wcn_sort_workspace_bytes(int M);
 /* rows_out = stable argsort of the row masks: rows with equal masks stay adjacent in ascending row
  * order, similar masks close. K <= 24 and K > 32: numeric order of the low min(K,64) bits;
  * 24 < K <= 32: order of a 24-bit compression of the mask (three radix passes instead of four; the
- * centre bit of an odd K is dropped, the lowest bits are folded in — see cuhash.cu);
- * WCN_FOLD_MASK_KEYS=0 in the environment keeps the numeric order. Any order is a valid plan. */
+ * centre bit of an odd K is dropped, the lowest bits are folded in — see cuhash.cu; bring-up builds
+ * keep the numeric order with WCN_FOLD_MASK_KEYS=0). Any order is a valid plan. */
 int wcn_sort_rows_by_key(const uint64_t* keys, int M, int K, int32_t* rows_out, void* workspace,
                          size_t workspace_bytes, void* stream);
 /* Tile plan in mask-sorted order. tile_rows is 128 or 256, m_pad = ceil(M/tile_rows)*tile_rows,

@@ -677,11 +677,16 @@ __global__ void narrow_keys_iota_kernel(const unsigned long long* __restrict__ k
   }
 }
 
-// WCN_FOLD_MASK_KEYS=0 in the environment keeps the full-width sort (read once)
+// bring-up builds (WCN_BRINGUP=1 build.sh): WCN_FOLD_MASK_KEYS=0 in the environment keeps the
+// full-width sort for A/B measurements (read once); the default build always compresses
+#ifdef WCN_BRINGUP
 static const bool g_fold_mask_keys = [] {
   const char* v = getenv("WCN_FOLD_MASK_KEYS");
   return !(v && v[0] == '0');
 }();
+#else
+static constexpr bool g_fold_mask_keys = true;
+#endif
 
 int sort_rows_by_key(const unsigned long long* keys, int M, int K, int* rows_out, void* workspace,
                      size_t ws_bytes, cudaStream_t s) {
