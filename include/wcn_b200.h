@@ -119,6 +119,24 @@ int wcn_reverse_pair_table(const int32_t* pair_table, int K, int M, int32_t* rev
 int wcn_csr_to_pair_table(const int32_t* val_maps, const int32_t* row_maps, const int32_t* offsets,
                           int K, int n_rows, int num_pairs, int32_t* table, void* stream);
 int wcn_mask_keys(const int32_t* table, int K, int M, uint64_t* keys, void* stream);
+/* ---- coordinate-set operations ----------------------------------------------
+ * Replaces the torch glue of warpconvnet/geometry/coords/ops/stride.py:18-56 (stride_coords:
+ * floor division + hash-unique + batch argsort), ops/expand.py:17-75 (expand_coords) and
+ * geometry/types/voxels.py:271-278 (Voxels.unique) with one device chain and NO host sync:
+ *   rows = unique{ (b, floor(x / sx) + ox_k, floor(y / sy) + oy_k, floor(z / sz) + oz_k) }
+ * over all input rows and all K offsets (offsets3 = NULL with K = 1: no offsets), sorted by
+ * (batch, x, y, z).
+ *   out_coords  [n * K, 4] int32 upper-bound buffer; the first meta[n_batches] rows are valid
+ *   first_index [n * K] int32 or NULL: smallest source row of every output row (K = 1 only)
+ *   meta        [n_batches + 3] int32: offsets[0..n_batches] (per-batch row offsets), total,
+ *               status (bit 1 = a coordinate left the packed range b 0..511, xyz -131072..131071,
+ *               or b >= n_batches; such rows are dropped)
+ *   workspace   wcn_coords_unique_workspace_bytes(n * K) bytes */
+size_t wcn_coords_unique_workspace_bytes(long long n_keys);
+int wcn_coords_unique(const int32_t* bcoords, int n, int stride_x, int stride_y, int stride_z,
+                      const int32_t* offsets3, int K, int n_batches, int32_t* out_coords,
+                      int32_t* first_index, int32_t* meta, void* workspace, size_t workspace_bytes,
+                      void* stream);
 size_t wcn_sort_workspace_bytes(int M);
 /* rows_out = stable argsort of the row masks: rows with equal masks stay adjacent in ascending row
  * order, similar masks close. K <= 24 and K > 32: numeric order of the low min(K,64) bits;

@@ -61,6 +61,9 @@ SIGNATURES = {
     "wcn_csr_to_pair_table": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
                                       c_void_p]),
     "wcn_mask_keys": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "wcn_coords_unique_workspace_bytes": (c_size_t, [c_longlong]),
+    "wcn_coords_unique": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int,
+                                  c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "wcn_sort_workspace_bytes": (c_size_t, [c_int]),
     "wcn_sort_rows_by_key": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t,
                                      c_void_p]),

@@ -42,6 +42,22 @@ def _p(t: Optional[Tensor]):
     return None if t is None else t.data_ptr()
 
 
+def _pc(t: Optional[Tensor], numel: int, what: str, like: Optional[Tensor] = None,
+        dtype: torch.dtype = torch.float32):
+    """Raw pointer of a per-channel vector / small buffer the kernels read or write with a FIXED
+    element type: the dtype, element count, contiguity and device are checked here because the
+    library only sees ``void*`` (a 2-byte buffer behind a ``float*`` is an out-of-bounds write)."""
+    if t is None:
+        return None
+    if t.dtype != dtype or not t.is_contiguous() or t.numel() < numel or not t.is_cuda or (
+            like is not None and t.device != like.device):
+        raise _lib.WcnError(
+            f"{what}: expected a contiguous {dtype} CUDA buffer of >= {numel} elements"
+            f"{'' if like is None else ' on ' + str(like.device)}, got {t.dtype} "
+            f"{tuple(t.shape)} on {t.device} (contiguous={t.is_contiguous()})")
+    return t.data_ptr()
+
+
 def _require_cuda(*tensors: Tensor) -> None:
     for t in tensors:
         if t is not None and not t.is_cuda:
@@ -146,6 +162,31 @@ def kernel_map_scatter(pair_table: Tensor, block_prefix: Tensor, offsets_dev: Te
                                          _p(in_maps), _p(out_maps), K, M, _stream()),
               "kernel_map_scatter")
     return in_maps, out_maps
+
+
+def coords_unique(bcoords: Tensor, stride: Tuple[int, int, int], offsets3: Optional[Tensor],
+                  n_batches: int, want_index: bool = False):
+    """unique{(b, floor(xyz / stride) + offset_k)} over all rows and offsets, sorted by
+    (b, x, y, z) — no host sync. Returns (rows [n * K, 4] int32 upper-bound buffer,
+    first_index [n] int32 | None, meta [n_batches + 3] int32 = offsets[0..n_batches], total,
+    status). Only the first ``total`` rows are valid."""
+    _require_cuda(bcoords, offsets3)
+    assert bcoords.dtype == torch.int32 and bcoords.is_contiguous() and bcoords.shape[1] == 4
+    n = bcoords.shape[0]
+    K = 1 if offsets3 is None else offsets3.shape[0]
+    if offsets3 is not None:
+        assert offsets3.dtype == torch.int32 and offsets3.is_contiguous() and offsets3.shape[1] == 3
+    assert not (want_index and K != 1)
+    dev = bcoords.device
+    rows = torch.empty((max(n * K, 1), 4), dtype=torch.int32, device=dev)
+    first = torch.empty(max(n, 1), dtype=torch.int32, device=dev) if want_index else None
+    meta = torch.empty(n_batches + 3, dtype=torch.int32, device=dev)
+    ws_bytes = lib.wcn_coords_unique_workspace_bytes(n * K)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    check(lib.wcn_coords_unique(_p(bcoords), n, int(stride[0]), int(stride[1]), int(stride[2]),
+                                _p(offsets3), K, n_batches, _p(rows), _p(first), _p(meta), _p(ws),
+                                ws_bytes, _stream()), "coords_unique")
+    return rows, first, meta
 
 
 def reverse_pair_table(pair_table: Tensor, n_in: int) -> Tensor:
@@ -283,8 +324,7 @@ def gather_gemm(feats: Tensor, wimg: Tensor, plan: TilePlan, groups: int, cin_g:
     if out is None:
         out = torch.empty((plan.n_rows, groups * cout_g), dtype=feats.dtype, device=feats.device)
     assert out.stride(1) == 1 and out.dtype == feats.dtype
-    if bias is not None:
-        assert bias.dtype == torch.float32 and bias.is_contiguous()
+    _pc(bias, groups * cout_g, "bias", feats)
     check(lib.wcn_gather_gemm(_p(feats), feats.shape[0], feats.stride(0), _p(wimg), _p(out), out.stride(0),
                               _p(plan.step_nbr), _p(plan.step_k), _p(plan.rows), _p(plan.tile_nk),
                               _p(plan.tile_cum), plan.num_tiles, plan.tile_rows, plan.m_pad,
@@ -399,8 +439,11 @@ def bn_finalize(sums: Tensor, n: int, gamma: Optional[Tensor], beta: Optional[Te
     c = sums.shape[1]
     buf = torch.empty((4, c), dtype=torch.float32, device=sums.device)
     scale, shift, mean_rstd = buf[0], buf[1], buf[2:]
-    check(lib.wcn_bn_finalize(_p(sums), n, c, _p(gamma), _p(beta), ctypes.c_float(eps),
-                              ctypes.c_float(momentum), _p(running_mean), _p(running_var),
+    check(lib.wcn_bn_finalize(_pc(sums, 2 * c, "sums", dtype=torch.float64), n, c,
+                              _pc(gamma, c, "gamma", sums), _pc(beta, c, "beta", sums),
+                              ctypes.c_float(eps), ctypes.c_float(momentum),
+                              _pc(running_mean, c, "running_mean", sums),
+                              _pc(running_var, c, "running_var", sums),
                               _p(scale), _p(shift), _p(mean_rstd), _stream()), "bn_finalize")
     return scale, shift, mean_rstd
 
@@ -417,8 +460,9 @@ def scale_shift_act(x: Tensor, scale: Tensor, shift: Tensor, residual: Optional[
     pr, ldr = _rows(residual) if residual is not None else (None, 0)
     if residual is not None:
         assert residual.shape == x.shape and residual.dtype == x.dtype
-    check(lib.wcn_scale_shift_act(px, ldx, pr, ldr, po, ldo, n, c, dtype_code(x.dtype), _p(scale),
-                                  _p(shift), int(relu), _stream()), "scale_shift_act")
+    check(lib.wcn_scale_shift_act(px, ldx, pr, ldr, po, ldo, n, c, dtype_code(x.dtype),
+                                  _pc(scale, c, "scale", x), _pc(shift, c, "shift", x),
+                                  int(relu), _stream()), "scale_shift_act")
     return out
 
 
@@ -433,7 +477,9 @@ def bn_bwd_reduce(dy: Tensor, x: Tensor, y: Optional[Tensor], mean_rstd: Tensor,
     px, ldx = _rows(x)
     py, ldy = _rows(y) if y is not None else (None, 0)
     check(lib.wcn_bn_bwd_reduce(pd, ldd, px, ldx, py, ldy, n, c, dtype_code(x.dtype),
-                                _p(mean_rstd), _p(mask_scale), _p(mask_shift), _p(sums),
+                                _pc(mean_rstd, 2 * c, "mean_rstd", x),
+                                _pc(mask_scale, c, "mask_scale", x),
+                                _pc(mask_shift, c, "mask_shift", x), _p(sums),
                                 _stream()), "bn_bwd_reduce")
     return sums
 
@@ -452,8 +498,11 @@ def bn_bwd_apply(dy: Tensor, x: Optional[Tensor], y: Optional[Tensor], gamma: Te
     pdx, lddx = _rows(dx)
     pdr, lddr = _rows(dres) if dres is not None else (None, 0)
     check(lib.wcn_bn_bwd_apply(pd, ldd, px, ldx, py, ldy, pdx, lddx, pdr, lddr, n, c,
-                               dtype_code(dy.dtype), _p(gamma), _p(mean_rstd), _p(sums),
-                               _p(mask_scale), _p(mask_shift), int(training), _stream()),
+                               dtype_code(dy.dtype), _pc(gamma, c, "gamma / scale", dy),
+                               _pc(mean_rstd, 2 * c, "mean_rstd", dy),
+                               _pc(sums, 2 * c, "sums", dy, torch.float64),
+                               _pc(mask_scale, c, "mask_scale", dy),
+                               _pc(mask_shift, c, "mask_shift", dy), int(training), _stream()),
           "bn_bwd_apply")
     return dx, dres
 
@@ -540,9 +589,13 @@ def bn_forward(x: Tensor, gamma: Optional[Tensor], beta: Optional[Tensor], eps: 
     px, ldx = _rows(x)
     py, ldy = _rows(y)
     pr, ldr = _rows(residual) if residual is not None else (None, 0)
-    check(lib.wcn_bn_forward(px, ldx, pr, ldr, py, ldy, n, c, dtype_code(x.dtype), _p(gamma),
-                             _p(beta), ctypes.c_float(eps), ctypes.c_float(momentum),
-                             _p(running_mean), _p(running_var), _p(sums), _p(buf), int(relu),
+    if residual is not None:
+        assert residual.shape == x.shape and residual.dtype == x.dtype
+    check(lib.wcn_bn_forward(px, ldx, pr, ldr, py, ldy, n, c, dtype_code(x.dtype),
+                             _pc(gamma, c, "gamma", x), _pc(beta, c, "beta", x),
+                             ctypes.c_float(eps), ctypes.c_float(momentum),
+                             _pc(running_mean, c, "running_mean", x),
+                             _pc(running_var, c, "running_var", x), _p(sums), _p(buf), int(relu),
                              _stream()), "bn_forward")
     return y, buf[0], buf[1], buf[2:]
 
@@ -559,7 +612,11 @@ def bn_backward(dy: Tensor, x: Tensor, y: Optional[Tensor], gamma: Tensor, mean_
     py, ldy = _rows(y) if y is not None else (None, 0)
     pdx, lddx = _rows(dx)
     pdr, lddr = _rows(dres) if dres is not None else (None, 0)
+    assert dy.shape == x.shape and dy.dtype == x.dtype
     check(lib.wcn_bn_backward(pd, ldd, px, ldx, py, ldy, pdx, lddx, pdr, lddr, n, c,
-                              dtype_code(dy.dtype), _p(gamma), _p(mean_rstd), _p(mask_scale),
-                              _p(mask_shift), _p(sums), _stream()), "bn_backward")
+                              dtype_code(dy.dtype), _pc(gamma, c, "gamma", x),
+                              _pc(mean_rstd, 2 * c, "mean_rstd", x),
+                              _pc(mask_scale, c, "mask_scale", x),
+                              _pc(mask_shift, c, "mask_shift", x), _p(sums), _stream()),
+          "bn_backward")
     return dx, dres, sums

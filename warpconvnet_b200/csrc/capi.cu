@@ -29,6 +29,10 @@ size_t sort_workspace_bytes(int);
 int sort_rows_by_key(const unsigned long long*, int, int, int*, void*, size_t, cudaStream_t);
 int build_tiles(const int*, int, int, const int*, int, int, int*, int*, int*, int*, int*, int, int*,
                 cudaStream_t);
+// coords.cu
+size_t coords_unique_workspace_bytes(long long);
+int coords_unique(const int*, int, int, int, int, const int*, int, int, int*, int*, int*, void*,
+                  size_t, cudaStream_t);
 // knn.cu
 size_t knn_workspace_bytes(int, int, int);
 int knn_dims_for(int, int);
@@ -196,6 +200,18 @@ int wcn_csr_to_pair_table(const int32_t* val_maps, const int32_t* row_maps, cons
 int wcn_mask_keys(const int32_t* table, int K, int M, uint64_t* keys, void* stream) {
   if (M > 0 && (!table || !keys)) return kErrInvalidArg;
   return mask_keys_from_table(table, K, M, reinterpret_cast<unsigned long long*>(keys), S(stream));
+}
+size_t wcn_coords_unique_workspace_bytes(long long n_keys) {
+  return coords_unique_workspace_bytes(n_keys);
+}
+int wcn_coords_unique(const int32_t* bcoords, int n, int stride_x, int stride_y, int stride_z,
+                      const int32_t* offsets3, int K, int n_batches, int32_t* out_coords,
+                      int32_t* first_index, int32_t* meta, void* workspace, size_t workspace_bytes,
+                      void* stream) {
+  if (!meta || (n > 0 && (!bcoords || !out_coords || !workspace))) return kErrInvalidArg;
+  if (K > 1 && !offsets3) return kErrInvalidArg;
+  return coords_unique(bcoords, n, stride_x, stride_y, stride_z, offsets3, K, n_batches,
+                       out_coords, first_index, meta, workspace, workspace_bytes, S(stream));
 }
 size_t wcn_sort_workspace_bytes(int M) { return sort_workspace_bytes(M); }
 int wcn_sort_rows_by_key(const uint64_t* keys, int M, int K, int32_t* rows_out, void* workspace,

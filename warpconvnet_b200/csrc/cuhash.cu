@@ -30,6 +30,13 @@ __host__ __device__ __forceinline__ uint64_t pack_key(int b, int x, int y, int z
          ((uint64_t)(y & 0x3FFFF) << 18) | (uint64_t)(z & 0x3FFFF);
 }
 
+// true when (b, x, y, z) fits the packed key: a probe outside the range is a MISS (masking it
+// would alias a cell 2^18 voxels away by wrap-around)
+__device__ __forceinline__ bool key_in_range(int b, int x, int y, int z) {
+  return (unsigned)b <= 511u && (unsigned)(x + 131072) < 262144u &&
+         (unsigned)(y + 131072) < 262144u && (unsigned)(z + 131072) < 262144u;
+}
+
 __device__ __forceinline__ uint32_t splitmix_slot(uint64_t key, uint32_t mask) {
   key ^= key >> 30;
   key *= 0xBF58476D1CE4E5B9ull;
@@ -91,7 +98,8 @@ __global__ void hash_search_kernel(const uint64_t* __restrict__ keys,
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int4 c = __ldg(queries + i);
-  results[i] = table_lookup(keys, values, pack_key(c.x, c.y, c.z, c.w), mask);
+  results[i] = key_in_range(c.x, c.y, c.z, c.w)
+                   ? table_lookup(keys, values, pack_key(c.x, c.y, c.z, c.w), mask) : -1;
 }
 
 // --------------------------------------------------------------------------------------------
@@ -131,8 +139,10 @@ kernel_map_search_kernel(const uint64_t* __restrict__ keys, const int* __restric
     for (int u = 0; u < 4; ++u) {
       const int k = k0 + u;
       res[u] = -1;
-      if (k < K && live) {
-        key[u] = pack_key(c.x, bx + s_off[3 * k], by + s_off[3 * k + 1], bz + s_off[3 * k + 2]);
+      const int qx = k < K ? bx + s_off[3 * k] : 0, qy = k < K ? by + s_off[3 * k + 1] : 0,
+                qz = k < K ? bz + s_off[3 * k + 2] : 0;
+      if (k < K && live && key_in_range(c.x, qx, qy, qz)) {
+        key[u] = pack_key(c.x, qx, qy, qz);
         slot[u] = splitmix_slot(key[u], mask);
         got[u] = __ldg(keys + slot[u]);
       } else {
@@ -203,8 +213,10 @@ kernel_map_search_sym_kernel(const uint64_t* __restrict__ keys, const int* __res
 #pragma unroll
     for (int u = 0; u < kSymBatch; ++u) {
       const int k = k0 + u;
-      if (k < k_end) {
-        key[u] = pack_key(c.x, c.y + s_off[3 * k], c.z + s_off[3 * k + 1], c.w + s_off[3 * k + 2]);
+      const int qx = k < k_end ? c.y + s_off[3 * k] : 0, qy = k < k_end ? c.z + s_off[3 * k + 1] : 0,
+                qz = k < k_end ? c.w + s_off[3 * k + 2] : 0;
+      if (k < k_end && key_in_range(c.x, qx, qy, qz)) {
+        key[u] = pack_key(c.x, qx, qy, qz);
         slot[u] = splitmix_slot(key[u], mask);
         got[u] = __ldg(keys + slot[u]);
       } else {

@@ -27,8 +27,14 @@ def shard_scenes(num_scenes: int, rank: int, world_size: int) -> List[int]:
 
 class FlatGradBucket:
     """One contiguous fp32 buffer holding the gradients of `params`; ``param.grad`` are views
-    into it, so the wgrad kernels' output (cast/accumulated by autograd into .grad) is reduced
-    with a single collective and no packing copy."""
+    into it, so the wgrad kernels' output (accumulated by autograd into .grad) is reduced with a
+    single collective and no packing copy.
+
+    ``optimizer.zero_grad(set_to_none=True)`` (torch's default) drops the views: autograd then
+    allocates fresh ``.grad`` tensors. ``all_reduce`` therefore re-binds first — a gradient that no
+    longer aliases the buffer is copied into its slot and ``.grad`` is pointed back at the slot —
+    so the collective never reduces a stale buffer. Use ``bucket.zero()`` (or
+    ``zero_grad(set_to_none=False)``) between steps to keep the views and skip that copy."""
 
     def __init__(self, params: Iterable[torch.nn.Parameter]):
         self.params = [p for p in params if p.requires_grad]
@@ -37,22 +43,44 @@ class FlatGradBucket:
         dev = self.params[0].device
         total = sum(p.numel() for p in self.params)
         self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self._slots = []
         off = 0
         for p in self.params:
             n = p.numel()
-            p.grad = self.flat[off:off + n].view_as(p)
+            self._slots.append(self.flat[off:off + n].view_as(p))
             off += n
+        self.bind()
+
+    def bind(self) -> int:
+        """Point every ``param.grad`` at its slot; returns how many had to be re-bound."""
+        rebound = 0
+        for p, slot in zip(self.params, self._slots):
+            g = p.grad
+            if g is not None and g.data_ptr() == slot.data_ptr() and g.dtype == torch.float32:
+                continue
+            if g is None:
+                slot.zero_()
+            else:
+                slot.copy_(g)
+            p.grad = slot
+            rebound += 1
+        return rebound
 
     def zero(self) -> None:
         self.flat.zero_()
+        self.bind()
 
     def all_reduce(self, average: bool = False, async_op: bool = False):
+        """Sum (or mean) over all ranks. With ``average`` the buffer is pre-scaled by 1 / world
+        BEFORE the collective, so the result is already the mean when an ``async_op`` handle
+        completes."""
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            self.bind()
             return None
-        work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, async_op=async_op)
-        if average and not async_op:
-            self.flat.div_(dist.get_world_size())
-        return work
+        self.bind()
+        if average:
+            self.flat.mul_(1.0 / dist.get_world_size())
+        return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, async_op=async_op)
 
 
 def all_reduce_wgrad(tensors: Sequence[torch.Tensor], average: bool = False) -> None:

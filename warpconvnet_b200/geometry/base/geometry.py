@@ -15,6 +15,11 @@ from torch import Tensor
 from .batched import CatFeatures, Coords, Features, to_batched_features
 
 
+# caches whose entries index the rows of one particular coordinate set (kernel maps, strided
+# coordinates, spatial grids): dropped whenever a new Geometry is built on other rows / devices
+_ROW_CACHES = ("_cache", "_stride_cache", "_spatial_cache")
+
+
 class Geometry:
     def __init__(self, batched_coordinates, batched_features, **kwargs):
         offsets = kwargs.pop("offsets", None)
@@ -35,13 +40,13 @@ class Geometry:
     def __getitem__(self, idx: int) -> "Geometry":
         coords = self.batched_coordinates[idx]
         feats = self.batched_features[idx]
-        attrs = {k: v for k, v in self._extra_attributes.items() if k != "_cache"}
+        attrs = {k: v for k, v in self._extra_attributes.items() if k not in _ROW_CACHES}
         return self.__class__(coords, feats, offsets=torch.tensor([0, len(coords)]), **attrs)
 
     def to(self, device=None, dtype=None) -> "Geometry":
         coords = self.batched_coordinates.to(device=device)
         feats = self.batched_features.to(device=device, dtype=dtype)
-        attrs = {k: v for k, v in self._extra_attributes.items() if k != "_cache"}
+        attrs = {k: v for k, v in self._extra_attributes.items() if k not in _ROW_CACHES}
         return self.__class__(coords, feats, **attrs)
 
     @property

@@ -55,9 +55,9 @@ class IntCoords(Coords):
         return self._bcoords
 
     def unique(self) -> "IntCoords":
-        from warpconvnet_b200.geometry.coords.ops.stride import unique_coords
-        uniq, _ = unique_coords(self.batch_indexed_coordinates)
-        return self.__class__(uniq[:, 1:].contiguous(), offsets_from_batch_index(uniq[:, 0]),
+        from warpconvnet_b200.geometry.coords.ops.stride import unique_with_offsets
+        uniq, _, offs = unique_with_offsets(self.batch_indexed_coordinates, len(self.offsets) - 1)
+        return self.__class__(uniq[:, 1:].contiguous(), offs,
                               voxel_size=self.voxel_size, tensor_stride=self.tensor_stride)
 
     def prune(self, mask: Tensor) -> "IntCoords":
@@ -85,7 +85,7 @@ class IntCoords(Coords):
         from warpconvnet_b200.geometry.coords.ops.expand import expand_coords
         nd = self.num_spatial_dims
         out, offs = expand_coords(self.batch_indexed_coordinates, ntuple(kernel_size, ndim=nd),
-                                  ntuple(dilation, ndim=nd))
+                                  ntuple(dilation, ndim=nd), n_batches=len(self.offsets) - 1)
         return self.__class__(out[:, 1:].contiguous(), offs.to(self.offsets.dtype),
                               voxel_size=self.voxel_size, tensor_stride=self.tensor_stride)
 

@@ -17,6 +17,36 @@ from torch import Tensor
 from warpconvnet_b200 import _ops
 
 
+# Deferred kernel maps whose (offsets, status) copy is still in flight. The conv path never reads
+# them on the host, so without this list an out-of-range coordinate or a full hash table (status
+# word) would go unnoticed and training would continue on a wrong kernel map. Every map build and
+# every conv backward polls the list WITHOUT blocking; entries whose copy has landed are checked
+# (ValueError / RuntimeError like the reference raises at build time) and dropped, and the oldest
+# entries are waited for once more than _MAX_PENDING are outstanding, so a failure surfaces within
+# the step that caused it.
+_PENDING_STATUS: List[tuple] = []
+_MAX_PENDING = 256
+
+
+def _register_pending(host: Tensor, event, on_ready) -> None:
+    if event is not None and on_ready is not None:
+        _PENDING_STATUS.append((host, event, on_ready))
+
+
+def check_pending_kernel_maps(block: bool = False) -> int:
+    """Raises the deferred hash-table errors of kernel maps built so far whose status has reached
+    the host (``block=True``: waits for all of them — call it at the end of a step when a
+    guaranteed check is wanted). Returns the number still in flight."""
+    while _PENDING_STATUS:
+        host, event, on_ready = _PENDING_STATUS[0]
+        if not (block or len(_PENDING_STATUS) > _MAX_PENDING or event.query()):
+            break
+        event.synchronize()
+        _PENDING_STATUS.pop(0)
+        on_ready(int(host[-1]))
+    return len(_PENDING_STATUS)
+
+
 class RealSearchResult:
     """CSR neighbour lists (search_results.py:13-52)."""
 
@@ -93,6 +123,7 @@ class IntSearchResult:
         self._in_maps = self._out_maps = self._offsets = None
         self._in_buf, self._out_buf = in_buf, out_buf
         self._pending = (host, event, on_ready)
+        _register_pending(host, event, on_ready)
         self._init_common(identity_map_index, offsets_dev)
         return self
 

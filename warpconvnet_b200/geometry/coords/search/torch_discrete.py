@@ -20,10 +20,13 @@ from torch import Tensor
 from warpconvnet_b200 import _ops
 from warpconvnet_b200.utils.ntuple import ntuple
 from .packed_hashmap import PackedHashTable
-from .search_results import IntSearchResult
+from .search_results import IntSearchResult, check_pending_kernel_maps
 
 _OFFSET_CACHE: Dict[tuple, Tensor] = {}
-_DEFERRED_MAX_PAIRS = 1 << 25  # upper-bound CSR buffers of at most 2 x 128 MiB
+# Upper-bound CSR buffers of at most 2 x 512 MiB (K * M int32 each; the real pair count is ~1/3 of
+# it on surface data): a 27-offset map of 2.4 M voxels (MinkUNet-14 full resolution, 8 scenes)
+# stays on the sync-free path. Above it the exact length is read back (one host sync).
+_DEFERRED_MAX_PAIRS = 1 << 27
 
 
 def _pinned_host(n: int) -> Tensor:
@@ -105,6 +108,9 @@ def generate_kernel_map(
         same_coords = batch_indexed_in_coords is batch_indexed_out_coords or (
             batch_indexed_in_coords.data_ptr() == batch_indexed_out_coords.data_ptr()
             and batch_indexed_in_coords.shape == batch_indexed_out_coords.shape)
+
+    if not torch.cuda.is_current_stream_capturing():
+        check_pending_kernel_maps()  # non-blocking: raises deferred errors of earlier maps
 
     in_c, out_c = batch_indexed_in_coords, batch_indexed_out_coords
     kernel_size = tuple(int(k) for k in kernel_size)

@@ -9,7 +9,7 @@ import torch
 from torch import Tensor
 
 from warpconvnet_b200.geometry.base.batched import CatFeatures, to_batched_features
-from warpconvnet_b200.geometry.base.geometry import Geometry
+from warpconvnet_b200.geometry.base.geometry import _ROW_CACHES, Geometry
 from warpconvnet_b200.geometry.coords.integer import RealCoords
 from warpconvnet_b200.geometry.coords.search.cache import RealSearchCache
 from warpconvnet_b200.geometry.coords.search.search_configs import RealSearchConfig
@@ -51,7 +51,7 @@ class Points(Geometry):
         return cls(RealCoords(list(coordinates)), CatFeatures(list(features)))
 
     def _take(self, rows: Tensor, offsets: Tensor, **extra) -> "Points":
-        attrs = {k: v for k, v in self._extra_attributes.items() if k != "_cache"}
+        attrs = {k: v for k, v in self._extra_attributes.items() if k not in _ROW_CACHES}
         attrs.update(extra)
         return self.__class__(RealCoords(self.coordinate_tensor[rows], offsets),
                               CatFeatures(self.feature_tensor[rows], offsets), **attrs)

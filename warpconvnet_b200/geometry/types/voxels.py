@@ -10,7 +10,7 @@ import torch
 from torch import Tensor
 
 from warpconvnet_b200.geometry.base.batched import CatFeatures, Features, to_batched_features
-from warpconvnet_b200.geometry.base.geometry import Geometry
+from warpconvnet_b200.geometry.base.geometry import _ROW_CACHES, Geometry
 from warpconvnet_b200.geometry.coords.integer import IntCoords
 from warpconvnet_b200.geometry.coords.ops.batch_index import offsets_from_batch_index
 
@@ -93,7 +93,7 @@ class Voxels(Geometry):
             return self
         res = encode(self.coordinate_tensor, batch_offsets=self.offsets, order=ordering,
                      return_perm=True)
-        attrs = {k: v for k, v in self._extra_attributes.items() if k != "_cache"}
+        attrs = {k: v for k, v in self._extra_attributes.items() if k not in _ROW_CACHES}
         attrs.update(ordering=ordering, code=res.codes)
         coords = IntCoords(self.coordinate_tensor[res.perm], self.offsets,
                            voxel_size=self.batched_coordinates.voxel_size,
@@ -104,12 +104,11 @@ class Voxels(Geometry):
     def unique(self) -> "Voxels":
         """One voxel per distinct coordinate (voxels.py:271-278); keeps the first occurrence,
         rows sorted by (batch, x, y, z)."""
-        from warpconvnet_b200.geometry.coords.ops.stride import unique_coords
-        uniq, idx = unique_coords(self.batch_indexed_coordinates)
-        offs = offsets_from_batch_index(uniq[:, 0], self.batch_size)
+        from warpconvnet_b200.geometry.coords.ops.stride import unique_with_offsets
+        uniq, idx, offs = unique_with_offsets(self.batch_indexed_coordinates, self.batch_size)
         coords = IntCoords(uniq[:, 1:].contiguous(), offs, tensor_stride=self.tensor_stride)
         feats = CatFeatures(self.batched_features.batched_tensor[idx], offs)
-        attrs = {k: v for k, v in self._extra_attributes.items() if k != "_cache"}
+        attrs = {k: v for k, v in self._extra_attributes.items() if k not in _ROW_CACHES}
         return self.__class__(coords, feats, **attrs)
 
     @property

@@ -16,6 +16,20 @@ from torch import Tensor
 from warpconvnet_b200 import _ops
 
 
+def _fp32_stat(t: Optional[Tensor], c: int, device) -> Optional[Tensor]:
+    """The tensor itself when the native kernel may update it in place (fp32, contiguous, [c], on
+    the feature device), else an fp32 copy the caller writes back."""
+    if t is None:
+        return None
+    if t.numel() != c:
+        raise ValueError(f"running statistic has {t.numel()} entries for {c} channels")
+    if t.device != device:
+        raise ValueError(f"running statistic lives on {t.device}, features on {device}")
+    if t.dtype == torch.float32 and t.is_contiguous():
+        return t
+    return t.detach().float().contiguous()
+
+
 class _BatchNormAct(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x: Tensor, weight: Optional[Tensor], bias: Optional[Tensor],
@@ -31,18 +45,31 @@ class _BatchNormAct(torch.autograd.Function):
             residual = residual if residual.stride(1) == 1 else residual.contiguous()
         use_batch = training or running_mean is None
         if use_batch:
-            if n == 0:
-                raise ValueError("BatchNorm in training mode needs at least one row")
+            if n <= 1:
+                # nn.BatchNorm1d: "Expected more than 1 value per channel when training" (the
+                # unbiased running variance divides by n - 1)
+                raise ValueError(f"BatchNorm in training mode needs more than one row, got {n}")
+            rm = running_mean if training else None
+            rv = running_var if training else None
+            # the native kernel reads and writes the running statistics as fp32: after
+            # model.half() / .bfloat16() the nn.BatchNorm1d buffers are 2-byte types, so update
+            # fp32 temporaries and copy them back (never hand a narrower buffer to the kernel)
+            rm32, rv32 = _fp32_stat(rm, c, x.device), _fp32_stat(rv, c, x.device)
             y, scale, shift, mean_rstd = _ops.bn_forward(
-                x, gamma, beta, eps, momentum, running_mean if training else None,
-                running_var if training else None, residual, relu)
+                x, gamma, beta, eps, momentum, rm32, rv32, residual, relu)
+            if rm32 is not rm and rm is not None:
+                rm.copy_(rm32)
+            if rv32 is not rv and rv is not None:
+                rv.copy_(rv32)
         else:
             rstd = torch.rsqrt(running_var.float() + eps)
             scale = rstd if gamma is None else gamma * rstd
             shift = -running_mean.float() * scale
             if beta is not None:
                 shift = shift + beta
-            scale, shift, mean_rstd = scale.contiguous(), shift.contiguous(), None
+            scale, shift = scale.contiguous(), shift.contiguous()
+            # (mean, rstd) of the frozen statistics: backward needs them for d gamma
+            mean_rstd = torch.stack([running_mean.float(), rstd]).contiguous()
             y = _ops.scale_shift_act(x, scale, shift, residual, relu)
         ctx.use_batch = use_batch
         ctx.relu = relu
@@ -80,9 +107,11 @@ class _BatchNormAct(torch.autograd.Function):
             dx, dres = _ops.bn_bwd_apply(dy, None, y, eval_scale, None, None, False, need_res)
             dgamma = dbeta = None
             if ctx.has_w or ctx.has_b:
-                raise NotImplementedError(
-                    "gradients of BatchNorm affine parameters in eval mode are not on the hot "
-                    "path; call .requires_grad_(False) on them or use training mode")
+                # frozen statistics, trainable affine (fine-tuning with BN in .eval()):
+                # d beta = sum dz, d gamma = sum dz * (x - mean) * rstd, dz = dy * relu mask
+                sums = _ops.bn_bwd_reduce(dy, x, y, mean_rstd)
+                dgamma = sums[1].to(ctx.w_dtype) if ctx.has_w else None
+                dbeta = sums[0].to(ctx.b_dtype) if ctx.has_b else None
         return dx, dgamma, dbeta, dres, None, None, None, None, None, None
 
 
@@ -96,7 +125,5 @@ def batch_norm_act(x: Tensor, weight: Optional[Tensor] = None, bias: Optional[Te
         raise RuntimeError("warpconvnet_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
     if x.dim() != 2:
         raise ValueError(f"expected a feature matrix [n, c], got {tuple(x.shape)}")
-    if not training and (weight is not None and weight.requires_grad and torch.is_grad_enabled()):
-        weight, bias = weight.detach(), (bias.detach() if bias is not None else None)
     return _BatchNormAct.apply(x, weight, bias, residual, running_mean, running_var, training,
                                float(momentum), float(eps), bool(relu))

@@ -23,7 +23,8 @@ from torch import Tensor
 from torch.autograd import Function
 
 from warpconvnet_b200 import _ops
-from warpconvnet_b200.geometry.coords.search.search_results import IntSearchResult
+from warpconvnet_b200.geometry.coords.search.search_results import (IntSearchResult,
+                                                                    check_pending_kernel_maps)
 
 
 class SPARSE_CONV_AB_ALGO_MODE(Enum):
@@ -261,6 +262,8 @@ class UnifiedSpatiallySparseConvFunction(Function):
     def backward(ctx, grad_output):
         x, w = ctx.saved_tensors   # fused path: w is the dgrad weight image (or None)
         kernel_map = ctx.kernel_map
+        if not torch.cuda.is_current_stream_capturing():
+            check_pending_kernel_maps()  # deferred coordinate-range / table-full errors
         gy = grad_output
         if gy.dtype != x.dtype:
             gy = gy.to(x.dtype)

@@ -52,7 +52,8 @@ def _apply_generative_policy(input_sparse_tensor: Voxels, kernel_size, kernel_di
         ex = _intcoords_from_batch_indexed(input_coords, scaled, input_sparse_tensor.offsets
                                            ).expand(kernel_size, kernel_dilation)
         return ex.batch_indexed_coordinates, ex.offsets, scaled
-    strided, strided_offsets = stride_coords(bin_coords, stride)
+    strided, strided_offsets = stride_coords(bin_coords, stride,
+                                             n_batches=len(input_sparse_tensor.offsets) - 1)
     strided_coords = _intcoords_from_batch_indexed(input_coords, strided, strided_offsets)
     ex = strided_coords.expand(kernel_size, kernel_dilation)
     km_in = bin_coords if stride_mode == STRIDED_CONV_MODE.STRIDE_ONLY \
@@ -182,14 +183,35 @@ def generate_output_coords_and_kernel_map(input_sparse_tensor, kernel_size, kern
         bout, out_offsets, bin_coords = _apply_generative_policy(
             input_sparse_tensor, kernel_size, kernel_dilation, stride, stride_mode, transposed)
     elif any(s != 1 for s in stride):
-        cache = input_sparse_tensor._extra_attributes.setdefault("_stride_cache", {})
-        key = (tuple(stride), tuple(int(v) for v in input_sparse_tensor.offsets.tolist()))
+        # Strided coordinates are memoised on the input's IntCoords OBJECT (not in the
+        # _extra_attributes dict that replace() shares with every descendant tensor): the object
+        # is replaced whenever the coordinates change, so a later level with the same per-scene
+        # counts can never be handed this level's result, and .to(device) / sort / unique (which
+        # build new IntCoords) drop it. The reference recomputes stride_coords on every call.
+        cobj = input_sparse_tensor.batched_coordinates
+        cache = cobj.__dict__.setdefault("_stride_cache", {})
+        key = (tuple(stride), bin_coords.data_ptr(), bin_coords.shape[0])
         if key not in cache:
-            cache[key] = stride_coords(bin_coords, stride)
+            cache[key] = stride_coords(bin_coords, stride,
+                                       n_batches=len(input_sparse_tensor.offsets) - 1)
         bout, out_offsets = cache[key]
     else:
         bout, out_offsets = bin_coords, input_sparse_tensor.offsets
         same_coords = True
+
+    # Output-row ordering (helper.py:435-442): any ordering but RANDOM re-sorts the output
+    # coordinates of every batch item along the requested space-filling curve before the map is
+    # built (the ordered rows are no longer the input's rows, so no submanifold shortcuts).
+    if order is not None:
+        from warpconvnet_b200.geometry.coords.ops.serialization import (POINT_ORDERING,
+                                                                        STR2POINT_ORDERING, encode)
+        if isinstance(order, str):
+            order = STR2POINT_ORDERING[order.lower()]
+        if order is not POINT_ORDERING.RANDOM:
+            perm = encode(bout[:, 1:], batch_offsets=out_offsets, order=order,
+                          return_perm=True).perm
+            bout = bout[perm].contiguous()
+            same_coords = False
 
     key = IntSearchCacheKey(kernel_size=kernel_size, kernel_dilation=kernel_dilation,
                             transposed=transposed, generative=generative,

@@ -8,11 +8,11 @@ from __future__ import annotations
 import torch
 from torch import Tensor
 
-from warpconvnet_b200.geometry.base.geometry import Geometry
+from warpconvnet_b200.geometry.base.geometry import _ROW_CACHES, Geometry
 from warpconvnet_b200.geometry.types.voxels import Voxels
 
 # kernel maps / strided coordinate sets cached on a tensor index its OLD rows
-_ROW_INDEXED_ATTRS = ("_cache", "_stride_cache", "_spatial_cache")
+_ROW_INDEXED_ATTRS = _ROW_CACHES
 
 
 def cat_spatially_sparse_tensors(*sparse_tensors: Voxels) -> Voxels:

@@ -60,7 +60,7 @@ def sparse_reduce(voxels: Voxels, kernel_size: Union[int, Tuple[int, ...]],
     out_stride = tuple(o * s for o, s in zip(stride, in_stride))
 
     bin_coords = voxels.batch_indexed_coordinates
-    bout, out_offsets = stride_coords(bin_coords, stride)
+    bout, out_offsets = stride_coords(bin_coords, stride, n_batches=len(voxels.offsets) - 1)
     key = IntSearchCacheKey(kernel_size=kernel_size, kernel_dilation=ntuple(1, ndim=nd),
                             transposed=False, generative=False,
                             stride_mode="STRIDED_CONV_MODE.STRIDE_ONLY",
