@@ -174,6 +174,186 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
+# BASELINE config 4: MinkUNet-14 shape, 8 scenes x ~300k voxels, strong scaling over the ranks
+# ------------------------------------------------------------------------------------------------
+C4_SCENES, C4_EXTENT = 8, 548
+
+
+def run_c4(dev, rank, world, dist, steps=10, warmup=3):
+    """MinkUNet-14 shape (tools/minkunet14.py = the reference's MinkUNetBase(3, 20,
+    planes=(32,64,128,256,128,128,96,96), layers=(1,)*8), models/mink_unet.py:259-336), global batch
+    of 8 surface scenes (300 304 voxels each) sharded round-robin over the ranks (STRONG scaling:
+    8 / 4 / 2 / 1 scenes per rank), AMP bf16, fwd + bwd + one flat all-reduce of the fp32 gradients
+    + SGD(momentum) step. Kernel maps are rebuilt from the coordinates in EVERY step (fresh Voxels),
+    which the reference's own protocol (scripts/bench_unet_gb300.py:82-93) does not do — its maps
+    stay cached on the Voxels across iterations; `maps_cached_ms` times that protocol too.
+    Timed three ways: eager launches (CUDA events + wall clock), and the whole step replayed as ONE
+    CUDA graph (sizes from the SizeTape of the eager warm-up; valid because the geometry is fixed)."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from minkunet14 import MinkUNet14, surface_scene
+    from warpconvnet_b200.dist import FlatGradBucket, shard_scenes
+    from warpconvnet_b200.geometry.types.voxels import Voxels
+    from warpconvnet_b200.utils.graph import capture_step
+
+    mine = shard_scenes(C4_SCENES, rank, world)
+    coords = [surface_scene(C4_EXTENT, s).to(dev) for s in mine]
+    g = torch.Generator().manual_seed(100 + rank)
+    feats = [torch.randn(len(c), 3, generator=g).to(dev) for c in coords]
+    n_local = sum(len(c) for c in coords)
+    torch.manual_seed(0)                                   # identical initial weights on all ranks
+    net = MinkUNet14(3, 20).to(dev)
+    opt = torch.optim.SGD(net.parameters(), lr=1e-3, momentum=0.9)
+    bucket = FlatGradBucket(net.parameters()) if world > 1 else None
+    cached_vox = Voxels(coords, feats)
+
+    def make_step(fresh_maps: bool):
+        def step():
+            x = Voxels(coords, feats) if fresh_maps else cached_vox.replace(
+                batched_features=cached_vox.feature_tensor.detach())
+            if world > 1:
+                bucket.zero()          # .grad stay views into the flat all-reduce buffer
+            else:
+                opt.zero_grad(set_to_none=True)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                out = net(x)
+            loss = out.feature_tensor.float().square().mean()
+            loss.backward()
+            if world > 1:
+                bucket.all_reduce(average=True)
+            opt.step()
+            return loss
+        return step
+
+    step = make_step(True)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, k, w):
+        for _ in range(w):
+            fn()
+        sync_all()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        s.record()
+        for _ in range(k):
+            fn()
+        e.record()
+        sync_all()
+        wall = (time.perf_counter() - t0) * 1e3 / k
+        t = torch.tensor([s.elapsed_time(e) / k, wall], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), float(t[1])
+
+    eager_ms, eager_wall = timed(step, steps, warmup)
+    cached_ms, _ = timed(make_step(False), steps, 2)
+    graph_ms = graph_note = None
+    try:
+        graph, tape, _ = capture_step(step, warmup=1)
+        graph_ms, graph_wall = timed(graph.replay, steps, 2)
+        tape.verify()
+    except Exception as exc:  # pragma: no cover
+        graph_note = f"graph capture failed: {type(exc).__name__}: {str(exc)[:200]}"
+        torch.cuda.synchronize()
+    counts = torch.zeros(world, device=dev, dtype=torch.float64)
+    counts[rank] = n_local
+    if world > 1:
+        dist.all_reduce(counts)
+    total = float(counts.sum().item())
+    best = graph_ms if graph_ms is not None else eager_ms
+    out = {
+        "workload": ("C4: MinkUNet-14 shape (%.2f M params), global batch %d scenes x 300 304 voxels "
+                     "(surface height field 548^2), AMP bf16, fwd+bwd+all-reduce(grads)+SGD, "
+                     "kernel maps rebuilt every step" % (sum(p.numel() for p in net.parameters()) / 1e6,
+                                                          C4_SCENES)),
+        "scaling": "strong", "n_gpus": world, "scenes_per_rank": len(mine),
+        "voxels_per_rank": [int(v) for v in counts.tolist()], "voxels_total": int(total),
+        "ms_per_step": best, "value": total / (best * 1e-3), "unit": "voxels/s",
+        "graph_replay_ms": graph_ms, "eager_ms": eager_ms, "eager_wall_ms": eager_wall,
+        "maps_cached_eager_ms": cached_ms,
+        "timing": "CUDA events around K steps, max over ranks; graph_replay = whole step "
+                  "(coordinate hierarchy, 9 kernel maps, 24 convs fwd+bwd, norms, all-reduce, SGD) "
+                  "as one CUDA graph; eager_wall = host wall clock of the same eager steps",
+        "grad_allreduce_bytes": int(bucket.flat.numel() * 4) if bucket is not None else 0,
+        "peak_mem_GiB": torch.cuda.max_memory_allocated() / 2 ** 30,
+        "steps": steps, "warmup": warmup,
+    }
+    if graph_note:
+        out["graph_note"] = graph_note
+    del net, opt, bucket, cached_vox
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_side_blocks(dev, flush):
+    """C3-R, C2 and C5 on one GPU (SURVEY.md §8d says R must be reported next to S)."""
+    from warpconvnet_b200 import _ops
+    from warpconvnet_b200.geometry.coords.search.torch_discrete import generate_kernel_map
+    from warpconvnet_b200.nn.functional.sparse_conv import (sparse_conv_dgrad, sparse_conv_forward,
+                                                            sparse_conv_wgrad)
+
+    def timed(fn, k=10, w=3):
+        for _ in range(w):
+            fn()
+        torch.cuda.synchronize()
+        evs = []
+        for _ in range(k):
+            flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        return float(np.mean([a.elapsed_time(b) for a, b in evs]))
+
+    peaks = load_peaks()
+    blocks = {}
+    # ---- C3-R: uniform-random occupancy (adversarial for output-stationary designs) ----------
+    c = make_coords("R", 0)
+    n = len(c)
+    bc = torch.from_numpy(np.concatenate([np.zeros((n, 1), np.int32), c], 1)).to(dev)
+    x_h, w_h, gy_h = make_tensors(n, 0)
+    x, w, gy = x_h.to(dev).bfloat16(), w_h.to(dev).bfloat16(), gy_h.to(dev).bfloat16()
+    km = generate_kernel_map(bc, bc, (1, 1, 1), (KS,) * 3, same_coords=True)
+    L = int(km.offsets[-1])
+    plan = km.fwd_plan(n)
+    img, img_t = _ops.weight_image_pair(w.view(K, 1, CIN, COUT), K, 1, CIN, COUT, w.dtype)
+    t_map = timed(lambda: generate_kernel_map(bc, bc, (1, 1, 1), (KS,) * 3, same_coords=True))
+    t_f = timed(lambda: _ops.gather_gemm(x, img, plan, 1, CIN, COUT))
+    bplan, kflip = km.bwd_plan(n)
+    t_d = timed(lambda: _ops.gather_gemm(gy, img_t, bplan, 1, COUT, CIN, kflip=kflip))
+    t_w = timed(lambda: sparse_conv_wgrad(x, gy, (K, CIN, COUT), km))
+    fl = 2.0 * L * CIN * COUT
+    blocks["c3_R"] = {
+        "workload": workload_name("R", n, 1), "pairs_L": L,
+        "kernel_map_plus_plan_ms": t_map, "fwd_ms": t_f, "dgrad_ms": t_d, "wgrad_ms": t_w,
+        "step_ms_sum": t_map + t_f + t_d + t_w, "voxels_per_s": n / ((t_map + t_f + t_d + t_w) * 1e-3),
+        "fwd_TFLOPs": fl / (t_f * 1e-3) / 1e12, "fwd_frac_of_sustained_peak": fl / (t_f * 1e-3) / 1e12 / peaks["tflops"],
+        "plan_steps": int(plan.tile_nk.sum().item()), "tile_rows": plan.tile_rows}
+    # ---- C2: 64 -> 128, ~100k voxels, forward only ------------------------------------------
+    rng_c = make_coords("S", 0)
+    sel = (rng_c[:, 0] < 317) & (rng_c[:, 1] < 317)
+    c2 = rng_c[sel]
+    n2 = len(c2)
+    bc2 = torch.from_numpy(np.concatenate([np.zeros((n2, 1), np.int32), c2], 1)).to(dev)
+    g = torch.Generator().manual_seed(2)
+    x2 = torch.randn(n2, 64, generator=g).to(dev).bfloat16()
+    w2 = (torch.randn(27, 64, 128, generator=g) * (27 * 64) ** -0.5).to(dev).bfloat16()
+    km2 = generate_kernel_map(bc2, bc2, (1, 1, 1), (3, 3, 3), same_coords=True)
+    L2 = int(km2.offsets[-1])
+    t_map2 = timed(lambda: generate_kernel_map(bc2, bc2, (1, 1, 1), (3, 3, 3), same_coords=True))
+    t_f2 = timed(lambda: sparse_conv_forward(x2, w2, km2, n2))
+    blocks["c2"] = {"workload": "C2: SparseConv3d 3^3 64->128 bf16, %d voxels (S), fwd only" % n2,
+                    "pairs_L": L2, "kernel_map_plus_plan_ms": t_map2, "fwd_ms": t_f2,
+                    "voxels_per_s": n2 / ((t_map2 + t_f2) * 1e-3),
+                    "fwd_TFLOPs": 2.0 * L2 * 64 * 128 / (t_f2 * 1e-3) / 1e12}
+    return blocks
+
+
+# ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
 def run_ours(args):
@@ -403,6 +583,24 @@ def run_ours(args):
         clocks["window"] = ("all timed regions of this run (graph steps, eager steps, kernel-only "
                             "launches, e2e loop)")
 
+    # ---- side blocks (never allowed to take the headline line down) ----------------------------
+    side = {}
+    if world == 1 and not args.no_side:
+        try:
+            side = run_side_blocks(dev, flush)
+        except Exception as exc:  # pragma: no cover
+            side = {"error": f"{type(exc).__name__}: {str(exc)[:300]}"}
+    c4 = None
+    if not args.no_c4:
+        # free the C3 working set first
+        try:
+            c4 = run_c4(dev, rank, world, dist, steps=max(5, min(args.steps, 10)), warmup=3)
+        except Exception as exc:  # pragma: no cover
+            import traceback
+            c4 = {"error": f"{type(exc).__name__}: {str(exc)[:300]}",
+                  "trace": traceback.format_exc()[-800:]}
+            torch.cuda.synchronize()
+
     peaks = load_peaks()
     steps_total = int(plan.tile_nk.sum().item())
     # Secondary (informational) bound, DESIGN.md 4.3: every gathered row crosses the L2->SM path
@@ -460,7 +658,9 @@ def run_ours(args):
                      "l2_to_sm": l2sm},
         "phases_ms": phases,
         "wall_s_timed_region": wall,
+        "c4": c4,
     }
+    out.update(side)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"], _ = run_cpu_baseline(args.dist, reps=2, warmup=1)
     if rank == 0:
@@ -514,6 +714,8 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA graph replay")
+    ap.add_argument("--no-c4", action="store_true", help="skip the MinkUNet-14 (config C4) block")
+    ap.add_argument("--no-side", action="store_true", help="skip the C3-R / C2 side blocks")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

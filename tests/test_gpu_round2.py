@@ -1,0 +1,360 @@
+# SPDX-License-Identifier: Apache-2.0
+"""Round-2 additions, all through the C-ABI on the device:
+
+* native coordinate-set chain (csrc/coords.cu): stride_coords / unique / expand_coords vs the oracle
+  and the host implementation, edge cases (negative coordinates, empty batch items, duplicates,
+  out-of-range rows), no implicit host sync on the conv path (torch sync-debug mode);
+* whole-step CUDA-graph capture with the SizeTape (utils/graph.py) vs the eager step;
+* BatchNorm fixes (running statistics in 16-bit dtypes, eval-mode affine gradients, n = 1);
+* deferred kernel-map status: an out-of-range coordinate raises inside the step;
+* the reference-dispatcher adapters (integration/reference_backend.py) executed on the GPU with
+  synthetic FwdCtx / BwdCtx, and — when baseline/_ref holds the built reference — through the
+  reference's own SparseConv3d with ``fwd_algo=["wcn_b200"]``, plus the kernel map cross-checked
+  against the reference's ``_C.cuhash`` build.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import random_coords, surface_coords
+from oracle import conv as oconv
+from oracle import kernel_map as okm
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+pytestmark = pytest.mark.gpu
+
+
+def _bc(scenes):
+    return okm.batch_indexed(scenes)
+
+
+# ------------------------------------------------------------------------------------------------
+# coordinate-set chain
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("stride", [(2, 2, 2), (2, 1, 2), (3, 3, 3), (4, 2, 1)])
+def test_stride_coords_native_matches_oracle(stride):
+    from warpconvnet_b200.geometry.coords.ops.stride import stride_coords
+    scenes = [random_coords(3000, 0.3, 1) - 7, random_coords(1700, 0.2, 2) - 30,
+              random_coords(2500, 0.4, 3) + 100]
+    bc = _bc(scenes)
+    out, offs = stride_coords(torch.from_numpy(bc).cuda(), stride, n_batches=3)
+    ref, ref_offs = okm.stride_coords(bc, stride)
+    assert np.array_equal(out.cpu().numpy(), ref)
+    assert offs.tolist() == [int(v) for v in ref_offs]
+
+
+def test_stride_coords_empty_batch_items_and_unknown_batch_count():
+    from warpconvnet_b200.geometry.coords.ops.stride import stride_coords
+    a, b = random_coords(500, 0.3, 4), random_coords(400, 0.3, 5)
+    bc = np.concatenate([np.concatenate([np.full((len(a), 1), 1, np.int32), a], 1),
+                         np.concatenate([np.full((len(b), 1), 3, np.int32), b], 1)])
+    out, offs = stride_coords(torch.from_numpy(bc).cuda(), (2, 2, 2), n_batches=5)
+    ref, _ = okm.stride_coords(bc, (2, 2, 2))
+    assert np.array_equal(out.cpu().numpy(), ref)
+    n1 = int((ref[:, 0] == 1).sum())
+    assert offs.tolist() == [0, 0, n1, n1, len(ref), len(ref)]
+    out2, offs2 = stride_coords(torch.from_numpy(bc).cuda(), (2, 2, 2))   # batch count unknown
+    assert np.array_equal(out2.cpu().numpy(), ref) and offs2.tolist() == [0, 0, n1, n1, len(ref)]
+
+
+def test_unique_native_first_occurrence_and_offsets():
+    from warpconvnet_b200.geometry.coords.ops.stride import unique_with_offsets
+    base = _bc([random_coords(800, 0.3, 6) - 3, random_coords(600, 0.3, 7)])
+    g = np.random.RandomState(0)
+    dup = base[g.randint(0, len(base), 900)]
+    allc = np.concatenate([base, dup])
+    order = np.argsort(allc[:, 0], kind="stable")          # keep batch-sorted, duplicates anywhere
+    allc = allc[order]
+    t = torch.from_numpy(allc)
+    u_gpu, i_gpu, o_gpu = unique_with_offsets(t.cuda(), 2)
+    u_cpu, i_cpu, o_cpu = unique_with_offsets(t, 2)
+    assert torch.equal(u_gpu.cpu(), u_cpu) and torch.equal(i_gpu.cpu(), i_cpu)
+    assert o_gpu.tolist() == o_cpu.tolist()
+    assert len(u_gpu) == len(base)
+
+
+def test_expand_coords_native_matches_host_path():
+    from warpconvnet_b200.geometry.coords.ops.expand import expand_coords
+    bc = torch.from_numpy(_bc([random_coords(700, 0.2, 8) - 5, random_coords(300, 0.2, 9)]))
+    for ks, dil in (((3, 3, 3), (1, 1, 1)), ((2, 2, 2), (1, 1, 1)), ((3, 1, 3), (2, 1, 1))):
+        g_out, g_offs = expand_coords(bc.cuda(), ks, dil, n_batches=2)
+        c_out, c_offs = expand_coords(bc, ks, dil, n_batches=2)
+        assert torch.equal(g_out.cpu(), c_out) and g_offs.tolist() == c_offs.tolist()
+
+
+def test_out_of_range_coordinates_raise_in_coordinate_chain_and_in_the_conv_step():
+    from warpconvnet_b200.geometry.coords.ops.stride import stride_coords
+    from warpconvnet_b200.geometry.coords.search.search_results import check_pending_kernel_maps
+    from warpconvnet_b200.geometry.types.voxels import Voxels
+    from warpconvnet_b200.nn.modules.sparse_conv import SparseConv3d
+    c = random_coords(500, 0.3, 10)
+    c[17] = (5, 200000, 3)                                   # beyond the 18-bit packed range
+    bc = torch.from_numpy(_bc([c])).cuda()
+    with pytest.raises(ValueError):
+        stride_coords(bc, (2, 2, 2), n_batches=1)
+    # submanifold conv: nothing on the conv path reads the kernel map on the host, the deferred
+    # status must still surface before the step ends (polled in backward / at the next map build)
+    conv = SparseConv3d(16, 16, 3, bias=False).cuda()
+    v = Voxels([torch.from_numpy(c)], [torch.randn(len(c), 16)], device="cuda")
+    v.batched_features.batched_tensor.requires_grad_(True)
+    with pytest.raises(ValueError):
+        out = conv(v)
+        torch.cuda.synchronize()
+        out.feature_tensor.sum().backward()
+        check_pending_kernel_maps(block=True)
+    check_pending_kernel_maps(block=True)                    # the list is drained
+
+
+def test_no_implicit_host_sync_on_the_strided_conv_path():
+    """torch's sync-debug mode turns every implicit synchronisation of the compute stream
+    (.item(), .cpu(), nonzero, boolean-mask indexing, pageable H2D ...) into an error: a strided
+    conv + transposed conv + submanifold conv step, forward and backward, must pass under it.
+    (The coordinate chain waits on its own side-stream event, which is explicit and does not
+    drain the compute stream.)"""
+    from warpconvnet_b200.geometry.types.voxels import Voxels
+    from warpconvnet_b200.nn.modules.sparse_conv import SparseConv3d
+    torch.manual_seed(0)
+    coords = [torch.from_numpy(surface_coords(80, s)).cuda() for s in (0, 1)]
+    feats = [torch.randn(len(c), 16, device="cuda") for c in coords]
+    down = SparseConv3d(16, 32, 2, 2, bias=False).cuda()
+    mid = SparseConv3d(32, 32, 3, bias=False).cuda()
+    up = SparseConv3d(32, 16, 2, 2, transposed=True, bias=False).cuda()
+
+    def step():
+        x = Voxels(coords, feats)
+        x.batched_features.batched_tensor.requires_grad_(True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            y = up(mid(down(x)), x)
+        y.feature_tensor.float().square().mean().backward()
+
+    step()                                                   # warm-up (lazy inits, offset tables)
+    torch.cuda.synchronize()
+    torch.cuda.set_sync_debug_mode("error")
+    try:
+        step()
+    finally:
+        torch.cuda.set_sync_debug_mode("default")
+    torch.cuda.synchronize()
+
+
+# ------------------------------------------------------------------------------------------------
+# whole-step CUDA graph
+# ------------------------------------------------------------------------------------------------
+def test_whole_network_step_captured_in_one_cuda_graph_matches_eager():
+    from minkunet14 import MinkUNet14, surface_scene
+    from warpconvnet_b200.geometry.types.voxels import Voxels
+    from warpconvnet_b200.utils.graph import capture_step
+    torch.manual_seed(0)
+    coords = [surface_scene(72, s).cuda() for s in (0, 1)]
+    feats = [torch.randn(len(c), 3, device="cuda") for c in coords]
+    net = MinkUNet14(3, 20).cuda()
+    for m in net.modules():                                   # momentum-free statistics: replays
+        if isinstance(m, torch.nn.BatchNorm1d):               # and eager passes stay comparable
+            m.momentum = 0.0
+    state = {}
+
+    def step():
+        x = Voxels(coords, feats)
+        for p in net.parameters():
+            p.grad = None
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out = net(x)
+        loss = out.feature_tensor.float().square().mean()
+        loss.backward()
+        state["loss"] = loss
+        state["gsum"] = torch.stack([p.grad.float().abs().sum() for p in net.parameters()]).sum()
+        return loss
+
+    step()
+    torch.cuda.synchronize()
+    eager = (float(state["loss"]), float(state["gsum"]))
+    graph, tape, _ = capture_step(step, warmup=1)
+    assert len(tape.entries) == 4                             # one coordinate set per level change
+    for _ in range(2):
+        graph.replay()
+    torch.cuda.synchronize()
+    tape.verify()
+    got = (float(state["loss"]), float(state["gsum"]))
+    assert abs(got[0] - eager[0]) <= 1e-3 * abs(eager[0]) + 1e-6
+    assert abs(got[1] - eager[1]) <= 2e-2 * abs(eager[1])     # bf16 atomics order in wgrad
+
+
+def test_capture_without_a_size_tape_fails_loudly():
+    from warpconvnet_b200.geometry.coords.ops.stride import stride_coords
+    bc = torch.from_numpy(_bc([random_coords(400, 0.3, 11)])).cuda()
+    stride_coords(bc, (2, 2, 2), n_batches=1)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with pytest.raises(RuntimeError, match="SizeTape"):
+        with torch.cuda.graph(g, capture_error_mode="relaxed"):
+            stride_coords(bc, (2, 2, 2), n_batches=1)
+
+
+# ------------------------------------------------------------------------------------------------
+# BatchNorm fixes
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_batchnorm_running_statistics_in_16bit_module(dtype):
+    """model.half() / .bfloat16() turns the BatchNorm1d buffers into 2-byte types; the kernel
+    updates fp32 temporaries (no out-of-bounds write) and the result matches torch."""
+    from warpconvnet_b200.nn.modules.normalizations import BatchNorm
+    torch.manual_seed(0)
+    c = 48
+    bn = BatchNorm(c).cuda().to(dtype)
+    ref = torch.nn.BatchNorm1d(c).cuda().to(dtype)
+    guard = torch.full((4096,), 7.0, device="cuda", dtype=dtype)  # neighbours in the allocator
+    x = torch.randn(1000, c, device="cuda", dtype=dtype)
+    y = bn(x)
+    y_ref = ref(x)
+    torch.cuda.synchronize()
+    assert bn.norm.running_mean.dtype == dtype
+    assert torch.allclose(bn.norm.running_mean.float(), ref.running_mean.float(), atol=2e-2)
+    assert torch.allclose(bn.norm.running_var.float(), ref.running_var.float(), atol=2e-2)
+    assert torch.allclose(y.float(), y_ref.float(), atol=6e-2)
+    assert bool((guard == 7.0).all())
+
+
+def test_batchnorm_eval_mode_affine_gradients_match_torch():
+    from warpconvnet_b200.nn.functional.normalizations import batch_norm_act
+    torch.manual_seed(1)
+    n, c = 700, 32
+    x = torch.randn(n, c, device="cuda")
+    rm, rv = torch.randn(c, device="cuda") * 0.1, torch.rand(c, device="cuda") + 0.5
+    w = torch.randn(c, device="cuda", requires_grad=True)
+    b = torch.randn(c, device="cuda", requires_grad=True)
+    xg = x.clone().requires_grad_(True)
+    y = batch_norm_act(xg, w, b, rm, rv, training=False, relu=True)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    w2, b2, x2 = (t.detach().double().requires_grad_(True) for t in (w, b, x))
+    y2 = torch.relu(torch.nn.functional.batch_norm(x2, rm.double(), rv.double(), w2, b2, False))
+    y2.backward(gy.double())
+    assert torch.allclose(y.double(), y2, atol=1e-4)
+    assert torch.allclose(w.grad.double(), w2.grad, rtol=1e-3, atol=1e-3)
+    assert torch.allclose(b.grad.double(), b2.grad, rtol=1e-3, atol=1e-3)
+    assert torch.allclose(xg.grad.double(), x2.grad, rtol=1e-3, atol=1e-4)
+
+
+def test_batchnorm_single_row_in_training_raises_and_bad_buffers_are_rejected():
+    from warpconvnet_b200 import _ops
+    from warpconvnet_b200._lib import WcnError
+    from warpconvnet_b200.nn.functional.normalizations import batch_norm_act
+    x = torch.randn(1, 8, device="cuda")
+    with pytest.raises(ValueError):
+        batch_norm_act(x, None, None, None, None, training=True)
+    x = torch.randn(64, 8, device="cuda")
+    with pytest.raises(WcnError):   # a 2-byte buffer must never reach the float* parameter
+        _ops.bn_forward(x, None, None, 1e-5, 0.1, torch.zeros(8, device="cuda", dtype=torch.bfloat16),
+                        torch.ones(8, device="cuda"), None, False)
+
+
+# ------------------------------------------------------------------------------------------------
+# reference-dispatcher adapters on the GPU
+# ------------------------------------------------------------------------------------------------
+def _oracle_case(n=3000, cin=32, cout=64, seed=0):
+    c = random_coords(n, 0.3, seed)
+    bc = _bc([c])
+    km = okm.generate_kernel_map(bc, bc, (1, 1, 1), (3, 3, 3))
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(n, cin, generator=g)
+    w = torch.randn(27, cin, cout, generator=g) * (27 * cin) ** -0.5
+    gy = torch.randn(n, cout, generator=g)
+    return bc, km, x, w, gy
+
+
+def test_reference_backend_adapters_execute_on_gpu_with_synthetic_ctx():
+    from warpconvnet_b200.integration import reference_backend as rb
+    bc, km, x, w, gy = _oracle_case()
+    n = len(bc)
+    # what the reference hands its backends: CSR maps on the device, offsets on the CPU
+    ref_map = types.SimpleNamespace(in_maps=torch.from_numpy(km["in_maps"]).cuda(),
+                                    out_maps=torch.from_numpy(km["out_maps"]).cuda(),
+                                    offsets=torch.from_numpy(km["offsets"]).long(),
+                                    identity_map_index=13)
+    fctx = types.SimpleNamespace(in_features=x.cuda(), weight=w.cuda(), kernel_map=ref_map,
+                                 num_out_coords=n, compute_dtype=torch.bfloat16, groups=1)
+    y = rb.forward_adapter(fctx)
+    assert isinstance(y, torch.Tensor) and y.dtype == torch.float32
+    xb, wb, gb = x.bfloat16().float(), w.bfloat16().float(), gy.bfloat16().float()
+    args = (km["in_maps"], km["out_maps"], km["offsets"])
+    assert oconv.rel_max_err(y, oconv.forward(xb, wb, *args, n)) < 1e-2
+    bctx = types.SimpleNamespace(grad_output=gy.cuda(), in_features=x.cuda(), weight=w.cuda(),
+                                 kernel_map=ref_map, compute_dtype=torch.bfloat16, groups=1,
+                                 needs_input_grad=(True, True))
+    dx, dw = rb.backward_adapter(bctx)
+    dx_ref, dw_ref = oconv.backward(gb, xb, wb, *args)
+    assert oconv.rel_max_err(dx, dx_ref) < 1e-2 and oconv.rel_max_err(dw, dw_ref) < 1e-2
+    # unsupported shape -> negative status, not an exception (backends.py:489-510)
+    bad = types.SimpleNamespace(in_features=x.cuda(), weight=torch.randn(27, 4, 3, 5).cuda(),
+                                kernel_map=ref_map, num_out_coords=n,
+                                compute_dtype=torch.bfloat16, groups=4)
+    assert rb.forward_adapter(bad) == rb.STATUS_UNSUPPORTED
+
+
+def _load_built_reference():
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref, "warpconvnet")):
+        pytest.skip("baseline/_ref (the built reference) is not present")
+    os.environ.setdefault("WARPCONVNET_BENCHMARK_CACHE_DIR", os.path.join(ROOT, "gpurun_out", "ref_cache"))
+    os.environ.setdefault("WARPCONVNET_AUTOTUNE_LOG", "false")
+    if ref not in sys.path:
+        sys.path.insert(0, ref)
+    try:
+        import warpconvnet  # noqa: F401
+    except Exception as exc:
+        pytest.skip(f"built reference does not import: {type(exc).__name__}: {exc}")
+
+
+def test_kernel_map_equals_the_reference_cuhash_build():
+    """offsets equal and per-offset pair SETS equal against the reference's own _C.cuhash kernel
+    map on the same coordinates (stride 1 / 3^3 and stride 2 / 2^3)."""
+    _load_built_reference()
+    from warpconvnet.geometry.coords.search.torch_discrete import generate_kernel_map as ref_gkm
+    from warpconvnet_b200.geometry.coords.ops.stride import stride_coords
+    from warpconvnet_b200.geometry.coords.search.torch_discrete import generate_kernel_map
+    for c, ks, st in ((surface_coords(200, 0), 3, 1), (random_coords(40000, 0.3, 1), 3, 1),
+                      (surface_coords(160, 2), 2, 2), (random_coords(20000, 0.3, 3) - 40, 3, 2)):
+        bc = torch.from_numpy(_bc([c])).cuda()
+        out_bc = bc if st == 1 else stride_coords(bc, (st,) * 3, n_batches=1)[0]
+        rk = ref_gkm(bc, out_bc, (st,) * 3, (ks,) * 3)
+        ok_ = generate_kernel_map(bc, out_bc, (st,) * 3, (ks,) * 3)
+        assert torch.equal(rk.offsets.cpu().long(), ok_.offsets.cpu().long())
+        assert rk.identity_map_index == ok_.identity_map_index
+        n_in = len(bc)
+        for k in range(len(rk)):
+            (ri, ro), (oi, oo) = rk[k], ok_[k]
+            a = torch.sort(ro.long() * n_in + ri.long()).values
+            b = torch.sort(oo.long() * n_in + oi.long()).values
+            assert torch.equal(a, b), f"pair set of offset {k} differs"
+
+
+def test_reference_sparseconv3d_runs_this_library_through_its_own_dispatcher():
+    """INTEGRATION.md seam A end to end: the reference's SparseConv3d, Voxels and autograd
+    function, with ``fwd_algo = dgrad_algo = wgrad_algo = ["wcn_b200"]``, against the oracle."""
+    _load_built_reference()
+    from warpconvnet.geometry.types.voxels import Voxels as RVoxels
+    from warpconvnet.nn.modules.sparse_conv import SparseConv3d as RConv
+    from warpconvnet_b200.integration import reference_backend as rb
+    name = rb.register()
+    bc, km, x, w, gy = _oracle_case(n=5000, cin=64, cout=64, seed=3)
+    n = len(bc)
+    conv = RConv(64, 64, 3, bias=False, fwd_algo=[name], dgrad_algo=[name], wgrad_algo=[name]).cuda()
+    with torch.no_grad():
+        conv.weight.copy_(w.cuda())
+    feats = x.cuda().bfloat16().requires_grad_(True)
+    vox = RVoxels([torch.from_numpy(bc[:, 1:].copy()).cuda()], [feats])
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out = conv(vox)
+    out.feature_tensor.backward(gy.cuda().to(out.feature_tensor.dtype))
+    torch.cuda.synchronize()
+    xb, wb, gb = x.bfloat16().float(), w.bfloat16().float(), gy.bfloat16().float()
+    args = (km["in_maps"], km["out_maps"], km["offsets"])
+    assert oconv.rel_max_err(out.feature_tensor, oconv.forward(xb, wb, *args, n)) < 1e-2
+    dx_ref, dw_ref = oconv.backward(gb, xb, wb, *args)
+    assert oconv.rel_max_err(feats.grad, dx_ref) < 1e-2
+    assert oconv.rel_max_err(conv.weight.grad, dw_ref) < 1e-2
