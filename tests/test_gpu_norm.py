@@ -41,9 +41,10 @@ def test_batch_norm_act_training(dtype, n, c, relu, with_res):
     rm, rv = torch.zeros(c).cuda(), torch.ones(c).cuda()
     gy = torch.randn(n, c, generator=g).to(dtype).cuda()
     if n == 1:
-        # nn.BatchNorm1d refuses a single row in training mode; ours normalises it to beta
-        y = batch_norm_act(x, w, b, rm, rv, training=True, relu=False, residual=None)
-        assert torch.allclose(y.float(), b.detach().to(dtype).float().expand(1, c), atol=1e-2)
+        # nn.BatchNorm1d refuses a single row in training mode ("Expected more than 1 value per
+        # channel when training": the unbiased running variance divides by n - 1); so does ours
+        with pytest.raises(ValueError):
+            batch_norm_act(x, w, b, rm, rv, training=True, relu=False, residual=None)
         return
     rx, rw, rb, rres, ry, rrm, rrv = _ref(x, w, b, res, relu, True, rm, rv)
     y = batch_norm_act(x, w, b, rm, rv, training=True, relu=relu, residual=res)

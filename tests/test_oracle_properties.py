@@ -109,3 +109,24 @@ def test_compressed_mask_keys_keep_the_plan_quality(extent, seed):
     folded = steps(np.argsort(keys, kind="stable"))
     unsorted = steps(np.arange(n))
     assert folded <= 1.02 * full and folded < 0.6 * unsorted, (full, folded, unsorted)
+
+
+def test_probes_outside_the_key_range_miss_like_the_dictionary_pin():
+    """Voxels at opposite ends of the 18-bit range are NOT neighbours: the vectorised oracle agrees
+    with the Python-dict enumeration (the reference tests' pin); ``wrap=True`` reproduces the
+    masking of the reference's CUDA kernel, which aliases them, and differs only there."""
+    lim = 131071
+    c = np.array([[lim, lim, lim], [lim - 1, lim, lim], [-131072, -131072, -131072],
+                  [-131071, -131072, -131072], [0, 0, 0], [lim, -131072, 0]], np.int32)
+    bc = okm.batch_indexed([c])
+    km = okm.generate_kernel_map(bc, bc, (1, 1, 1), (3, 3, 3))
+    got = {(k, int(i), int(o)) for k in range(27)
+           for i, o in zip(km["in_maps"][km["offsets"][k]:km["offsets"][k + 1]],
+                           km["out_maps"][km["offsets"][k]:km["offsets"][k + 1]])}
+    assert got == okm.brute_force_pairs(bc, bc, (1, 1, 1), (3, 3, 3))
+    wrapped = okm.generate_kernel_map(bc, bc, (1, 1, 1), (3, 3, 3), wrap=True)
+    assert int(wrapped["offsets"][-1]) > int(km["offsets"][-1])
+    inner = okm.batch_indexed([c[[1, 3, 4]] // 2])
+    a = okm.generate_kernel_map(inner, inner, (1, 1, 1), (3, 3, 3))
+    b = okm.generate_kernel_map(inner, inner, (1, 1, 1), (3, 3, 3), wrap=True)
+    assert np.array_equal(a["pair_table"], b["pair_table"])

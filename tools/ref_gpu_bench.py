@@ -35,6 +35,27 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
 
 PLANES = (32, 64, 128, 256, 128, 128, 96, 96)
 
+# The reference's auto-tuner SEGFAULTS on this B200 inside _C.mask_gemm.dgrad when it reaches the
+# last two candidates of its default dgrad pool (native "pcoff" dgrad tiles; the 13 candidates
+# before them run: gpurun_out/r2d_ref_diag.log, profiles/r2_reference_gpu_head_to_head.md). To get
+# a reference number at all, its dgrad pool is restricted — through its own public attribute
+# SparseConv3d.dgrad_algo (a list of backend names, nn/modules/sparse_conv.py:130-137) — to every
+# other family it would have tried, including the one that measured fastest in that sweep
+# (mask_gemm_fwd_as_dgrad, 0.44 ms vs 0.48-0.49 ms for the excluded family's working tiles).
+# Forward and wgrad keep the reference's default "auto".
+REF_DGRAD_POOL = ["mask_gemm_fwd_as_dgrad", "cutlass_implicit_gemm", "cute_grouped",
+                  "cutlass_grouped_hybrid", "explicit_gemm", "implicit_gemm"]
+
+
+def pin_ref_dgrad_pool(module):
+    import warpconvnet.nn.modules.sparse_conv as rsc
+    n = 0
+    for m in module.modules():
+        if isinstance(m, rsc.SpatiallySparseConv):
+            m.dgrad_algo = list(REF_DGRAD_POOL)
+            n += 1
+    return n
+
 
 def surface(extent, seed):
     rng = np.random.RandomState(seed)
@@ -87,6 +108,8 @@ def conv_layer_section(name, coords, RVoxels, RConv):
     out = {"section": name, "voxels": n}
     for arm, VoxT, ConvT in (("ref", RVoxels, RConv), ("ours", Voxels, SparseConv3d)):
         conv = ConvT(128, 128, 3, bias=False).to(dev)
+        if arm == "ref":
+            pin_ref_dgrad_pool(conv)
         with torch.no_grad():
             conv.weight.copy_(w)
         vox = VoxT([c], [x.bfloat16()])
@@ -177,6 +200,7 @@ def c4_section(scenes, RVoxels):
         torch.manual_seed(0)
         if arm == "ref":
             net = MinkUNetBase(3, 20, planes=PLANES, layers=(1,) * 8).to(dev)
+            out["ref_convs_with_pinned_dgrad_pool"] = pin_ref_dgrad_pool(net)
             VoxT = RVoxels
         else:
             net = MinkUNet14(3, 20).to(dev)

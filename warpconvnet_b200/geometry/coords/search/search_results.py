@@ -132,6 +132,10 @@ class IntSearchResult:
             return
         host, event, on_ready = self._pending
         self._pending = None
+        for i, entry in enumerate(_PENDING_STATUS):  # this map is checked right here
+            if entry[0] is host:
+                del _PENDING_STATUS[i]
+                break
         if event is not None:
             event.synchronize()
         else:

@@ -173,18 +173,36 @@ def _wgrad_identity(kernel_map, K: int):
     return {"identity_k": K // 2, "status": None if table is None else table.status_tensor}
 
 
+# Dense-row wgrad (csrc/conv_wgrad.cu): offsets that pair >= 60 % of the output rows are walked over
+# ALL output rows in row order — dY arrives as dense TMA tiles, only X is gathered through the pair
+# table — which halves the gathered (LSU) bytes of those offsets; the kernel is LSU-bound.
+_WGRAD_DENSE_ROWS = os.environ.get("WCN_WGRAD_DENSE_ROWS", "1") == "1"
+_WGRAD_DENSE_ROUNDS = 2   # chunks per CTA of the weighted virtual list (evens out dense / sparse)
+
+
 def _wgrad_order(x: Tensor, gy: Tensor, kernel_map, K: int):
     bp = getattr(kernel_map, "_block_prefix", None)
-    work = x.numel() * x.element_size() + gy.numel() * gy.element_size()
-    if (bp is None or _WGRAD_ROUNDS <= 1 or work < _WGRAD_LOCALITY_BYTES
-            or _WGRAD_ROUNDS * K > 1024 or bp.shape[0] != K or bp.shape[1] < _WGRAD_ROUNDS):
+    if bp is None or bp.shape[0] != K or K > 256:
         return {}
-    return {"row_block_prefix": bp, "row_parts": _WGRAD_ROUNDS, "rounds": _WGRAD_ROUNDS}
+    work = x.numel() * x.element_size() + gy.numel() * gy.element_size()
+    big = (_WGRAD_ROUNDS > 1 and work >= _WGRAD_LOCALITY_BYTES and _WGRAD_ROUNDS * K <= 1024
+           and bp.shape[1] >= _WGRAD_ROUNDS)
+    order = {"row_block_prefix": bp, "row_parts": _WGRAD_ROUNDS, "rounds": _WGRAD_ROUNDS} if big else {}
+    pt = getattr(kernel_map, "_pair_table", None)
+    if (_WGRAD_DENSE_ROWS and pt is not None and pt.shape == (K, gy.shape[0])
+            and x.dtype in (torch.bfloat16, torch.float16) and gy.shape[1] * 2 <= 256
+            and x.shape[1] * 2 <= 256 and bp.shape[1] * 256 >= gy.shape[0]):
+        if not order:
+            order = {"row_block_prefix": bp, "row_parts": 1, "rounds": _WGRAD_DENSE_ROUNDS}
+        order["pair_table"] = pt
+    return order
 
 
 def _wgrad_call(x: Tensor, gy: Tensor, kernel_map, K: int, G: int, cin_g: int, cout_g: int) -> Tensor:
     im, om, od = kernel_map._in_buf, kernel_map._out_buf, kernel_map.offsets_dev
     order = dict(_wgrad_order(x, gy, kernel_map, K), **_wgrad_identity(kernel_map, K))
+    if G != 1:
+        order.pop("pair_table", None)  # dense-row mode: dense (ungrouped) convs only
     if x.dtype != torch.float32:
         return _ops.wgrad(x, gy, im, om, od, K, G, cin_g, cout_g, **order)
     # fp32 operands: the contraction runs over gathered rows (MN-major operands), which the
