@@ -93,7 +93,7 @@ def test_out_of_range_coordinates_raise_in_coordinate_chain_and_in_the_conv_step
     from warpconvnet_b200.geometry.types.voxels import Voxels
     from warpconvnet_b200.nn.modules.sparse_conv import SparseConv3d
     c = random_coords(500, 0.3, 10)
-    c[17] = (5, 200000, 3)                                   # beyond the 18-bit packed range
+    c[17] = (5, 600000, 3)                                   # beyond the packed range, also after / 2
     bc = torch.from_numpy(_bc([c])).cuda()
     with pytest.raises(ValueError):
         stride_coords(bc, (2, 2, 2), n_batches=1)
@@ -166,9 +166,11 @@ def test_whole_network_step_captured_in_one_cuda_graph_matches_eager():
             out = net(x)
         loss = out.feature_tensor.float().square().mean()
         loss.backward()
-        state["loss"] = loss
+        # detached copies only: a live autograd graph from the eager pass would keep AccumulateGrad
+        # nodes bound to the eager stream while the capture runs on its own stream
+        state["loss"] = loss.detach().clone()
         state["gsum"] = torch.stack([p.grad.float().abs().sum() for p in net.parameters()]).sum()
-        return loss
+        return None
 
     step()
     torch.cuda.synchronize()

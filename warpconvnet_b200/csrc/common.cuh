@@ -34,6 +34,17 @@ constexpr int kNumSMsB200 = 148;
 // Per-role wait-cycle counters of the GEMM kernels (tools/exp_dbg.py, tools/exp_wgrad.py) are a
 // bring-up aid: the clock reads are compiled in only with -DWCN_KERNEL_COUNTERS
 // (WCN_KERNEL_COUNTERS=1 csrc/build.sh); the shipped library carries none of them.
+// Experiment switches (GemmParams::debug bits, per-CTA counter dumps through dbg_out) exist only
+// in bring-up builds (WCN_BRINGUP=1 csrc/build.sh): in the shipped library WCN_DBG is the
+// constant false and WCN_DBG_OUT the constant nullptr, so the predicates, the counter stores and
+// the %globaltimer reads behind them are removed by the compiler.
+#ifdef WCN_BRINGUP
+#define WCN_DBG(params, bits) ((((params).debug) & (bits)) != 0)
+#define WCN_DBG_OUT(params) ((params).dbg_out)
+#else
+#define WCN_DBG(params, bits) (false)
+#define WCN_DBG_OUT(params) (static_cast<long long*>(nullptr))
+#endif
 #ifdef WCN_KERNEL_COUNTERS
 #define WCN_CLOCK() clock64()
 #else

@@ -153,10 +153,10 @@ gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
   const int warp = tid >> 5;
   const int lane = tid & 31;
   const int slab = blockIdx.y;
-  if (p.dbg_out != nullptr && tid == 0) {  // bring-up: absolute ns at kernel entry
+  if (WCN_DBG_OUT(p) != nullptr && tid == 0) {  // bring-up: absolute ns at kernel entry
     unsigned long long ns;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns));
-    p.dbg_out[blockIdx.x * 16 + 8] = (long long)ns;
+    WCN_DBG_OUT(p)[blockIdx.x * 16 + 8] = (long long)ns;
   }
 
   constexpr int kASub = GC * kAStageBytes;  // one 128-row sub-tile: GC slabs of 128 rows x 128 B
@@ -285,8 +285,10 @@ gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
     uint32_t phase = 0;
     long long w_empty = 0;
     const long long t_start = WCN_CLOCK();
-    unsigned long long ns_start;
+    unsigned long long ns_start = 0;
+#ifdef WCN_BRINGUP
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns_start));
+#endif
 #pragma unroll 1
     while (cur.valid(t_end)) {
       int idx_own[TM];
@@ -317,7 +319,7 @@ gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
         if (tid == 0) {
           const int chunks_here = min(GC, n_chunks - g * GC);
           const uint32_t b_bytes = (uint32_t)(chunks_here * b_chunk_bytes);
-          if (p.debug & 8) {  // bring-up: no weight traffic
+          if WCN_DBG(p, 8) {  // bring-up: no weight traffic
             mbar_arrive(full_bar);
           } else {
             mbar_arrive_expect_tx(full_bar, b_bytes);
@@ -327,7 +329,7 @@ gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
           }
         }
         const int seg_off = g * GC * 128;  // byte offset of this chunk group inside the row
-        const bool lane_active = seg_off + u * 16 < row_bytes && !(p.debug & 2);
+        const bool lane_active = seg_off + u * 16 < row_bytes && !WCN_DBG(p, 2);
         const uint8_t* seg_base = col_base + seg_off;
 #pragma unroll
         for (int j = 0; j < TM; ++j) {
@@ -376,14 +378,14 @@ gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
         if (++stage == stages) { stage = 0; phase ^= 1u; }
       }
     }
-    if (p.dbg_out != nullptr && tid == 0) {
-      p.dbg_out[blockIdx.x * 16 + 0] = WCN_CLOCK() - t_start;
-      p.dbg_out[blockIdx.x * 16 + 1] = w_empty;
+    if (WCN_DBG_OUT(p) != nullptr && tid == 0) {
+      WCN_DBG_OUT(p)[blockIdx.x * 16 + 0] = WCN_CLOCK() - t_start;
+      WCN_DBG_OUT(p)[blockIdx.x * 16 + 1] = w_empty;
       unsigned long long ns_end;
       asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns_end));
-      p.dbg_out[blockIdx.x * 16 + 7] = (long long)(ns_end - ns_start);
-      p.dbg_out[blockIdx.x * 16 + 9] = (long long)ns_start;
-      p.dbg_out[blockIdx.x * 16 + 10] = (long long)ns_end;
+      WCN_DBG_OUT(p)[blockIdx.x * 16 + 7] = (long long)(ns_end - ns_start);
+      WCN_DBG_OUT(p)[blockIdx.x * 16 + 9] = (long long)ns_start;
+      WCN_DBG_OUT(p)[blockIdx.x * 16 + 10] = (long long)ns_end;
     }
   } else if (warp == kMmaWarp) {
     // ======================================= MMA issuer =========================================
@@ -432,7 +434,7 @@ gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
                   const uint32_t idesc_sw =
                       make_idesc(ElemTraits<T>::kFmt, kTileM, (hi - lo) * kTileM, 0, 0);
                   for (int m = 0; m < n_mma; ++m) {
-                    if (p.debug & 4) continue;  // bring-up: no tensor work
+                    if WCN_DBG(p, 4) continue;  // bring-up: no tensor work
                     const uint64_t wdesc =
                         make_smem_desc_sw128(b_smem + cc * b_chunk_bytes + m * 32, 16, 1024);
                     const uint64_t xdesc = make_smem_desc_sw128(
@@ -445,7 +447,7 @@ gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
                   for (int j = 0; j < TM; ++j) {
                     if (TM > 1 && (j < lo || j >= hi)) continue;  // sub-tile not ours
                     for (int m = 0; m < n_mma; ++m) {
-                      if (p.debug & 4) continue;  // bring-up: no tensor work
+                      if WCN_DBG(p, 4) continue;  // bring-up: no tensor work
                       const uint64_t adesc = make_smem_desc_sw128(
                           a_smem + j * kASub + cc * kAStageBytes + m * 32, 16, 1024);
                       const uint64_t bdesc =
@@ -465,10 +467,10 @@ gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
           ++use;
         }
       }
-      if (p.dbg_out != nullptr) {
-        p.dbg_out[blockIdx.x * 16 + 2] = WCN_CLOCK() - t_start;
-        p.dbg_out[blockIdx.x * 16 + 3] = w_full;
-        p.dbg_out[blockIdx.x * 16 + 4] = w_acc;
+      if (WCN_DBG_OUT(p) != nullptr) {
+        WCN_DBG_OUT(p)[blockIdx.x * 16 + 2] = WCN_CLOCK() - t_start;
+        WCN_DBG_OUT(p)[blockIdx.x * 16 + 3] = w_full;
+        WCN_DBG_OUT(p)[blockIdx.x * 16 + 4] = w_acc;
       }
     }
   } else {
@@ -542,7 +544,7 @@ gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
                 const int row = it * kRowsPerSt + s_row;
                 const int orow = __shfl_sync(0xffffffffu, out_row, row);
                 const uint4 val = ld_shared_v4(stage_warp + row * kRowB + s_piece * 16);
-                if (orow >= 0 && piece_valid && !(p.debug & 1))
+                if (orow >= 0 && piece_valid && !WCN_DBG(p, 1))
                   *reinterpret_cast<uint4*>(out + (long long)orow * out_ld_bytes +
                                             (long long)(col_base + q * 32) * kElem +
                                             s_piece * 16) = val;
@@ -602,7 +604,7 @@ gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
               const int orow = __shfl_sync(0xffffffffu, out_row, row);
               const uint4 val =
                   ld_shared_v4(stage_warp + row * 256 + ((piece ^ (row & 15)) << 4));
-              if (orow >= 0 && piece_ok && !(p.debug & 1))  // debug 1: skip stores (bring-up)
+              if (orow >= 0 && piece_ok && !WCN_DBG(p, 1))  // debug 1: skip stores (bring-up)
                 *reinterpret_cast<uint4*>(out + (long long)orow * out_ld_bytes +
                                           (long long)(col_base + c0) * kElem + piece * 16) = val;
             }
@@ -617,18 +619,18 @@ gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
         }
       }
     }
-    if (p.dbg_out != nullptr && tid == 5 * 32) {
-      p.dbg_out[blockIdx.x * 16 + 5] = WCN_CLOCK() - t_start;
-      p.dbg_out[blockIdx.x * 16 + 6] = w_accf;
+    if (WCN_DBG_OUT(p) != nullptr && tid == 5 * 32) {
+      WCN_DBG_OUT(p)[blockIdx.x * 16 + 5] = WCN_CLOCK() - t_start;
+      WCN_DBG_OUT(p)[blockIdx.x * 16 + 6] = w_accf;
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (p.dbg_out != nullptr && tid == 0) {  // bring-up: absolute ns when every role is done
+  if (WCN_DBG_OUT(p) != nullptr && tid == 0) {  // bring-up: absolute ns when every role is done
     unsigned long long ns;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns));
-    p.dbg_out[blockIdx.x * 16 + 11] = (long long)ns;
+    WCN_DBG_OUT(p)[blockIdx.x * 16 + 11] = (long long)ns;
   }
   if (warp == kMmaWarp) {
     tc_fence_after();
@@ -683,13 +685,13 @@ static int launch_gather_gemm_tm(const GatherGemmParams& p, int n_slabs, int max
   // TM = 2: two 128-row sub-tiles share each weight slice when the plan has 256-row tiles and
   // both accumulators (double buffered) fit the 512 TMEM columns.
   // GC = 2: a stage covers two 128-byte channel chunks so gathers are 256-byte requests.
-  const bool tm2 = p.tile_rows == 2 * kTileM && p.bn <= 128 && !(p.debug & 16);  // 16: bring-up
-  const bool gc2 = p.cin * (int)sizeof(T) > 128 && !(p.debug & 32);             // 32: bring-up
+  const bool tm2 = p.tile_rows == 2 * kTileM && p.bn <= 128 && !WCN_DBG(p, 16);  // 16: bring-up
+  const bool gc2 = p.cin * (int)sizeof(T) > 128 && !WCN_DBG(p, 32);             // 32: bring-up
   // SWAP: Cout is exactly one M = 128 operand and the tile's 256 rows form the N operand
   // (bn < 128 pads M to 128 with don't-care rows: correct for every bn, but measured slower than
   // the row-major form at bn <= 96 on the MinkUNet-14 layers — 422 vs 402 us at 96 channels, 140 vs
   // 117 us at 32/64 — so it is only taken where the padding is small)
-  const bool swap = tm2 && p.bn > 96 && p.bn <= kTileM && !(p.debug & 64);       // 64: bring-up
+  const bool swap = tm2 && p.bn > 96 && p.bn <= kTileM && !WCN_DBG(p, 64);       // 64: bring-up
   if (swap) {
     return gc2 ? launch_gather_gemm_t<T, 2, 2, true>(p, n_slabs, max_ctas, n_range_ctas, stream)
                : launch_gather_gemm_t<T, 2, 1, true>(p, n_slabs, max_ctas, n_range_ctas, stream);

@@ -427,14 +427,14 @@ wgrad_kernel(const __grid_constant__ WgradParams p, const __grid_constant__ CUte
         }
       }
     }
-    if (p.dbg_out != nullptr && tid == 0 && (p.debug & 1024)) {
-      p.dbg_out[blockIdx.x * 8 + 3] = t_issue;
-      p.dbg_out[blockIdx.x * 8 + 4] = t_arrive;
+    if (WCN_DBG_OUT(p) != nullptr && tid == 0 && WCN_DBG(p, 1024)) {
+      WCN_DBG_OUT(p)[blockIdx.x * 8 + 3] = t_issue;
+      WCN_DBG_OUT(p)[blockIdx.x * 8 + 4] = t_arrive;
     }
-    if (p.dbg_out != nullptr && tid == 0) {
-      p.dbg_out[blockIdx.x * 8 + 0] = WCN_CLOCK() - t_start;
-      p.dbg_out[blockIdx.x * 8 + 1] = w_empty;
-      p.dbg_out[blockIdx.x * 8 + 7] = n_stage;
+    if (WCN_DBG_OUT(p) != nullptr && tid == 0) {
+      WCN_DBG_OUT(p)[blockIdx.x * 8 + 0] = WCN_CLOCK() - t_start;
+      WCN_DBG_OUT(p)[blockIdx.x * 8 + 1] = w_empty;
+      WCN_DBG_OUT(p)[blockIdx.x * 8 + 7] = n_stage;
     }
   } else if (warp == 4) {
     // ======================================= MMA issuer =========================================
@@ -464,12 +464,12 @@ wgrad_kernel(const __grid_constant__ WgradParams p, const __grid_constant__ CUte
             mbar_wait(smem_u32(&ctrl->full[stage]), phase);
             w_full += WCN_CLOCK() - t0;
           }
-          if (!(p.debug & 64)) fence_proxy_async_smem();  // cp.async = generic-proxy writes
+          if (!WCN_DBG(p, 64)) fence_proxy_async_smem();  // cp.async = generic-proxy writes
           tc_fence_after();
           const uint32_t a_smem = smem_base + stage * stage_bytes;
           const uint32_t b_smem = a_smem + kAStage;
 #pragma unroll
-          for (int j = 0; j < kPairs / kKPerMma && !(p.debug & 256); ++j) {
+          for (int j = 0; j < kPairs / kKPerMma && !WCN_DBG(p, 256); ++j) {
             const uint32_t koff = j * kKPerMma * 128;  // kKPerMma pair rows of 128 bytes
             const uint64_t adesc = make_smem_desc_sw128(a_smem + koff, kPairs * 128, 1024);
             const uint64_t bdesc = make_smem_desc_sw128(b_smem + koff, kPairs * 128, 1024);
@@ -482,10 +482,10 @@ wgrad_kernel(const __grid_constant__ WgradParams p, const __grid_constant__ CUte
         umma_commit(smem_u32(&ctrl->acc_full[acc]));
         ++use;
       }
-      if (p.dbg_out != nullptr && !(p.debug & 1024)) {
-        p.dbg_out[blockIdx.x * 8 + 2] = WCN_CLOCK() - t_start;
-        p.dbg_out[blockIdx.x * 8 + 3] = w_full;
-        p.dbg_out[blockIdx.x * 8 + 4] = w_acc;
+      if (WCN_DBG_OUT(p) != nullptr && !WCN_DBG(p, 1024)) {
+        WCN_DBG_OUT(p)[blockIdx.x * 8 + 2] = WCN_CLOCK() - t_start;
+        WCN_DBG_OUT(p)[blockIdx.x * 8 + 3] = w_full;
+        WCN_DBG_OUT(p)[blockIdx.x * 8 + 4] = w_acc;
       }
     }
   } else {
@@ -548,9 +548,9 @@ wgrad_kernel(const __grid_constant__ WgradParams p, const __grid_constant__ CUte
       mbar_arrive(smem_u32(&ctrl->acc_empty[acc]));
       ++use;
     }
-    if (p.dbg_out != nullptr && tid == 5 * 32) {
-      p.dbg_out[blockIdx.x * 8 + 5] = WCN_CLOCK() - t_start;
-      p.dbg_out[blockIdx.x * 8 + 6] = w_accf;
+    if (WCN_DBG_OUT(p) != nullptr && tid == 5 * 32) {
+      WCN_DBG_OUT(p)[blockIdx.x * 8 + 5] = WCN_CLOCK() - t_start;
+      WCN_DBG_OUT(p)[blockIdx.x * 8 + 6] = w_accf;
     }
   }
 
@@ -638,7 +638,7 @@ static int launch_wgrad_t(WgradParams p, int cin_slabs, int cout_slabs, int max_
                                       ElemTraits<T>::kFmt == 0) &&
                     make_row_tile_map(&tmap_dy, p.gout, p.out_ld, p.cout, n_out_rows, kElem, kPairs,
                                       ElemTraits<T>::kFmt == 0);
-    if (p.debug & 2048)  // bring-up: WCN_DEBUG=2048 reports whether the TMA identity path is on
+    if WCN_DBG(p, 2048)  // bring-up: WCN_DEBUG=2048 reports whether the TMA identity path is on
       fprintf(stderr, "wcn wgrad: identity_k=%d tma_tiles=%d (encode fn %p)\n", p.identity_k, (int)ok,
               (void*)encode_tiled_fn());
     if (!ok) p.identity_k = -1;

@@ -16,7 +16,6 @@ from __future__ import annotations
 from enum import Enum
 from typing import Optional
 
-import os
 
 import torch
 from torch import Tensor
@@ -152,7 +151,7 @@ def sparse_conv_dgrad(grad_output: Tensor, weight: Tensor, kernel_map: IntSearch
 # restarts the index prefetch and flushes an accumulator; 4 windows: 119 MB, +7 %). Below the
 # threshold the plain offset-major order is kept.
 _WGRAD_LOCALITY_BYTES = 48 << 20
-_WGRAD_ROUNDS = int(os.environ.get("WCN_WGRAD_ROUNDS", "2"))
+_WGRAD_ROUNDS = 2  # module constant: the product path reads no experiment switches from the environment
 
 
 # Measured on C3-S: fetching the identity offset's rows (11 % of the pairs) as TMA tiles leaves the
@@ -160,7 +159,7 @@ _WGRAD_ROUNDS = int(os.environ.get("WCN_WGRAD_ROUNDS", "2"))
 # static pair-count partition does not hand them more work, and a TMA-fed stage is still paced by
 # its four 128x128x16 MMAs (~600 of the 1 140 cycles of a gathered stage). Kept behind the C-ABI,
 # off by default (the two tensor-map encodes also cost host time per call).
-_WGRAD_IDENTITY_TMA = os.environ.get("WCN_WGRAD_IDENTITY_TMA", "0") == "1"
+_WGRAD_IDENTITY_TMA = False
 
 
 def _wgrad_identity(kernel_map, K: int):
@@ -175,8 +174,13 @@ def _wgrad_identity(kernel_map, K: int):
 
 # Dense-row wgrad (csrc/conv_wgrad.cu): offsets that pair >= 60 % of the output rows are walked over
 # ALL output rows in row order — dY arrives as dense TMA tiles, only X is gathered through the pair
-# table — which halves the gathered (LSU) bytes of those offsets; the kernel is LSU-bound.
-_WGRAD_DENSE_ROWS = os.environ.get("WCN_WGRAD_DENSE_ROWS", "1") == "1"
+# table — which halves the LSU-gathered bytes of those offsets. MEASURED SLOWER and therefore OFF
+# (profiles/r2_wgrad_dense_rows_negative_result.md): C3-S 152.6 -> 170.9 us, C3-R 143.7 -> 159.3 us
+# against the same unit order without it. A dense stage (64 rows, X gathered + dY by TMA) costs
+# ~0.86 of a pair-list stage, not the ~0.54 its LSU bytes suggest: what bounds the kernel is the
+# bytes that cross L2 -> SM, whichever unit requests them, and the TMA tiles move the same bytes
+# (plus the rows of missing pairs). Kept behind the C-ABI, parity-tested, for the record.
+_WGRAD_DENSE_ROWS = False
 _WGRAD_DENSE_ROUNDS = 2   # chunks per CTA of the weighted virtual list (evens out dense / sparse)
 
 
