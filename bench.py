@@ -205,6 +205,12 @@ def run_c4(dev, rank, world, dist, steps=10, warmup=3):
     opt = torch.optim.SGD(net.parameters(), lr=1e-3, momentum=0.9)
     bucket = FlatGradBucket(net.parameters()) if world > 1 else None
     cached_vox = Voxels(coords, feats)
+    # replace() copies the attribute dict, so a kernel-map cache only survives across steps when it
+    # exists on the template object BEFORE the first replace (otherwise every step's copy creates
+    # its own and the next step starts empty again — which is also what happens in the reference's
+    # scripts/bench_unet_gb300.py, whose "cached" maps are in fact rebuilt every iteration)
+    from warpconvnet_b200.geometry.coords.search.cache import IntSearchCache
+    cached_vox._extra_attributes["_cache"] = IntSearchCache()
 
     def make_step(fresh_maps: bool):
         def step():
@@ -289,6 +295,40 @@ def run_c4(dev, rank, world, dist, steps=10, warmup=3):
     return out
 
 
+def run_ref_gpu(sections, timeout_s):
+    """Same-box head-to-head against the UNMODIFIED reference's own GPU build (baseline/_ref, built
+    by baseline/build_ref.sh) through tools/ref_gpu_bench.py, in a SUBPROCESS: the reference's
+    auto-tuner is known to segfault on B200 (tools/ref_gpu_bench.py: REF_DGRAD_POOL) and must not
+    be able to take this process down. Returns the tool's JSON lines keyed by section."""
+    ref_dir = os.path.join(ROOT, "baseline", "_ref", "warpconvnet")
+    if not os.path.isdir(ref_dir):
+        return {"unavailable": "baseline/_ref absent (bash baseline/build_ref.sh builds it, ~15 min)"}
+    out_path = os.path.join(tempfile.gettempdir(), f"wcn_ref_gpu_{os.getpid()}.jsonl")
+    cmd = [sys.executable, os.path.join(ROOT, "tools", "ref_gpu_bench.py"), *sections, "--out", out_path]
+    t0 = time.perf_counter()
+    try:
+        proc = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s)
+        note = None if proc.returncode == 0 else f"exit code {proc.returncode}"
+    except subprocess.TimeoutExpired:
+        note = f"timed out after {timeout_s} s"
+    res = {"tool": "tools/ref_gpu_bench.py " + " ".join(sections),
+           "protocol": "reference's own scripts/bench_unet_gb300.py protocol: 8 warm-up steps (its "
+                       "auto-tuner runs there) + 20 timed, CUDA events; both arms in one process on "
+                       "identical inputs; *_ms are per step",
+           "wall_s": round(time.perf_counter() - t0, 1)}
+    if note:
+        res["note"] = note
+    if os.path.exists(out_path):
+        for line in open(out_path):
+            try:
+                r = json.loads(line)
+                res[r.pop("section")] = r
+            except Exception:
+                pass
+        os.remove(out_path)
+    return res
+
+
 def run_side_blocks(dev, flush):
     """C3-R, C2 and C5 on one GPU (SURVEY.md §8d says R must be reported next to S)."""
     from warpconvnet_b200 import _ops
@@ -350,6 +390,46 @@ def run_side_blocks(dev, flush):
                     "pairs_L": L2, "kernel_map_plus_plan_ms": t_map2, "fwd_ms": t_f2,
                     "voxels_per_s": n2 / ((t_map2 + t_f2) * 1e-3),
                     "fwd_TFLOPs": 2.0 * L2 * 64 * 128 / (t_f2 * 1e-3) / 1e12}
+    # ---- C5 (one rank's share of the 8-GPU config): group conv 512 -> 512, groups = 64, and
+    # PointConv(64, 64, knn_k = 16) on 125k points, bf16 --------------------------------------
+    from warpconvnet_b200.geometry.coords.search.search_configs import RealSearchConfig
+    from warpconvnet_b200.geometry.types.points import Points
+    from warpconvnet_b200.nn.modules.point_conv import PointConv
+    sel5 = (rng_c[:, 0] < 354) & (rng_c[:, 1] < 354)
+    c5 = rng_c[sel5]
+    n5 = len(c5)
+    bc5 = torch.from_numpy(np.concatenate([np.zeros((n5, 1), np.int32), c5], 1)).to(dev)
+    km5 = generate_kernel_map(bc5, bc5, (1, 1, 1), (3, 3, 3), same_coords=True)
+    x5 = torch.randn(n5, 512, device=dev).bfloat16()
+    gy5 = torch.randn(n5, 512, device=dev).bfloat16()
+    w5 = (torch.randn(27, 64, 8, 8, device=dev) * (27 * 8) ** -0.5).bfloat16()
+
+    def gstep():
+        sparse_conv_forward(x5, w5, km5, n5, groups=64)
+        sparse_conv_dgrad(gy5, w5, km5, n5, groups=64)
+        sparse_conv_wgrad(x5, gy5, tuple(w5.shape), km5, groups=64)
+
+    t_g = timed(gstep)
+    npts = 125000
+    gp = torch.Generator().manual_seed(5)
+    pts = torch.rand(npts, 3, generator=gp).to(dev)
+    pf = torch.randn(npts, 64, generator=gp).to(dev)
+    offs = torch.tensor([0, npts], dtype=torch.int64)
+    pconv = PointConv(64, 64, RealSearchConfig("knn", knn_k=16)).to(dev)
+    t_knn = timed(lambda: _ops.knn_search(pts, offs, pts, offs, 16))
+
+    def pstep():
+        pc = Points(pts, pf.detach().requires_grad_(True), offsets=offs)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out_pc = pconv(pc)
+        out_pc.feature_tensor.float().square().mean().backward()
+
+    t_pc = timed(pstep, k=5, w=2)
+    blocks["c5_rank_share"] = {
+        "workload": "C5 (1/8 of the 8-GPU config): SparseConv3d(512,512,3,groups=64) on %d voxels "
+                    "fwd+dgrad+wgrad; PointConv(64,64,knn_k=16) on %d points fwd+bwd, bf16" % (n5, npts),
+        "group_conv_fwd_bwd_ms": t_g, "group_conv_voxels_per_s": n5 / (t_g * 1e-3),
+        "knn_ms": t_knn, "pointconv_fwd_bwd_ms": t_pc, "pointconv_points_per_s": npts / (t_pc * 1e-3)}
     return blocks
 
 
@@ -568,7 +648,7 @@ def run_ours(args):
     barrier()
     # The loop is paced by the host thread and the PCIe copies, so single K-step measurements
     # scatter (1.0 - 1.4 ms on the same box): K steps are timed three times, each max-reduced over
-    # ranks, and the best repetition is reported (all three are listed in e2e.runs_ms).
+    # ranks, and the MEDIAN repetition is reported (all three are listed in e2e.runs_ms).
     e2e_runs = []
     for _ in range(3):
         s_ev, e_ev = e2e_run(args.steps)
@@ -577,7 +657,7 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_runs.append(float(t.item()))
-    e2e_ms = min(e2e_runs)
+    e2e_ms = float(np.median(e2e_runs))
     clocks = sampler.stop() if sampler else None
     if clocks is not None:
         clocks["window"] = ("all timed regions of this run (graph steps, eager steps, kernel-only "
@@ -590,6 +670,10 @@ def run_ours(args):
             side = run_side_blocks(dev, flush)
         except Exception as exc:  # pragma: no cover
             side = {"error": f"{type(exc).__name__}: {str(exc)[:300]}"}
+    ref_gpu = None
+    if world == 1 and rank == 0 and args.ref_gpu != "none":
+        torch.cuda.empty_cache()
+        ref_gpu = run_ref_gpu(args.ref_gpu.split(","), args.ref_gpu_timeout)
     c4 = None
     if not args.no_c4:
         # free the C3 working set first
@@ -634,7 +718,8 @@ def run_ours(args):
         },
         "e2e": {"value": total_vox / (e2e_ms * 1e-3), "unit": "voxels/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "runs_ms": e2e_runs, "runs": "3 repetitions of K steps, best reported",
+                "runs_ms": e2e_runs, "runs": "3 repetitions of K steps, median reported",
+                "warmup_steps": max(args.warmup, 50),
                 "api": "Voxels(pinned host coords+feats) -> SparseConv3d.forward (autocast bf16) -> "
                        "backward -> weight.grad to pinned host",
                 "pipeline": "H2D of step i+1 overlaps compute of step i (copy stream, 2 buffers); "
@@ -659,6 +744,7 @@ def run_ours(args):
         "phases_ms": phases,
         "wall_s_timed_region": wall,
         "c4": c4,
+        "ref_gpu": ref_gpu,
     }
     out.update(side)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -715,7 +801,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA graph replay")
     ap.add_argument("--no-c4", action="store_true", help="skip the MinkUNet-14 (config C4) block")
-    ap.add_argument("--no-side", action="store_true", help="skip the C3-R / C2 side blocks")
+    ap.add_argument("--no-side", action="store_true", help="skip the C3-R / C2 / C5 side blocks")
+    ap.add_argument("--ref-gpu", default="kmap,c3s", help="sections of tools/ref_gpu_bench.py to run "
+                    "against the built reference (N = 1 only): kmap,c3s,c3r,c4 or 'none'; c4 needs "
+                    "~5 min for the reference's auto-tuner")
+    ap.add_argument("--ref-gpu-timeout", type=int, default=240)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

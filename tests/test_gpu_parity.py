@@ -258,6 +258,33 @@ def test_full_size_properties_c3():
     assert abs(a - b) / scale < 2e-3 and abs(a - cc) / scale < 2e-3
 
 
+@pytest.mark.parametrize("dist,n,cin,cout", [("S", 200704, 128, 128), ("R", 200000, 128, 128),
+                                             ("S", 100489, 64, 128)])
+def test_full_size_all_rows_vs_fp64_oracle(dist, n, cin, cout):
+    """BASELINE C3 (S and R) and C2 at FULL size, EVERY row: forward, dgrad and wgrad against the
+    fp64 CPU oracle (oracle/conv.py, the reference's explicit gather-matmul-scatter) on the same
+    bf16-rounded operands. The kernel map handed to the oracle is the device's own CSR, which
+    test_kernel_map_full_size_invariants pins bit-exact against the NumPy kernel-map oracle."""
+    from warpconvnet_b200.nn.functional.sparse_conv import (sparse_conv_dgrad,
+                                                            sparse_conv_forward, sparse_conv_wgrad)
+    km, x, w, gy, n_in, n_out = _case(n, cin, cout, torch.bfloat16, dist=dist)
+    y = sparse_conv_forward(x, w, km, n_out)
+    dx = sparse_conv_dgrad(gy, w, km, n_in)
+    dw = sparse_conv_wgrad(x, gy, tuple(w.shape), km)
+    im, om, offs = km.in_maps.cpu().numpy(), km.out_maps.cpu().numpy(), km.offsets.numpy()
+    xf, wf, gf = x.float().cpu(), w.float().cpu(), gy.float().cpu()
+    y_ref = oconv.forward(xf, wf, im, om, offs, n_out)
+    dx_ref, dw_ref = oconv.backward(gf, xf, wf, im, om, offs)
+    assert y.shape == y_ref.shape and dx.shape == dx_ref.shape
+    assert oconv.rel_max_err(y, y_ref) < 1e-2          # bf16 output rounding: 2^-9 of max|ref|
+    assert oconv.rel_max_err(dx, dx_ref) < 1e-2
+    assert oconv.rel_max_err(dw, dw_ref) < 1e-4         # fp32 accumulation of exact bf16 products
+    # mean relative error (the reference's own bar is 1e-1 for bf16, tests/nn/test_mask_gemm_numerical.py)
+    for got, ref in ((y, y_ref), (dx, dx_ref)):
+        d = (got.double().cpu() - ref).abs().mean() / ref.abs().mean()
+        assert float(d) < 5e-3
+
+
 # ------------------------------------------------------------------------------------------------
 # module / autograd / groups / transposed / cache
 # ------------------------------------------------------------------------------------------------

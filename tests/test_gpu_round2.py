@@ -417,3 +417,36 @@ def test_wgrad_dense_rows_strided_map_and_ragged_tail():
     _, dw_ref = oconv.backward(gy.float(), x.float(), torch.zeros(8, 32, 64),
                                ref["in_maps"], ref["out_maps"], ref["offsets"])
     assert oconv.rel_max_err(dw, dw_ref) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------
+# PointConv values pinned by the reference's own module (tests/golden/make_golden_pointconv.py)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,cin,cout,k,kw", [
+    ("pointconv_knn8", 16, 32, 8, {}),
+    ("pointconv_knn16_relpos", 8, 24, 16, dict(use_rel_pos=True, reductions=("mean", "max"))),
+])
+def test_pointconv_matches_reference_generated_fixture(name, cin, cout, k, kw):
+    """Same weights (the reference module's state_dict loads unchanged), same points: our
+    PointConv (grid kNN kernel + CSR reductions) must reproduce the REFERENCE PointConv's output
+    and neighbour lists (fp32, CPU reference: cdist + topk + segment_csr)."""
+    from warpconvnet_b200.geometry.coords.search.search_configs import RealSearchConfig
+    from warpconvnet_b200.geometry.types.points import Points
+    from warpconvnet_b200.nn.modules.point_conv import PointConv
+    d = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+    conv = PointConv(cin, cout, RealSearchConfig("knn", knn_k=k), **kw)
+    state = {key: torch.from_numpy(d["p__" + key]) for key in d["state_keys"]}
+    conv.load_state_dict(state, strict=True)
+    conv = conv.cuda().eval()
+    pc = Points(torch.from_numpy(d["coords"]).cuda(), torch.from_numpy(d["feats"]).cuda(),
+                offsets=torch.from_numpy(d["offsets"]))
+    with torch.no_grad():
+        out = conv(pc)
+    nbrs = pc.neighbors(RealSearchConfig("knn", knn_k=k))
+    got_knn = nbrs.neighbor_indices.reshape(-1, k).cpu().numpy()
+    # neighbour SETS per row (order among equidistant neighbours is unspecified upstream; the
+    # random float coordinates of the fixture have no ties, so the ordered lists agree too)
+    assert np.array_equal(np.sort(got_knn, 1), np.sort(d["knn"], 1))
+    ref = torch.from_numpy(d["out"])
+    assert out.feature_tensor.shape == ref.shape
+    assert oconv.rel_max_err(out.feature_tensor, ref.double()) < 2e-4
