@@ -394,13 +394,15 @@ def test_wgrad_dense_rows_matches_pair_list_form_and_oracle(extent, cin, cout, m
     assert oconv.rel_max_err(dw_dense, dw_list.cpu()) < 1e-4
 
 
-def test_wgrad_dense_rows_strided_map_and_ragged_tail():
+def test_wgrad_dense_rows_strided_map_and_ragged_tail(monkeypatch):
     """A strided map (table rows = OUTPUT rows != input rows) whose row count is not a multiple of
     the 64-row stage or the 256-row block; occupancy forced above the threshold by a dense cube."""
     from warpconvnet_b200.geometry.coords.ops.stride import stride_coords
     from warpconvnet_b200.geometry.coords.search.torch_discrete import generate_kernel_map
     from warpconvnet_b200.nn.functional.sparse_conv import sparse_conv_wgrad
-    side = 23
+    import warpconvnet_b200.nn.functional.sparse_conv.detail.unified as uni
+    monkeypatch.setattr(uni, "_WGRAD_DENSE_ROWS", True)
+    side = 25
     idx = np.arange(side ** 3)
     c = np.stack([idx // (side * side), (idx // side) % side, idx % side], 1).astype(np.int32)
     bc_np = _bc([c])

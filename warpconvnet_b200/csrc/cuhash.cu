@@ -189,7 +189,7 @@ kernel_map_search_kernel(const uint64_t* __restrict__ keys, const int* __restric
 // Submanifold variant (in == out coordinates, odd kernel, stride 1): offset K-1-k is the mirror
 // of offset k, so a hit "voxel v sits at m + off_k" also says "voxel m sits at v + off_{K-1-k}".
 // Only the first K/2 offsets (+ the centre) are probed and every hit writes both entries; the
-// table is pre-filled with -1, so misses cost no store. Requires unique coordinates: when the
+// mirrored half of the table is pre-filled with -1. Requires unique coordinates: when the
 // insert kernel flagged a duplicate (status bit 2) every offset is probed instead (no mirrors).
 // The per-block hit counts and the per-row offset masks (what kernel_map_stats_kernel derives from
 // a second pass over the finished table) are produced in the same pass: own hits are
@@ -262,10 +262,10 @@ kernel_map_search_sym_kernel(const uint64_t* __restrict__ keys, const int* __res
       if (k >= k_end) break;  // warp-uniform
       const bool hit = val[u] >= 0;
       const bool mirror = hit && !has_dups && k < K / 2;
-      if (hit) {
-        pair_table[(size_t)k * M + m] = val[u];
-        if (mirror) pair_table[(size_t)(K - 1 - k) * M + val[u]] = m;
-      }
+      // own probes are written hit or miss (coalesced), so only the mirrored rows k > K/2 of the
+      // table need the -1 pre-fill
+      if (live) pair_table[(size_t)k * M + m] = val[u];
+      if (mirror) pair_table[(size_t)(K - 1 - k) * M + val[u]] = m;
       if (fused) {
         if (hit) own_bits ^= 1ull << (k & 63);
         const unsigned ballot = __ballot_sync(0xffffffffu, hit);
@@ -572,8 +572,29 @@ tile_scan_kernel(const int* __restrict__ tile_nk, int n, int* __restrict__ tile_
 static inline int cuda_ok() { return cudaGetLastError() == cudaSuccess ? kOk : kErrCuda; }
 static inline bool is_pow2(long long v) { return v > 0 && (v & (v - 1)) == 0; }
 
+// keys = empty (0), values = 0x7f7f7f7f (+inf for the atomicMin of the insert kernel): one launch
+// instead of two memset nodes
+__global__ void hash_prepare_kernel(uint4* __restrict__ keys16, uint4* __restrict__ values16,
+                                    int n_keys16, int n_values16) {
+  const int stride = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_keys16; i += stride)
+    keys16[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_values16; i += stride)
+    values16[i] = make_uint4(0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu);
+}
+
 int hash_prepare(uint64_t* keys, int* values, int capacity, cudaStream_t s) {
   if (!is_pow2(capacity)) return kErrInvalidArg;
+  if (capacity >= 4 && (reinterpret_cast<uintptr_t>(keys) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(values) & 15) == 0) {
+    const int nk = capacity / 2, nv = capacity / 4;  // 16-byte words
+    int blocks = (nk + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    hash_prepare_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<uint4*>(keys),
+                                               reinterpret_cast<uint4*>(values), nk, nv);
+    count_launch();
+    return cuda_ok();
+  }
   if (cudaMemsetAsync(keys, 0, (size_t)capacity * 8, s) != cudaSuccess) return kErrCuda;
   if (cudaMemsetAsync(values, 0x7F, (size_t)capacity * 4, s) != cudaSuccess) return kErrCuda;
   return kOk;
@@ -622,7 +643,10 @@ int kernel_map_search_sym(const uint64_t* keys, const int* values, int capacity,
   if ((block_counts == nullptr) != (mask_keys == nullptr)) return kErrInvalidArg;
   if (M == 0) return kOk;
   const int nb = kernel_map_num_blocks(M);
-  if (cudaMemsetAsync(pair_table, 0xFF, (size_t)K * M * 4, s) != cudaSuccess) return kErrCuda;
+  // rows 0 .. K/2 are written in full by the kernel; rows K/2+1 .. K-1 receive mirrored hits only
+  if (K > 1 && cudaMemsetAsync(pair_table + (size_t)(K / 2 + 1) * M, 0xFF,
+                               (size_t)(K - K / 2 - 1) * M * 4, s) != cudaSuccess)
+    return kErrCuda;
   if (block_counts != nullptr) {
     // one memset when the caller laid the two statistics arrays out back to back
     const uint8_t* bc_end = reinterpret_cast<const uint8_t*>(block_counts) + (size_t)K * nb * 4;

@@ -59,7 +59,7 @@ def forward_adapter(ctx):
     try:
         y = sparse_conv_forward(x, w, wrap_kernel_map(ctx.kernel_map), ctx.num_out_coords,
                                 groups=ctx.groups)
-    except WcnError:
+    except (WcnError, ValueError):  # unsupported shape / channel configuration
         return STATUS_UNSUPPORTED
     return y.to(ctx.in_features.dtype)
 
@@ -79,7 +79,7 @@ def backward_adapter(ctx):
         if len(ctx.needs_input_grad) > 1 and ctx.needs_input_grad[1]:
             grad_w = sparse_conv_wgrad(x, gy, tuple(ctx.weight.shape), km,
                                        groups=ctx.groups).to(ctx.weight.dtype)
-    except WcnError:
+    except (WcnError, ValueError):
         return STATUS_UNSUPPORTED, None
     return grad_in, grad_w
 
