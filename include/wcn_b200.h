@@ -252,19 +252,13 @@ int wcn_gather_gemm(const void* feats, int n_in_rows, long long in_ld, const voi
  * unique coordinates); its contiguous rows are then fetched as 2-D TMA tiles instead of row gathers.
  * `status` (optional) = the hash table's status word, whose duplicate bit (4) switches the
  * shortcut off on the device; n_in_rows / n_out_rows = rows of feats / gout (tensor-map bounds).
- * Pass -1 / NULL / 0 / 0 when unknown.
- * Optional dense-row mode: pair_table = the kernel map's [K][n_out_rows] table (input row of every
- * output row, -1 = none; wcn_kernel_map_search). With row_block_prefix given, offsets that pair at
- * least 60 % of the output rows are contracted over ALL output rows in row order: gout arrives as
- * dense 2-D TMA tiles and only feats rows are gathered (zero rows where the table holds -1), which
- * halves the gathered bytes of those offsets. Results are identical up to fp32 summation order.
- * NULL = off (also dropped silently for group conv, K > 256 or operands TMA cannot map). */
+ * Pass -1 / NULL / 0 / 0 when unknown. */
 int wcn_wgrad(const void* feats, long long in_ld, const void* gout, long long out_ld, float* dw,
               const int32_t* in_maps, const int32_t* out_maps, const int32_t* offsets, int K,
               int groups, int cin_g, int cout_g, int dtype, float alpha, int unit_pairs,
               int max_ctas, const int32_t* row_block_prefix, int n_row_blocks, int row_parts,
               int rounds, int identity_k, const int32_t* status, long long n_in_rows,
-              long long n_out_rows, const int32_t* pair_table, void* stream);
+              long long n_out_rows, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Per-channel normalisation + activation + residual on the [n, c] feature matrix             */

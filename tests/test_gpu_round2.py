@@ -363,65 +363,6 @@ def test_reference_sparseconv3d_runs_this_library_through_its_own_dispatcher():
 
 
 # ------------------------------------------------------------------------------------------------
-# wgrad: dense-row form of high-occupancy offsets (dY as TMA tiles, X gathered via the pair table)
-# ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("extent,cin,cout", [(120, 64, 64), (200, 128, 128), (97, 32, 96)])
-def test_wgrad_dense_rows_matches_pair_list_form_and_oracle(extent, cin, cout, monkeypatch):
-    from warpconvnet_b200.geometry.coords.search.torch_discrete import generate_kernel_map
-    from warpconvnet_b200.nn.functional.sparse_conv import sparse_conv_wgrad
-    import warpconvnet_b200.nn.functional.sparse_conv.detail.unified as uni
-    c = surface_coords(extent, 3)
-    bc_np = _bc([c])
-    n = len(bc_np)
-    bc = torch.from_numpy(bc_np).cuda()
-    km = generate_kernel_map(bc, bc, (1, 1, 1), (3, 3, 3), same_coords=True)
-    occ = np.diff(km.offsets.numpy()) / n
-    assert (occ >= 0.6).sum() >= 5 and (occ < 0.6).sum() >= 10   # both forms are exercised
-    g = torch.Generator().manual_seed(extent)
-    x = torch.randn(n, cin, generator=g).bfloat16()
-    gy = torch.randn(n, cout, generator=g).bfloat16()
-    monkeypatch.setattr(uni, "_WGRAD_DENSE_ROWS", True)
-    assert "pair_table" in uni._wgrad_order(x.cuda(), gy.cuda(), km, 27)
-    dw_dense = sparse_conv_wgrad(x.cuda(), gy.cuda(), (27, cin, cout), km)
-    monkeypatch.setattr(uni, "_WGRAD_DENSE_ROWS", False)
-    assert "pair_table" not in uni._wgrad_order(x.cuda(), gy.cuda(), km, 27)
-    dw_list = sparse_conv_wgrad(x.cuda(), gy.cuda(), (27, cin, cout), km)
-    ref = okm.generate_kernel_map(bc_np, bc_np, (1, 1, 1), (3, 3, 3))
-    _, dw_ref = oconv.backward(gy.float(), x.float(), torch.zeros(27, cin, cout),
-                               ref["in_maps"], ref["out_maps"], ref["offsets"])
-    assert oconv.rel_max_err(dw_dense, dw_ref) < 1e-4          # fp32 accumulation of exact products
-    assert oconv.rel_max_err(dw_list, dw_ref) < 1e-4
-    assert oconv.rel_max_err(dw_dense, dw_list.cpu()) < 1e-4
-
-
-def test_wgrad_dense_rows_strided_map_and_ragged_tail(monkeypatch):
-    """A strided map (table rows = OUTPUT rows != input rows) whose row count is not a multiple of
-    the 64-row stage or the 256-row block; occupancy forced above the threshold by a dense cube."""
-    from warpconvnet_b200.geometry.coords.ops.stride import stride_coords
-    from warpconvnet_b200.geometry.coords.search.torch_discrete import generate_kernel_map
-    from warpconvnet_b200.nn.functional.sparse_conv import sparse_conv_wgrad
-    import warpconvnet_b200.nn.functional.sparse_conv.detail.unified as uni
-    monkeypatch.setattr(uni, "_WGRAD_DENSE_ROWS", True)
-    side = 25
-    idx = np.arange(side ** 3)
-    c = np.stack([idx // (side * side), (idx // side) % side, idx % side], 1).astype(np.int32)
-    bc_np = _bc([c])
-    bc = torch.from_numpy(bc_np).cuda()
-    out_bc, _ = stride_coords(bc, (2, 2, 2), n_batches=1)
-    km = generate_kernel_map(bc, out_bc, (2, 2, 2), (2, 2, 2))
-    n_in, n_out = len(bc_np), out_bc.shape[0]
-    assert n_out % 64 != 0
-    g = torch.Generator().manual_seed(5)
-    x = torch.randn(n_in, 32, generator=g).bfloat16()
-    gy = torch.randn(n_out, 64, generator=g).bfloat16()
-    dw = sparse_conv_wgrad(x.cuda(), gy.cuda(), (8, 32, 64), km)
-    ref = okm.generate_kernel_map(bc_np, out_bc.cpu().numpy(), (2, 2, 2), (2, 2, 2))
-    _, dw_ref = oconv.backward(gy.float(), x.float(), torch.zeros(8, 32, 64),
-                               ref["in_maps"], ref["out_maps"], ref["offsets"])
-    assert oconv.rel_max_err(dw, dw_ref) < 1e-4
-
-
-# ------------------------------------------------------------------------------------------------
 # PointConv values pinned by the reference's own module (tests/golden/make_golden_pointconv.py)
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name,cin,cout,k,kw", [
@@ -452,3 +393,35 @@ def test_pointconv_matches_reference_generated_fixture(name, cin, cout, k, kw):
     ref = torch.from_numpy(d["out"])
     assert out.feature_tensor.shape == ref.shape
     assert oconv.rel_max_err(out.feature_tensor, ref.double()) < 2e-4
+
+
+def test_reference_sparseconv3d_through_the_capi_stub():
+    """The self-contained ctypes binding of INTEGRATION.md seam A (integration/capi_backend_stub.py:
+    ctypes + torch only, straight onto include/wcn_b200.h) registered in the reference's own
+    dispatcher and driven through the reference's SparseConv3d, against the oracle."""
+    _load_built_reference()
+    import importlib.util
+    from warpconvnet.geometry.types.voxels import Voxels as RVoxels
+    from warpconvnet.nn.modules.sparse_conv import SparseConv3d as RConv
+    spec = importlib.util.spec_from_file_location(
+        "capi_backend_stub", os.path.join(ROOT, "warpconvnet_b200", "integration", "capi_backend_stub.py"))
+    stub = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(stub)
+    name = stub.register(os.path.join(ROOT, "warpconvnet_b200", "csrc", "libwcn_b200.so"))
+    bc, km, x, w, gy = _oracle_case(n=6000, cin=32, cout=64, seed=5)
+    n = len(bc)
+    conv = RConv(32, 64, 3, bias=False, fwd_algo=[name], dgrad_algo=[name], wgrad_algo=[name]).cuda()
+    with torch.no_grad():
+        conv.weight.copy_(w.cuda())
+    feats = x.cuda().bfloat16().requires_grad_(True)
+    vox = RVoxels([torch.from_numpy(bc[:, 1:].copy()).cuda()], [feats])
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out = conv(vox)
+    out.feature_tensor.backward(gy.cuda().to(out.feature_tensor.dtype))
+    torch.cuda.synchronize()
+    xb, wb, gb = x.bfloat16().float(), w.bfloat16().float(), gy.bfloat16().float()
+    args = (km["in_maps"], km["out_maps"], km["offsets"])
+    assert oconv.rel_max_err(out.feature_tensor, oconv.forward(xb, wb, *args, n)) < 1e-2
+    dx_ref, dw_ref = oconv.backward(gb, xb, wb, *args)
+    assert oconv.rel_max_err(feats.grad, dx_ref) < 1e-2
+    assert oconv.rel_max_err(conv.weight.grad, dw_ref) < 1e-2

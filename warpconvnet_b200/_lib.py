@@ -118,7 +118,7 @@ SIGNATURES = {
     "wcn_wgrad": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p,
                           c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_int,
                           c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_longlong, c_longlong,
-                          c_void_p, c_void_p]),
+                          c_void_p]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

@@ -342,30 +342,24 @@ def wgrad(feats: Tensor, gout: Tensor, in_maps: Tensor, out_maps: Tensor, offset
           K: int, groups: int, cin_g: int, cout_g: int, dw: Optional[Tensor] = None,
           alpha: float = 1.0, unit_pairs: int = 0, max_ctas: int = 0,
           row_block_prefix: Optional[Tensor] = None, row_parts: int = 1,
-          rounds: int = 1, identity_k: int = -1, status: Optional[Tensor] = None,
-          pair_table: Optional[Tensor] = None) -> Tensor:
+          rounds: int = 1, identity_k: int = -1, status: Optional[Tensor] = None) -> Tensor:
     """dW[K, groups, cin_g, cout_g] (fp32) += X[in_maps]^T @ dY[out_maps] per offset.
 
     ``row_block_prefix`` ([K, n_row_blocks] int32, the scanned block counts of the kernel map)
     switches on the row-block-major unit order; ``identity_k`` (+ the hash table's ``status``
-    word) marks the identity offset of a submanifold map, fetched as TMA tiles; ``pair_table``
-    ([K, n_out_rows] int32) switches on the dense-row form of high-occupancy offsets (see
-    wcn_wgrad)."""
+    word) marks the identity offset of a submanifold map, fetched as TMA tiles (see wcn_wgrad)."""
     _require_cuda(feats, gout, in_maps, out_maps, offsets_dev)
     assert feats.stride(1) == 1 and gout.stride(1) == 1 and feats.dtype == gout.dtype
     code = dtype_code(feats.dtype)
     if dw is None:
         dw = torch.zeros((K, groups, cin_g, cout_g), dtype=torch.float32, device=feats.device)
     assert dw.dtype == torch.float32 and dw.is_contiguous()
-    if pair_table is not None:
-        assert pair_table.dtype == torch.int32 and pair_table.is_contiguous() \
-            and tuple(pair_table.shape) == (K, gout.shape[0]) and row_block_prefix is not None
     check(lib.wcn_wgrad(_p(feats), feats.stride(0), _p(gout), gout.stride(0), _p(dw), _p(in_maps),
                         _p(out_maps), _p(offsets_dev), K, groups, cin_g, cout_g, code,
                         ctypes.c_float(alpha), unit_pairs, max_ctas, _p(row_block_prefix),
                         0 if row_block_prefix is None else row_block_prefix.shape[1],
                         row_parts, rounds, identity_k, _p(status), feats.shape[0], gout.shape[0],
-                        _p(pair_table), _stream()), "wgrad")
+                        _stream()), "wgrad")
     return dw
 
 

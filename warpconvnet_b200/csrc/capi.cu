@@ -388,7 +388,7 @@ int wcn_wgrad(const void* feats, long long in_ld, const void* gout, long long ou
               int groups, int cin_g, int cout_g, int dtype, float alpha, int unit_pairs,
               int max_ctas, const int32_t* row_block_prefix, int n_row_blocks, int row_parts,
               int rounds, int identity_k, const int32_t* status, long long n_in_rows,
-              long long n_out_rows, const int32_t* pair_table, void* stream) {
+              long long n_out_rows, void* stream) {
   if (!feats || !gout || !dw || !offsets) return kErrInvalidArg;
   if (dtype < 0 || dtype > 2) return kErrUnsupportedDtype;
   if (groups < 1 || cin_g < 1 || cout_g < 1) return kErrInvalidArg;
@@ -416,20 +416,12 @@ int wcn_wgrad(const void* feats, long long in_ld, const void* gout, long long ou
   p.identity_k = (identity_k >= 0 && identity_k < K && n_in_rows > 0 && n_out_rows > 0) ? identity_k
                                                                                         : -1;
   p.status = status;
-  p.pair_table = nullptr;
-  p.n_table_rows = 0;
-  const bool want_dense = pair_table != nullptr && n_out_rows > 0 && n_out_rows < (1ll << 31) &&
-                          groups == 1 && K <= 256;
   if (row_block_prefix != nullptr && row_parts >= 1 && rounds >= 1 && n_row_blocks >= row_parts &&
-      (long long)row_parts * K <= 1024 && (row_parts > 1 || rounds > 1 || want_dense)) {
+      (long long)row_parts * K <= 1024 && (row_parts > 1 || rounds > 1)) {
     p.blk_prefix = row_block_prefix;
     p.n_row_blocks = n_row_blocks;
     p.row_parts = row_parts;
     p.rounds = rounds;
-    if (want_dense && (long long)n_row_blocks * 256 >= n_out_rows) {
-      p.pair_table = pair_table;  // dense-row mode (the launcher drops it when TMA cannot map dY)
-      p.n_table_rows = (int)n_out_rows;
-    }
   }
   p.debug = 0;
   p.dbg_out = nullptr;

@@ -65,13 +65,6 @@ struct WgradParams {
   // coordinates were seen, the identity property does not hold then).
   int identity_k;
   const int* status;
-  // optional dense-row mode (needs blk_prefix): pair_table[k][r] = input row paired with OUTPUT
-  // row r under offset k, -1 = none ([K][n_table_rows], the kernel map's own table). Offsets
-  // whose occupancy L_k / n_table_rows reaches 60 % are then contracted over ALL output rows in
-  // row order: dY arrives as dense 2-D TMA tiles (no gather), only X is gathered through the pair
-  // table (zero rows for missing pairs). nullptr = off.
-  const int* pair_table;
-  int n_table_rows;
   long long in_ld;
   long long out_ld;
   long long dw_k_stride;  // elements between offsets

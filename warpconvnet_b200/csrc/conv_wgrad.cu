@@ -29,12 +29,7 @@ constexpr int kWgTmemCols = 512;
 constexpr int kWgAccStride = 256;
 constexpr int kWgMaxK = 65535;
 constexpr int kWgMaxUnits = 1024;  // (row parts) x K units of the row-block-major order
-constexpr int kWgSegTableBytes = (3 * kWgMaxUnits + 2) * 4 + 256;  // vstart, ustart, ulen, flags
-// Dense-row offsets: a stage of 64 output rows costs about 5/9 of a stage of 64 gathered pairs
-// (half the LSU bytes; measured ~620 vs ~1140 cycles), so a dense unit of r rows weighs
-// ceil(5 r / 9) slots of the virtual list that is split evenly over the CTAs.
-constexpr int kWgDenseNum = 5, kWgDenseDen = 9;
-constexpr int kWgDenseOccNum = 6, kWgDenseOccDen = 10;  // dense when L_k / M >= 0.6
+constexpr int kWgSegTableBytes = (2 * kWgMaxUnits + 2) * 4;
 
 struct WgSmemCtrl {
   uint64_t full[kWgMaxStages];
@@ -62,16 +57,12 @@ struct WgSegCursor {
   const int* offsets;
   const int* vstart;  // shared memory [U + 1] or nullptr
   const int* ustart;  // shared memory [U]
-  const int* ulen;    // shared memory [U]: real length of a unit (pairs, or rows when dense)
-  const uint8_t* dense;  // shared memory [K] or nullptr: offset k is walked in dense-row form
   int K, U, G, R, b;
   int pair_begin, pair_end, k;  // default order
   int r, u;                     // row-block-major order
   long long v0, v1;
 
-  // dense_out: the segment is a ROW range [first, first + count) of a dense-row offset
-  __device__ __forceinline__ bool next(int& k_out, int& first, int& count, bool& dense_out) {
-    dense_out = false;
+  __device__ __forceinline__ bool next(int& k_out, int& first, int& count) {
     if (vstart == nullptr) {
       for (; k < K; ++k) {
         const int ob = __ldg(offsets + k), oe = __ldg(offsets + k + 1);
@@ -106,19 +97,6 @@ struct WgSegCursor {
       const int cu = u++;
       if (e <= s) continue;
       k_out = cu % K;
-      if (dense != nullptr && dense[k_out]) {
-        // virtual slots -> rows (same map on both sides of a chunk boundary: no gap, no overlap)
-        const long long rows_u = ulen[cu];
-        long long a = (s - vstart[cu]) * kWgDenseDen / kWgDenseNum;
-        long long b = (e == vstart[cu + 1]) ? rows_u : (e - vstart[cu]) * kWgDenseDen / kWgDenseNum;
-        a = min(a, rows_u);
-        b = min(b, rows_u);
-        if (b <= a) continue;
-        first = ustart[cu] + (int)a;
-        count = (int)(b - a);
-        dense_out = true;
-        return true;
-      }
       first = ustart[cu] + (int)(s - vstart[cu]);
       count = (int)(e - s);
       return true;
@@ -159,19 +137,8 @@ wgrad_kernel(const __grid_constant__ WgradParams p, const __grid_constant__ CUte
   WgSmemCtrl* ctrl = reinterpret_cast<WgSmemCtrl*>(smem_gen + (size_t)stages * stage_bytes);
   int* seg_vstart = reinterpret_cast<int*>(ctrl + 1);  // [U + 1]
   int* seg_ustart = seg_vstart + kWgMaxUnits + 1;       // [U]
-  int* seg_ulen = seg_ustart + kWgMaxUnits;             // [U]
-  uint8_t* seg_dense = reinterpret_cast<uint8_t*>(seg_ulen + kWgMaxUnits + 1);  // [K] (K <= 256)
   const bool blocked = p.blk_prefix != nullptr;
   const int n_units = blocked ? p.row_parts * p.K : 0;
-  const bool dense_on = blocked && p.pair_table != nullptr && p.K <= 256 && NSEGB == 1 &&
-                        PAIRS == 64;
-  if (dense_on) {
-    for (int k = tid; k < p.K; k += kWgThreads) {
-      const long long lk = __ldg(p.offsets + k + 1) - __ldg(p.offsets + k);
-      seg_dense[k] = lk * kWgDenseOccDen >= (long long)p.n_table_rows * kWgDenseOccNum ? 1 : 0;
-    }
-    __syncthreads();
-  }
   if (blocked) {
     // unit (part, k): pairs of offset k with output row in [256*blk(part), 256*blk(part+1))
     const int nb = p.n_row_blocks, P = p.row_parts;
@@ -179,20 +146,10 @@ wgrad_kernel(const __grid_constant__ WgradParams p, const __grid_constant__ CUte
       const int part = un / p.K, k = un - part * p.K;
       const int ob = __ldg(p.offsets + k);
       const int b0 = (int)((long long)part * nb / P), b1 = (int)((long long)(part + 1) * nb / P);
-      if (dense_on && seg_dense[k]) {
-        // dense-row unit: all output rows of the part (row blocks are 256 rows)
-        const int r0 = min(b0 * 256, p.n_table_rows), r1 = min(b1 * 256, p.n_table_rows);
-        const int r_hi = (part == P - 1) ? p.n_table_rows : r1;
-        seg_ustart[un] = r0;
-        seg_ulen[un] = r_hi - r0;
-        seg_vstart[un + 1] = ((r_hi - r0) * kWgDenseNum + kWgDenseDen - 1) / kWgDenseDen;
-        continue;
-      }
       const int lo = ob + (part == 0 ? 0 : __ldg(p.blk_prefix + (size_t)k * nb + b0));
       const int hi = (part == P - 1) ? __ldg(p.offsets + k + 1)
                                      : ob + __ldg(p.blk_prefix + (size_t)k * nb + b1);
       seg_ustart[un] = lo;
-      seg_ulen[un] = hi - lo;
       seg_vstart[un + 1] = hi - lo;  // length; turned into a prefix sum below
     }
     __syncthreads();
@@ -260,8 +217,6 @@ wgrad_kernel(const __grid_constant__ WgradParams p, const __grid_constant__ CUte
     c.offsets = p.offsets;
     c.vstart = blocked ? seg_vstart : nullptr;
     c.ustart = seg_ustart;
-    c.ulen = seg_ulen;
-    c.dense = dense_on ? seg_dense : nullptr;
     c.K = p.K; c.U = n_units; c.G = gridDim.x; c.R = p.rounds; c.b = blockIdx.x;
     c.pair_begin = pair_begin; c.pair_end = pair_end; c.k = k_first;
     c.r = 0; c.u = -1; c.v0 = c.v1 = 0;
@@ -308,23 +263,16 @@ wgrad_kernel(const __grid_constant__ WgradParams p, const __grid_constant__ CUte
                         (p.status == nullptr || (__ldg(p.status) & 4) == 0);
     WgSegCursor seg = make_cursor();
     int k, first, count;
-    bool dense;
-    while (seg.next(k, first, count, dense)) {
+    while (seg.next(k, first, count)) {
       const int n_st = (count + kPairs - 1) / kPairs;
       const bool ident = tma_ok && k == p.identity_k;
-      // identity offset: pair j of the list is (j, j); a dense-row segment already counts rows
-      const int ident_row0 = ident ? (dense ? first : first - __ldg(p.offsets + k)) : 0;
-      const int* dense_tab = dense ? p.pair_table + (size_t)k * p.n_table_rows : nullptr;
+      const int ident_row0 = ident ? first - __ldg(p.offsets + k) : 0;
       // lane l < kRowsPerWarp holds the input row, lane 16 + ... the output row of pair
       // warp*kRowsPerWarp + l of the stage (kRowsPerWarp = 16: both in one register)
       auto load_idx = [&](int st, int& vi, int& vo) {
         const int pr = st * kPairs + warp * kRowsPerWarp + (lane % kRowsPerWarp);
         const bool ok = pr < count;
-        if (dense) {
-          // output row first + pr: its input row straight from the pair table (coalesced)
-          vi = (ok && lane < kRowsPerWarp) ? __ldg(dense_tab + first + pr) : -1;
-          vo = vi;
-        } else if (kRowsPerWarp == 16) {
+        if (kRowsPerWarp == 16) {
           const int* src = (lane < 16) ? p.in_maps : p.out_maps;
           vi = ok ? __ldg(src + first + pr) : -1;
           vo = vi;
@@ -367,29 +315,6 @@ wgrad_kernel(const __grid_constant__ WgradParams p, const __grid_constant__ CUte
               tma_load_2d(a_smem + kPairs * 128, &tmap_x, kBlkElems, r, bar);
               tma_load_2d(b_smem, &tmap_dy, 0, r, bar);
               tma_load_2d(b_smem + kPairs * 128, &tmap_dy, kBlkElems, r, bar);
-            }
-            cp_async_mbar_arrive_noinc(smem_u32(&ctrl->full[stage]));
-            if (++stage == stages) { stage = 0; phase ^= 1u; }
-            continue;
-          }
-          if (dense) {
-            // dY rows [first + st*64, +64) as two 64-row x 128-byte TMA boxes (rows past the
-            // matrix are zero-filled by the TMA unit; rows past `count` meet zero X rows), X rows
-            // gathered through the pair table: half the LSU bytes of a pair-list stage
-            if (tid == 0) {
-              const uint32_t bar = smem_u32(&ctrl->full[stage]);
-              const int r = first + st * kPairs;
-              mbar_expect_tx(bar, 2u * kPairs * 128u);
-              tma_load_2d(b_smem, &tmap_dy, 0, r, bar);
-              tma_load_2d(b_smem + kPairs * 128, &tmap_dy, kBlkElems, r, bar);
-            }
-#pragma unroll
-            for (int q = 0; q < kInstr; ++q) {
-              const int row = 2 * q + sub;
-              const int pi = __shfl_sync(0xffffffffu, vi, row);
-              const uint8_t* xrow = a_base + (unsigned long long)(uint32_t)max(pi, 0) * in_ld_bytes;
-              const uint32_t soff = off_par[q & 3] + (uint32_t)(q >> 2) * 1024u;
-              cp_async_16(a_smem + soff, xrow, (pi >= 0 && u * 16 < cin_bytes) ? 16u : 0u);
             }
             cp_async_mbar_arrive_noinc(smem_u32(&ctrl->full[stage]));
             if (++stage == stages) { stage = 0; phase ^= 1u; }
@@ -447,8 +372,7 @@ wgrad_kernel(const __grid_constant__ WgradParams p, const __grid_constant__ CUte
       const long long t_start = WCN_CLOCK();
       WgSegCursor seg = make_cursor();
       int k, first, count;
-      bool dense;
-      while (seg.next(k, first, count, dense)) {
+      while (seg.next(k, first, count)) {
         const uint32_t acc = use & 1u;
         {
           const long long t0 = WCN_CLOCK();
@@ -498,8 +422,7 @@ wgrad_kernel(const __grid_constant__ WgradParams p, const __grid_constant__ CUte
     const long long t_start = WCN_CLOCK();
     WgSegCursor seg = make_cursor();
     int k, first, count;
-    bool dense;
-    while (seg.next(k, first, count, dense)) {
+    while (seg.next(k, first, count)) {
       const uint32_t acc = use & 1u;
       {
         const long long t0 = WCN_CLOCK();
@@ -621,19 +544,9 @@ static int launch_wgrad_t(WgradParams p, int cin_slabs, int cout_slabs, int max_
   CUtensorMap tmap_x, tmap_dy;
   memset(&tmap_x, 0, sizeof(tmap_x));
   memset(&tmap_dy, 0, sizeof(tmap_dy));
-  const bool tma_shape_ok = NSEGB == 1 && kPairs == 64 && kElem == 2 && cin_slabs == 1 &&
-                           cout_slabs == 1 && p.gps == 1 && p.in_coff == 0 && p.out_coff == 0;
-  if (p.pair_table != nullptr) {
-    // dense-row mode: dY as TMA tiles; needs the row-block prefix (unit table) and a table
-    // whose rows are the dY rows
-    const bool ok = tma_shape_ok && p.blk_prefix != nullptr && p.K <= 256 &&
-                    p.n_table_rows == n_out_rows &&
-                    make_row_tile_map(&tmap_dy, p.gout, p.out_ld, p.cout, n_out_rows, kElem, kPairs,
-                                      ElemTraits<T>::kFmt == 0);
-    if (!ok) p.pair_table = nullptr;
-  }
   if (p.identity_k >= 0) {
-    const bool ok = tma_shape_ok && p.identity_k < p.K &&
+    const bool ok = NSEGB == 1 && kPairs == 64 && kElem == 2 && cin_slabs == 1 && cout_slabs == 1 &&
+                    p.gps == 1 && p.in_coff == 0 && p.out_coff == 0 && p.identity_k < p.K &&
                     make_row_tile_map(&tmap_x, p.feats, p.in_ld, p.cin, n_in_rows, kElem, kPairs,
                                       ElemTraits<T>::kFmt == 0) &&
                     make_row_tile_map(&tmap_dy, p.gout, p.out_ld, p.cout, n_out_rows, kElem, kPairs,

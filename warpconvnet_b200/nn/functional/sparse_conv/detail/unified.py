@@ -172,6 +172,30 @@ def _wgrad_identity(kernel_map, K: int):
     return {"identity_k": K // 2, "status": None if table is None else table.status_tensor}
 
 
+def _wgrad_order(x: Tensor, gy: Tensor, kernel_map, K: int):
+    """Row-block-major unit order once the operands exceed the L2-comfortable size.
+    (A "dense rows" form — dY of high-occupancy offsets as TMA tiles, X gathered through the pair
+    table — was built and measured SLOWER, 152.6 -> 170.9 us on C3-S: the kernel is bound by the
+    bytes crossing L2 -> SM whichever unit requests them. Removed again; the measurement and the
+    commit that holds the code are in profiles/r2_wgrad_dense_rows_negative_result.md.)"""
+    bp = getattr(kernel_map, "_block_prefix", None)
+    work = x.numel() * x.element_size() + gy.numel() * gy.element_size()
+    if (bp is None or _WGRAD_ROUNDS <= 1 or work < _WGRAD_LOCALITY_BYTES
+            or _WGRAD_ROUNDS * K > 1024 or bp.shape[0] != K or bp.shape[1] < _WGRAD_ROUNDS):
+        return {}
+    return {"row_block_prefix": bp, "row_parts": _WGRAD_ROUNDS, "rounds": _WGRAD_ROUNDS}
+
+
+def _wgrad_identity(kernel_map, K: int):
+    """The centre offset of a submanifold map (same coordinates, odd kernel, stride 1) pairs every
+    row with itself, in order: wgrad can fetch those rows as TMA tiles. The hash table's status
+    word tells the kernel when duplicate coordinates break that property."""
+    if not _WGRAD_IDENTITY_TMA or not getattr(kernel_map, "_symmetric", False) or K % 2 == 0:
+        return {}
+    table = getattr(kernel_map, "_hashtable", None)
+    return {"identity_k": K // 2, "status": None if table is None else table.status_tensor}
+
+
 # Dense-row wgrad (csrc/conv_wgrad.cu): offsets that pair >= 60 % of the output rows are walked over
 # ALL output rows in row order — dY arrives as dense TMA tiles, only X is gathered through the pair
 # table — which halves the LSU-gathered bytes of those offsets. MEASURED SLOWER and therefore OFF
@@ -205,8 +229,6 @@ def _wgrad_order(x: Tensor, gy: Tensor, kernel_map, K: int):
 def _wgrad_call(x: Tensor, gy: Tensor, kernel_map, K: int, G: int, cin_g: int, cout_g: int) -> Tensor:
     im, om, od = kernel_map._in_buf, kernel_map._out_buf, kernel_map.offsets_dev
     order = dict(_wgrad_order(x, gy, kernel_map, K), **_wgrad_identity(kernel_map, K))
-    if G != 1:
-        order.pop("pair_table", None)  # dense-row mode: dense (ungrouped) convs only
     if x.dtype != torch.float32:
         return _ops.wgrad(x, gy, im, om, od, K, G, cin_g, cout_g, **order)
     # fp32 operands: the contraction runs over gathered rows (MN-major operands), which the
