@@ -647,10 +647,10 @@ def run_ours(args):
     e2e_run(max(args.warmup, 50))
     barrier()
     # The loop is paced by the host thread and the PCIe copies, so single K-step measurements
-    # scatter (1.0 - 1.4 ms on the same box): K steps are timed three times, each max-reduced over
+    # scatter (1.0 - 1.4 ms on the same box): K steps are timed five times, each max-reduced over
     # ranks, and the MEDIAN repetition is reported (all three are listed in e2e.runs_ms).
     e2e_runs = []
-    for _ in range(3):
+    for _ in range(5):
         s_ev, e_ev = e2e_run(args.steps)
         barrier()
         t = torch.tensor([s_ev.elapsed_time(e_ev) / args.steps], device=dev, dtype=torch.float64)
@@ -718,7 +718,7 @@ def run_ours(args):
         },
         "e2e": {"value": total_vox / (e2e_ms * 1e-3), "unit": "voxels/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "runs_ms": e2e_runs, "runs": "3 repetitions of K steps, median reported",
+                "runs_ms": e2e_runs, "runs": "5 repetitions of K steps, median reported",
                 "warmup_steps": max(args.warmup, 50),
                 "api": "Voxels(pinned host coords+feats) -> SparseConv3d.forward (autocast bf16) -> "
                        "backward -> weight.grad to pinned host",

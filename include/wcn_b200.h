@@ -90,14 +90,10 @@ int wcn_kernel_map_search(const uint64_t* keys, const int32_t* values, int capac
  * probes only the first K/2 offsets plus the centre and mirrors every hit into offset K-1-k
  * (same idea as the reference's skip_symmetric_kernel_map, torch_discrete.py:296-432). `status`
  * is the word wcn_hash_insert wrote; if it reports duplicate coordinates (bit 2) every offset is
- * probed instead, so the result always equals wcn_kernel_map_search. Fills the whole table.
- * block_counts [K][num_blocks] + mask_keys [M] (both or neither; NULL = table only): the per-block
- * hit counts and per-row offset masks of wcn_kernel_map_search, produced in the SAME pass (no
- * second sweep over the table with wcn_kernel_map_stats); zero-filled here. */
+ * probed instead, so the result always equals wcn_kernel_map_search. Fills the whole table. */
 int wcn_kernel_map_search_symmetric(const uint64_t* keys, const int32_t* values, int capacity,
                                     const int32_t* coords, int M, const int32_t* offsets3, int K,
-                                    const int32_t* status, int32_t* pair_table,
-                                    int32_t* block_counts, uint64_t* mask_keys, void* stream);
+                                    const int32_t* status, int32_t* pair_table, void* stream);
 /* block_counts[K][num_blocks] and mask_keys[M] (optional) from a finished pair table. */
 int wcn_kernel_map_stats(const int32_t* pair_table, int K, int M, int32_t* block_counts,
                          uint64_t* mask_keys, void* stream);

@@ -52,8 +52,7 @@ SIGNATURES = {
     "wcn_kernel_map_search": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int,
                                       c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "wcn_kernel_map_search_symmetric": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p,
-                                                c_int, c_void_p, c_void_p, c_void_p, c_void_p,
-                                                c_void_p]),
+                                                c_int, c_void_p, c_void_p, c_void_p]),
     "wcn_kernel_map_stats": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "wcn_kernel_map_count": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "wcn_kernel_map_scatter": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,

@@ -132,16 +132,13 @@ def kernel_map_search_symmetric(keys: Tensor, values: Tensor, coords: Tensor, of
     dev = coords.device
     nb = lib.wcn_kernel_map_num_blocks(M)
     pair_table = torch.empty((K, M), dtype=torch.int32, device=dev)
-    # block counts and row masks come out of the search pass itself; laid out back to back so the
-    # library zero-fills them with one memset
-    n_cnt = (K * nb + 1) // 2 * 2
-    aux = torch.empty(n_cnt // 2 + M, dtype=torch.int64, device=dev)
-    block_counts = aux[: n_cnt // 2].view(torch.int32)[: K * nb].view(K, nb)
-    mask_keys = aux[n_cnt // 2:]
+    block_counts = torch.empty((K, nb), dtype=torch.int32, device=dev)
+    mask_keys = torch.empty(M, dtype=torch.int64, device=dev)
     check(lib.wcn_kernel_map_search_symmetric(_p(keys), _p(values), keys.numel(), _p(coords), M,
                                               _p(offsets3), K, _p(status), _p(pair_table),
-                                              _p(block_counts), _p(mask_keys), _stream()),
-          "kernel_map_search_symmetric")
+                                              _stream()), "kernel_map_search_symmetric")
+    check(lib.wcn_kernel_map_stats(_p(pair_table), K, M, _p(block_counts), _p(mask_keys),
+                                   _stream()), "kernel_map_stats")
     return pair_table, block_counts, mask_keys
 
 

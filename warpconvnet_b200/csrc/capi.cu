@@ -19,7 +19,7 @@ int kernel_map_search(const uint64_t*, const int*, int, const int*, int, const i
                       int, int*, int*, unsigned long long*, cudaStream_t);
 int kernel_map_count(int*, int, int, int*, int*, cudaStream_t);
 int kernel_map_search_sym(const uint64_t*, const int*, int, const int*, int, const int*, int,
-                          const int*, int*, int*, unsigned long long*, cudaStream_t);
+                          const int*, int*, cudaStream_t);
 int kernel_map_stats(const int*, int, int, int*, unsigned long long*, cudaStream_t);
 int kernel_map_scatter(const int*, const int*, const int*, int*, int*, int, int, cudaStream_t);
 int reverse_pair_table(const int*, int, int, int*, int, cudaStream_t);
@@ -162,12 +162,10 @@ int wcn_kernel_map_search(const uint64_t* keys, const int32_t* values, int capac
 }
 int wcn_kernel_map_search_symmetric(const uint64_t* keys, const int32_t* values, int capacity,
                                     const int32_t* coords, int M, const int32_t* offsets3, int K,
-                                    const int32_t* status, int32_t* pair_table,
-                                    int32_t* block_counts, uint64_t* mask_keys, void* stream) {
+                                    const int32_t* status, int32_t* pair_table, void* stream) {
   if (!keys || !values || !offsets3 || !status || (M > 0 && (!coords || !pair_table)))
     return kErrInvalidArg;
   return kernel_map_search_sym(keys, values, capacity, coords, M, offsets3, K, status, pair_table,
-                               block_counts, reinterpret_cast<unsigned long long*>(mask_keys),
                                S(stream));
 }
 int wcn_kernel_map_stats(const int32_t* pair_table, int K, int M, int32_t* block_counts,

@@ -188,36 +188,26 @@ kernel_map_search_kernel(const uint64_t* __restrict__ keys, const int* __restric
 
 // Submanifold variant (in == out coordinates, odd kernel, stride 1): offset K-1-k is the mirror
 // of offset k, so a hit "voxel v sits at m + off_k" also says "voxel m sits at v + off_{K-1-k}".
-// Only the first K/2 offsets (+ the centre) are probed and every hit writes both entries; the
-// mirrored half of the table is pre-filled with -1. Requires unique coordinates: when the
-// insert kernel flagged a duplicate (status bit 2) every offset is probed instead (no mirrors).
-// The per-block hit counts and the per-row offset masks (what kernel_map_stats_kernel derives from
-// a second pass over the finished table) are produced in the same pass: own hits are
-// warp-aggregated into shared-memory counters, mirrored hits go to the mirror row's block counter
-// (aggregated over the lanes that target the same block) and mask word with global atomics.
-// block_counts and mask_keys must be zero-filled; both may be nullptr (table only).
+// Only the first K/2 offsets (+ the centre) are probed and every hit writes both entries. Own
+// probes are written hit or miss (coalesced stores), so only the mirrored rows k > K/2 of the
+// table need the -1 pre-fill. Requires unique coordinates: when the insert kernel flagged a
+// duplicate (status bit 2) every offset is probed instead (no mirrors).
+// (Producing the block counts and row masks in this pass with atomics on the mirror rows was
+// measured SLOWER than the separate coalesced pass of kernel_map_stats_kernel: 55.7 us vs
+// 32.8 + 13.2 us on C3, profiles/r2_kernel_map_chain.md.)
 __global__ void __launch_bounds__(kMapBlock)
 kernel_map_search_sym_kernel(const uint64_t* __restrict__ keys, const int* __restrict__ values,
                              uint32_t mask, const int4* __restrict__ coords, int M,
                              const int* __restrict__ offs, int K, const int* __restrict__ status,
-                             int* __restrict__ pair_table, int* __restrict__ block_counts,
-                             unsigned long long* __restrict__ mask_keys) {
-  extern __shared__ int s_mem[];  // [3K] offsets, [K] own hit counts
-  int* s_off = s_mem;
-  int* s_cnt = s_mem + 3 * K;
+                             int* __restrict__ pair_table) {
+  extern __shared__ int s_off[];  // [3K]
   for (int i = threadIdx.x; i < 3 * K; i += blockDim.x) s_off[i] = offs[i];
-  for (int i = threadIdx.x; i < K; i += blockDim.x) s_cnt[i] = 0;
   __syncthreads();
   const int m = blockIdx.x * kMapBlock + threadIdx.x;
-  const bool live = m < M;
+  if (m >= M) return;
   const bool has_dups = (__ldg(status) & 4) != 0;
   const int k_end = has_dups ? K : K / 2 + 1;
-  const int nb = gridDim.x;
-  const int lane = threadIdx.x & 31;
-  const bool fused = block_counts != nullptr && mask_keys != nullptr;
-  int4 c = make_int4(0, 0, 0, 0);
-  if (live) c = __ldg(coords + m);
-  unsigned long long own_bits = 0ull;
+  const int4 c = __ldg(coords + m);
   // kSymBatch probes in flight per thread: first the key slots, then the values of the hits
   // (two rounds of independent loads instead of a dependent chain per offset)
   constexpr int kSymBatch = 4;  // 8 measured slower (41.9 vs 36.5 us on C3: registers, occupancy)
@@ -229,7 +219,7 @@ kernel_map_search_sym_kernel(const uint64_t* __restrict__ keys, const int* __res
       const int k = k0 + u;
       const int qx = k < k_end ? c.y + s_off[3 * k] : 0, qy = k < k_end ? c.z + s_off[3 * k + 1] : 0,
                 qz = k < k_end ? c.w + s_off[3 * k + 2] : 0;
-      if (live && k < k_end && key_in_range(c.x, qx, qy, qz)) {
+      if (k < k_end && key_in_range(c.x, qx, qy, qz)) {
         key[u] = pack_key(c.x, qx, qy, qz);
         slot[u] = splitmix_slot(key[u], mask);
         got[u] = __ldg(keys + slot[u]);
@@ -259,34 +249,12 @@ kernel_map_search_sym_kernel(const uint64_t* __restrict__ keys, const int* __res
 #pragma unroll
     for (int u = 0; u < kSymBatch; ++u) {
       const int k = k0 + u;
-      if (k >= k_end) break;  // warp-uniform
-      const bool hit = val[u] >= 0;
-      const bool mirror = hit && !has_dups && k < K / 2;
-      // own probes are written hit or miss (coalesced), so only the mirrored rows k > K/2 of the
-      // table need the -1 pre-fill
-      if (live) pair_table[(size_t)k * M + m] = val[u];
-      if (mirror) pair_table[(size_t)(K - 1 - k) * M + val[u]] = m;
-      if (fused) {
-        if (hit) own_bits ^= 1ull << (k & 63);
-        const unsigned ballot = __ballot_sync(0xffffffffu, hit);
-        if (lane == 0 && ballot) atomicAdd(&s_cnt[k], __popc(ballot));
-        // mirrored hit: row val[u] gains offset K-1-k. Lanes whose mirror rows share a 256-row
-        // block send ONE count update (neighbouring rows have neighbouring mirrors).
-        const int vb = mirror ? (val[u] / kMapBlock) : (-1 - lane);
-        const unsigned peers = __match_any_sync(0xffffffffu, vb);
-        if (mirror) {
-          if ((peers & ((1u << lane) - 1u)) == 0u)
-            atomicAdd(block_counts + (size_t)(K - 1 - k) * nb + vb, __popc(peers));
-          atomicXor(mask_keys + val[u], 1ull << ((K - 1 - k) & 63));
-        }
+      if (k < k_end) {
+        pair_table[(size_t)k * M + m] = val[u];
+        if (val[u] >= 0 && !has_dups && k < K / 2) pair_table[(size_t)(K - 1 - k) * M + val[u]] = m;
       }
     }
   }
-  if (!fused) return;
-  if (live && own_bits) atomicXor(mask_keys + m, own_bits);
-  __syncthreads();
-  for (int i = threadIdx.x; i < k_end; i += blockDim.x)
-    if (s_cnt[i]) atomicAdd(block_counts + (size_t)i * nb + blockIdx.x, s_cnt[i]);
 }
 
 // block_counts[k][block] = hits of offset k among the block's 256 rows; mask_keys[m] = offset
@@ -638,31 +606,17 @@ int kernel_map_search(const uint64_t* keys, const int* values, int capacity, con
 
 int kernel_map_search_sym(const uint64_t* keys, const int* values, int capacity, const int* coords,
                           int M, const int* offsets3, int K, const int* status, int* pair_table,
-                          int* block_counts, unsigned long long* mask_keys, cudaStream_t s) {
+                          cudaStream_t s) {
   if (!is_pow2(capacity) || M < 0 || K < 1 || K > 4096 || (K & 1) == 0) return kErrInvalidArg;
-  if ((block_counts == nullptr) != (mask_keys == nullptr)) return kErrInvalidArg;
   if (M == 0) return kOk;
-  const int nb = kernel_map_num_blocks(M);
   // rows 0 .. K/2 are written in full by the kernel; rows K/2+1 .. K-1 receive mirrored hits only
   if (K > 1 && cudaMemsetAsync(pair_table + (size_t)(K / 2 + 1) * M, 0xFF,
                                (size_t)(K - K / 2 - 1) * M * 4, s) != cudaSuccess)
     return kErrCuda;
-  if (block_counts != nullptr) {
-    // one memset when the caller laid the two statistics arrays out back to back
-    const uint8_t* bc_end = reinterpret_cast<const uint8_t*>(block_counts) + (size_t)K * nb * 4;
-    const uint8_t* mk = reinterpret_cast<const uint8_t*>(mask_keys);
-    if (mk >= bc_end && mk - bc_end < 16) {
-      if (cudaMemsetAsync(block_counts, 0, (size_t)(mk - reinterpret_cast<const uint8_t*>(block_counts)) +
-                                               (size_t)M * 8, s) != cudaSuccess)
-        return kErrCuda;
-    } else {
-      if (cudaMemsetAsync(block_counts, 0, (size_t)K * nb * 4, s) != cudaSuccess) return kErrCuda;
-      if (cudaMemsetAsync(mask_keys, 0, (size_t)M * 8, s) != cudaSuccess) return kErrCuda;
-    }
-  }
-  kernel_map_search_sym_kernel<<<nb, kMapBlock, (size_t)4 * K * sizeof(int), s>>>(
-      keys, values, (uint32_t)(capacity - 1), reinterpret_cast<const int4*>(coords), M, offsets3, K,
-      status, pair_table, block_counts, mask_keys);
+  kernel_map_search_sym_kernel<<<kernel_map_num_blocks(M), kMapBlock, (size_t)3 * K * sizeof(int),
+                                 s>>>(keys, values, (uint32_t)(capacity - 1),
+                                      reinterpret_cast<const int4*>(coords), M, offsets3, K, status,
+                                      pair_table);
   count_launch();
   return cuda_ok();
 }
