@@ -12,7 +12,7 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tools"))
 from minkunet14 import MinkUNet14, surface_scene  # noqa: E402
 from warpconvnet_b200.geometry.types.voxels import Voxels  # noqa: E402
 
-scenes, extent = 8, 548
+scenes, extent = (int(sys.argv[1]) if len(sys.argv) > 1 else 8), 548
 coords = [surface_scene(extent, s).cuda() for s in range(scenes)]
 feats = [torch.randn(len(c), 3, device="cuda") for c in coords]
 net = MinkUNet14(3, 20).cuda()

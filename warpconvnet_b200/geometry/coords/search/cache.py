@@ -10,7 +10,17 @@ from .search_results import IntSearchResult, RealSearchResult
 
 
 def _tensor_key(t: Tensor) -> Tuple[int, ...]:
-    return tuple(int(v) for v in t.detach().cpu().reshape(-1).tolist())
+    """Hashable copy of a (CPU) offsets tensor; memoised on the tensor object — the same offsets
+    tensor is turned into a key several times per conv (the reference walks ``offsets.tolist()``
+    on every lookup, cache.py:126-136)."""
+    key = getattr(t, "_wcn_key", None)
+    if key is None or key[0] != t._version:
+        key = (t._version, tuple(int(v) for v in t.detach().cpu().reshape(-1).tolist()))
+        try:
+            t._wcn_key = key
+        except Exception:  # tensor subclasses without a __dict__
+            pass
+    return key[1]
 
 
 class IntSearchCacheKey:
