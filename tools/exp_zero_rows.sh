@@ -11,8 +11,8 @@ WCN_ZERO_ROWS_SECOND_PASS=1 bash warpconvnet_b200/csrc/build.sh > gpurun_out/zer
 python tools/exp_fwd.py > gpurun_out/zero_rows_second_pass.log 2>&1
 timeout 150 python -m pytest tests/test_gpu_parity.py tests/test_gpu_edge_cases.py -m gpu -x -q \
   > gpurun_out/zero_rows_parity.log 2>&1
-python bench.py --no-cpu-baseline --dist R > gpurun_out/zero_rows_bench_R.json 2>/dev/null
-python bench.py --no-cpu-baseline > gpurun_out/zero_rows_bench_S.json 2>/dev/null
+python bench.py --no-cpu-baseline --no-c4 --no-side --ref-gpu none --dist R > gpurun_out/zero_rows_bench_R.json 2>/dev/null
+python bench.py --no-cpu-baseline --no-c4 --no-side --ref-gpu none > gpurun_out/zero_rows_bench_S.json 2>/dev/null
 bash warpconvnet_b200/csrc/build.sh >> gpurun_out/zero_rows_build.log 2>&1   # restore the default
 grep -h "plan=\|stages=" gpurun_out/zero_rows_default.log gpurun_out/zero_rows_second_pass.log
 tail -2 gpurun_out/zero_rows_parity.log
