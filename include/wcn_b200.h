@@ -222,13 +222,16 @@ int wcn_weight_image_pair(const void* weight, int src_dtype, void* image_fwd, vo
  * feats [n_in_rows, in_ld] (16-byte aligned base and pitch), out [n_out, out_ld]; channels: cin_total = groups*cin_g gathered per row
  * (dgrad: pass cout/cin swapped and a transpose_w=1 image); bias (optional fp32[groups*cout_g]);
  * kflip=1 uses weight K-1-k for table row k (dgrad of a submanifold conv on the forward table).
- * The plan arrays come from wcn_build_tiles. */
+ * The plan arrays come from wcn_build_tiles.  * stats (optional, fp64 [2][groups * cout_g], caller zero-fills): per-channel sum and sum of squares
+ * of the output AS STORED (after bias / ReLU / rounding to the feature dtype), accumulated in the
+ * epilogue — the statistics pass of the BatchNorm that follows the conv in the reference's ConvBlock
+ * (models/mink_unet.py:31-53) without re-reading Y. NULL = off. */
 int wcn_gather_gemm(const void* feats, int n_in_rows, long long in_ld, const void* wimg, void* out,
                     long long out_ld, const int32_t* step_nbr, const int32_t* step_k,
                     const int32_t* rows, const int32_t* tile_nk, const int32_t* tile_cum,
                     int num_tiles, int tile_rows, int m_pad, int K, int groups, int cin_g,
                     int cout_g, int dtype, const float* bias, int relu, int kflip, int max_ctas,
-                    const int32_t* cta_units, int n_range_ctas, void* stream);
+                    const int32_t* cta_units, int n_range_ctas, double* stats, void* stream);
 
 /* wgrad AtB_gather_gather
  * (replaces _C.mask_gemm.wgrad: csrc/bindings/mask_gemm_bindings.cu:1755-2040 and

@@ -66,7 +66,7 @@ def test_argument_errors_without_gpu():
     assert lib.wcn_hash_insert(None, None, None, 4, 16, None, None) == -1
     assert lib.wcn_kernel_map_num_blocks(1000) == 4
     assert lib.wcn_gather_gemm(None, 0, 0, None, None, 0, None, None, None, None, None, 4, 128, 512,
-                               27, 1, 64, 64, 0, None, 0, 0, 0, None, 0, None) == -1
+                               27, 1, 64, 64, 0, None, 0, 0, 0, None, 0, None, None) == -1
     assert lib.wcn_wgrad(None, 0, None, 0, None, None, None, None, 27, 1, 64, 64, 0, 1.0, 0, 0,
                          None, 0, 1, 1, -1, None, 0, 0, None) == -1
     assert lib.wcn_depthwise_conv(None, 0, None, 0, None, None, None, 8, 27, 64, 0, 0, 0,

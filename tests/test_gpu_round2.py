@@ -425,3 +425,75 @@ def test_reference_sparseconv3d_through_the_capi_stub():
     dx_ref, dw_ref = oconv.backward(gb, xb, wb, *args)
     assert oconv.rel_max_err(feats.grad, dx_ref) < 1e-2
     assert oconv.rel_max_err(conv.weight.grad, dw_ref) < 1e-2
+
+
+# ------------------------------------------------------------------------------------------------
+# GEMM-epilogue fusion: bias, ReLU and the BatchNorm statistics
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32])
+@pytest.mark.parametrize("n,cin,cout,relu", [
+    (40000, 128, 128, False),   # 256-row tiles, swap-AB form
+    (40000, 64, 96, True),      # 256-row tiles, row-major form
+    (40000, 32, 32, False),     # one 64-byte chunk per row
+    (3000, 64, 128, True),      # 128-row tiles
+    (3000, 48, 256, False),     # two 256-byte column chunks (16-bit) / four (fp32)
+    (700, 16, 16, True),
+])
+def test_gemm_epilogue_statistics_match_the_stored_output(dtype, n, cin, cout, relu):
+    """stats[0] = sum_r y, stats[1] = sum_r y^2 of the output AS STORED (bias, ReLU, rounding),
+    for every kernel form; compared with an fp64 reduction of the stored tensor."""
+    from warpconvnet_b200.geometry.coords.search.torch_discrete import generate_kernel_map
+    from warpconvnet_b200.nn.functional.sparse_conv import sparse_conv_forward
+    c = surface_coords(int(n ** 0.5), 1)
+    bc = torch.from_numpy(_bc([c])).cuda()
+    m = len(c)
+    km = generate_kernel_map(bc, bc, (1, 1, 1), (3, 3, 3), same_coords=True)
+    g = torch.Generator().manual_seed(n + cout)
+    x = torch.randn(m, cin, generator=g).cuda().to(dtype)
+    w = (torch.randn(27, cin, cout, generator=g) * (27 * cin) ** -0.5).cuda().to(dtype)
+    bias = torch.randn(cout, generator=g).cuda()
+    stats = torch.zeros((2, cout), dtype=torch.float64, device="cuda")
+    y = sparse_conv_forward(x, w, km, m, bias=bias, relu=relu, stats=stats)
+    y_plain = sparse_conv_forward(x, w, km, m, bias=bias, relu=relu)
+    assert torch.equal(y, y_plain)                          # the statistics do not touch the output
+    ref0 = y.double().sum(0)
+    ref1 = y.double().square().sum(0)
+    assert torch.allclose(stats[0], ref0, rtol=1e-5, atol=1e-4 * float(y.double().abs().sum(0).max()))
+    assert torch.allclose(stats[1], ref1, rtol=1e-5, atol=1e-6 * float(ref1.max()))
+
+
+def test_conv_bias_and_batchnorm_statistics_through_the_epilogue_module_path():
+    """SparseConv3d(bias=True, emit_bn_stats) -> BatchNorm(relu): bias is added in the epilogue
+    (and gets its gradient), BatchNorm consumes the epilogue's statistics; the result and every
+    gradient equal the unfused path (separate statistics pass) and torch's BatchNorm."""
+    from warpconvnet_b200.geometry.types.voxels import Voxels
+    from warpconvnet_b200.nn.modules.normalizations import BatchNorm
+    from warpconvnet_b200.nn.modules.sparse_conv import SparseConv3d
+    import warpconvnet_b200._ops as ops
+    torch.manual_seed(3)
+    coords = [torch.from_numpy(surface_coords(90, s)) for s in (0, 1)]
+    feats = [torch.randn(len(c), 32) for c in coords]
+    results = {}
+    for fused in (True, False):
+        torch.manual_seed(4)
+        conv = SparseConv3d(32, 64, 3, bias=True).cuda()
+        conv.emit_bn_stats = fused
+        bn = BatchNorm(64, relu=True).cuda()
+        v = Voxels(coords, feats, device="cuda")
+        v.batched_features.batched_tensor.requires_grad_(True)
+        calls = []
+        orig = ops.bn_forward
+        ops.bn_forward = lambda *a, **k: (calls.append(k.get("sums") is not None), orig(*a, **k))[1]
+        try:
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                out = bn(conv(v))
+        finally:
+            ops.bn_forward = orig
+        assert calls == [fused]                               # the fused path really was taken
+        out.feature_tensor.float().square().mean().backward()
+        results[fused] = (out.feature_tensor.float(), conv.bias.grad.clone(), conv.weight.grad.clone(),
+                          bn.norm.weight.grad.clone(), v.batched_features.batched_tensor.grad.clone(),
+                          bn.norm.running_var.clone())
+    for a, b in zip(results[True], results[False]):
+        assert oconv.rel_max_err(a, b.double().cpu()) < 2e-3
+    assert float(results[True][1].abs().sum()) > 0            # bias received a gradient

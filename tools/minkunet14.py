@@ -22,6 +22,7 @@ class ConvBlock(nn.Module):
     def __init__(self, cin, cout, kernel_size=3, stride=1, act=True):
         super().__init__()
         self.conv = SparseConv3d(cin, cout, kernel_size, stride, bias=False)
+        self.conv.emit_bn_stats = True   # BatchNorm statistics come out of the GEMM epilogue
         self.bn = BatchNorm(cout, relu=act)
 
     def forward(self, x, residual=None):
@@ -32,6 +33,7 @@ class ConvTrBlock(nn.Module):
     def __init__(self, cin, cout):
         super().__init__()
         self.conv_tr = SparseConv3d(cin, cout, 2, 2, transposed=True, bias=False)
+        self.conv_tr.emit_bn_stats = True
         self.bn = BatchNorm(cout, relu=True)
 
     def forward(self, x, target):

@@ -85,7 +85,7 @@ SIGNATURES = {
     "wcn_gather_gemm": (c_int, [c_void_p, c_int, c_longlong, c_void_p, c_void_p, c_longlong, c_void_p,
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                 c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int,
-                                c_void_p, c_int, c_void_p]),
+                                c_void_p, c_int, c_void_p, c_void_p]),
     "wcn_bn_forward": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong, c_int,
                                c_int, c_int, c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p,
                                c_void_p, c_void_p, c_int, c_void_p]),

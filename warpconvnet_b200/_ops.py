@@ -313,11 +313,14 @@ def weight_image_pair(weight: Tensor, K: int, groups: int, cin_g: int, cout_g: i
 
 def gather_gemm(feats: Tensor, wimg: Tensor, plan: TilePlan, groups: int, cin_g: int,
                 cout_g: int, out: Optional[Tensor] = None, bias: Optional[Tensor] = None,
-                relu: bool = False, kflip: bool = False, max_ctas: int = 0) -> Tensor:
+                relu: bool = False, kflip: bool = False, max_ctas: int = 0,
+                stats: Optional[Tensor] = None) -> Tensor:
     """out[plan.rows] = sum_k feats[plan.nbr[k]] @ W_k (forward AB / dgrad ABt gather-scatter).
 
     Every row of ``out`` (n_rows = plan.n_rows) is written exactly once, so ``out`` may be
-    uninitialised memory (the reference zero-fills, detail/mask_gemm.py:723)."""
+    uninitialised memory (the reference zero-fills, detail/mask_gemm.py:723).
+    ``stats``: zero-filled fp64 [2, groups * cout_g]; receives the per-channel sum / sum of squares
+    of the stored output (the BatchNorm statistics, accumulated in the epilogue)."""
     _require_cuda(feats, wimg)
     assert feats.dim() == 2 and feats.stride(1) == 1
     code = dtype_code(feats.dtype)
@@ -330,6 +333,7 @@ def gather_gemm(feats: Tensor, wimg: Tensor, plan: TilePlan, groups: int, cin_g:
                               _p(plan.tile_cum), plan.num_tiles, plan.tile_rows, plan.m_pad,
                               plan.K, groups, cin_g, cout_g, code, _p(bias), int(relu),
                               int(kflip), max_ctas, _p(plan.cta_units), plan.n_range_ctas,
+                              _pc(stats, 2 * groups * cout_g, "stats", feats, torch.float64),
                               _stream()),
           "gather_gemm")
     return out
@@ -578,11 +582,17 @@ def depthwise_wgrad_plan(feats: Tensor, gout: Tensor, plan: "TilePlan") -> Tenso
 
 def bn_forward(x: Tensor, gamma: Optional[Tensor], beta: Optional[Tensor], eps: float,
                momentum: float, running_mean: Optional[Tensor], running_var: Optional[Tensor],
-               residual: Optional[Tensor], relu: bool):
+               residual: Optional[Tensor], relu: bool, sums: Optional[Tensor] = None):
     """Training-mode BatchNorm (+ residual) (+ ReLU) in one native call.
-    Returns (y, scale, shift, mean_rstd[2, c])."""
+    Returns (y, scale, shift, mean_rstd[2, c]). ``sums`` (fp64 [2, c]): per-channel sum / sum of
+    squares of x already accumulated by the producing conv's epilogue — the statistics pass over
+    x is skipped."""
     _require_cuda(x, residual)
     n, c = x.shape
+    if sums is not None:
+        scale, shift, mean_rstd = bn_finalize(sums, n, gamma, beta, eps, momentum, running_mean,
+                                              running_var)
+        return scale_shift_act(x, scale, shift, residual, relu), scale, shift, mean_rstd
     y = torch.empty((n, c), dtype=x.dtype, device=x.device)
     sums = torch.empty((2, c), dtype=torch.float64, device=x.device)
     buf = torch.empty((4, c), dtype=torch.float32, device=x.device)

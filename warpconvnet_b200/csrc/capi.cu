@@ -327,7 +327,7 @@ int wcn_gather_gemm(const void* feats, int n_in_rows, long long in_ld, const voi
                     const int32_t* rows, const int32_t* tile_nk, const int32_t* tile_cum,
                     int num_tiles, int tile_rows, int m_pad, int K, int groups, int cin_g,
                     int cout_g, int dtype, const float* bias, int relu, int kflip, int max_ctas,
-                    const int32_t* cta_units, int n_range_ctas, void* stream) {
+                    const int32_t* cta_units, int n_range_ctas, double* stats, void* stream) {
   if (num_tiles > 0 && (!feats || !wimg || !out || !step_nbr || !step_k || !rows || !tile_nk ||
                         !tile_cum))
     return kErrInvalidArg;
@@ -365,6 +365,8 @@ int wcn_gather_gemm(const void* feats, int n_in_rows, long long in_ld, const voi
   p.kflip = kflip;
   p.stages = 0;
   p.relu = relu;
+  p.stats = stats;
+  p.stats_c = groups * cout_g;
   p.debug = 0;
   p.dbg_out = nullptr;
 #ifdef WCN_BRINGUP  // bring-up builds only (WCN_BRINGUP=1 build.sh): experiment switches of tools/exp_*.py

@@ -193,6 +193,49 @@ __device__ __forceinline__ void st_shared_elem<__half>(uint32_t addr, float f) {
                : "memory");
 }
 
+// fp32 -> T (round to nearest) -> fp32: the value a stored element of T holds
+template <typename T>
+__device__ __forceinline__ float round_to(float f);
+template <>
+__device__ __forceinline__ float round_to<float>(float f) { return f; }
+template <>
+__device__ __forceinline__ float round_to<__nv_bfloat16>(float f) {
+  return __bfloat162float(__float2bfloat16_rn(f));
+}
+template <>
+__device__ __forceinline__ float round_to<__half>(float f) {
+  return __half2float(__float2half_rn(f));
+}
+
+// the 16 / sizeof(T) elements of one 16-byte piece as fp32
+template <typename T>
+__device__ __forceinline__ void unpack_piece(const uint4& v, float (&f)[16 / sizeof(T)]);
+template <>
+__device__ __forceinline__ void unpack_piece<float>(const uint4& v, float (&f)[4]) {
+  f[0] = __uint_as_float(v.x); f[1] = __uint_as_float(v.y);
+  f[2] = __uint_as_float(v.z); f[3] = __uint_as_float(v.w);
+}
+template <>
+__device__ __forceinline__ void unpack_piece<__nv_bfloat16>(const uint4& v, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+template <>
+__device__ __forceinline__ void unpack_piece<__half>(const uint4& v, float (&f)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __half22float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+
 // adds to the pending transaction count of the current phase without arriving
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes)

@@ -142,7 +142,9 @@ struct StepCursor {
 // paces it: measured ~150 cycles per instruction); the 128x256x16 form reads 12 KB for twice the
 // work, i.e. the weight slice is fetched once per step instead of once per sub-tile. Both
 // operands are K-major in the same canonical 128B-swizzled layout, so no image changes.
-template <typename T, int TM, int GC, bool SWAP>
+// STATS: the epilogue also accumulates the per-channel sum and sum of squares of the stored output
+// (see GatherGemmParams::stats). A template flag, so the plain kernel is unchanged.
+template <typename T, int TM, int GC, bool SWAP, bool STATS>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -486,6 +488,16 @@ gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
     uint32_t use = 0;
     long long w_accf = 0;
     const long long t_start = WCN_CLOCK();
+    // STATS accumulators. SWAP: this thread owns ONE output channel (q*32 + lane). Row-major:
+    // the store loop hands this thread 16-byte piece (lane & 15) of every second staged row, i.e.
+    // kPieceElems fixed columns per 256-byte column chunk.
+    constexpr int kPieceElems = 16 / kElem;
+    constexpr int kStatChunks = SWAP ? 1 : (256 * kElem) / 256;  // column chunks of a 256-col slab
+    float st_s[kStatChunks][SWAP ? 1 : kPieceElems], st_q[kStatChunks][SWAP ? 1 : kPieceElems];
+#pragma unroll
+    for (int a = 0; a < kStatChunks; ++a)
+#pragma unroll
+      for (int b = 0; b < (SWAP ? 1 : kPieceElems); ++b) st_s[a][b] = st_q[a][b] = 0.f;
     for (int tile = t_begin; tile < t_end; ++tile) {
       const int nk = __ldg(p.tile_nk + tile);
       int lo, hi;
@@ -532,11 +544,20 @@ gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] = 0u;
               }
+              unsigned row_ok = 0u;
+              if constexpr (STATS) row_ok = __ballot_sync(0xffffffffu, out_row >= 0);
 #pragma unroll
               for (int i = 0; i < 32; ++i) {
                 float f = __uint_as_float(v[i]) + bias_c;
                 if (p.relu) f = fmaxf(f, 0.f);
                 st_shared_elem<T>(stage_warp + i * kRowB + lane * kElem, f);
+                if constexpr (STATS) {
+                  const float fr = round_to<T>(f);  // the value as stored
+                  if ((row_ok >> i) & 1u) {
+                    st_s[0][0] += fr;
+                    st_q[0][0] = fmaf(fr, fr, st_q[0][0]);
+                  }
+                }
               }
               __syncwarp();
 #pragma unroll
@@ -561,7 +582,7 @@ gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
           // 256-byte column chunks: TMEM -> registers -> (bias, ReLU, convert) -> XOR-swizzled
           // staging rows in shared memory -> 16 lanes write one output row's 256 contiguous
           // bytes (two rows per store instruction instead of 32 scattered 16-byte pieces)
-          for (int c0 = 0; c0 < p.bn; c0 += kChunkCols) {
+          for (int c0 = 0, ci = 0; c0 < p.bn; c0 += kChunkCols, ++ci) {
             const int c1 = min(p.bn, c0 + kChunkCols);
             for (int col = c0; col < c1; col += 16) {
               uint32_t v[16];
@@ -607,6 +628,22 @@ gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
               if (orow >= 0 && piece_ok && !WCN_DBG(p, 1))  // debug 1: skip stores (bring-up)
                 *reinterpret_cast<uint4*>(out + (long long)orow * out_ld_bytes +
                                           (long long)(col_base + c0) * kElem + piece * 16) = val;
+              if constexpr (STATS && !SWAP) {
+                if (orow >= 0 && piece_ok) {
+                  float fe[kPieceElems];
+                  unpack_piece<T>(val, fe);
+#pragma unroll
+                  for (int cc = 0; cc < kStatChunks; ++cc) {  // static register indexing
+                    if (cc == ci) {
+#pragma unroll
+                      for (int e = 0; e < kPieceElems; ++e) {
+                        st_s[cc][e] += fe[e];
+                        st_q[cc][e] = fmaf(fe[e], fe[e], st_q[cc][e]);
+                      }
+                    }
+                  }
+                }
+              }
             }
             __syncwarp();
           }
@@ -616,6 +653,39 @@ gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
           tc_fence_before();
           mbar_arrive(smem_u32(&ctrl->acc_empty[acc]));
           ++use;
+        }
+      }
+    }
+    if constexpr (STATS) {
+      if constexpr (SWAP) {
+        const int ch = q * 32 + lane;
+        if (ch < p.bn) {
+          atomicAdd(p.stats + col_base + ch, (double)st_s[0][0]);
+          atomicAdd(p.stats + p.stats_c + col_base + ch, (double)st_q[0][0]);
+        }
+      } else {
+        // merge the four epilogue warps (and the two half-warps that share a piece) in shared
+        // memory — the staging blocks are free now — then one fp64 atomic per column and CTA
+        float* sh = reinterpret_cast<float*>(smem_gen + (size_t)stages * stage_bytes);  // [2][256]
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int i = tid - 5 * 32; i < 2 * 256; i += 128) sh[i] = 0.f;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int piece = lane & 15;
+#pragma unroll
+        for (int ci = 0; ci < (256 * kElem) / 256; ++ci) {
+#pragma unroll
+          for (int e = 0; e < kPieceElems; ++e) {
+            const int col = ci * kChunkCols + piece * kPieceElems + e;
+            if (col < p.bn) {
+              atomicAdd(sh + col, st_s[ci][e]);
+              atomicAdd(sh + 256 + col, st_q[ci][e]);
+            }
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int i = tid - 5 * 32; i < p.bn; i += 128) {
+          atomicAdd(p.stats + col_base + i, (double)sh[i]);
+          atomicAdd(p.stats + p.stats_c + col_base + i, (double)sh[256 + i]);
         }
       }
     }
@@ -654,9 +724,9 @@ static int pick_gemm_stages(int bn, int tm, int gc) {
   return s;
 }
 
-template <typename T, int TM, int GC, bool SWAP>
-static int launch_gather_gemm_t(GatherGemmParams p, int n_slabs, int max_ctas, int n_range_ctas,
-                                cudaStream_t stream) {
+template <typename T, int TM, int GC, bool SWAP, bool STATS>
+static int launch_gather_gemm_ts(GatherGemmParams p, int n_slabs, int max_ctas, int n_range_ctas,
+                                 cudaStream_t stream) {
   const int max_stages = pick_gemm_stages(p.bn, TM, GC);
   if (p.stages <= 0 || p.stages > max_stages) p.stages = max_stages;
   if (p.stages < 2) return kErrUnsupportedShape;
@@ -664,7 +734,7 @@ static int launch_gather_gemm_t(GatherGemmParams p, int n_slabs, int max_ctas, i
   static int configured[kMaxDevices] = {};  // per instantiation and device
   int& configured_smem = configured[current_device_slot()];
   if ((int)smem > configured_smem) {
-    cudaError_t e = cudaFuncSetAttribute(gather_gemm_kernel<T, TM, GC, SWAP>,
+    cudaError_t e = cudaFuncSetAttribute(gather_gemm_kernel<T, TM, GC, SWAP, STATS>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return kErrCuda;
     configured_smem = (int)smem;
@@ -674,9 +744,17 @@ static int launch_gather_gemm_t(GatherGemmParams p, int n_slabs, int max_ctas, i
   if (ctas < 1) return kOk;
   if (p.cta_units != nullptr && ctas != n_range_ctas) p.cta_units = nullptr;  // other grid: search
   dim3 grid(ctas, n_slabs, 1);
-  gather_gemm_kernel<T, TM, GC, SWAP><<<grid, kGemmThreads, smem, stream>>>(p);
+  gather_gemm_kernel<T, TM, GC, SWAP, STATS><<<grid, kGemmThreads, smem, stream>>>(p);
   count_launch();
   return cudaGetLastError() == cudaSuccess ? kOk : kErrCuda;
+}
+
+template <typename T, int TM, int GC, bool SWAP>
+static int launch_gather_gemm_t(const GatherGemmParams& p, int n_slabs, int max_ctas,
+                                int n_range_ctas, cudaStream_t stream) {
+  return p.stats != nullptr
+             ? launch_gather_gemm_ts<T, TM, GC, SWAP, true>(p, n_slabs, max_ctas, n_range_ctas, stream)
+             : launch_gather_gemm_ts<T, TM, GC, SWAP, false>(p, n_slabs, max_ctas, n_range_ctas, stream);
 }
 
 template <typename T>

@@ -21,6 +21,12 @@ struct GatherGemmParams {
   const int* tile_cum;      // [num_tiles + 1] exclusive prefix sum of tile_nk
   const int* cta_units;     // optional [gridDim.x + 1] precomputed unit range of every CTA
   const float* bias;        // optional [cout_total] fp32, added in the epilogue
+  // optional per-channel statistics of the OUTPUT as stored (after bias / ReLU / rounding to the
+  // feature dtype): stats[ch] += sum_r y[r, ch], stats[stats_c + ch] += sum_r y[r, ch]^2, fp64,
+  // caller zero-fills. What the BatchNorm that follows a conv needs (csrc/rownorm.cu bn_stats),
+  // accumulated in the epilogue while the tile is in registers: saves one read pass over Y.
+  double* stats;
+  int stats_c;              // channel count of the statistics buffer (= total output channels)
   long long in_ld;          // row strides in elements
   long long out_ld;
   int n_in_rows;            // rows of feats (bounds documentation; neighbours are < n_in_rows)

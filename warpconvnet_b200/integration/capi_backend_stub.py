@@ -44,7 +44,7 @@ def _load(path):
         "wcn_weight_image_bytes": (c_size_t, [I, I, I, I, I, I, P, P]),
         "wcn_weight_image": (I, [P, P, I, I, I, I, I, I, P]),
         "wcn_gather_gemm": (I, [P, I, LL, P, P, LL, P, P, P, P, P, I, I, I, I, I, I, I, I, P, I, I,
-                                I, P, I, P]),
+                                I, P, I, P, P]),
         "wcn_wgrad": (I, [P, LL, P, LL, P, P, P, P, I, I, I, I, I, c_float, I, I, P, I, I, I, I, P,
                           LL, LL, P]),
     }
@@ -133,7 +133,7 @@ def _gather_gemm(x, img, plan, cin, cout):
         x.data_ptr(), x.shape[0], x.stride(0), img.data_ptr(), out.data_ptr(), out.stride(0),
         plan.step_nbr.data_ptr(), plan.step_k.data_ptr(), plan.rows.data_ptr(),
         plan.tile_nk.data_ptr(), plan.tile_cum.data_ptr(), plan.num_tiles, plan.tile_rows,
-        plan.m_pad, plan.K, 1, cin, cout, _DT[x.dtype], None, 0, 0, 0, None, 0, _stream())
+        plan.m_pad, plan.K, 1, cin, cout, _DT[x.dtype], None, 0, 0, 0, None, 0, None, _stream())
     return out if status == 0 else status
 
 

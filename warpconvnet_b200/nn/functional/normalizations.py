@@ -35,7 +35,7 @@ class _BatchNormAct(torch.autograd.Function):
     def forward(ctx, x: Tensor, weight: Optional[Tensor], bias: Optional[Tensor],
                 residual: Optional[Tensor], running_mean: Optional[Tensor],
                 running_var: Optional[Tensor], training: bool, momentum: float, eps: float,
-                relu: bool):
+                relu: bool, sums: Optional[Tensor] = None):
         x = x if x.stride(1) == 1 else x.contiguous()
         n, c = x.shape
         gamma = weight.detach().float().contiguous() if weight is not None else None
@@ -56,7 +56,7 @@ class _BatchNormAct(torch.autograd.Function):
             # fp32 temporaries and copy them back (never hand a narrower buffer to the kernel)
             rm32, rv32 = _fp32_stat(rm, c, x.device), _fp32_stat(rv, c, x.device)
             y, scale, shift, mean_rstd = _ops.bn_forward(
-                x, gamma, beta, eps, momentum, rm32, rv32, residual, relu)
+                x, gamma, beta, eps, momentum, rm32, rv32, residual, relu, sums=sums)
             if rm32 is not rm and rm is not None:
                 rm.copy_(rm32)
             if rv32 is not rv and rv is not None:
@@ -112,18 +112,23 @@ class _BatchNormAct(torch.autograd.Function):
                 sums = _ops.bn_bwd_reduce(dy, x, y, mean_rstd)
                 dgamma = sums[1].to(ctx.w_dtype) if ctx.has_w else None
                 dbeta = sums[0].to(ctx.b_dtype) if ctx.has_b else None
-        return dx, dgamma, dbeta, dres, None, None, None, None, None, None
+        return dx, dgamma, dbeta, dres, None, None, None, None, None, None, None
 
 
 def batch_norm_act(x: Tensor, weight: Optional[Tensor] = None, bias: Optional[Tensor] = None,
                    running_mean: Optional[Tensor] = None, running_var: Optional[Tensor] = None,
                    training: bool = True, momentum: float = 0.1, eps: float = 1e-5,
-                   relu: bool = False, residual: Optional[Tensor] = None) -> Tensor:
+                   relu: bool = False, residual: Optional[Tensor] = None,
+                   sums: Optional[Tensor] = None) -> Tensor:
     """``act(batch_norm(x) (+ residual))`` on a CUDA feature matrix ``[n, c]`` (bf16 / fp16 /
-    fp32); same arguments as ``torch.nn.functional.batch_norm`` plus the fused tail."""
+    fp32); same arguments as ``torch.nn.functional.batch_norm`` plus the fused tail. ``sums``:
+    fp64 [2, c] sum / sum of squares of x from the producing conv's epilogue (training mode)."""
     if not x.is_cuda:
         raise RuntimeError("warpconvnet_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
     if x.dim() != 2:
         raise ValueError(f"expected a feature matrix [n, c], got {tuple(x.shape)}")
+    if sums is not None and (not training or sums.shape != (2, x.shape[1])
+                             or sums.dtype != torch.float64):
+        sums = None
     return _BatchNormAct.apply(x, weight, bias, residual, running_mean, running_var, training,
-                               float(momentum), float(eps), bool(relu))
+                               float(momentum), float(eps), bool(relu), sums)

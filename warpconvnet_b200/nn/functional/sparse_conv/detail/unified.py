@@ -117,7 +117,7 @@ def _fusable_weight(weight: Tensor, compute_dtype: torch.dtype, groups: int):
 
 def sparse_conv_forward(in_features: Tensor, weight: Tensor, kernel_map: IntSearchResult,
                         num_out_coords: int, groups: int = 1, bias: Optional[Tensor] = None,
-                        relu: bool = False) -> Tensor:
+                        relu: bool = False, stats: Optional[Tensor] = None) -> Tensor:
     """Y[M, Cout] = sum_k X[in_k] @ W_k  on the tensor cores (no autograd)."""
     w4, cin_g, cout_g, cin_r, cout_r = _canon_weight(weight, groups)
     K = w4.shape[0]
@@ -126,8 +126,14 @@ def sparse_conv_forward(in_features: Tensor, weight: Tensor, kernel_map: IntSear
     img = _ops.weight_image(w4, K, groups, cin_g, cout_g, transpose_w=False)
     if bias is not None and cout_g != cout_r:
         bias = torch.nn.functional.pad(bias.float(), (0, cout_g - cout_r))
+    pad_stats = None
+    if stats is not None and cout_g != cout_r:  # padded channels: statistics into a padded buffer
+        pad_stats = torch.zeros((2, groups * cout_g), dtype=torch.float64, device=x.device)
     y = _ops.gather_gemm(x, img, plan, groups, cin_g, cout_g,
-                         bias=None if bias is None else bias.float().contiguous(), relu=relu)
+                         bias=None if bias is None else bias.float().contiguous(), relu=relu,
+                         stats=stats if pad_stats is None else pad_stats)
+    if pad_stats is not None:
+        stats.copy_(pad_stats[:, :cout_r])
     return y if cout_g == cout_r else y[:, :cout_r]
 
 
@@ -269,7 +275,9 @@ class UnifiedSpatiallySparseConvFunction(Function):
     def forward(ctx, in_features, weight, kernel_map, num_out_coords, fwd_algo=None,
                 dgrad_algo=None, wgrad_algo=None, compute_dtype=None, fwd_block_size=None,
                 bwd_block_size=None, in_tensor_stride=None, conv_cache_metadata=None, groups=1,
-                use_fp16_accum=False):
+                use_fp16_accum=False, bias=None, stats=None):
+        """``bias`` (fp32 [Cout]) is added in the GEMM epilogue; ``stats`` (zero-filled fp64
+        [2, Cout]) receives the per-channel sum / sum of squares of the stored output."""
         if not in_features.is_cuda:
             raise RuntimeError("warpconvnet_b200 sparse conv needs CUDA tensors (no CPU fallback)")
         out_dtype = in_features.dtype
@@ -286,12 +294,15 @@ class UnifiedSpatiallySparseConvFunction(Function):
             img, img_t = _ops.weight_image_pair(w4, K, G, cin_g, cout_g, x.dtype,
                                                 want_transposed=bool(ctx.needs_input_grad[0]))
             xp = _pad_cols(x, G * cin_g)
-            y = _ops.gather_gemm(xp, img, kernel_map.fwd_plan(num_out_coords), G, cin_g, cout_g)
+            y = _ops.gather_gemm(xp, img, kernel_map.fwd_plan(num_out_coords), G, cin_g, cout_g,
+                                 bias=None if bias is None else bias.detach().float().contiguous(),
+                                 stats=stats)
             ctx.save_for_backward(x, img_t)
             ctx.fused_dims = (G, cin_g, cout_g)
         else:
             w = weight if weight.dtype == x.dtype else weight.to(x.dtype)
-            y = sparse_conv_forward(x, w, kernel_map, num_out_coords, groups)
+            y = sparse_conv_forward(x, w, kernel_map, num_out_coords, groups,
+                                    bias=None if bias is None else bias.detach(), stats=stats)
             ctx.save_for_backward(x, w)
             ctx.fused_dims = None
         ctx.kernel_map = kernel_map
@@ -300,6 +311,7 @@ class UnifiedSpatiallySparseConvFunction(Function):
         ctx.w_dtype = weight.dtype
         ctx.num_in = in_features.shape[0]
         ctx.weight_shape = tuple(weight.shape)
+        ctx.bias_dtype = None if bias is None else bias.dtype
         return y if compute_dtype is None else y.to(out_dtype)
 
     @staticmethod
@@ -326,4 +338,7 @@ class UnifiedSpatiallySparseConvFunction(Function):
             grad_w = grad_w.to(ctx.w_dtype)
             if grad_w.shape != ctx.weight_shape:
                 grad_w = grad_w.reshape(ctx.weight_shape)
-        return (grad_in, grad_w) + (None,) * 12
+        grad_b = None
+        if ctx.bias_dtype is not None and ctx.needs_input_grad[14]:
+            grad_b = grad_output.sum(dim=0, dtype=torch.float32).to(ctx.bias_dtype)
+        return (grad_in, grad_w) + (None,) * 12 + (grad_b, None)

@@ -70,7 +70,7 @@ def spatially_sparse_conv(input_sparse_tensor, weight, kernel_size, stride=1, ke
                           wgrad_algo=SPARSE_CONV_ATB_ALGO_MODE.TCGEN05,
                           stride_mode=STRIDED_CONV_MODE.STRIDE_ONLY, stride_reduce="max", order=None,
                           compute_dtype=None, implicit_matmul_fwd_block_size=16,
-                          implicit_matmul_bwd_block_size=16) -> Geometry:
+                          implicit_matmul_bwd_block_size=16, bn_stats: bool = False) -> Geometry:
     """Functional sparse convolution (same keywords as the reference's, helper.py:147-358)."""
     if not isinstance(input_sparse_tensor, Voxels):
         raise TypeError("Native spatially_sparse_conv expects input_sparse_tensor of type Voxels, "
@@ -143,12 +143,18 @@ def spatially_sparse_conv(input_sparse_tensor, weight, kernel_size, stride=1, ke
     if x.dtype != effective_compute_dtype:
         x = x.to(effective_compute_dtype)
 
+    # bias (and, on request, the statistics of the BatchNorm that follows) go through the GEMM
+    # epilogue: no separate add pass over Y, no separate statistics pass
+    stats = None
+    if bn_stats and num_out > 0:
+        stats = torch.zeros((2, weight.shape[-1] * (groups if weight.dim() == 4 else 1)),
+                            dtype=torch.float64, device=x.device)
     out = UnifiedSpatiallySparseConvFunction.apply(
         x, w, kernel_map, num_out, fwd_algo, dgrad_algo, wgrad_algo, effective_compute_dtype,
         implicit_matmul_fwd_block_size, implicit_matmul_bwd_block_size, in_tensor_stride, None,
-        groups, bool(use_fp16_accum))
-    if bias is not None:
-        out = out + bias.to(out.dtype)
+        groups, bool(use_fp16_accum), bias, stats)
+    if stats is not None:
+        out._wcn_bn_sums = (stats, out.shape[0], out._version)
 
     out_offsets_cpu = out_offsets if out_offsets.device.type == "cpu" else out_offsets.cpu()
     if bout is input_sparse_tensor.batch_indexed_coordinates:

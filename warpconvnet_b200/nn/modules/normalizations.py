@@ -44,10 +44,15 @@ class BatchNorm(NormalizationBase):
             bn.num_batches_tracked.add_(1)
             if momentum is None:  # cumulative moving average, as nn.BatchNorm1d
                 momentum = 1.0 / float(bn.num_batches_tracked)
+        # statistics left behind by the producing conv's epilogue (SparseConv3d.emit_bn_stats):
+        # valid for exactly this tensor in exactly this state
+        pre = getattr(feats, "_wcn_bn_sums", None)
+        sums = pre[0] if (pre is not None and pre[1] == feats.shape[0]
+                          and pre[2] == feats._version) else None
         out = batch_norm_act(feats, bn.weight, bn.bias, bn.running_mean, bn.running_var,
                              training=self.training or bn.running_mean is None,
                              momentum=0.0 if momentum is None else momentum, eps=bn.eps,
-                             relu=self.relu, residual=res)
+                             relu=self.relu, residual=res, sums=sums)
         if isinstance(input, Geometry):
             return input.replace(batched_features=out)
         return out

@@ -70,6 +70,11 @@ class SpatiallySparseConv(BaseSpatialModule):
                      implicit_matmul_bwd_block_size=implicit_matmul_bwd_block_size)
         for key, value in plain.items():
             setattr(self, key, value)
+        # Extension (not a reference argument): when a BatchNorm follows this conv, set
+        # ``conv.emit_bn_stats = True`` and the GEMM epilogue accumulates the per-channel sum / sum of
+        # squares of the output it stores; warpconvnet_b200.nn.modules.BatchNorm picks them up
+        # and skips its statistics pass over Y.
+        self.emit_bn_stats = False
 
         volume = int(np.prod(self.kernel_size))
         shape = ((volume, in_channels, out_channels) if groups == 1
@@ -119,7 +124,8 @@ class SpatiallySparseConv(BaseSpatialModule):
         return _F.spatially_sparse_conv(
             input_sparse_tensor=input_sparse_tensor, weight=self.weight,
             kernel_size=self.kernel_size, kernel_dilation=self.dilation,
-            output_spatially_sparse_tensor=output_spatially_sparse_tensor, **options)
+            output_spatially_sparse_tensor=output_spatially_sparse_tensor,
+            bn_stats=self.emit_bn_stats and self.training, **options)
 
 
 def _with_dims(nd: int, name: str):
