@@ -98,8 +98,13 @@ def cpu_port_step(coords: np.ndarray, x, w, gy):
     return time.perf_counter() - t0, int(km["offsets"][-1])
 
 
+_ALL_CPUS = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+
+
 def run_cpu_baseline(dist: str, reps: int, warmup: int, budget_s: float = 40.0):
-    cores = os.cpu_count() or 1
+    if _ALL_CPUS is not None:
+        os.sched_setaffinity(0, _ALL_CPUS)   # the CPU arm uses every host core (undo the NUMA binding)
+    cores = len(_ALL_CPUS) if _ALL_CPUS is not None else (os.cpu_count() or 1)
     torch.set_num_threads(cores)
     coords = make_coords(dist, 0)
     x, w, gy = make_tensors(len(coords), 0)
@@ -433,6 +438,33 @@ def run_side_blocks(dev, flush):
     return blocks
 
 
+def bind_to_gpu_numa_node(local_rank: int):
+    """Pin this process (and therefore the pinned host buffers it allocates afterwards) to the CPU
+    cores of the NUMA node its GPU hangs off, so the per-step H2D copies of the e2e loop do not
+    cross the socket interconnect. Best effort: returns a description or the reason it was skipped."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dev = bus.lower()[-12:]                       # 0000:xx:yy.z
+        node = int(open(f"/sys/bus/pci/devices/{dev}/numa_node").read().strip())
+        if node < 0:
+            return {"numa_node": None, "note": "platform reports no NUMA affinity for the GPU"}
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.extend(range(int(a), int(b or a) + 1))
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return {"numa_node": node, "note": "no allowed CPU on that node"}
+        os.sched_setaffinity(0, allowed)
+        return {"numa_node": node, "cpus": len(allowed)}
+    except Exception as exc:  # pragma: no cover - depends on the box
+        return {"numa_node": None, "note": f"{type(exc).__name__}: {str(exc)[:80]}"}
+
+
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
@@ -444,6 +476,7 @@ def run_ours(args):
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -718,6 +751,7 @@ def run_ours(args):
         },
         "e2e": {"value": total_vox / (e2e_ms * 1e-3), "unit": "voxels/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "h2d_GBps_per_rank": h2d / (e2e_ms * 1e-3) / 1e9, "numa_binding": numa,
                 "runs_ms": e2e_runs, "runs": "5 repetitions of K steps, median reported",
                 "warmup_steps": max(args.warmup, 50),
                 "api": "Voxels(pinned host coords+feats) -> SparseConv3d.forward (autocast bf16) -> "

@@ -523,3 +523,32 @@ def test_bias_through_the_epilogue_forward_and_gradient():
     gy = torch.randn_like(out.feature_tensor)
     out.feature_tensor.backward(gy)
     assert torch.allclose(conv.bias.grad, gy.sum(0), rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("groups,cin,cout", [(16, 64, 64), (8, 32, 16), (3, 12, 6)])
+def test_group_conv_with_fewer_than_8_channels_per_group(groups, cin, cout):
+    """The reference's mask_gemm path rejects groups of fewer than 8 channels
+    (detail/dispatch.py:42-50); here they run on the dense kernels through the block-diagonal
+    weight. Forward, dX and the [K, G, Cin/G, Cout/G] weight gradient vs the per-group oracle."""
+    from warpconvnet_b200.geometry.types.voxels import Voxels
+    from warpconvnet_b200.nn.modules.sparse_conv import SparseConv3d
+    torch.manual_seed(groups)
+    c = random_coords(2500, 0.3, groups)
+    bc = _bc([c])
+    km = okm.generate_kernel_map(bc, bc, (1, 1, 1), (3, 3, 3))
+    f = torch.randn(len(c), cin)
+    conv = SparseConv3d(cin, cout, 3, groups=groups, bias=False).cuda()
+    assert conv.weight.shape == (27, groups, cin // groups, cout // groups)
+    v = Voxels([torch.from_numpy(c)], [f], device="cuda")
+    v.batched_features.batched_tensor.requires_grad_(True)
+    out = conv(v)
+    gy = torch.randn(len(c), cout)
+    out.feature_tensor.backward(gy.cuda())
+    w = conv.weight.detach().cpu()
+    args = (km["in_maps"], km["out_maps"], km["offsets"])
+    y_ref = oconv.forward_grouped(f, w, *args, len(c))
+    dx_ref, dw_ref = oconv.backward_grouped(gy, f, w, *args)
+    assert oconv.rel_max_err(out.feature_tensor, y_ref) < 5e-3      # fp32 in: TF32 tensor cores
+    assert oconv.rel_max_err(v.batched_features.batched_tensor.grad, dx_ref) < 5e-3
+    assert conv.weight.grad.shape == conv.weight.shape
+    assert oconv.rel_max_err(conv.weight.grad, dw_ref) < 1e-3

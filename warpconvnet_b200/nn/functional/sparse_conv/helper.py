@@ -142,12 +142,21 @@ def spatially_sparse_conv(input_sparse_tensor, weight, kernel_size, stride=1, ke
     x, w = feats, weight
     if x.dtype != effective_compute_dtype:
         x = x.to(effective_compute_dtype)
+    if groups > 1 and (weight.shape[2] % 8 or weight.shape[3] % 8):
+        # fewer than 8 channels per group (the reference's mask_gemm path rejects these outright,
+        # detail/dispatch.py:42-50): run the DENSE tensor-core kernels on the block-diagonal
+        # [K, Cin, Cout] weight. The off-diagonal zeros cost G x the useful FLOPs, on matrices this
+        # narrow the kernels stay gather-bound; autograd returns the diagonal blocks of dW.
+        eye = torch.eye(groups, dtype=weight.dtype, device=weight.device)
+        kk, gg, cig, cog = weight.shape
+        w = torch.einsum("kgio,gh->kgiho", weight, eye).reshape(kk, gg * cig, gg * cog)
+        groups = 1
 
     # bias (and, on request, the statistics of the BatchNorm that follows) go through the GEMM
     # epilogue: no separate add pass over Y, no separate statistics pass
     stats = None
     if bn_stats and num_out > 0:
-        stats = torch.zeros((2, weight.shape[-1] * (groups if weight.dim() == 4 else 1)),
+        stats = torch.zeros((2, w.shape[-1] * (groups if w.dim() == 4 else 1)),
                             dtype=torch.float64, device=x.device)
     out = UnifiedSpatiallySparseConvFunction.apply(
         x, w, kernel_map, num_out, fwd_algo, dgrad_algo, wgrad_algo, effective_compute_dtype,
