@@ -34,6 +34,36 @@ constexpr int kNumSMsB200 = 148;
 // Per-role wait-cycle counters of the GEMM kernels (tools/exp_dbg.py, tools/exp_wgrad.py) are a
 // bring-up aid: the clock reads are compiled in only with -DWCN_KERNEL_COUNTERS
 // (WCN_KERNEL_COUNTERS=1 csrc/build.sh); the shipped library carries none of them.
+// Programmatic dependent launch (PDL): every kernel of this library is launched with the
+// programmatic-stream-serialization attribute and starts with pdl_begin(): it lets the NEXT kernel
+// of the stream be scheduled right away (griddepcontrol.launch_dependents) and then waits until
+// everything before it in the stream has completed and flushed (griddepcontrol.wait), so the
+// grid is already resident when its predecessor drains — the ~1-2 us launch gap between two
+// dependent kernels disappears, in eager launches and as programmatic edges of a captured CUDA
+// graph alike. Semantics are unchanged: nothing is read or written before the wait.
+__device__ __forceinline__ void pdl_begin() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+inline cudaError_t wcn_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                              cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 // Experiment switches (GemmParams::debug bits, per-CTA counter dumps through dbg_out) exist only
 // in bring-up builds (WCN_BRINGUP=1 csrc/build.sh): in the shipped library WCN_DBG is the
 // constant false and WCN_DBG_OUT the constant nullptr, so the predicates, the counter stores and

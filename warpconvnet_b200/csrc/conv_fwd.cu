@@ -147,6 +147,7 @@ struct StepCursor {
 template <typename T, int TM, int GC, bool SWAP, bool STATS>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
+  pdl_begin();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -744,7 +745,7 @@ static int launch_gather_gemm_ts(GatherGemmParams p, int n_slabs, int max_ctas, 
   if (ctas < 1) return kOk;
   if (p.cta_units != nullptr && ctas != n_range_ctas) p.cta_units = nullptr;  // other grid: search
   dim3 grid(ctas, n_slabs, 1);
-  gather_gemm_kernel<T, TM, GC, SWAP, STATS><<<grid, kGemmThreads, smem, stream>>>(p);
+  wcn_launch(gather_gemm_kernel<T, TM, GC, SWAP, STATS>, dim3(grid), dim3(kGemmThreads), smem, stream, p);
   count_launch();
   return cudaGetLastError() == cudaSuccess ? kOk : kErrCuda;
 }

@@ -114,6 +114,7 @@ template <typename T, int PAIRS, int NSEGB>
 __global__ void __launch_bounds__(kWgThreads, 1)
 wgrad_kernel(const __grid_constant__ WgradParams p, const __grid_constant__ CUtensorMap tmap_x,
              const __grid_constant__ CUtensorMap tmap_dy) {
+  pdl_begin();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -568,7 +569,7 @@ static int launch_wgrad_t(WgradParams p, int cin_slabs, int cout_slabs, int max_
   int per_slab = max_ctas / (cin_slabs * cout_slabs);
   if (per_slab < 1) per_slab = 1;
   dim3 grid(per_slab, cin_slabs, cout_slabs);
-  wgrad_kernel<T, PAIRS, NSEGB><<<grid, kWgThreads, smem, stream>>>(p, tmap_x, tmap_dy);
+  wcn_launch(wgrad_kernel<T, PAIRS, NSEGB>, dim3(grid), dim3(kWgThreads), smem, stream, p, tmap_x, tmap_dy);
   count_launch();
   return cudaGetLastError() == cudaSuccess ? kOk : kErrCuda;
 }

@@ -53,6 +53,7 @@ coords_keys_kernel(const int4* __restrict__ bcoords, int n, int sx, int sy, int 
                    const int* __restrict__ offs, int K, int n_batches,
                    unsigned long long* __restrict__ keys, int* __restrict__ idx,
                    int* __restrict__ status) {
+  pdl_begin();
   const long long total = (long long)n * K;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= total) return;
@@ -80,6 +81,7 @@ coords_keys_kernel(const int4* __restrict__ bcoords, int n, int sx, int sy, int 
 __global__ void __launch_bounds__(kUniqBlock)
 coords_heads_kernel(const unsigned long long* __restrict__ keys, long long n, int n_batches,
                     int* __restrict__ block_counts) {
+  pdl_begin();
   const unsigned long long parked = parked_key(n_batches);
   __shared__ int s_warp[kUniqBlock / 32];
   const long long base = (long long)blockIdx.x * kUniqTile + (long long)threadIdx.x * kUniqItems;
@@ -109,6 +111,7 @@ coords_heads_kernel(const unsigned long long* __restrict__ keys, long long n, in
 // meta[n_batches + 1] (the "total" word); the per-batch offsets are filled by the compaction pass
 __global__ void __launch_bounds__(1024)
 coords_scan_kernel(int* __restrict__ block_counts, int nb, int* __restrict__ meta, int n_batches) {
+  pdl_begin();
   __shared__ int s_warp[32];
   __shared__ int s_carry;
   if (threadIdx.x == 0) s_carry = 0;
@@ -155,6 +158,7 @@ coords_compact_kernel(const unsigned long long* __restrict__ keys, const int* __
                       long long n, const int* __restrict__ block_prefix,
                       int4* __restrict__ out_coords, int* __restrict__ first_index,
                       int* __restrict__ meta, int n_batches) {
+  pdl_begin();
   __shared__ int s_warp[kUniqBlock / 32];
   const unsigned long long parked = parked_key(n_batches);
   const long long base = (long long)blockIdx.x * kUniqTile + (long long)threadIdx.x * kUniqItems;
@@ -204,6 +208,7 @@ coords_compact_kernel(const unsigned long long* __restrict__ keys, const int* __
 
 // offsets of batch items after the last one that has rows: the total
 __global__ void coords_offsets_tail_kernel(int* __restrict__ meta, int n_batches) {
+  pdl_begin();
   const int total = meta[n_batches];
   for (int b = threadIdx.x; b < n_batches; b += blockDim.x)
     if (meta[b] == 0x7fffffff) meta[b] = total;
@@ -250,7 +255,7 @@ int coords_unique(const int* bcoords, int n, int sx, int sy, int sz, const int* 
   size_t temp_bytes = ws_bytes - (2 * kb + 2 * ib + align_up_sz((size_t)nb * 4, 256));
   int* status = meta + n_batches + 2;
   const bool want_idx = first_index != nullptr;
-  coords_keys_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
+  wcn_launch(coords_keys_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, 
       reinterpret_cast<const int4*>(bcoords), n, sx, sy, sz, offsets3, K, n_batches, keys_in,
       want_idx ? idx_in : nullptr, status);
   count_launch();
@@ -265,15 +270,15 @@ int coords_unique(const int* bcoords, int n, int sx, int sy, int sz, const int* 
   else
     e = cub::DeviceRadixSort::SortKeys(temp, temp_bytes, keys_in, keys_out, total, 0, end_bit, s);
   if (e != cudaSuccess) return kErrCuda;
-  coords_heads_kernel<<<nb, kUniqBlock, 0, s>>>(keys_out, total, n_batches, block_counts);
+  wcn_launch(coords_heads_kernel, dim3(nb), dim3(kUniqBlock), 0, s, keys_out, total, n_batches, block_counts);
   count_launch();
-  coords_scan_kernel<<<1, 1024, 0, s>>>(block_counts, nb, meta, n_batches);
+  wcn_launch(coords_scan_kernel, dim3(1), dim3(1024), 0, s, block_counts, nb, meta, n_batches);
   count_launch();
-  coords_compact_kernel<<<nb, kUniqBlock, 0, s>>>(keys_out, want_idx ? idx_out : nullptr, total,
+  wcn_launch(coords_compact_kernel, dim3(nb), dim3(kUniqBlock), 0, s, keys_out, want_idx ? idx_out : nullptr, total,
                                                   block_counts, reinterpret_cast<int4*>(out_coords),
                                                   first_index, meta, n_batches);
   count_launch();
-  coords_offsets_tail_kernel<<<1, 256, 0, s>>>(meta, n_batches);
+  wcn_launch(coords_offsets_tail_kernel, dim3(1), dim3(256), 0, s, meta, n_batches);
   count_launch();
   return cuda_ok2();
 }

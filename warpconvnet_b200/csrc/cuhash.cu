@@ -65,6 +65,7 @@ __device__ __forceinline__ int table_lookup(const uint64_t* __restrict__ keys,
 __global__ void hash_insert_kernel(uint64_t* __restrict__ keys, int* __restrict__ values,
                                    const int4* __restrict__ coords, int n, uint32_t mask,
                                    int* __restrict__ status) {
+  pdl_begin();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int4 c = __ldg(coords + i);  // (batch, x, y, z): one coalesced 16-byte load
@@ -95,6 +96,7 @@ __global__ void hash_search_kernel(const uint64_t* __restrict__ keys,
                                    const int* __restrict__ values,
                                    const int4* __restrict__ queries, int* __restrict__ results,
                                    int n, uint32_t mask) {
+  pdl_begin();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int4 c = __ldg(queries + i);
@@ -114,6 +116,7 @@ kernel_map_search_kernel(const uint64_t* __restrict__ keys, const int* __restric
                          const int* __restrict__ offs, int K, int sx, int sy, int sz,
                          int* __restrict__ pair_table, int* __restrict__ block_counts,
                          unsigned long long* __restrict__ mask_keys) {
+  pdl_begin();
   extern __shared__ int s_mem[];  // [K] counts, then [3K] offsets
   int* s_cnt = s_mem;
   int* s_off = s_mem + K;
@@ -200,6 +203,7 @@ kernel_map_search_sym_kernel(const uint64_t* __restrict__ keys, const int* __res
                              uint32_t mask, const int4* __restrict__ coords, int M,
                              const int* __restrict__ offs, int K, const int* __restrict__ status,
                              int* __restrict__ pair_table) {
+  pdl_begin();
   extern __shared__ int s_off[];  // [3K]
   for (int i = threadIdx.x; i < 3 * K; i += blockDim.x) s_off[i] = offs[i];
   __syncthreads();
@@ -266,6 +270,7 @@ __global__ void __launch_bounds__(kMapBlock)
 kernel_map_stats_kernel(const int* __restrict__ pair_table, int K, int M,
                         int* __restrict__ block_counts,
                         unsigned long long* __restrict__ mask_keys) {
+  pdl_begin();
   __shared__ int s_cnt[32][kMapBlock / 32];
   const int m = blockIdx.x * kMapBlock + threadIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -299,6 +304,7 @@ kernel_map_stats_kernel(const int* __restrict__ pair_table, int K, int M,
 // exclusive scan of block_counts[k][0..nb) in place, total into counts[k]; one block per offset
 __global__ void __launch_bounds__(256)
 block_scan_kernel(int* __restrict__ block_counts, int nb, int* __restrict__ counts) {
+  pdl_begin();
   __shared__ int s_warp[8];
   __shared__ int s_carry;
   int* row = block_counts + (size_t)blockIdx.x * nb;
@@ -329,6 +335,7 @@ block_scan_kernel(int* __restrict__ block_counts, int nb, int* __restrict__ coun
 
 // offsets[0..K] = exclusive scan of counts; single small block
 __global__ void offsets_kernel(const int* __restrict__ counts, int K, int* __restrict__ offsets) {
+  pdl_begin();
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     int acc = 0;
     for (int k = 0; k < K; ++k) {
@@ -345,6 +352,7 @@ __global__ void __launch_bounds__(kMapBlock)
 kernel_map_scatter_kernel(const int* __restrict__ pair_table, const int* __restrict__ block_prefix,
                           const int* __restrict__ offsets, int* __restrict__ in_maps,
                           int* __restrict__ out_maps, int K, int M) {
+  pdl_begin();
   __shared__ int s_cnt[32][kMapBlock / 32];
   __shared__ int s_base[32];
   const int m = blockIdx.x * kMapBlock + threadIdx.x;
@@ -384,6 +392,7 @@ kernel_map_scatter_kernel(const int* __restrict__ pair_table, const int* __restr
 // rev[k][in] = out  for every valid pair (rev must be pre-filled with -1)
 __global__ void reverse_table_kernel(const int* __restrict__ pair_table, int K, int M,
                                      int* __restrict__ rev, int n_in) {
+  pdl_begin();
   const long long total = (long long)K * M;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
        t += (long long)gridDim.x * blockDim.x) {
@@ -401,6 +410,7 @@ __global__ void csr_to_table_kernel(const int* __restrict__ val_maps,
                                     const int* __restrict__ row_maps,
                                     const int* __restrict__ offsets, int K, int n_rows,
                                     int* __restrict__ table) {
+  pdl_begin();
   extern __shared__ int s_offs[];  // [K+1]
   for (int i = threadIdx.x; i <= K; i += blockDim.x) s_offs[i] = offsets[i];
   __syncthreads();
@@ -417,6 +427,7 @@ __global__ void csr_to_table_kernel(const int* __restrict__ val_maps,
 
 __global__ void mask_keys_kernel(const int* __restrict__ table, int K, int M,
                                  unsigned long long* __restrict__ keys) {
+  pdl_begin();
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= M) return;
   unsigned long long bits = 0ull;
@@ -426,6 +437,7 @@ __global__ void mask_keys_kernel(const int* __restrict__ table, int K, int M,
 }
 
 __global__ void iota_kernel(int* __restrict__ v, int n) {
+  pdl_begin();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) v[i] = i;
 }
@@ -437,6 +449,7 @@ __global__ void __launch_bounds__(256)
 build_tiles_kernel(const int* __restrict__ table, int K, int M, const int* __restrict__ sorted_rows,
                    int tile_rows, int* __restrict__ step_nbr, int* __restrict__ step_k,
                    int* __restrict__ rows_padded, int* __restrict__ tile_nk) {
+  pdl_begin();
   // 32 offsets per chunk: the 32 table loads of a thread are independent (one round trip instead
   // of a dependent chain with a block barrier per offset: 20.4 us on C3), the tile's union mask of
   // the chunk is ONE shared-memory OR, and every thread then writes its neighbours of the active
@@ -480,6 +493,7 @@ build_tiles_kernel(const int* __restrict__ table, int K, int M, const int* __res
 __global__ void __launch_bounds__(1024)
 tile_scan_kernel(const int* __restrict__ tile_nk, int n, int* __restrict__ tile_cum, int U,
                  int n_ctas, int* __restrict__ cta_units) {
+  pdl_begin();
   __shared__ int s_warp[32];
   __shared__ int s_carry;
   if (threadIdx.x == 0) s_carry = 0;
@@ -544,6 +558,7 @@ static inline bool is_pow2(long long v) { return v > 0 && (v & (v - 1)) == 0; }
 // instead of two memset nodes
 __global__ void hash_prepare_kernel(uint4* __restrict__ keys16, uint4* __restrict__ values16,
                                     int n_keys16, int n_values16) {
+  pdl_begin();
   const int stride = gridDim.x * blockDim.x;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_keys16; i += stride)
     keys16[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -558,7 +573,7 @@ int hash_prepare(uint64_t* keys, int* values, int capacity, cudaStream_t s) {
     const int nk = capacity / 2, nv = capacity / 4;  // 16-byte words
     int blocks = (nk + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    hash_prepare_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<uint4*>(keys),
+    wcn_launch(hash_prepare_kernel, dim3(blocks), dim3(256), 0, s, reinterpret_cast<uint4*>(keys),
                                                reinterpret_cast<uint4*>(values), nk, nv);
     count_launch();
     return cuda_ok();
@@ -572,7 +587,7 @@ int hash_insert(uint64_t* keys, int* values, const int* coords, int n, int capac
                 cudaStream_t s) {
   if (!is_pow2(capacity) || n < 0) return kErrInvalidArg;
   if (n == 0) return kOk;
-  hash_insert_kernel<<<(n + 255) / 256, 256, 0, s>>>(keys, values,
+  wcn_launch(hash_insert_kernel, dim3((n + 255) / 256), dim3(256), 0, s, keys, values,
                                                     reinterpret_cast<const int4*>(coords), n,
                                                     (uint32_t)(capacity - 1), status);
   count_launch();
@@ -583,7 +598,7 @@ int hash_search(const uint64_t* keys, const int* values, const int* queries, int
                 int capacity, cudaStream_t s) {
   if (!is_pow2(capacity) || n < 0) return kErrInvalidArg;
   if (n == 0) return kOk;
-  hash_search_kernel<<<(n + 255) / 256, 256, 0, s>>>(
+  wcn_launch(hash_search_kernel, dim3((n + 255) / 256), dim3(256), 0, s, 
       keys, values, reinterpret_cast<const int4*>(queries), results, n, (uint32_t)(capacity - 1));
   count_launch();
   return cuda_ok();
@@ -597,7 +612,7 @@ int kernel_map_search(const uint64_t* keys, const int* values, int capacity, con
   if (!is_pow2(capacity) || M < 0 || K < 1 || K > 4096) return kErrInvalidArg;
   if (M == 0) return kOk;
   const int nb = kernel_map_num_blocks(M);
-  kernel_map_search_kernel<<<nb, kMapBlock, (size_t)4 * K * sizeof(int), s>>>(
+  wcn_launch(kernel_map_search_kernel, dim3(nb), dim3(kMapBlock), (size_t)4 * K * sizeof(int), s, 
       keys, values, (uint32_t)(capacity - 1), reinterpret_cast<const int4*>(out_coords), M,
       offsets3, K, sx, sy, sz, pair_table, block_counts, mask_keys);
   count_launch();
@@ -613,8 +628,7 @@ int kernel_map_search_sym(const uint64_t* keys, const int* values, int capacity,
   if (K > 1 && cudaMemsetAsync(pair_table + (size_t)(K / 2 + 1) * M, 0xFF,
                                (size_t)(K - K / 2 - 1) * M * 4, s) != cudaSuccess)
     return kErrCuda;
-  kernel_map_search_sym_kernel<<<kernel_map_num_blocks(M), kMapBlock, (size_t)3 * K * sizeof(int),
-                                 s>>>(keys, values, (uint32_t)(capacity - 1),
+  wcn_launch(kernel_map_search_sym_kernel, dim3(kernel_map_num_blocks(M)), dim3(kMapBlock), (size_t)3 * K * sizeof(int), s, keys, values, (uint32_t)(capacity - 1),
                                       reinterpret_cast<const int4*>(coords), M, offsets3, K, status,
                                       pair_table);
   count_launch();
@@ -625,7 +639,7 @@ int kernel_map_stats(const int* pair_table, int K, int M, int* block_counts,
                      unsigned long long* mask_keys, cudaStream_t s) {
   if (K < 1 || M < 0) return kErrInvalidArg;
   if (M == 0) return kOk;
-  kernel_map_stats_kernel<<<kernel_map_num_blocks(M), kMapBlock, 0, s>>>(pair_table, K, M,
+  wcn_launch(kernel_map_stats_kernel, dim3(kernel_map_num_blocks(M)), dim3(kMapBlock), 0, s, pair_table, K, M,
                                                                         block_counts, mask_keys);
   count_launch();
   return cuda_ok();
@@ -634,12 +648,12 @@ int kernel_map_stats(const int* pair_table, int K, int M, int* block_counts,
 int kernel_map_count(int* block_counts, int K, int nb, int* counts, int* offsets, cudaStream_t s) {
   if (K < 1) return kErrInvalidArg;
   if (nb > 0) {
-    block_scan_kernel<<<K, 256, 0, s>>>(block_counts, nb, counts);
+    wcn_launch(block_scan_kernel, dim3(K), dim3(256), 0, s, block_counts, nb, counts);
   count_launch();
   } else {
     if (cudaMemsetAsync(counts, 0, (size_t)K * 4, s) != cudaSuccess) return kErrCuda;
   }
-  offsets_kernel<<<1, 32, 0, s>>>(counts, K, offsets);
+  wcn_launch(offsets_kernel, dim3(1), dim3(32), 0, s, counts, K, offsets);
   count_launch();
   return cuda_ok();
 }
@@ -647,7 +661,7 @@ int kernel_map_count(int* block_counts, int K, int nb, int* counts, int* offsets
 int kernel_map_scatter(const int* pair_table, const int* block_prefix, const int* offsets,
                        int* in_maps, int* out_maps, int K, int M, cudaStream_t s) {
   if (M == 0) return kOk;
-  kernel_map_scatter_kernel<<<kernel_map_num_blocks(M), kMapBlock, 0, s>>>(
+  wcn_launch(kernel_map_scatter_kernel, dim3(kernel_map_num_blocks(M)), dim3(kMapBlock), 0, s, 
       pair_table, block_prefix, offsets, in_maps, out_maps, K, M);
   count_launch();
   return cuda_ok();
@@ -659,7 +673,7 @@ int reverse_pair_table(const int* pair_table, int K, int M, int* rev, int n_in, 
   if (total == 0) return kOk;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 32) blocks = 148 * 32;
-  reverse_table_kernel<<<blocks, 256, 0, s>>>(pair_table, K, M, rev, n_in);
+  wcn_launch(reverse_table_kernel, dim3(blocks), dim3(256), 0, s, pair_table, K, M, rev, n_in);
   count_launch();
   return cuda_ok();
 }
@@ -670,7 +684,7 @@ int csr_to_table(const int* val_maps, const int* row_maps, const int* offsets, i
   if (L_upper <= 0) return kOk;
   int blocks = (L_upper + 255) / 256;
   if (blocks > 148 * 32) blocks = 148 * 32;
-  csr_to_table_kernel<<<blocks, 256, (size_t)(K + 1) * sizeof(int), s>>>(val_maps, row_maps,
+  wcn_launch(csr_to_table_kernel, dim3(blocks), dim3(256), (size_t)(K + 1) * sizeof(int), s, val_maps, row_maps,
                                                                         offsets, K, n_rows, table);
   count_launch();
   return cuda_ok();
@@ -678,7 +692,7 @@ int csr_to_table(const int* val_maps, const int* row_maps, const int* offsets, i
 
 int mask_keys_from_table(const int* table, int K, int M, unsigned long long* keys, cudaStream_t s) {
   if (M == 0) return kOk;
-  mask_keys_kernel<<<(M + 255) / 256, 256, 0, s>>>(table, K, M, keys);
+  wcn_launch(mask_keys_kernel, dim3((M + 255) / 256), dim3(256), 0, s, table, K, M, keys);
   count_launch();
   return cuda_ok();
 }
@@ -707,6 +721,7 @@ size_t sort_workspace_bytes(int M) {
 __global__ void narrow_keys_iota_kernel(const unsigned long long* __restrict__ keys,
                                         unsigned* __restrict__ keys32, int* __restrict__ rows,
                                         int M, int drop_bit, int fold_bits) {
+  pdl_begin();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < M) {
     unsigned k = (unsigned)keys[i];
@@ -747,7 +762,7 @@ int sort_rows_by_key(const unsigned long long* keys, int M, int K, int* rows_out
         fold_bits = key_bits - 24;
         key_bits = 24;
       }
-      narrow_keys_iota_kernel<<<(M + 255) / 256, 256, 0, s>>>(keys, k32_in, rows_in, M, drop_bit,
+      wcn_launch(narrow_keys_iota_kernel, dim3((M + 255) / 256), dim3(256), 0, s, keys, k32_in, rows_in, M, drop_bit,
                                                               fold_bits);
       count_launch();
       cudaError_t e32 = cub::DeviceRadixSort::SortPairs(temp, temp_bytes, k32_in, k32_out, rows_in,
@@ -755,7 +770,7 @@ int sort_rows_by_key(const unsigned long long* keys, int M, int K, int* rows_out
       return e32 == cudaSuccess ? cuda_ok() : kErrCuda;
     }
   }
-  iota_kernel<<<(M + 255) / 256, 256, 0, s>>>(rows_in, M);
+  wcn_launch(iota_kernel, dim3((M + 255) / 256), dim3(256), 0, s, rows_in, M);
   count_launch();
   const int end_bit = K < 64 ? K : 64;
   // LSD radix sort is stable: equal masks keep ascending row order (deterministic tiles)
@@ -771,11 +786,11 @@ int build_tiles(const int* table, int K, int M, const int* sorted_rows, int tile
   if (m_pad % tile_rows != 0 || m_pad < M || K < 1) return kErrInvalidArg;
   const int num_tiles = m_pad / tile_rows;
   if (num_tiles > 0) {
-    build_tiles_kernel<<<num_tiles, tile_rows, 0, s>>>(table, K, M, sorted_rows, tile_rows,
+    wcn_launch(build_tiles_kernel, dim3(num_tiles), dim3(tile_rows), 0, s, table, K, M, sorted_rows, tile_rows,
                                                       step_nbr, step_k, rows_padded, tile_nk);
     count_launch();
   }
-  tile_scan_kernel<<<1, 1024, 0, s>>>(tile_nk, num_tiles, tile_cum, tile_rows / 128, n_range_ctas,
+  wcn_launch(tile_scan_kernel, dim3(1), dim3(1024), 0, s, tile_nk, num_tiles, tile_cum, tile_rows / 128, n_range_ctas,
                                       cta_units);
   count_launch();
   return cuda_ok();

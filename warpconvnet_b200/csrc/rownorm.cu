@@ -96,6 +96,7 @@ __device__ __forceinline__ void rn_merge(const RnMap& m, int c, const float (&a)
 // ---- forward statistics: sums[ch] += sum_r x[r,ch], sums[c+ch] += sum_r x[r,ch]^2 -------------
 template <typename T, int V>
 __global__ void __launch_bounds__(kRnThreads) bn_stats_kernel(const RowNormParams p) {
+  pdl_begin();
   extern __shared__ float sh[];
   const RnMap m = rn_map<V>(p.c);
   float s[V], q[V];
@@ -135,6 +136,7 @@ __global__ void __launch_bounds__(kRnThreads) bn_stats_kernel(const RowNormParam
 // ---- y = act(x * scale + shift (+ res)) -----------------------------------------------------------
 template <typename T, int V>
 __global__ void __launch_bounds__(kRnThreads) scale_shift_act_kernel(const RowNormParams p) {
+  pdl_begin();
   const RnMap m = rn_map<V>(p.c);
   if (!m.active) return;
   float sc[V], sf[V];
@@ -177,6 +179,7 @@ __global__ void __launch_bounds__(kRnThreads) scale_shift_act_kernel(const RowNo
 // ---- backward reduce: dz = dy * (y > 0); sums += (sum dz, sum dz * xhat) ---------------------------
 template <typename T, int V>
 __global__ void __launch_bounds__(kRnThreads, 2) bn_bwd_reduce_kernel(const RowNormParams p) {
+  pdl_begin();
   extern __shared__ float sh[];
   const RnMap m = rn_map<V>(p.c);
   float s1[V], s2[V];
@@ -230,6 +233,7 @@ __global__ void __launch_bounds__(kRnThreads, 2) bn_bwd_reduce_kernel(const RowN
 // (2 resident blocks: 133 registers would leave one block of 256 threads per SM)
 template <typename T, int V>
 __global__ void __launch_bounds__(kRnThreads, 2) bn_bwd_apply_kernel(const RowNormParams p) {
+  pdl_begin();
   const RnMap m = rn_map<V>(p.c);
   if (!m.active) return;
   float mu[V], rs[V], g[V], m1[V], m2[V], msc[V], msh[V];
@@ -302,6 +306,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, int n, int c
                                    float eps, float momentum, float* running_mean,
                                    float* running_var, float* scale, float* shift,
                                    float* mean_rstd) {
+  pdl_begin();
   const int ch = blockIdx.x * blockDim.x + threadIdx.x;
   if (ch >= c) return;
   const double mean = sums[ch] / (double)n;
@@ -362,10 +367,10 @@ static int rn_launch_tv(int which, const RowNormParams& p, cudaStream_t s) {
   }
   const int grid = rn_grid(p.n, p.c, V, occ[which], which == kStats || which == kBwdReduce);
   switch (which) {
-    case kStats: bn_stats_kernel<T, V><<<grid, kRnThreads, sh, s>>>(p); break;
-    case kApply: scale_shift_act_kernel<T, V><<<grid, kRnThreads, 0, s>>>(p); break;
-    case kBwdReduce: bn_bwd_reduce_kernel<T, V><<<grid, kRnThreads, sh, s>>>(p); break;
-    default: bn_bwd_apply_kernel<T, V><<<grid, kRnThreads, 0, s>>>(p); break;
+    case kStats: wcn_launch(bn_stats_kernel<T, V>, dim3(grid), dim3(kRnThreads), sh, s, p); break;
+    case kApply: wcn_launch(scale_shift_act_kernel<T, V>, dim3(grid), dim3(kRnThreads), 0, s, p); break;
+    case kBwdReduce: wcn_launch(bn_bwd_reduce_kernel<T, V>, dim3(grid), dim3(kRnThreads), sh, s, p); break;
+    default: wcn_launch(bn_bwd_apply_kernel<T, V>, dim3(grid), dim3(kRnThreads), 0, s, p); break;
   }
   count_launch();
   return cudaGetLastError() == cudaSuccess ? kOk : kErrCuda;
@@ -404,7 +409,7 @@ int bn_finalize(const double* sums, int n, int c, const float* gamma, const floa
                 float momentum, float* running_mean, float* running_var, float* scale,
                 float* shift, float* mean_rstd, cudaStream_t s) {
   if (c < 1 || n < 1) return kErrInvalidArg;
-  bn_finalize_kernel<<<(c + 127) / 128, 128, 0, s>>>(sums, n, c, gamma, beta, eps, momentum,
+  wcn_launch(bn_finalize_kernel, dim3((c + 127) / 128), dim3(128), 0, s, sums, n, c, gamma, beta, eps, momentum,
                                                      running_mean, running_var, scale, shift,
                                                      mean_rstd);
   count_launch();

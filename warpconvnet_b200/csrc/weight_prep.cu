@@ -20,6 +20,7 @@ namespace wcn {
 // (dgrad) image of the same weights, optionally converting fp32 master weights to the 16-bit
 // compute type on the way (replaces weight.to(bf16) + two image launches per layer and step).
 __global__ void weight_image_kernel(const WeightPrepParams pa, const WeightPrepParams pb) {
+  pdl_begin();
   const WeightPrepParams& p = blockIdx.y == 0 ? pa : pb;
   const int bn = p.gps * p.rg;
   const int cdim = p.gps * p.cg;
@@ -81,7 +82,7 @@ int launch_weight_image(const WeightPrepParams& p, const WeightPrepParams* secon
   if (total == 0) return kOk;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  weight_image_kernel<<<dim3(blocks, second ? 2 : 1), 256, 0, stream>>>(p, second ? *second : p);
+  wcn_launch(weight_image_kernel, dim3(dim3(blocks, second ? 2 : 1)), dim3(256), 0, stream, p, second ? *second : p);
   count_launch();
   return cudaGetLastError() == cudaSuccess ? kOk : kErrCuda;
 }
