@@ -552,3 +552,44 @@ def test_group_conv_with_fewer_than_8_channels_per_group(groups, cin, cout):
     assert oconv.rel_max_err(v.batched_features.batched_tensor.grad, dx_ref) < 5e-3
     assert conv.weight.grad.shape == conv.weight.shape
     assert oconv.rel_max_err(conv.weight.grad, dw_ref) < 1e-3
+
+
+# ------------------------------------------------------------------------------------------------
+# single-kernel mask sort (csrc/cuhash.cu mask_sort_kernel) vs a stable argsort of the same keys
+# ------------------------------------------------------------------------------------------------
+def _narrowed(keys: torch.Tensor, K: int) -> torch.Tensor:
+    """The sort key wcn_sort_rows_by_key derives from a K-bit mask (K <= 32): masks of 25..32 bits
+    are compressed to 24 (centre bit of an odd K dropped, low bits XOR-folded)."""
+    k = keys.clone() & 0xFFFFFFFF
+    bits = K
+    if K > 24:
+        if K & 1:
+            d = K // 2
+            k = ((k >> (d + 1)) << d) | (k & ((1 << d) - 1))
+            bits -= 1
+        f = bits - 24
+        if f > 0:
+            k = (k >> f) ^ (k & ((1 << f) - 1))
+    return k
+
+
+@pytest.mark.parametrize("K", [8, 27, 32, 24, 17])
+@pytest.mark.parametrize("M", [1, 31, 513, 7001, 200704, (1 << 20) + 5])
+def test_mask_sort_is_a_stable_sort_of_the_narrowed_keys(K, M):
+    from warpconvnet_b200 import _ops
+    from warpconvnet_b200._lib import check, lib
+    g = torch.Generator().manual_seed(K * 1000 + M % 997)
+    # few distinct values (structured masks) mixed with random ones
+    pool = torch.randint(0, 1 << K, (37,), generator=g, dtype=torch.int64)
+    keys = torch.where(torch.rand(M, generator=g) < 0.7,
+                       pool[torch.randint(0, 37, (M,), generator=g)],
+                       torch.randint(0, 1 << K, (M,), generator=g, dtype=torch.int64)).cuda()
+    rows = torch.empty(M, dtype=torch.int32, device="cuda")
+    ws_bytes = lib.wcn_sort_workspace_bytes(M)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+    for _ in range(2):  # twice on the same workspace: the barrier counter is re-armed per launch
+        check(lib.wcn_sort_rows_by_key(keys.data_ptr(), M, K, rows.data_ptr(), ws.data_ptr(), ws_bytes,
+                                       _ops._stream()), "sort_rows_by_key")
+        torch.cuda.synchronize()
+        expect = torch.argsort(_narrowed(keys, K), stable=True)
+        assert torch.equal(rows.long(), expect)

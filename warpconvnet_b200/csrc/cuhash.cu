@@ -699,13 +699,21 @@ int mask_keys_from_table(const int* table, int K, int M, unsigned long long* key
 
 // workspace: [keys_out M*8][rows_in M*4][cub temp]
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+constexpr int kSortThreads = 512;     // single-kernel mask sort (mask_sort_kernel below)
+constexpr int kSortMaxCtas = 148;
+constexpr int kSortMaxRows = 1 << 20;
 
 size_t sort_workspace_bytes(int M) {
   size_t temp = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, temp, (const unsigned long long*)nullptr,
                                   (unsigned long long*)nullptr, (const int*)nullptr, (int*)nullptr,
                                   M > 0 ? M : 1, 0, 64, (cudaStream_t)0);
-  return align_up((size_t)M * 8, 256) + align_up((size_t)M * 4, 256) + align_up(temp, 256) + 256;
+  const size_t cub_bytes =
+      align_up((size_t)M * 8, 256) + align_up((size_t)M * 4, 256) + align_up(temp, 256) + 256;
+  // single-kernel mask sort: 2 key + 2 value buffers, the [cta][256] count matrix, barrier words
+  const size_t own_bytes = 4 * align_up((size_t)M * 4, 256) +
+                           align_up((size_t)kSortMaxCtas * 256 * 4, 256) + 256;
+  return cub_bytes > own_bytes ? cub_bytes : own_bytes;
 }
 
 // K <= 32: the offset masks fit 32 bits; sorting (u32 key, row) pairs moves 8 instead of 12 bytes
@@ -732,8 +740,148 @@ __global__ void narrow_keys_iota_kernel(const unsigned long long* __restrict__ k
   }
 }
 
+// --------------------------------------------------------------------------------------------
+// Mask sort in ONE kernel (maps of up to 2^20 rows, K <= 32). The CUB onesweep sort of the 24-bit
+// mask keys is latency-bound at this size (3 passes of 12.7 us with ~50 blocks each, plus a
+// histogram, a scan and the key-narrowing kernel: 45 us of the C3 step). Here one persistent grid
+// (<= 148 CTAs, all resident) runs every 8-bit LSD pass itself: per pass a shared-memory digit
+// histogram of the CTA's contiguous chunk, a grid barrier, the CTA's global bases from the
+// [cta][digit] count matrix (coalesced column reads + a block scan over the digits), and a STABLE
+// scatter (warps take turns inside a 512-key round, lanes ranked with match.any). Pass 0 narrows
+// the 64-bit masks on the fly (centre bit dropped, low bits folded) and creates the row iota, so
+// the separate narrowing kernel is gone too. The barrier is a monotonic counter in the workspace,
+// zeroed by the launcher.
+// --------------------------------------------------------------------------------------------
+
+struct MaskSortParams {
+  const unsigned long long* keys64;
+  unsigned* k_a;   // ping
+  unsigned* k_b;   // pong
+  int* v_a;
+  int* v_b;
+  int* rows_out;   // values of the last pass
+  int* counts;     // [gridDim.x][256]
+  unsigned* bar;   // arrivals (monotonic counter, zero at launch)
+  int M, per_cta, passes, drop_bit, fold_bits;
+};
+
+__device__ __forceinline__ unsigned narrow_mask_key(unsigned long long k64, int drop_bit,
+                                                    int fold_bits) {
+  unsigned k = (unsigned)k64;
+  if (drop_bit >= 0) k = ((k >> (drop_bit + 1)) << drop_bit) | (k & ((1u << drop_bit) - 1u));
+  if (fold_bits > 0) k = (k >> fold_bits) ^ (k & ((1u << fold_bits) - 1u));
+  return k;
+}
+
+__device__ __forceinline__ void sort_grid_barrier(unsigned* bar, unsigned n_ctas, unsigned& gen) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1u);
+    const unsigned target = (gen + 1u) * n_ctas;
+    unsigned seen;
+    do {
+      asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(seen) : "l"(bar) : "memory");
+    } while (seen < target);
+    __threadfence();
+  }
+  ++gen;
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kSortThreads, 1) mask_sort_kernel(const MaskSortParams p) {
+  pdl_begin();
+  __shared__ int s_hist[256];      // histogram of the chunk, then running digit counters
+  __shared__ int s_base[256];      // global position of the CTA's first key of every digit
+  __shared__ int s_scan[256];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int G = gridDim.x, c = blockIdx.x;
+  const int begin = min(p.M, c * p.per_cta), end = min(p.M, begin + p.per_cta);
+  unsigned gen = 0;
+  for (int pass = 0; pass < p.passes; ++pass) {
+    const unsigned* k_src = (pass & 1) ? p.k_b : p.k_a;
+    const int* v_src = (pass & 1) ? p.v_b : p.v_a;
+    unsigned* k_dst = (pass & 1) ? p.k_a : p.k_b;
+    int* v_dst = (pass == p.passes - 1) ? p.rows_out : ((pass & 1) ? p.v_a : p.v_b);
+    const int shift = 8 * pass;
+    auto load_key = [&](int i) -> unsigned {
+      // __ldcg: written by other CTAs in the previous pass (never trust a stale L1 line)
+      return pass == 0 ? narrow_mask_key(__ldg(p.keys64 + i), p.drop_bit, p.fold_bits)
+                       : __ldcg(k_src + i);
+    };
+    // ---- phase 1: digit histogram of this CTA's chunk ------------------------------------------
+    if (tid < 256) s_hist[tid] = 0;
+    __syncthreads();
+    for (int i = begin + tid; i < end; i += kSortThreads)
+      atomicAdd(&s_hist[(load_key(i) >> shift) & 255u], 1);
+    __syncthreads();
+    if (tid < 256) p.counts[c * 256 + tid] = s_hist[tid];
+    sort_grid_barrier(p.bar, (unsigned)G, gen);
+    // ---- phase 2: base[d] = (keys of smaller digits, all CTAs) + (digit d in earlier CTAs) ----
+    if (tid < 256) {
+      int before = 0, total = 0;
+      for (int cc = 0; cc < G; ++cc) {
+        const int v = __ldcg(p.counts + cc * 256 + tid);
+        total += v;
+        if (cc < c) before += v;
+      }
+      s_scan[tid] = total;
+      s_base[tid] = before;
+      s_hist[tid] = 0;  // now: keys of digit d already placed by this CTA
+    }
+    __syncthreads();
+    if (warp == 0) {  // exclusive scan of the 256 digit totals: 8 per lane
+      int loc[8], sum = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { loc[j] = s_scan[lane * 8 + j]; sum += loc[j]; }
+      int incl = sum;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+      }
+      int run = incl - sum;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s_scan[lane * 8 + j] = run; run += loc[j]; }
+    }
+    __syncthreads();
+    if (tid < 256) s_base[tid] += s_scan[tid];
+    __syncthreads();
+    // ---- phase 3: stable scatter, 512 keys per round, warps in order -------------------------
+    for (int r0 = begin; r0 < end; r0 += kSortThreads) {
+      const int i = r0 + tid;
+      const bool live = i < end;
+      unsigned key = 0u;
+      int val = 0;
+      if (live) {
+        key = load_key(i);
+        val = pass == 0 ? i : __ldcg(v_src + i);
+      }
+      const unsigned digit = (key >> shift) & 255u;
+      // lanes of the warp with the same digit (dead lanes get a private value)
+      const unsigned peers = __match_any_sync(0xffffffffu, live ? digit : (256u + lane));
+      const int rank_in_warp = __popc(peers & ((1u << lane) - 1u));
+      int pos = 0;
+      for (int w = 0; w < kSortThreads / 32; ++w) {
+        if (warp == w && live) {
+          pos = s_base[digit] + s_hist[digit] + rank_in_warp;
+        }
+        __syncwarp();
+        if (warp == w && live && rank_in_warp == 0) s_hist[digit] += __popc(peers);
+        __syncthreads();
+      }
+      if (live) {
+        if (pass != p.passes - 1) k_dst[pos] = key;
+        v_dst[pos] = val;
+      }
+    }
+    if (pass != p.passes - 1) sort_grid_barrier(p.bar, (unsigned)G, gen);
+  }
+}
+
 // bring-up builds (WCN_BRINGUP=1 build.sh): WCN_FOLD_MASK_KEYS=0 in the environment keeps the
 // full-width sort for A/B measurements (read once); the default build always compresses
+static constexpr bool g_own_mask_sort = true;  // false: CUB onesweep for every size (A/B builds)
 #ifdef WCN_BRINGUP
 static const bool g_fold_mask_keys = [] {
   const char* v = getenv("WCN_FOLD_MASK_KEYS");
@@ -752,6 +900,40 @@ int sort_rows_by_key(const unsigned long long* keys, int M, int K, int* rows_out
   int* rows_in = reinterpret_cast<int*>(ws + align_up((size_t)M * 8, 256));
   void* temp = ws + align_up((size_t)M * 8, 256) + align_up((size_t)M * 4, 256);
   size_t temp_bytes = ws_bytes - (align_up((size_t)M * 8, 256) + align_up((size_t)M * 4, 256));
+  if (K <= 32 && M <= kSortMaxRows && g_own_mask_sort) {
+    int drop_bit = -1, fold_bits = 0, key_bits = K;
+    if (K > 24 && g_fold_mask_keys) {
+      if (K & 1) { drop_bit = K / 2; --key_bits; }
+      fold_bits = key_bits - 24;
+      key_bits = 24;
+    }
+    const size_t mb = align_up((size_t)M * 4, 256);
+    MaskSortParams sp;
+    sp.keys64 = keys;
+    sp.k_a = reinterpret_cast<unsigned*>(ws);
+    sp.k_b = reinterpret_cast<unsigned*>(ws + mb);
+    sp.v_a = reinterpret_cast<int*>(ws + 2 * mb);
+    sp.v_b = reinterpret_cast<int*>(ws + 3 * mb);
+    sp.counts = reinterpret_cast<int*>(ws + 4 * mb);
+    sp.bar = reinterpret_cast<unsigned*>(ws + 4 * mb + align_up((size_t)kSortMaxCtas * 256 * 4, 256));
+    sp.rows_out = rows_out;
+    sp.M = M;
+    sp.passes = (key_bits + 7) / 8;
+    sp.drop_bit = drop_bit;
+    sp.fold_bits = fold_bits;
+    int ctas = (M + kSortThreads - 1) / kSortThreads;
+    if (ctas > kSortMaxCtas) ctas = kSortMaxCtas;
+    int sms = 0, dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0 &&
+        ctas > sms)
+      ctas = sms;  // every CTA must be resident: the passes meet at a grid barrier
+    sp.per_cta = ((M + ctas - 1) / ctas + kSortThreads - 1) / kSortThreads * kSortThreads;
+    if (cudaMemsetAsync(sp.bar, 0, 8, s) != cudaSuccess) return kErrCuda;  // barrier counter
+    wcn_launch(mask_sort_kernel, dim3(ctas), dim3(kSortThreads), 0, s, sp);
+    count_launch();
+    return cuda_ok();
+  }
   if (K <= 32) {
     unsigned* k32_in = reinterpret_cast<unsigned*>(ws);            // the u64 key_out region holds
     unsigned* k32_out = k32_in + align_up((size_t)M, 32);          // both u32 key buffers
