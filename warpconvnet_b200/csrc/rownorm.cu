@@ -177,8 +177,15 @@ __global__ void __launch_bounds__(kRnThreads) scale_shift_act_kernel(const RowNo
 }
 
 // ---- backward reduce: dz = dy * (y > 0); sums += (sum dz, sum dz * xhat) ---------------------------
-template <typename T, int V>
-__global__ void __launch_bounds__(kRnThreads, 2) bn_bwd_reduce_kernel(const RowNormParams p) {
+// Register diet (round 2): the kernel streams two tensors and is bound by the bytes its resident
+// threads keep in flight, so occupancy matters more than instruction count. Per channel only the
+// mean and the two mask constants stay in registers; sum dz * (x - mean) is accumulated and the
+// factor rstd is applied once per block when the partial sums leave (4 resident blocks per SM
+// instead of 2: 2.2 -> TB/s figures in profiles/r2_norm_kernels.md).
+// MASK: 0 = no ReLU behind the norm, 1 = mask from the saved output y_in, 2 = mask recomputed from
+// x (x * mask_scale + mask_shift > 0). A template parameter: the unused paths cost registers.
+template <typename T, int V, int MASK>
+__global__ void __launch_bounds__(kRnThreads, 3) bn_bwd_reduce_kernel(const RowNormParams p) {
   pdl_begin();
   extern __shared__ float sh[];
   const RnMap m = rn_map<V>(p.c);
@@ -186,30 +193,31 @@ __global__ void __launch_bounds__(kRnThreads, 2) bn_bwd_reduce_kernel(const RowN
 #pragma unroll
   for (int i = 0; i < V; ++i) s1[i] = s2[i] = 0.f;
   if (m.active) {
-    float mu[V], rs[V], msc[V], msh[V];
-    const bool mask_x = p.mask_scale != nullptr;  // recompute the ReLU mask from x
+    float mu[V], msc[MASK == 2 ? V : 1], msh[MASK == 2 ? V : 1];
+    constexpr bool mask_x = MASK == 2;
 #pragma unroll
     for (int i = 0; i < V; ++i) {
       const int ch = min(m.vc * V + i, p.c - 1);
       mu[i] = __ldg(p.mean_rstd + ch);
-      rs[i] = __ldg(p.mean_rstd + p.c + ch);
-      msc[i] = mask_x ? __ldg(p.mask_scale + ch) : 0.f;
-      msh[i] = mask_x ? __ldg(p.mask_shift + ch) : 1.f;
+      if constexpr (MASK == 2) {
+        msc[i] = __ldg(p.mask_scale + ch);
+        msh[i] = __ldg(p.mask_shift + ch);
+      }
     }
     const T* x = reinterpret_cast<const T*>(p.x) + m.vc * V;
     const T* dy = reinterpret_cast<const T*>(p.dy) + m.vc * V;
-    const T* yin = (p.y_in && !mask_x) ? reinterpret_cast<const T*>(p.y_in) + m.vc * V : nullptr;
+    const T* yin = MASK == 1 ? reinterpret_cast<const T*>(p.y_in) + m.vc * V : nullptr;
     constexpr int U = 2;  // rows in flight per thread
     const long long stride = (long long)gridDim.x * m.rpb;
     for (long long r0 = (long long)blockIdx.x * m.rpb + m.rl; r0 < p.n; r0 += U * stride) {
-      float fx[U][V], fd[U][V], fy[U][V];
+      float fx[U][V], fd[U][V], fy[MASK == 1 ? U : 1][V];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const long long r = r0 + u * stride;
         if (r < p.n) {
           load_vec<T, V>(x + r * p.ld_x, fx[u]);
           load_vec<T, V>(dy + r * p.ld_dy, fd[u]);
-          if (yin) load_vec<T, V>(yin + r * p.ld_yin, fy[u]);
+          if constexpr (MASK == 1) load_vec<T, V>(yin + r * p.ld_yin, fy[u]);
         }
       }
 #pragma unroll
@@ -217,83 +225,104 @@ __global__ void __launch_bounds__(kRnThreads, 2) bn_bwd_reduce_kernel(const RowN
         if (r0 + u * stride >= p.n) break;
 #pragma unroll
         for (int i = 0; i < V; ++i) {
-          const bool off = yin ? !(fy[u][i] > 0.f)
-                               : (mask_x && !(fmaf(fx[u][i], msc[i], msh[i]) > 0.f));
+          bool off = false;
+          if constexpr (MASK == 1) off = !(fy[u][i] > 0.f);
+          if constexpr (mask_x) off = !(fmaf(fx[u][i], msc[i], msh[i]) > 0.f);
           const float d = off ? 0.f : fd[u][i];
           s1[i] += d;
-          s2[i] = fmaf(d, (fx[u][i] - mu[i]) * rs[i], s2[i]);
+          s2[i] = fmaf(d, fx[u][i] - mu[i], s2[i]);
         }
       }
     }
   }
-  rn_merge<V>(m, p.c, s1, s2, p.sums, sh);
+  // block merge; the second half leaves multiplied by rstd: sum dz * xhat = rstd * sum dz * (x - mean)
+  for (int i = threadIdx.x; i < 2 * p.c; i += kRnThreads) sh[i] = 0.f;
+  __syncthreads();
+  if (m.active) {
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const int ch = m.vc * V + i;
+      if (ch < p.c) {
+        atomicAdd(sh + ch, s1[i]);
+        atomicAdd(sh + p.c + ch, s2[i]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * p.c; i += kRnThreads) {
+    const float f = i < p.c ? 1.f : __ldg(p.mean_rstd + i);  // mean_rstd[c + ch] = rstd
+    atomicAdd(p.sums + i, (double)sh[i] * (double)f);
+  }
 }
 
 // ---- backward apply: dx = gamma * rstd * (dz - s1/n - xhat * s2/n); dres = dz ----------------------
-// (2 resident blocks: 133 registers would leave one block of 256 threads per SM)
-template <typename T, int V>
-__global__ void __launch_bounds__(kRnThreads, 2) bn_bwd_apply_kernel(const RowNormParams p) {
+// folded per channel into dx = A * dz + B * x + C (A = gamma * rstd, B = -A * rstd * s2/n,
+// C = -A * s1/n - B * mean): three constants + the two mask constants per channel in registers.
+template <typename T, int V, int MASK, bool TRAIN>
+__global__ void __launch_bounds__(kRnThreads, 3) bn_bwd_apply_kernel(const RowNormParams p) {
   pdl_begin();
   const RnMap m = rn_map<V>(p.c);
   if (!m.active) return;
-  float mu[V], rs[V], g[V], m1[V], m2[V], msc[V], msh[V];
-  const bool mask_x = p.mask_scale != nullptr && p.training;  // x is only read in training mode
+  float ca[V], cb[TRAIN ? V : 1], cc[TRAIN ? V : 1], msc[MASK == 2 ? V : 1], msh[MASK == 2 ? V : 1];
+  constexpr bool mask_x = MASK == 2;  // (the launcher only picks it in training mode: x is read)
   const float inv_n = 1.f / (float)p.n;
 #pragma unroll
   for (int i = 0; i < V; ++i) {
     const int ch = min(m.vc * V + i, p.c - 1);
-    g[i] = __ldg(p.scale + ch);  // gamma (training) or gamma * rstd_running (eval)
-    msc[i] = mask_x ? __ldg(p.mask_scale + ch) : 0.f;
-    msh[i] = mask_x ? __ldg(p.mask_shift + ch) : 1.f;
-    if (p.training) {
-      mu[i] = __ldg(p.mean_rstd + ch);
-      rs[i] = __ldg(p.mean_rstd + p.c + ch);
-      m1[i] = (float)(p.sums[ch] * (double)inv_n);
-      m2[i] = (float)(p.sums[p.c + ch] * (double)inv_n);
+    const float g = __ldg(p.scale + ch);  // gamma (training) or gamma * rstd_running (eval)
+    if constexpr (MASK == 2) {
+      msc[i] = __ldg(p.mask_scale + ch);
+      msh[i] = __ldg(p.mask_shift + ch);
+    }
+    if constexpr (TRAIN) {
+      const float mu = __ldg(p.mean_rstd + ch);
+      const float rs = __ldg(p.mean_rstd + p.c + ch);
+      const float m1 = (float)(p.sums[ch] * (double)inv_n);
+      const float m2 = (float)(p.sums[p.c + ch] * (double)inv_n);
+      ca[i] = g * rs;
+      cb[i] = -ca[i] * rs * m2;
+      cc[i] = -ca[i] * m1 - cb[i] * mu;
     } else {
-      mu[i] = 0.f; rs[i] = 1.f; m1[i] = 0.f; m2[i] = 0.f;
+      ca[i] = g;
     }
   }
   const T* x = reinterpret_cast<const T*>(p.x) + m.vc * V;
   const T* dy = reinterpret_cast<const T*>(p.dy) + m.vc * V;
-  const T* yin = (p.y_in && !mask_x) ? reinterpret_cast<const T*>(p.y_in) + m.vc * V : nullptr;
+  const T* yin = MASK == 1 ? reinterpret_cast<const T*>(p.y_in) + m.vc * V : nullptr;
   T* dx = reinterpret_cast<T*>(p.y) + m.vc * V;
   T* dres = p.dres ? reinterpret_cast<T*>(p.dres) + m.vc * V : nullptr;
   constexpr int U = 2;  // rows in flight per thread
   const long long stride = (long long)gridDim.x * m.rpb;
   for (long long r0 = (long long)blockIdx.x * m.rpb + m.rl; r0 < p.n; r0 += U * stride) {
-    float fx[U][V], fd[U][V], fy[U][V];
+    float fx[TRAIN ? U : 1][V], fd[U][V], fy[MASK == 1 ? U : 1][V];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long r = r0 + u * stride;
       if (r < p.n) {
         load_vec<T, V>(dy + r * p.ld_dy, fd[u]);
-        if (yin) load_vec<T, V>(yin + r * p.ld_yin, fy[u]);
-        if (p.training) load_vec<T, V>(x + r * p.ld_x, fx[u]);
+        if constexpr (MASK == 1) load_vec<T, V>(yin + r * p.ld_yin, fy[u]);
+        if constexpr (TRAIN) load_vec<T, V>(x + r * p.ld_x, fx[u]);
       }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long r = r0 + u * stride;
       if (r >= p.n) break;
-      if (yin) {
+      if constexpr (MASK == 1) {
 #pragma unroll
         for (int i = 0; i < V; ++i) fd[u][i] = fy[u][i] > 0.f ? fd[u][i] : 0.f;
-      } else if (mask_x) {
+      } else if constexpr (mask_x) {
 #pragma unroll
         for (int i = 0; i < V; ++i)
           fd[u][i] = fmaf(fx[u][i], msc[i], msh[i]) > 0.f ? fd[u][i] : 0.f;
       }
       if (dres) store_vec<T, V>(dres + r * p.ld_dres, fd[u]);
-      if (p.training) {
+      if constexpr (TRAIN) {
 #pragma unroll
-        for (int i = 0; i < V; ++i) {
-          const float xh = (fx[u][i] - mu[i]) * rs[i];
-          fd[u][i] = g[i] * rs[i] * (fd[u][i] - m1[i] - xh * m2[i]);
-        }
+        for (int i = 0; i < V; ++i) fd[u][i] = fmaf(ca[i], fd[u][i], fmaf(cb[i], fx[u][i], cc[i]));
       } else {
 #pragma unroll
-        for (int i = 0; i < V; ++i) fd[u][i] *= g[i];
+        for (int i = 0; i < V; ++i) fd[u][i] *= ca[i];
       }
       store_vec<T, V>(dx + r * p.ld_y, fd[u]);
     }
@@ -361,16 +390,34 @@ static int rn_launch_tv(int which, const RowNormParams& p, cudaStream_t s) {
     switch (which) {
       case kStats: occ[which] = rn_occupancy(bn_stats_kernel<T, V>, sh); break;
       case kApply: occ[which] = rn_occupancy(scale_shift_act_kernel<T, V>, 0); break;
-      case kBwdReduce: occ[which] = rn_occupancy(bn_bwd_reduce_kernel<T, V>, sh); break;
-      default: occ[which] = rn_occupancy(bn_bwd_apply_kernel<T, V>, 0); break;
+      case kBwdReduce: occ[which] = rn_occupancy(bn_bwd_reduce_kernel<T, V, 2>, sh); break;
+      default: occ[which] = rn_occupancy(bn_bwd_apply_kernel<T, V, 2, true>, 0); break;
     }
   }
   const int grid = rn_grid(p.n, p.c, V, occ[which], which == kStats || which == kBwdReduce);
   switch (which) {
     case kStats: wcn_launch(bn_stats_kernel<T, V>, dim3(grid), dim3(kRnThreads), sh, s, p); break;
     case kApply: wcn_launch(scale_shift_act_kernel<T, V>, dim3(grid), dim3(kRnThreads), 0, s, p); break;
-    case kBwdReduce: wcn_launch(bn_bwd_reduce_kernel<T, V>, dim3(grid), dim3(kRnThreads), sh, s, p); break;
-    default: wcn_launch(bn_bwd_apply_kernel<T, V>, dim3(grid), dim3(kRnThreads), 0, s, p); break;
+    case kBwdReduce: {
+      const int mask = p.mask_scale != nullptr ? 2 : (p.y_in != nullptr ? 1 : 0);
+      if (mask == 2) wcn_launch(bn_bwd_reduce_kernel<T, V, 2>, dim3(grid), dim3(kRnThreads), sh, s, p);
+      else if (mask == 1) wcn_launch(bn_bwd_reduce_kernel<T, V, 1>, dim3(grid), dim3(kRnThreads), sh, s, p);
+      else wcn_launch(bn_bwd_reduce_kernel<T, V, 0>, dim3(grid), dim3(kRnThreads), sh, s, p);
+      break;
+    }
+    default: {
+      // the mask is recomputed from x only in training mode (eval mode does not read x)
+      const int mask = (p.mask_scale != nullptr && p.training) ? 2 : (p.y_in != nullptr ? 1 : 0);
+#define WCN_BN_APPLY(MK, TR) \
+  wcn_launch(bn_bwd_apply_kernel<T, V, MK, TR>, dim3(grid), dim3(kRnThreads), 0, s, p)
+      if (p.training) {
+        if (mask == 2) WCN_BN_APPLY(2, true); else if (mask == 1) WCN_BN_APPLY(1, true); else WCN_BN_APPLY(0, true);
+      } else {
+        if (mask == 1) WCN_BN_APPLY(1, false); else WCN_BN_APPLY(0, false);
+      }
+#undef WCN_BN_APPLY
+      break;
+    }
   }
   count_launch();
   return cudaGetLastError() == cudaSuccess ? kOk : kErrCuda;
