@@ -145,6 +145,11 @@ size_t wcn_sort_workspace_bytes(int M);
  * keep the numeric order with WCN_FOLD_MASK_KEYS=0). Any order is a valid plan. */
 int wcn_sort_rows_by_key(const uint64_t* keys, int M, int K, int32_t* rows_out, void* workspace,
                          size_t workspace_bytes, void* stream);
+/* Same order, with the masks derived from the table inside the sort kernel's first pass (no
+ * wcn_mask_keys / wcn_kernel_map_stats pass over the table on the critical path). Returns -2
+ * (unsupported shape) for K > 32 or M > 2^20: use wcn_mask_keys + wcn_sort_rows_by_key then. */
+int wcn_sort_rows_by_table(const int32_t* table, int K, int M, int32_t* rows_out, void* workspace,
+                           size_t workspace_bytes, void* stream);
 /* Tile plan in mask-sorted order. tile_rows is 128 or 256, m_pad = ceil(M/tile_rows)*tile_rows,
  * num_tiles = m_pad / tile_rows. For tile t (sorted positions t*tile_rows ...):
  *   rows_padded[p]                 = sorted_rows[p]  (-1 for padding)

@@ -593,3 +593,28 @@ def test_mask_sort_is_a_stable_sort_of_the_narrowed_keys(K, M):
         torch.cuda.synchronize()
         expect = torch.argsort(_narrowed(keys, K), stable=True)
         assert torch.equal(rows.long(), expect)
+
+
+@pytest.mark.parametrize("K,M", [(27, 200704), (27, 5000), (8, 30000), (9, 700), (32, 4097)])
+def test_mask_sort_from_the_table_equals_the_sort_of_explicit_masks(K, M):
+    """wcn_sort_rows_by_table derives the row masks inside the sort kernel: same permutation as
+    wcn_mask_keys + wcn_sort_rows_by_key on the same table."""
+    from warpconvnet_b200 import _ops
+    from warpconvnet_b200._lib import check, lib
+    g = torch.Generator().manual_seed(K + M)
+    table = torch.where(torch.rand(K, M, generator=g) < 0.4,
+                        torch.randint(0, M, (K, M), generator=g), torch.full((K, M), -1)).int().cuda()
+    ws_bytes = lib.wcn_sort_workspace_bytes(M)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+    r_tab = torch.empty(M, dtype=torch.int32, device="cuda")
+    r_key = torch.empty(M, dtype=torch.int32, device="cuda")
+    check(lib.wcn_sort_rows_by_table(table.data_ptr(), K, M, r_tab.data_ptr(), ws.data_ptr(), ws_bytes,
+                                     _ops._stream()), "sort_rows_by_table")
+    keys = _ops.mask_keys(table)
+    check(lib.wcn_sort_rows_by_key(keys.data_ptr(), M, K, r_key.data_ptr(), ws.data_ptr(), ws_bytes,
+                                   _ops._stream()), "sort_rows_by_key")
+    torch.cuda.synchronize()
+    assert torch.equal(r_tab, r_key)
+    bits = (table >= 0).long()
+    masks = (bits << torch.arange(K, device="cuda").view(K, 1)).sum(0)
+    assert torch.equal(r_tab.long(), torch.argsort(_narrowed(masks, K), stable=True))

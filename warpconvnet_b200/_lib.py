@@ -67,6 +67,8 @@ SIGNATURES = {
     "wcn_sort_workspace_bytes": (c_size_t, [c_int]),
     "wcn_sort_rows_by_key": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t,
                                      c_void_p]),
+    "wcn_sort_rows_by_table": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t,
+                                       c_void_p]),
     "wcn_build_tiles": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "wcn_knn_workspace_bytes": (c_size_t, [c_int, c_int]),

@@ -123,22 +123,34 @@ def kernel_map_search(keys: Tensor, values: Tensor, out_coords: Tensor, offsets3
     return pair_table, block_counts, mask_keys
 
 
+def kernel_map_stats(pair_table: Tensor, want_mask: bool = True):
+    """(block_counts[K, nb], mask_keys[M] | None) of a finished pair table."""
+    K, M = pair_table.shape
+    dev = pair_table.device
+    nb = lib.wcn_kernel_map_num_blocks(M)
+    block_counts = torch.empty((K, nb), dtype=torch.int32, device=dev)
+    mask_keys = torch.empty(M, dtype=torch.int64, device=dev) if want_mask else None
+    check(lib.wcn_kernel_map_stats(_p(pair_table), K, M, _p(block_counts), _p(mask_keys),
+                                   _stream()), "kernel_map_stats")
+    return block_counts, mask_keys
+
+
 def kernel_map_search_symmetric(keys: Tensor, values: Tensor, coords: Tensor, offsets3: Tensor,
-                                status: Tensor):
+                                status: Tensor, with_stats: bool = True):
     """Submanifold kernel map (in == out coordinates, odd kernel, stride 1): half the probes, hits
-    mirrored. Returns (pair_table[K,M], block_counts[K,nb], mask_keys[M])."""
+    mirrored. Returns (pair_table[K,M], block_counts[K,nb], mask_keys[M]); ``with_stats=False``
+    returns the table only (None, None) — the caller runs kernel_map_stats where it needs it."""
     _require_cuda(keys, values, coords, offsets3, status)
     M, K = coords.shape[0], offsets3.shape[0]
     dev = coords.device
     nb = lib.wcn_kernel_map_num_blocks(M)
     pair_table = torch.empty((K, M), dtype=torch.int32, device=dev)
-    block_counts = torch.empty((K, nb), dtype=torch.int32, device=dev)
-    mask_keys = torch.empty(M, dtype=torch.int64, device=dev)
     check(lib.wcn_kernel_map_search_symmetric(_p(keys), _p(values), keys.numel(), _p(coords), M,
                                               _p(offsets3), K, _p(status), _p(pair_table),
                                               _stream()), "kernel_map_search_symmetric")
-    check(lib.wcn_kernel_map_stats(_p(pair_table), K, M, _p(block_counts), _p(mask_keys),
-                                   _stream()), "kernel_map_stats")
+    if not with_stats:
+        return pair_table, None, None
+    block_counts, mask_keys = kernel_map_stats(pair_table)
     return pair_table, block_counts, mask_keys
 
 
@@ -244,14 +256,22 @@ def build_tile_plan(table: Tensor, keys: Optional[Tensor] = None,
     dev = table.device
     if tile_rows is None:
         tile_rows = 256 if M >= _TILE256_MIN_ROWS else TILE_M
-    if keys is None:
-        keys = mask_keys(table)
     rows_sorted = torch.empty(M, dtype=torch.int32, device=dev)
     ws_bytes = lib.wcn_sort_workspace_bytes(M)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    check(lib.wcn_sort_rows_by_key(_p(keys), M, K if key_bits is None else key_bits,
-                                   _p(rows_sorted), _p(ws), ws_bytes, _stream()),
-          "sort_rows_by_key")
+    status = -2
+    if keys is None and key_bits is None:
+        # masks derived from the table inside the sort kernel (K <= 32, M <= 2^20)
+        status = lib.wcn_sort_rows_by_table(_p(table), K, M, _p(rows_sorted), _p(ws), ws_bytes,
+                                            _stream())
+        if status not in (0, -2):
+            check(status, "sort_rows_by_table")
+    if status == -2:
+        if keys is None:
+            keys = mask_keys(table)
+        check(lib.wcn_sort_rows_by_key(_p(keys), M, K if key_bits is None else key_bits,
+                                       _p(rows_sorted), _p(ws), ws_bytes, _stream()),
+              "sort_rows_by_key")
     m_pad = (M + tile_rows - 1) // tile_rows * tile_rows
     num_tiles = m_pad // tile_rows
     step_nbr = torch.empty((max(num_tiles, 1), K, tile_rows), dtype=torch.int32, device=dev)

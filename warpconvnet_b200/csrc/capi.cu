@@ -27,6 +27,7 @@ int mask_keys_from_table(const int*, int, int, unsigned long long*, cudaStream_t
 int csr_to_table(const int*, const int*, const int*, int, int, int, int*, cudaStream_t);
 size_t sort_workspace_bytes(int);
 int sort_rows_by_key(const unsigned long long*, int, int, int*, void*, size_t, cudaStream_t);
+int sort_rows_by_table(const int*, int, int, int*, void*, size_t, cudaStream_t);
 int build_tiles(const int*, int, int, const int*, int, int, int*, int*, int*, int*, int*, int, int*,
                 cudaStream_t);
 // coords.cu
@@ -219,6 +220,11 @@ int wcn_sort_rows_by_key(const uint64_t* keys, int M, int K, int32_t* rows_out, 
   if (M > 0 && (!keys || !rows_out || !workspace)) return kErrInvalidArg;
   return sort_rows_by_key(reinterpret_cast<const unsigned long long*>(keys), M, K, rows_out,
                           workspace, workspace_bytes, S(stream));
+}
+int wcn_sort_rows_by_table(const int32_t* table, int K, int M, int32_t* rows_out, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+  if (M > 0 && (!table || !rows_out || !workspace)) return kErrInvalidArg;
+  return sort_rows_by_table(table, K, M, rows_out, workspace, workspace_bytes, S(stream));
 }
 int wcn_build_tiles(const int32_t* table, int K, int M, const int32_t* sorted_rows, int tile_rows,
                     int m_pad, int32_t* step_nbr, int32_t* step_k, int32_t* rows_padded,

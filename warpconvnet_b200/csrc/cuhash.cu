@@ -755,7 +755,9 @@ __global__ void narrow_keys_iota_kernel(const unsigned long long* __restrict__ k
 // --------------------------------------------------------------------------------------------
 
 struct MaskSortParams {
-  const unsigned long long* keys64;
+  const unsigned long long* keys64;  // per-row offset masks, or nullptr:
+  const int* table;                  // ... derive them from the [K][M] neighbour table in pass 0
+  int K;
   unsigned* k_a;   // ping
   unsigned* k_b;   // pong
   int* v_a;
@@ -806,16 +808,33 @@ __global__ void __launch_bounds__(kSortThreads, 1) mask_sort_kernel(const MaskSo
     unsigned* k_dst = (pass & 1) ? p.k_a : p.k_b;
     int* v_dst = (pass == p.passes - 1) ? p.rows_out : ((pass & 1) ? p.v_a : p.v_b);
     const int shift = 8 * pass;
+    // pass 0 of the table form: the row's offset mask from its K table entries (coalesced column
+    // reads of the L2-resident table the search kernel has just written), narrowed, kept in k_a
+    // (free during pass 0) so that the scatter phase does not read the table again
+    const bool from_table = pass == 0 && p.table != nullptr;
     auto load_key = [&](int i) -> unsigned {
       // __ldcg: written by other CTAs in the previous pass (never trust a stale L1 line)
-      return pass == 0 ? narrow_mask_key(__ldg(p.keys64 + i), p.drop_bit, p.fold_bits)
-                       : __ldcg(k_src + i);
+      if (pass != 0) return __ldcg(k_src + i);
+      if (p.table != nullptr) return p.k_a[i];  // stored by this thread in phase 1
+      return narrow_mask_key(__ldg(p.keys64 + i), p.drop_bit, p.fold_bits);
     };
     // ---- phase 1: digit histogram of this CTA's chunk ------------------------------------------
     if (tid < 256) s_hist[tid] = 0;
     __syncthreads();
-    for (int i = begin + tid; i < end; i += kSortThreads)
-      atomicAdd(&s_hist[(load_key(i) >> shift) & 255u], 1);
+    for (int i = begin + tid; i < end; i += kSortThreads) {
+      unsigned key;
+      if (from_table) {
+        unsigned long long bits = 0ull;
+#pragma unroll 9
+        for (int k = 0; k < p.K; ++k)
+          bits |= (unsigned long long)(__ldcg(p.table + (size_t)k * p.M + i) >= 0 ? 1u : 0u) << k;
+        key = narrow_mask_key(bits, p.drop_bit, p.fold_bits);
+        p.k_a[i] = key;
+      } else {
+        key = load_key(i);
+      }
+      atomicAdd(&s_hist[(key >> shift) & 255u], 1);
+    }
     __syncthreads();
     if (tid < 256) p.counts[c * 256 + tid] = s_hist[tid];
     sort_grid_barrier(p.bar, (unsigned)G, gen);
@@ -902,16 +921,9 @@ static const bool g_fold_mask_keys = [] {
 static constexpr bool g_fold_mask_keys = true;
 #endif
 
-int sort_rows_by_key(const unsigned long long* keys, int M, int K, int* rows_out, void* workspace,
-                     size_t ws_bytes, cudaStream_t s) {
-  if (M == 0) return kOk;
-  if (ws_bytes < sort_workspace_bytes(M)) return kErrWorkspace;
-  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
-  unsigned long long* keys_out = reinterpret_cast<unsigned long long*>(ws);
-  int* rows_in = reinterpret_cast<int*>(ws + align_up((size_t)M * 8, 256));
-  void* temp = ws + align_up((size_t)M * 8, 256) + align_up((size_t)M * 4, 256);
-  size_t temp_bytes = ws_bytes - (align_up((size_t)M * 8, 256) + align_up((size_t)M * 4, 256));
-  if (K <= 32 && M <= kSortMaxRows && g_own_mask_sort) {
+static int launch_mask_sort(const unsigned long long* keys, const int* table, int M, int K,
+                            int* rows_out, uint8_t* ws, cudaStream_t s) {
+  {
     int drop_bit = -1, fold_bits = 0, key_bits = K;
     if (K > 24 && g_fold_mask_keys) {
       if (K & 1) { drop_bit = K / 2; --key_bits; }
@@ -921,6 +933,8 @@ int sort_rows_by_key(const unsigned long long* keys, int M, int K, int* rows_out
     const size_t mb = align_up((size_t)M * 4, 256);
     MaskSortParams sp;
     sp.keys64 = keys;
+    sp.table = table;
+    sp.K = K;
     sp.k_a = reinterpret_cast<unsigned*>(ws);
     sp.k_b = reinterpret_cast<unsigned*>(ws + mb);
     sp.v_a = reinterpret_cast<int*>(ws + 2 * mb);
@@ -950,6 +964,29 @@ int sort_rows_by_key(const unsigned long long* keys, int M, int K, int* rows_out
     count_launch();
     return cuda_ok();
   }
+}
+
+// Rows sorted by the offset mask of their table column, masks derived inside the sort kernel
+// (no separate mask pass over the table). kErrUnsupportedShape: use wcn_mask_keys + sort_rows_by_key.
+int sort_rows_by_table(const int* table, int K, int M, int* rows_out, void* workspace,
+                       size_t ws_bytes, cudaStream_t s) {
+  if (M == 0) return kOk;
+  if (K < 1 || K > 32 || M > kSortMaxRows || !g_own_mask_sort) return kErrUnsupportedShape;
+  if (ws_bytes < sort_workspace_bytes(M)) return kErrWorkspace;
+  return launch_mask_sort(nullptr, table, M, K, rows_out, reinterpret_cast<uint8_t*>(workspace), s);
+}
+
+int sort_rows_by_key(const unsigned long long* keys, int M, int K, int* rows_out, void* workspace,
+                     size_t ws_bytes, cudaStream_t s) {
+  if (M == 0) return kOk;
+  if (ws_bytes < sort_workspace_bytes(M)) return kErrWorkspace;
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  unsigned long long* keys_out = reinterpret_cast<unsigned long long*>(ws);
+  int* rows_in = reinterpret_cast<int*>(ws + align_up((size_t)M * 8, 256));
+  void* temp = ws + align_up((size_t)M * 8, 256) + align_up((size_t)M * 4, 256);
+  size_t temp_bytes = ws_bytes - (align_up((size_t)M * 8, 256) + align_up((size_t)M * 4, 256));
+  if (K <= 32 && M <= kSortMaxRows && g_own_mask_sort)
+    return launch_mask_sort(keys, nullptr, M, K, rows_out, ws, s);
   if (K <= 32) {
     unsigned* k32_in = reinterpret_cast<unsigned*>(ws);            // the u64 key_out region holds
     unsigned* k32_out = k32_in + align_up((size_t)M, 32);          // both u32 key buffers

@@ -144,9 +144,15 @@ def generate_kernel_map(
     offs3 = _offsets3(kernel_size, kernel_dilation, kernel_center_offset, dev)
     symmetric = bool(same_coords and is_odd and all(s == 1 for s in stride)
                      and kernel_center_offset is None)
+    stats_on_side = False
     if symmetric and n_out > 0:
+        # Table only on the compute stream: the tile plan derives the row masks inside its sort
+        # kernel, and the per-block pair counts are only needed by the CSR branch, which runs on
+        # the side stream — the statistics pass over the table leaves the critical path.
+        stats_on_side = build_plan and K <= 32 and n_out <= (1 << 20)
         pair_table, block_counts, mask_keys = _ops.kernel_map_search_symmetric(
-            table.keys_tensor, table.values_tensor, out_c, offs3, table.status_tensor)
+            table.keys_tensor, table.values_tensor, out_c, offs3, table.status_tensor,
+            with_stats=not stats_on_side)
     else:
         pair_table, block_counts, mask_keys = _ops.kernel_map_search(
             table.keys_tensor, table.values_tensor, out_c, offs3, stride)
@@ -161,6 +167,8 @@ def generate_kernel_map(
     fork.record(main)
     side.wait_event(fork)
     with torch.cuda.stream(side):
+        if stats_on_side:
+            block_counts, _ = _ops.kernel_map_stats(pair_table, want_mask=False)
         offsets_dev = _ops.kernel_map_count(block_counts)
         if deferred:
             # No host sync: the CSR lists go into upper-bound sized buffers, (offsets, status)
@@ -190,9 +198,10 @@ def generate_kernel_map(
                                      identity_map_index=identity_map_index)
         join = torch.cuda.Event()
         join.record(side)
-    for t in (pair_table, block_counts, table.status_tensor):
+    for t in (pair_table, table.status_tensor) + (() if stats_on_side else (block_counts,)):
         t.record_stream(side)       # allocated on the main stream, read by the side stream
-    for t in (offsets_dev, in_maps, out_maps) + ((host,) if host.is_cuda else ()):
+    for t in (offsets_dev, in_maps, out_maps) + ((host,) if host.is_cuda else ()) + (
+            (block_counts,) if stats_on_side else ()):
         t.record_stream(main)       # allocated on the side stream, consumed on the main stream
     if build_plan and n_out > 0:
         result._fwd_plan = _ops.build_tile_plan(pair_table, mask_keys)
