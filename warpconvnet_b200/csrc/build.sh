@@ -12,6 +12,9 @@ if [ "${WCN_KERNEL_COUNTERS:-0}" = "1" ]; then FLAGS="$FLAGS -DWCN_KERNEL_COUNTE
 # WCN_ZERO_ROWS_SECOND_PASS=1: EXPERIMENT, off by default and not yet measured (profiles/r1i):
 # missing neighbours of a gather stage are written with st.shared after the copies are issued
 if [ "${WCN_ZERO_ROWS_SECOND_PASS:-0}" = "1" ]; then FLAGS="$FLAGS -DWCN_ZERO_ROWS_SECOND_PASS"; fi
+# WCN_ENABLE_PDL=1: launch every kernel with the programmatic-stream-serialization attribute
+# (off by default, see common.cuh)
+if [ "${WCN_ENABLE_PDL:-0}" = "1" ]; then FLAGS="$FLAGS -DWCN_ENABLE_PDL"; fi
 mkdir -p build
 pids=()
 for f in cuhash coords conv_fwd conv_wgrad weight_prep knn rownorm conv_depthwise capi; do

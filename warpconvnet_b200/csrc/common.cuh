@@ -2,6 +2,7 @@
 // Thin inline-PTX layer for sm_100a: mbarrier, cp.async, bulk copy (TMA unit), tcgen05/TMEM.
 // Everything here is hand-written for B200; nothing is borrowed from a template library.
 #pragma once
+#include <cstdlib>
 
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
@@ -34,13 +35,14 @@ constexpr int kNumSMsB200 = 148;
 // Per-role wait-cycle counters of the GEMM kernels (tools/exp_dbg.py, tools/exp_wgrad.py) are a
 // bring-up aid: the clock reads are compiled in only with -DWCN_KERNEL_COUNTERS
 // (WCN_KERNEL_COUNTERS=1 csrc/build.sh); the shipped library carries none of them.
-// Programmatic dependent launch (PDL): every kernel of this library is launched with the
-// programmatic-stream-serialization attribute and starts with pdl_begin(): it lets the NEXT kernel
-// of the stream be scheduled right away (griddepcontrol.launch_dependents) and then waits until
-// everything before it in the stream has completed and flushed (griddepcontrol.wait), so the
-// grid is already resident when its predecessor drains — the ~1-2 us launch gap between two
-// dependent kernels disappears, in eager launches and as programmatic edges of a captured CUDA
-// graph alike. Semantics are unchanged: nothing is read or written before the wait.
+// Programmatic dependent launch (PDL): every kernel of this library starts with pdl_begin()
+// (griddepcontrol.launch_dependents + griddepcontrol.wait: nothing is read or written before the
+// wait, so semantics are unchanged) and goes through wcn_launch(). With the launch attribute set
+// (-DWCN_ENABLE_PDL) the next kernel of a stream is resident before its predecessor has drained,
+// which removes the ~1-2 us gap between dependent kernels: C3 step 0.442 -> 0.436 ms. It is OFF in
+// the default build: together with the grid-barrier sort kernel and a second stream (the CSR
+// branch of the kernel-map build) back-to-back eager steps showed sporadic ~11 ms stalls
+// (profiles/r2_pdl_and_barrier_kernel.md); without the attribute pdl_begin() is a no-op.
 __device__ __forceinline__ void pdl_begin() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -59,7 +61,15 @@ inline cudaError_t wcn_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
+#ifdef WCN_ENABLE_PDL
   cfg.numAttrs = 1;
+#else
+  cfg.numAttrs = 0;
+#endif
+#ifdef WCN_BRINGUP  // bring-up builds: WCN_PDL_OFF=0 / 1 overrides the build default (A/B)
+  static const int pdl_env = [] { const char* e = getenv("WCN_PDL_OFF"); return e ? (e[0] == '1' ? 0 : 1) : -1; }();
+  if (pdl_env >= 0) cfg.numAttrs = pdl_env;
+#endif
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 #endif

@@ -23,6 +23,7 @@ from .packed_hashmap import PackedHashTable
 from .search_results import IntSearchResult, check_pending_kernel_maps
 
 _OFFSET_CACHE: Dict[tuple, Tensor] = {}
+_STATS_ON_SIDE = True  # submanifold maps: per-block pair counts computed on the CSR side stream
 # Upper-bound CSR buffers of at most 2 x 512 MiB (K * M int32 each; the real pair count is ~1/3 of
 # it on surface data): a 27-offset map of 2.4 M voxels (MinkUNet-14 full resolution, 8 scenes)
 # stays on the sync-free path. Above it the exact length is read back (one host sync).
@@ -149,7 +150,7 @@ def generate_kernel_map(
         # Table only on the compute stream: the tile plan derives the row masks inside its sort
         # kernel, and the per-block pair counts are only needed by the CSR branch, which runs on
         # the side stream — the statistics pass over the table leaves the critical path.
-        stats_on_side = build_plan and K <= 32 and n_out <= (1 << 20)
+        stats_on_side = _STATS_ON_SIDE and build_plan and K <= 32 and n_out <= (1 << 20)
         pair_table, block_counts, mask_keys = _ops.kernel_map_search_symmetric(
             table.keys_tensor, table.values_tensor, out_c, offs3, table.status_tensor,
             with_stats=not stats_on_side)
