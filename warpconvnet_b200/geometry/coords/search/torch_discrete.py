@@ -23,7 +23,8 @@ from .packed_hashmap import PackedHashTable
 from .search_results import IntSearchResult, check_pending_kernel_maps
 
 _OFFSET_CACHE: Dict[tuple, Tensor] = {}
-_STATS_ON_SIDE = True  # submanifold maps: per-block pair counts computed on the CSR side stream
+_STATS_ON_SIDE = False  # True: statistics pass of a submanifold map on the CSR side stream (no gain
+# in graph replays - the sort then derives the masks itself - and noisy eager / e2e steps: off)
 # Upper-bound CSR buffers of at most 2 x 512 MiB (K * M int32 each; the real pair count is ~1/3 of
 # it on surface data): a 27-offset map of 2.4 M voxels (MinkUNet-14 full resolution, 8 scenes)
 # stays on the sync-free path. Above it the exact length is read back (one host sync).
