@@ -741,9 +741,10 @@ def run_ours(args):
         "unit": "voxels/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {
-            "workload": workload_name(args.dist, n, world),
-            "voxels_per_gpu": n, "pairs_L": L, "parallelism": f"scene-sharded dp{world}",
+        # `config` is identical in both arms (--impl ours / reference); what differs is in `setup`
+        "config": {"workload": workload_name(args.dist, n, world), "voxels_per_gpu": n},
+        "setup": {
+            "pairs_L": L, "parallelism": f"scene-sharded dp{world}",
             "l2": "flushed with a 256 MiB write before every timed step (outside the events)",
             "timing": "CUDA events per step on the launching stream, mean over steps, max over ranks",
             "launch": ("one CUDA-graph replay per step (the path has no host sync)" if graph is not None
@@ -821,9 +822,10 @@ def run_reference(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         # same workload name as our arm's line; what differs is said in `arm`
         "config": {"workload": workload_name(args.dist, n, int(os.environ.get("WORLD_SIZE", 1))),
-                   "voxels_per_gpu": n,
-                   "arm": "host CPU, fp32: oracle kernel map + port of the reference's explicit "
-                          "gather-matmul-scatter (detail/explicit.py:22-101), rank 0 only"},
+                   "voxels_per_gpu": n},
+        "setup": {"arm": "host CPU, fp32: oracle kernel map + port of the reference's explicit "
+                         "gather-matmul-scatter (detail/explicit.py:22-101), rank 0 only; the "
+                         "reference's own GPU build is timed in the `ref_gpu` block of the other arm"},
         "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": base["value"], "unit": "voxels/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
