@@ -209,7 +209,12 @@ def run_c4(dev, rank, world, dist, steps=10, warmup=3):
     torch.manual_seed(0)                                   # identical initial weights on all ranks
     net = MinkUNet14(3, 20).to(dev)
     opt = torch.optim.SGD(net.parameters(), lr=1e-3, momentum=0.9)
-    bucket = FlatGradBucket(net.parameters()) if world > 1 else None
+    bucket = None
+    if world > 1:
+        try:  # gradients in NVLink peer-mapped memory, reduced by the library's own kernel
+            bucket = FlatGradBucket(net.parameters(), peer=True)
+        except Exception:  # symmetric memory unavailable: NCCL
+            bucket = FlatGradBucket(net.parameters())
     cached_vox = Voxels(coords, feats)
     # replace() copies the attribute dict, so a kernel-map cache only survives across steps when it
     # exists on the template object BEFORE the first replace (otherwise every step's copy creates
@@ -291,6 +296,9 @@ def run_c4(dev, rank, world, dist, steps=10, warmup=3):
                   "(coordinate hierarchy, 9 kernel maps, 24 convs fwd+bwd, norms, all-reduce, SGD) "
                   "as one CUDA graph; eager_wall = host wall clock of the same eager steps",
         "grad_allreduce_bytes": int(bucket.flat.numel() * 4) if bucket is not None else 0,
+        "grad_allreduce": ("none" if bucket is None else
+                           "own peer-memory kernel (wcn_peer_allreduce_f32)" if bucket.peer is not None
+                           else "NCCL"),
         "peak_mem_GiB": torch.cuda.max_memory_allocated() / 2 ** 30,
         "steps": steps, "warmup": warmup,
     }
@@ -503,6 +511,23 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # The only collective of the path: the sum of dW over ranks. Default: this library's own
+    # peer-memory all-reduce kernel (csrc/peer_allreduce.cu) on a side stream, reducing the
+    # symmetric buffer wgrad wrote into, under the dgrad kernel; --collective nccl keeps the
+    # library collective for comparison.
+    par = ar_stream = None
+    collective = "none"
+    if world > 1:
+        collective = args.collective
+        if collective == "peer":
+            try:
+                from warpconvnet_b200.dist import PeerAllReduce
+                par = PeerAllReduce(K * CIN * COUT, dev)
+                ar_stream = torch.cuda.Stream(device=dev)
+            except Exception as exc:  # symmetric memory not available on this box
+                collective = f"nccl (peer memory unavailable: {type(exc).__name__}: {str(exc)[:120]})"
+                par = None
+
     def step():
         """whole hot path, inputs resident in HBM; nothing in it synchronises with the host"""
         km = generate_kernel_map(bc, bc, (1, 1, 1), (KS,) * 3, same_coords=True)
@@ -510,12 +535,25 @@ def run_ours(args):
         # forward + dgrad weight images in one launch (what SparseConv3d's autograd function does)
         img, img_t = _ops.weight_image_pair(w.view(K, 1, CIN, COUT), K, 1, CIN, COUT, w.dtype)
         y = _ops.gather_gemm(x, img, plan, 1, CIN, COUT)           # forward AB_gather_scatter
-        dw = sparse_conv_wgrad(x, gy, (K, CIN, COUT), km)          # wgrad AtB_gather_gather
-        # the only collective of the path: all-reduce of dW, issued as soon as wgrad is enqueued
-        # so it overlaps dgrad (what DDP does with the rest of backward)
-        work = dist.all_reduce(dw, async_op=True) if world > 1 else None
+        # wgrad AtB_gather_gather (into the peer-mapped buffer when the own collective is used)
+        dw = sparse_conv_wgrad(x, gy, (K, CIN, COUT), km,
+                               out=None if par is None else par.buffer)
+        # all-reduce of dW under dgrad (what DDP does with the rest of backward). Own kernel: dgrad
+        # is enqueued FIRST, then the all-reduce on a side stream that forked after wgrad — its
+        # small CTAs (128 threads, no shared memory) slot in next to the resident dgrad CTAs; the
+        # other order makes the dgrad CTAs queue behind them (profiles/r2t_peer_allreduce.md)
+        work = None
         bplan, kflip = km.bwd_plan(n)                              # submanifold: fwd plan, k flipped
+        if par is not None:
+            cur = torch.cuda.current_stream()
+            ar_stream.wait_stream(cur)
+        elif world > 1:
+            work = dist.all_reduce(dw, async_op=True)
         dx = _ops.gather_gemm(gy, img_t, bplan, 1, COUT, CIN, kflip=kflip)  # dgrad ABt_gather_scatter
+        if par is not None:
+            with torch.cuda.stream(ar_stream):
+                par.all_reduce_()
+            cur.wait_stream(ar_stream)
         if work is not None:
             work.wait()
         return km, plan, img, y, dx, dw
@@ -665,7 +703,10 @@ def run_ours(args):
             out.feature_tensor.backward(gy)
             freed[i % 2].record(cur)
             g = conv.weight.grad
-            if world > 1:
+            if par is not None:
+                par.buffer.copy_(g.reshape(-1))
+                g = par.all_reduce_().view(K, CIN, COUT)
+            elif world > 1:
                 dist.all_reduce(g)
             dw_pin.copy_(g, non_blocking=True)
         e.record(cur)
@@ -745,6 +786,9 @@ def run_ours(args):
         "config": {"workload": workload_name(args.dist, n, world), "voxels_per_gpu": n},
         "setup": {
             "pairs_L": L, "parallelism": f"scene-sharded dp{world}",
+            "collective": {"none": "none (one rank)",
+                           "peer": "own kernel over NVLink peer memory (wcn_peer_allreduce_f32), "
+                                   "side stream, under dgrad"}.get(collective, collective),
             "l2": "flushed with a 256 MiB write before every timed step (outside the events)",
             "timing": "CUDA events per step on the launching stream, mean over steps, max over ranks",
             "launch": ("one CUDA-graph replay per step (the path has no host sync)" if graph is not None
@@ -837,6 +881,8 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--collective", choices=["peer", "nccl"], default="peer",
+                    help="all-reduce of dW at N > 1: own peer-memory kernel (default) or NCCL")
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--dist", choices=["S", "R"], default="S")

@@ -346,6 +346,18 @@ int wcn_bn_backward(const void* dy, long long ld_dy, const void* x, long long ld
                     int c, int dtype, const float* gamma, const float* mean_rstd,
                     const float* mask_scale, const float* mask_shift, double* sums, void* stream);
 
+/* All-reduce (fp32, in place: every buffer ends as scale * sum over ranks) of the weight gradients over NVLink / NVSwitch peer memory —
+ * the path's only collective (the reference has no collective code, users wrap
+ * DDP). bufs[r] / flags[r] are HOST arrays of `world` device pointers: the same buffer of `n` floats
+ * (n % 4 == 0, 16-byte aligned) and a flag buffer of wcn_peer_allreduce_flag_words() uint32,
+ * ZEROED ONCE at allocation, as mapped on this rank for every rank r of the box (CUDA IPC / VMM
+ * symmetric memory; torch.distributed._symmetric_memory provides both). Every rank calls it in
+ * the same order; n_ctas (<= 128, default 32 when < 1) must be equal on all ranks. Graph-capturable:
+ * the barrier epochs live in the flag buffer. */
+int wcn_peer_allreduce_flag_words(void);
+int wcn_peer_allreduce_f32(void* const* bufs, void* const* flags, int rank, int world,
+                           long long n, float scale, int n_ctas, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

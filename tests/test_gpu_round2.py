@@ -618,3 +618,41 @@ def test_mask_sort_from_the_table_equals_the_sort_of_explicit_masks(K, M):
     bits = (table >= 0).long()
     masks = (bits << torch.arange(K, device="cuda").view(K, 1)).sum(0)
     assert torch.equal(r_tab.long(), torch.argsort(_narrowed(masks, K), stable=True))
+
+
+# ------------------------------------------------------------------------------------------------
+# own all-reduce over NVLink peer memory (needs two GPUs: skipped on the one-GPU test box; run with
+# `gpurun --gpus 2 -- python -m pytest tests -m gpu -k peer_allreduce`)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_peer_allreduce_two_ranks_matches_nccl_and_replays_in_a_graph():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import json
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", "29533",
+           os.path.join(root, "tools", "exp_peer_allreduce.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr[-2000:]
+    line = [ln for ln in res.stdout.splitlines() if ln.startswith("{")][-1]
+    out = json.loads(line)
+    assert out["graph_replay"] == "ok"
+    for key in ("n442368", "n1000", "n4194308"):
+        assert out[key]["exact_on_integers"] and out[key]["max_abs_vs_nccl"] < 1e-4
+
+
+@pytest.mark.gpu
+def test_peer_allreduce_rejects_bad_arguments():
+    import ctypes
+    from warpconvnet_b200._lib import lib
+    arr = (ctypes.c_void_p * 2)(None, None)
+    assert lib.wcn_peer_allreduce_flag_words() >= 128 * 16
+    # world = 1 / n = 0: nothing to do
+    assert lib.wcn_peer_allreduce_f32(arr, arr, 0, 1, 1024, ctypes.c_float(1.0), 8, None) == 0
+    assert lib.wcn_peer_allreduce_f32(arr, arr, 0, 2, 0, ctypes.c_float(1.0), 8, None) == 0
+    # null peer pointers, n not a multiple of 4, rank outside the world
+    assert lib.wcn_peer_allreduce_f32(arr, arr, 0, 2, 1024, ctypes.c_float(1.0), 8, None) < 0
+    assert lib.wcn_peer_allreduce_f32(arr, arr, 0, 2, 1023, ctypes.c_float(1.0), 8, None) < 0
+    assert lib.wcn_peer_allreduce_f32(arr, arr, 2, 2, 1024, ctypes.c_float(1.0), 8, None) < 0

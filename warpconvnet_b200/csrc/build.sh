@@ -17,10 +17,10 @@ if [ "${WCN_ZERO_ROWS_SECOND_PASS:-0}" = "1" ]; then FLAGS="$FLAGS -DWCN_ZERO_RO
 if [ "${WCN_ENABLE_PDL:-0}" = "1" ]; then FLAGS="$FLAGS -DWCN_ENABLE_PDL"; fi
 mkdir -p build
 pids=()
-for f in cuhash coords conv_fwd conv_wgrad weight_prep knn rownorm conv_depthwise capi; do
+for f in cuhash coords conv_fwd conv_wgrad weight_prep knn rownorm conv_depthwise peer_allreduce capi; do
   $NVCC $FLAGS -c $f.cu -o build/$f.o &
   pids+=($!)
 done
 for p in "${pids[@]}"; do wait $p; done
-$NVCC -shared -o libwcn_b200.so build/cuhash.o build/coords.o build/conv_fwd.o build/conv_wgrad.o build/weight_prep.o build/knn.o build/rownorm.o build/conv_depthwise.o build/capi.o
+$NVCC -shared -o libwcn_b200.so build/cuhash.o build/coords.o build/conv_fwd.o build/conv_wgrad.o build/weight_prep.o build/knn.o build/rownorm.o build/conv_depthwise.o build/peer_allreduce.o build/capi.o
 echo "built $(pwd)/libwcn_b200.so"

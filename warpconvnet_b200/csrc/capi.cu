@@ -34,6 +34,9 @@ int build_tiles(const int*, int, int, const int*, int, int, int*, int*, int*, in
 size_t coords_unique_workspace_bytes(long long);
 int coords_unique(const int*, int, int, int, int, const int*, int, int, int*, int*, int*, void*,
                   size_t, cudaStream_t);
+// peer_allreduce.cu
+int peer_allreduce_f32(void* const*, void* const*, int, int, long long, float, int, cudaStream_t);
+int peer_allreduce_flag_words();
 // knn.cu
 size_t knn_workspace_bytes(int, int, int);
 int knn_dims_for(int, int);
@@ -638,6 +641,14 @@ int wcn_depthwise_wgrad(const void* feats, long long in_ld, const void* gout, lo
   if (!feats || !gout || !dw || !table) return kErrInvalidArg;
   return depthwise_launch(true, feats, in_ld, gout, gout_ld, nullptr, 0, nullptr, dw, nullptr, table,
                           n_rows, K, channels, 0, 0, dtype, S(stream));
+}
+
+int wcn_peer_allreduce_flag_words(void) { return peer_allreduce_flag_words(); }
+
+int wcn_peer_allreduce_f32(void* const* bufs, void* const* flags, int rank, int world,
+                           long long n, float scale, int n_ctas, void* stream) {
+  if (!bufs || !flags) return kErrInvalidArg;
+  return peer_allreduce_f32(bufs, flags, rank, world, n, scale, n_ctas, S(stream));
 }
 
 }  // extern "C"

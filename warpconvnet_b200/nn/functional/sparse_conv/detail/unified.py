@@ -232,9 +232,14 @@ def _wgrad_order(x: Tensor, gy: Tensor, kernel_map, K: int):
     return order
 
 
-def _wgrad_call(x: Tensor, gy: Tensor, kernel_map, K: int, G: int, cin_g: int, cout_g: int) -> Tensor:
+def _wgrad_call(x: Tensor, gy: Tensor, kernel_map, K: int, G: int, cin_g: int, cout_g: int,
+                out: Optional[Tensor] = None) -> Tensor:
     im, om, od = kernel_map._in_buf, kernel_map._out_buf, kernel_map.offsets_dev
     order = dict(_wgrad_order(x, gy, kernel_map, K), **_wgrad_identity(kernel_map, K))
+    if out is not None:  # caller's buffer (e.g. a peer-mapped all-reduce buffer): zero, then reduce into it
+        assert out.dtype == torch.float32 and out.is_contiguous() \
+            and out.numel() == K * G * cin_g * cout_g
+        order["dw"] = out.zero_().view(K, G, cin_g, cout_g)
     if x.dtype != torch.float32:
         return _ops.wgrad(x, gy, im, om, od, K, G, cin_g, cout_g, **order)
     # fp32 operands: the contraction runs over gathered rows (MN-major operands), which the
@@ -247,25 +252,30 @@ def _wgrad_call(x: Tensor, gy: Tensor, kernel_map, K: int, G: int, cin_g: int, c
     xl = (x - xh.float()).bfloat16()
     gl = (gy - gh.float()).bfloat16()
     dw = _ops.wgrad(xh, gh, im, om, od, K, G, cin_g, cout_g, **order)
-    _ops.wgrad(xh, gl, im, om, od, K, G, cin_g, cout_g, dw=dw, **order)
-    _ops.wgrad(xl, gh, im, om, od, K, G, cin_g, cout_g, dw=dw, **order)
+    order["dw"] = dw
+    _ops.wgrad(xh, gl, im, om, od, K, G, cin_g, cout_g, **order)
+    _ops.wgrad(xl, gh, im, om, od, K, G, cin_g, cout_g, **order)
     return dw
 
 
 def sparse_conv_wgrad(in_features: Tensor, grad_output: Tensor, weight_shape, kernel_map,
-                      groups: int = 1) -> Tensor:
-    """fp32 dW with the shape of the weight."""
+                      groups: int = 1, out: Optional[Tensor] = None) -> Tensor:
+    """fp32 dW with the shape of the weight. ``out`` (fp32, contiguous, the weight's element
+    count, channel counts that need no padding) receives the result in place of a fresh tensor —
+    e.g. a ``PeerAllReduce`` buffer, so the reduction needs no packing copy."""
     if groups == 1:
         K, cin, cout = weight_shape
         cin_p, cout_p = _round_up(cin, _CH_ALIGN), _round_up(cout, _CH_ALIGN)
+        if out is not None and (cin_p != cin or cout_p != cout):
+            raise ValueError("out= needs channel counts that are multiples of 16")
         x = _pad_cols(in_features, cin_p)
         gy = _pad_cols(grad_output, cout_p)
-        dw = _wgrad_call(x, gy, kernel_map, K, 1, cin_p, cout_p).view(K, cin_p, cout_p)
+        dw = _wgrad_call(x, gy, kernel_map, K, 1, cin_p, cout_p, out=out).view(K, cin_p, cout_p)
         return dw if (cin_p == cin and cout_p == cout) else dw[:, :cin, :cout]
     K, G, cin_g, cout_g = weight_shape
     x = _pad_cols(in_features, G * cin_g)
     gy = _pad_cols(grad_output, G * cout_g)
-    return _wgrad_call(x, gy, kernel_map, K, G, cin_g, cout_g)
+    return _wgrad_call(x, gy, kernel_map, K, G, cin_g, cout_g, out=out)
 
 
 class UnifiedSpatiallySparseConvFunction(Function):
