@@ -520,13 +520,19 @@ def run_ours(args):
     if world > 1:
         collective = args.collective
         if collective == "peer":
+            why = ""
             try:
                 from warpconvnet_b200.dist import PeerAllReduce
                 par = PeerAllReduce(K * CIN * COUT, dev)
                 ar_stream = torch.cuda.Stream(device=dev)
             except Exception as exc:  # symmetric memory not available on this box
-                collective = f"nccl (peer memory unavailable: {type(exc).__name__}: {str(exc)[:120]})"
+                why = f"{type(exc).__name__}: {str(exc)[:120]}"
                 par = None
+            ok = torch.tensor([0 if par is None else 1], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)   # every rank takes the same path
+            if int(ok.item()) == 0:
+                par = None
+                collective = f"nccl (peer memory unavailable on some rank{': ' + why if why else ''})"
 
     def step():
         """whole hot path, inputs resident in HBM; nothing in it synchronises with the host"""
@@ -794,6 +800,7 @@ def run_ours(args):
             "launch": ("one CUDA-graph replay per step (the path has no host sync)" if graph is not None
                        else (graph_note or "eager launches")),
             "eager_ms_per_step": eager_ms,
+            "peer_allreduce_barrier_timeouts": None if par is None else par.timeouts(),
         },
         "e2e": {"value": total_vox / (e2e_ms * 1e-3), "unit": "voxels/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

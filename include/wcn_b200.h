@@ -353,8 +353,11 @@ int wcn_bn_backward(const void* dy, long long ld_dy, const void* x, long long ld
  * ZEROED ONCE at allocation, as mapped on this rank for every rank r of the box (CUDA IPC / VMM
  * symmetric memory; torch.distributed._symmetric_memory provides both). Every rank calls it in
  * the same order; n_ctas (<= 128, default 32 when < 1) must be equal on all ranks. Graph-capturable:
- * the barrier epochs live in the flag buffer. */
+ * the barrier epochs live in the flag buffer. A barrier wait gives up after 10 s (a peer that
+ * never arrives must not hang the GPU) and counts that in word wcn_peer_allreduce_timeout_word()
+ * of this rank's flag buffer: non-zero = the buffer contents are not a valid sum. */
 int wcn_peer_allreduce_flag_words(void);
+int wcn_peer_allreduce_timeout_word(void);
 int wcn_peer_allreduce_f32(void* const* bufs, void* const* flags, int rank, int world,
                            long long n, float scale, int n_ctas, void* stream);
 

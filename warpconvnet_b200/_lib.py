@@ -95,6 +95,7 @@ SIGNATURES = {
                                 c_void_p, c_longlong, c_void_p, c_longlong, c_int, c_int, c_int,
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "wcn_peer_allreduce_flag_words": (c_int, []),
+    "wcn_peer_allreduce_timeout_word": (c_int, []),
     "wcn_peer_allreduce_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_longlong, c_float,
                                        c_int, c_void_p]),
     "wcn_depthwise_conv": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_void_p,

@@ -37,6 +37,7 @@ int coords_unique(const int*, int, int, int, int, const int*, int, int, int*, in
 // peer_allreduce.cu
 int peer_allreduce_f32(void* const*, void* const*, int, int, long long, float, int, cudaStream_t);
 int peer_allreduce_flag_words();
+int peer_allreduce_timeout_word();
 // knn.cu
 size_t knn_workspace_bytes(int, int, int);
 int knn_dims_for(int, int);
@@ -644,6 +645,7 @@ int wcn_depthwise_wgrad(const void* feats, long long in_ld, const void* gout, lo
 }
 
 int wcn_peer_allreduce_flag_words(void) { return peer_allreduce_flag_words(); }
+int wcn_peer_allreduce_timeout_word(void) { return peer_allreduce_timeout_word(); }
 
 int wcn_peer_allreduce_f32(void* const* bufs, void* const* flags, int rank, int world,
                            long long n, float scale, int n_ctas, void* stream) {

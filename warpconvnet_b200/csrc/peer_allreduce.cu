@@ -34,8 +34,11 @@ constexpr int kArMaxCtas = 128;
 // the dgrad CTAs queued behind them). A library collective with its own shared-memory and register
 // footprint has to wait.
 constexpr int kArThreads = 128;
-// flag buffer of one rank (uint32): [kArMaxCtas][kArMaxRanks] flags, then [kArMaxCtas] epochs
-constexpr int kArFlagWords = kArMaxCtas * kArMaxRanks + kArMaxCtas;
+// flag buffer of one rank (uint32): [kArMaxCtas][kArMaxRanks] flags, [kArMaxCtas] epochs, then one
+// word counting barrier waits that gave up (a peer that never arrives must not hang this GPU)
+constexpr int kArFlagWords = kArMaxCtas * kArMaxRanks + kArMaxCtas + 1;
+constexpr int kArTimeoutWord = kArMaxCtas * kArMaxRanks + kArMaxCtas;
+constexpr unsigned long long kArTimeoutNs = 10ull * 1000 * 1000 * 1000;
 
 struct PeerAllReduceParams {
   float* bufs[kArMaxRanks];        // the same buffer on every rank (peer-mapped pointers)
@@ -75,7 +78,18 @@ __device__ __forceinline__ void peer_barrier(const PeerAllReduceParams& p, int b
     const int peer = threadIdx.x;
     st_release_sys(p.flags[peer] + b * kArMaxRanks + p.rank, e);
     const unsigned* mine = p.flags[p.rank] + b * kArMaxRanks + peer;
+    unsigned long long t0 = 0;
+    unsigned spins = 0;
     while ((int)(ld_acquire_sys(mine) - e) < 0) {
+      if ((++spins & 0xfffu) == 0) {  // every 4096 polls: give up after 10 s, and say so
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        if (now - t0 > kArTimeoutNs) {
+          atomicAdd(p.flags[p.rank] + kArTimeoutWord, 1u);
+          break;
+        }
+      }
     }
   }
   __syncthreads();
@@ -165,5 +179,6 @@ int peer_allreduce_f32(void* const* bufs, void* const* flags, int rank, int worl
 }
 
 int peer_allreduce_flag_words() { return kArFlagWords; }
+int peer_allreduce_timeout_word() { return kArTimeoutWord; }
 
 }  // namespace wcn

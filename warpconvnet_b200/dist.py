@@ -120,6 +120,7 @@ class PeerAllReduce:
         self.n = (int(numel) + 3) // 4 * 4
         self.n_ctas = int(n_ctas)
         words = int(lib.wcn_peer_allreduce_flag_words())
+        self._timeout_word = int(lib.wcn_peer_allreduce_timeout_word())
         self._data = symm_mem.empty(self.n, dtype=torch.float32, device=device)
         self._flags = symm_mem.empty(words, dtype=torch.int32, device=device)
         self._data.zero_()
@@ -136,6 +137,11 @@ class PeerAllReduce:
         self.buffer = self._data[:int(numel)]
         torch.cuda.synchronize(device)
         dist.barrier(group)  # every rank's flags are zero before the first kernel touches them
+
+    def timeouts(self) -> int:
+        """Barrier waits that gave up (10 s) since construction — synchronises; non-zero means a
+        peer never arrived and the buffer is not a valid sum."""
+        return int(self._flags[self._timeout_word].item())
 
     def all_reduce_(self, average: bool = False) -> torch.Tensor:
         from ._lib import check, lib
