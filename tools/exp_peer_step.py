@@ -104,6 +104,41 @@ def main():
         wgrad(par.buffer)
         par.all_reduce_()
 
+    if "--trace" in sys.argv:
+        # kernel timeline (CUPTI through torch.profiler) of graph replays of the shipped order:
+        # is the all-reduce kernel inside the dgrad kernel's interval?
+        from torch.profiler import ProfilerActivity, profile
+        for _ in range(3):
+            v_wd_side_dfirst()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, capture_error_mode="relaxed"):
+            v_wd_side_dfirst()
+        for _ in range(5):
+            g.replay()
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(4):
+                flush.fill_(1)
+                g.replay()
+            torch.cuda.synchronize()
+        rows = []
+        for ev in prof.events():
+            if ev.device_type is not None and "CUDA" in str(ev.device_type):
+                rows.append((ev.time_range.start, ev.time_range.end - ev.time_range.start, ev.name[:60]))
+        rows.sort()
+        t0 = rows[0][0]
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", f"peer_timeline_rank{rank}_of{world}.txt"), "w") as f:
+            f.write("start_us  dur_us  kernel\n")
+            for st, du, nm in rows:
+                f.write(f"{st - t0:9.1f} {du:7.1f}  {nm}\n")
+        torch.cuda.synchronize()
+        dist.barrier()
+        os._exit(0)
+
     out = {}
     for name, fn in list(locals().items()):
         if not name.startswith("v_"):
