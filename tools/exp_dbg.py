@@ -75,6 +75,8 @@ for u in range(U * nt + 1):
     unit_cost[u] = U * cum[nt] if u == U * nt else U * cum[t] + (u - t * U) * nk[t]
 G = 148
 ub = [int(np.searchsorted(unit_cost, S * b // G, side="left")) for b in range(G + 1)]
+if plan.cta_units is not None and plan.n_range_ctas == G:
+    ub = plan.cta_units.cpu().numpy().astype(np.int64).tolist()   # the ranges the kernel really used
 nbr = plan.step_nbr.cpu().numpy().reshape(nt, plan.K, 256)
 valid_per_unit = np.zeros(U * nt, np.int64)
 for t in range(nt):
@@ -88,6 +90,8 @@ for b in range(G):
     valid = valid_per_unit[u0:u1].sum()
     partial = (u0 % 2) + (u1 % 2)
     rows.append((b, u1 - u0, steps, valid, partial, d[b, 0]))
+np.save(os.path.join(ROOT, "gpurun_out", "dbg_rows.npy"), np.array(rows))
+np.save(os.path.join(ROOT, "gpurun_out", "dbg_raw.npy"), d)
 rows = np.array(rows)
 print("corr(prod_total, unit-steps) =", np.corrcoef(rows[:, 5], rows[:, 2])[0, 1])
 print("corr(prod_total, valid rows) =", np.corrcoef(rows[:, 5], rows[:, 3])[0, 1])
@@ -99,3 +103,13 @@ for i in order[:8]:
 print("fastest CTAs:")
 for i in order[-8:]:
     print("   ", rows[i, :5].tolist(), rows[i, 5] // 1000)
+# least-squares model of a CTA's time: a * unit-steps + b * valid rows + c * partial tiles + d
+A = np.stack([rows[:, 2], rows[:, 3], rows[:, 4], np.ones(len(rows))], 1).astype(np.float64)
+for tgt, nm in ((rows[:, 5].astype(np.float64), "prod_total"), ((d[:, 11] - d[:, 8]).astype(np.float64), "cta_ns")):
+    coef, res, _, _ = np.linalg.lstsq(A, tgt, rcond=None)
+    pred = A @ coef
+    print(f"fit {nm}: per unit-step {coef[0]:.2f}, per valid row {coef[1]:.4f}, per partial tile {coef[2]:.1f}, "
+          f"const {coef[3]:.0f}; rms residual {np.sqrt(np.mean((tgt - pred) ** 2)):.0f} of mean {tgt.mean():.0f} "
+          f"(spread: min {tgt.min():.0f} max {tgt.max():.0f})")
+print("unit-steps per CTA: min", rows[:, 2].min(), "max", rows[:, 2].max(), "| valid rows per CTA: min",
+      rows[:, 3].min(), "max", rows[:, 3].max())
