@@ -268,10 +268,12 @@ def run_c4(dev, rank, world, dist, steps=10, warmup=3):
 
     eager_ms, eager_wall = timed(step, steps, warmup)
     cached_ms, _ = timed(make_step(False), steps, 2)
-    graph_ms = graph_note = None
+    graph_ms = graph_note = c4_clocks = None
     try:
         graph, tape, _ = capture_step(step, warmup=1)
-        graph_ms, graph_wall = timed(graph.replay, steps, 2)
+        c4_sampler = ClockSampler(dev.index if dev.index is not None else 0) if rank == 0 else None
+        graph_ms, graph_wall = timed(graph.replay, max(steps, 30), 2)   # >= 1 s of replays
+        c4_clocks = c4_sampler.stop() if c4_sampler is not None else None
         tape.verify()
     except Exception as exc:  # pragma: no cover
         graph_note = f"graph capture failed: {type(exc).__name__}: {str(exc)[:200]}"
@@ -301,6 +303,7 @@ def run_c4(dev, rank, world, dist, steps=10, warmup=3):
                            else "NCCL"),
         "peak_mem_GiB": torch.cuda.max_memory_allocated() / 2 ** 30,
         "steps": steps, "warmup": warmup,
+        "clocks_during_graph_replays": c4_clocks,
     }
     if graph_note:
         out["graph_note"] = graph_note

@@ -87,6 +87,7 @@ def test_out_of_range_coordinate_raises():
 
 def test_norm_tiny_and_wide():
     from warpconvnet_b200.nn.functional.normalizations import batch_norm_act
+    torch.manual_seed(11)  # 3 samples per channel: an unlucky draw has channels with var ~ 1e-4 mean^2
     for n, c in ((2, 8), (3, 1024), (5, 2)):
         x = torch.randn(n, c).cuda().requires_grad_(True)
         y = batch_norm_act(x, None, None, None, None, training=True, relu=False)

@@ -501,7 +501,9 @@ def test_conv_bias_and_batchnorm_statistics_through_the_epilogue_module_path():
             scale = float(results[True][2].abs().max())
             assert float(a.abs().max()) < 2e-2 * scale and float(b.abs().max()) < 2e-2 * scale
             continue
-        assert oconv.rel_max_err(a, b.double().cpu()) < 2e-3
+        # the two paths add the same bf16 values in a different order: scale / shift differ in the
+        # last fp32 bits, which can flip the bf16 rounding of single outputs (1 ulp = 3.9e-3)
+        assert oconv.rel_max_err(a, b.double().cpu()) < 1e-2
 
 
 def test_bias_through_the_epilogue_forward_and_gradient():

@@ -26,7 +26,7 @@ def timed(fn, iters=10):
     return float(np.median([a.elapsed_time(b) for a, b in evs])) * 1e-3
 
 
-for n, c in ((2402432, 96), (2402432, 32), (620000, 96), (160000, 128)):
+for n, c in ((2402432, 96), (754393, 96), (754393, 32), (208065, 128)):
     x = torch.randn(n, c, device="cuda").bfloat16()
     res = torch.randn(n, c, device="cuda").bfloat16()
     dy = torch.randn(n, c, device="cuda").bfloat16()
@@ -43,6 +43,12 @@ for n, c in ((2402432, 96), (2402432, 32), (620000, 96), (160000, 128)):
             ("bwd reduce (3r)", lambda: _ops.bn_bwd_reduce(dy, x, y, mr), 3 * B),
             ("bwd apply (3r 1w)", lambda: _ops.bn_bwd_apply(dy, x, y, gamma, mr, bsums, True, False), 4 * B),
             ("bwd apply + dres (3r 2w)", lambda: _ops.bn_bwd_apply(dy, x, y, gamma, mr, bsums, True, True), 5 * B),
+            ("bwd reduce mask-from-x (2r)", lambda: _ops.bn_bwd_reduce(dy, x, None, mr, scale, shift), 2 * B),
+            ("bwd apply mask-from-x (2r 1w)", lambda: _ops.bn_bwd_apply(dy, x, None, gamma, mr, bsums, True, False, scale, shift), 3 * B),
+            ("bwd reduce no mask (2r)", lambda: _ops.bn_bwd_reduce(dy, x, None, mr), 2 * B),
+            ("bwd apply no mask (2r 1w)", lambda: _ops.bn_bwd_apply(dy, x, None, gamma, mr, bsums, True, False), 3 * B),
+            ("bn_backward one call mask-x", lambda: _ops.bn_backward(dy, x, None, gamma, mr, scale, shift, False), 5 * B),
+            ("bn_forward from sums +relu", lambda: _ops.bn_forward(x, gamma, beta, 1e-5, 0.1, None, None, None, True, sums=sums), 2 * B),
             ("torch copy (1r 1w)", lambda: y.copy_(x), 2 * B)]
     for name, fn, nbytes in rows:
         t = timed(fn)

@@ -15,6 +15,8 @@ if [ "${WCN_ZERO_ROWS_SECOND_PASS:-0}" = "1" ]; then FLAGS="$FLAGS -DWCN_ZERO_RO
 # WCN_ENABLE_PDL=1: launch every kernel with the programmatic-stream-serialization attribute
 # (off by default, see common.cuh)
 if [ "${WCN_ENABLE_PDL:-0}" = "1" ]; then FLAGS="$FLAGS -DWCN_ENABLE_PDL"; fi
+# WCN_EXTRA_FLAGS: extra nvcc flags (bring-up experiments, e.g. -DWCN_RN_UF=8)
+FLAGS="$FLAGS ${WCN_EXTRA_FLAGS:-}"
 mkdir -p build
 pids=()
 for f in cuhash coords conv_fwd conv_wgrad weight_prep knn rownorm conv_depthwise peer_allreduce capi; do

@@ -53,6 +53,53 @@ __device__ __forceinline__ void store_vec(T* p, const float (&f)[V]) {
   }
 }
 
+// Raw 16-byte vectors: a kernel first issues ALL loads of an iteration as raw vectors (4 registers
+// each instead of 8 converted floats) and converts when it consumes them — the passes are pure
+// streaming, bound by the bytes the resident threads keep in flight (Little's law against ~1 us of
+// loaded HBM latency: >= 64 KB per SM), so rows in flight per thread x resident threads is the
+// quantity to maximise.
+template <typename T, int V>
+struct RawOf { using type = uint4; };
+template <typename T>
+struct RawOf<T, 1> { using type = T; };
+
+template <typename T, int V>
+__device__ __forceinline__ typename RawOf<T, V>::type load_raw(const T* p) {
+  if constexpr (V == 1) return p[0];
+  else return *reinterpret_cast<const uint4*>(p);
+}
+
+template <typename T, int V>
+__device__ __forceinline__ void unpack(const typename RawOf<T, V>::type& raw, float (&f)[V]) {
+  if constexpr (V == 1) {
+    f[0] = (float)raw;
+  } else if constexpr (sizeof(T) == 4) {
+    f[0] = __uint_as_float(raw.x); f[1] = __uint_as_float(raw.y);
+    f[2] = __uint_as_float(raw.z); f[3] = __uint_as_float(raw.w);
+  } else {
+    const T* h = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+    for (int i = 0; i < V; ++i) f[i] = (float)h[i];
+  }
+}
+
+// Measured on 2.4 M x 96 bf16 rows (tools/exp_norm.py, profiles/r2u_norm_kernels.md): the
+// one-tensor forward apply gains from 4 rows in flight (177 -> 156 us, 5.9 TB/s of the 6.35 TB/s a
+// torch copy reaches); with a residual (two tensors in flight) and in the backward kernels two rows
+// at three resident blocks are as good or better than four rows at two blocks.
+#ifndef WCN_RN_UF
+#define WCN_RN_UF 4   // rows in flight per thread, forward apply without a residual
+#endif
+#ifndef WCN_RN_UB
+#define WCN_RN_UB 2   // rows in flight per thread, backward reduce / apply
+#endif
+#ifndef WCN_RN_BB
+#define WCN_RN_BB 3   // resident blocks per SM the backward kernels are compiled for
+#endif
+#ifndef WCN_RN_BF
+#define WCN_RN_BF 3   // resident blocks per SM the forward apply kernel is compiled for
+#endif
+
 constexpr int kRnThreads = 256;
 
 // Thread -> (vector column vc, row lane rl): vecs = ceil(c / V) vectors per row, rpb = threads /
@@ -72,30 +119,39 @@ __device__ __forceinline__ RnMap rn_map(int c) {
   return m;
 }
 
-// block-level merge of per-thread partial sums a[V], b[V] into sums[0..c) and sums[c..2c)
+// Block-level merge of per-thread partial sums a[V], b[V] into sums[0..c) and sums[c..2c): every
+// thread parks its partials in shared memory ([rpb][2c] floats, <= 16 KB), 2c threads add the
+// columns and leave one fp64 atomic each (the second half multiplied by half2_scale[c + ch] when
+// given). No shared-memory atomics: fp32 atomicAdd on shared memory is a compare-and-swap loop,
+// and rpb = 21-64 threads per address made it a fixed ~25 us tail of every reduction kernel
+// (profiles/r2u_norm_kernels.md).
 template <int V>
 __device__ __forceinline__ void rn_merge(const RnMap& m, int c, const float (&a)[V],
-                                         const float (&b)[V], double* sums, float* sh) {
-  // sh: [2][c] floats, zeroed
-  for (int i = threadIdx.x; i < 2 * c; i += kRnThreads) sh[i] = 0.f;
-  __syncthreads();
+                                         const float (&b)[V], double* sums, float* sh,
+                                         const float* half2_scale = nullptr) {
   if (m.active) {
+    float* row = sh + (size_t)m.rl * 2 * c;
 #pragma unroll
     for (int i = 0; i < V; ++i) {
       const int ch = m.vc * V + i;
       if (ch < c) {
-        atomicAdd(sh + ch, a[i]);
-        atomicAdd(sh + c + ch, b[i]);
+        row[ch] = a[i];
+        row[c + ch] = b[i];
       }
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * c; i += kRnThreads) atomicAdd(sums + i, (double)sh[i]);
+  for (int i = threadIdx.x; i < 2 * c; i += kRnThreads) {
+    float t = 0.f;
+    for (int r = 0; r < m.rpb; ++r) t += sh[(size_t)r * 2 * c + i];
+    const float f = (half2_scale != nullptr && i >= c) ? __ldg(half2_scale + i) : 1.f;
+    atomicAdd(sums + i, (double)t * (double)f);
+  }
 }
 
 // ---- forward statistics: sums[ch] += sum_r x[r,ch], sums[c+ch] += sum_r x[r,ch]^2 -------------
 template <typename T, int V>
-__global__ void __launch_bounds__(kRnThreads) bn_stats_kernel(const RowNormParams p) {
+__global__ void __launch_bounds__(kRnThreads, 3) bn_stats_kernel(const RowNormParams p) {
   pdl_begin();
   extern __shared__ float sh[];
   const RnMap m = rn_map<V>(p.c);
@@ -103,30 +159,30 @@ __global__ void __launch_bounds__(kRnThreads) bn_stats_kernel(const RowNormParam
 #pragma unroll
   for (int i = 0; i < V; ++i) s[i] = q[i] = 0.f;
   if (m.active) {
-    const T* x = reinterpret_cast<const T*>(p.x) + m.vc * V;
-    // four independent 16-byte loads in flight per thread (the pass is pure HBM streaming)
+    // eight independent raw 16-byte loads in flight per thread (the pass is pure HBM streaming:
+    // 3 resident blocks x 256 threads x 8 x 16 B = 96 KB per SM)
+    constexpr int U = 8;
+    using Raw = typename RawOf<T, V>::type;
     const long long stride = (long long)gridDim.x * m.rpb;
-    long long r = (long long)blockIdx.x * m.rpb + m.rl;
-    for (; r + 3 * stride < p.n; r += 4 * stride) {
-      float f[4][V];
+    const T* xp = reinterpret_cast<const T*>(p.x) + m.vc * V +
+                  ((long long)blockIdx.x * m.rpb + m.rl) * p.ld_x;
+    const long long step = stride * p.ld_x;  // elements between two rows of this thread
+    for (long long r0 = (long long)blockIdx.x * m.rpb + m.rl; r0 < p.n; r0 += U * stride) {
+      Raw raw[U];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) load_vec<T, V>(x + (r + u * stride) * p.ld_x, f[u]);
+      for (int u = 0; u < U; ++u)
+        if (r0 + u * stride < p.n) raw[u] = load_raw<T, V>(xp + u * step);
+      xp += U * step;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < U; ++u) {
+        if (r0 + u * stride >= p.n) break;
+        float f[V];
+        unpack<T, V>(raw[u], f);
 #pragma unroll
         for (int i = 0; i < V; ++i) {
-          s[i] += f[u][i];
-          q[i] = fmaf(f[u][i], f[u][i], q[i]);
+          s[i] += f[i];
+          q[i] = fmaf(f[i], f[i], q[i]);
         }
-      }
-    }
-    for (; r < p.n; r += stride) {
-      float f[V];
-      load_vec<T, V>(x + r * p.ld_x, f);
-#pragma unroll
-      for (int i = 0; i < V; ++i) {
-        s[i] += f[i];
-        q[i] = fmaf(f[i], f[i], q[i]);
       }
     }
   }
@@ -134,8 +190,8 @@ __global__ void __launch_bounds__(kRnThreads) bn_stats_kernel(const RowNormParam
 }
 
 // ---- y = act(x * scale + shift (+ res)) -----------------------------------------------------------
-template <typename T, int V>
-__global__ void __launch_bounds__(kRnThreads) scale_shift_act_kernel(const RowNormParams p) {
+template <typename T, int V, bool RES>
+__global__ void __launch_bounds__(kRnThreads, WCN_RN_BF) scale_shift_act_kernel(const RowNormParams p) {
   pdl_begin();
   const RnMap m = rn_map<V>(p.c);
   if (!m.active) return;
@@ -147,31 +203,35 @@ __global__ void __launch_bounds__(kRnThreads) scale_shift_act_kernel(const RowNo
     sf[i] = __ldg(p.shift + ch);
   }
   const T* x = reinterpret_cast<const T*>(p.x) + m.vc * V;
-  const T* res = p.res ? reinterpret_cast<const T*>(p.res) + m.vc * V : nullptr;
+  const T* res = RES ? reinterpret_cast<const T*>(p.res) + m.vc * V : nullptr;
   T* y = reinterpret_cast<T*>(p.y) + m.vc * V;
-  constexpr int U = 2;  // rows in flight per thread
+  constexpr int U = RES ? 2 : WCN_RN_UF;  // rows in flight per thread
+  using Raw = typename RawOf<T, V>::type;
   const long long stride = (long long)gridDim.x * m.rpb;
   for (long long r0 = (long long)blockIdx.x * m.rpb + m.rl; r0 < p.n; r0 += U * stride) {
-    float f[U][V], g[U][V];
+    Raw rx[U], rr[RES ? U : 1];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long r = r0 + u * stride;
       if (r < p.n) {
-        load_vec<T, V>(x + r * p.ld_x, f[u]);
-        if (res) load_vec<T, V>(res + r * p.ld_res, g[u]);
+        rx[u] = load_raw<T, V>(x + r * p.ld_x);
+        if constexpr (RES) rr[u] = load_raw<T, V>(res + r * p.ld_res);
       }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long r = r0 + u * stride;
       if (r >= p.n) break;
+      float f[V], g[V];
+      unpack<T, V>(rx[u], f);
+      if constexpr (RES) unpack<T, V>(rr[u], g);
 #pragma unroll
       for (int i = 0; i < V; ++i) {
-        float v = fmaf(f[u][i], sc[i], sf[i]);
-        if (res) v += g[u][i];
-        f[u][i] = p.relu ? fmaxf(v, 0.f) : v;
+        float v = fmaf(f[i], sc[i], sf[i]);
+        if constexpr (RES) v += g[i];
+        f[i] = p.relu ? fmaxf(v, 0.f) : v;
       }
-      store_vec<T, V>(y + r * p.ld_y, f[u]);
+      store_vec<T, V>(y + r * p.ld_y, f);
     }
   }
 }
@@ -185,7 +245,7 @@ __global__ void __launch_bounds__(kRnThreads) scale_shift_act_kernel(const RowNo
 // MASK: 0 = no ReLU behind the norm, 1 = mask from the saved output y_in, 2 = mask recomputed from
 // x (x * mask_scale + mask_shift > 0). A template parameter: the unused paths cost registers.
 template <typename T, int V, int MASK>
-__global__ void __launch_bounds__(kRnThreads, 3) bn_bwd_reduce_kernel(const RowNormParams p) {
+__global__ void __launch_bounds__(kRnThreads, WCN_RN_BB) bn_bwd_reduce_kernel(const RowNormParams p) {
   pdl_begin();
   extern __shared__ float sh[];
   const RnMap m = rn_map<V>(p.c);
@@ -207,59 +267,49 @@ __global__ void __launch_bounds__(kRnThreads, 3) bn_bwd_reduce_kernel(const RowN
     const T* x = reinterpret_cast<const T*>(p.x) + m.vc * V;
     const T* dy = reinterpret_cast<const T*>(p.dy) + m.vc * V;
     const T* yin = MASK == 1 ? reinterpret_cast<const T*>(p.y_in) + m.vc * V : nullptr;
-    constexpr int U = 2;  // rows in flight per thread
+    constexpr int U = WCN_RN_UB;  // rows in flight per thread
+    using Raw = typename RawOf<T, V>::type;
     const long long stride = (long long)gridDim.x * m.rpb;
     for (long long r0 = (long long)blockIdx.x * m.rpb + m.rl; r0 < p.n; r0 += U * stride) {
-      float fx[U][V], fd[U][V], fy[MASK == 1 ? U : 1][V];
+      Raw rx[U], rd[U], ry[MASK == 1 ? U : 1];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const long long r = r0 + u * stride;
         if (r < p.n) {
-          load_vec<T, V>(x + r * p.ld_x, fx[u]);
-          load_vec<T, V>(dy + r * p.ld_dy, fd[u]);
-          if constexpr (MASK == 1) load_vec<T, V>(yin + r * p.ld_yin, fy[u]);
+          rx[u] = load_raw<T, V>(x + r * p.ld_x);
+          rd[u] = load_raw<T, V>(dy + r * p.ld_dy);
+          if constexpr (MASK == 1) ry[u] = load_raw<T, V>(yin + r * p.ld_yin);
         }
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         if (r0 + u * stride >= p.n) break;
+        float fx[V], fd[V], fy[V];
+        unpack<T, V>(rx[u], fx);
+        unpack<T, V>(rd[u], fd);
+        if constexpr (MASK == 1) unpack<T, V>(ry[u], fy);
 #pragma unroll
         for (int i = 0; i < V; ++i) {
           bool off = false;
-          if constexpr (MASK == 1) off = !(fy[u][i] > 0.f);
-          if constexpr (mask_x) off = !(fmaf(fx[u][i], msc[i], msh[i]) > 0.f);
-          const float d = off ? 0.f : fd[u][i];
+          if constexpr (MASK == 1) off = !(fy[i] > 0.f);
+          if constexpr (mask_x) off = !(fmaf(fx[i], msc[i], msh[i]) > 0.f);
+          const float d = off ? 0.f : fd[i];
           s1[i] += d;
-          s2[i] = fmaf(d, fx[u][i] - mu[i], s2[i]);
+          s2[i] = fmaf(d, fx[i] - mu[i], s2[i]);
         }
       }
     }
   }
-  // block merge; the second half leaves multiplied by rstd: sum dz * xhat = rstd * sum dz * (x - mean)
-  for (int i = threadIdx.x; i < 2 * p.c; i += kRnThreads) sh[i] = 0.f;
-  __syncthreads();
-  if (m.active) {
-#pragma unroll
-    for (int i = 0; i < V; ++i) {
-      const int ch = m.vc * V + i;
-      if (ch < p.c) {
-        atomicAdd(sh + ch, s1[i]);
-        atomicAdd(sh + p.c + ch, s2[i]);
-      }
-    }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 2 * p.c; i += kRnThreads) {
-    const float f = i < p.c ? 1.f : __ldg(p.mean_rstd + i);  // mean_rstd[c + ch] = rstd
-    atomicAdd(p.sums + i, (double)sh[i] * (double)f);
-  }
+  // block merge; the second half leaves multiplied by rstd (mean_rstd[c + ch]):
+  // sum dz * xhat = rstd * sum dz * (x - mean)
+  rn_merge<V>(m, p.c, s1, s2, p.sums, sh, p.mean_rstd);
 }
 
 // ---- backward apply: dx = gamma * rstd * (dz - s1/n - xhat * s2/n); dres = dz ----------------------
 // folded per channel into dx = A * dz + B * x + C (A = gamma * rstd, B = -A * rstd * s2/n,
 // C = -A * s1/n - B * mean): three constants + the two mask constants per channel in registers.
 template <typename T, int V, int MASK, bool TRAIN>
-__global__ void __launch_bounds__(kRnThreads, 3) bn_bwd_apply_kernel(const RowNormParams p) {
+__global__ void __launch_bounds__(kRnThreads, WCN_RN_BB) bn_bwd_apply_kernel(const RowNormParams p) {
   pdl_begin();
   const RnMap m = rn_map<V>(p.c);
   if (!m.active) return;
@@ -291,40 +341,44 @@ __global__ void __launch_bounds__(kRnThreads, 3) bn_bwd_apply_kernel(const RowNo
   const T* yin = MASK == 1 ? reinterpret_cast<const T*>(p.y_in) + m.vc * V : nullptr;
   T* dx = reinterpret_cast<T*>(p.y) + m.vc * V;
   T* dres = p.dres ? reinterpret_cast<T*>(p.dres) + m.vc * V : nullptr;
-  constexpr int U = 2;  // rows in flight per thread
+  constexpr int U = WCN_RN_UB;  // rows in flight per thread
+  using Raw = typename RawOf<T, V>::type;
   const long long stride = (long long)gridDim.x * m.rpb;
   for (long long r0 = (long long)blockIdx.x * m.rpb + m.rl; r0 < p.n; r0 += U * stride) {
-    float fx[TRAIN ? U : 1][V], fd[U][V], fy[MASK == 1 ? U : 1][V];
+    Raw rx[TRAIN ? U : 1], rd[U], ry[MASK == 1 ? U : 1];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long r = r0 + u * stride;
       if (r < p.n) {
-        load_vec<T, V>(dy + r * p.ld_dy, fd[u]);
-        if constexpr (MASK == 1) load_vec<T, V>(yin + r * p.ld_yin, fy[u]);
-        if constexpr (TRAIN) load_vec<T, V>(x + r * p.ld_x, fx[u]);
+        rd[u] = load_raw<T, V>(dy + r * p.ld_dy);
+        if constexpr (MASK == 1) ry[u] = load_raw<T, V>(yin + r * p.ld_yin);
+        if constexpr (TRAIN) rx[u] = load_raw<T, V>(x + r * p.ld_x);
       }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long r = r0 + u * stride;
       if (r >= p.n) break;
+      float fx[V], fd[V], fy[V];
+      unpack<T, V>(rd[u], fd);
+      if constexpr (TRAIN) unpack<T, V>(rx[u], fx);
       if constexpr (MASK == 1) {
+        unpack<T, V>(ry[u], fy);
 #pragma unroll
-        for (int i = 0; i < V; ++i) fd[u][i] = fy[u][i] > 0.f ? fd[u][i] : 0.f;
+        for (int i = 0; i < V; ++i) fd[i] = fy[i] > 0.f ? fd[i] : 0.f;
       } else if constexpr (mask_x) {
 #pragma unroll
-        for (int i = 0; i < V; ++i)
-          fd[u][i] = fmaf(fx[u][i], msc[i], msh[i]) > 0.f ? fd[u][i] : 0.f;
+        for (int i = 0; i < V; ++i) fd[i] = fmaf(fx[i], msc[i], msh[i]) > 0.f ? fd[i] : 0.f;
       }
-      if (dres) store_vec<T, V>(dres + r * p.ld_dres, fd[u]);
+      if (dres) store_vec<T, V>(dres + r * p.ld_dres, fd);
       if constexpr (TRAIN) {
 #pragma unroll
-        for (int i = 0; i < V; ++i) fd[u][i] = fmaf(ca[i], fd[u][i], fmaf(cb[i], fx[u][i], cc[i]));
+        for (int i = 0; i < V; ++i) fd[i] = fmaf(ca[i], fd[i], fmaf(cb[i], fx[i], cc[i]));
       } else {
 #pragma unroll
-        for (int i = 0; i < V; ++i) fd[u][i] *= ca[i];
+        for (int i = 0; i < V; ++i) fd[i] *= ca[i];
       }
-      store_vec<T, V>(dx + r * p.ld_y, fd[u]);
+      store_vec<T, V>(dx + r * p.ld_y, fd);
     }
   }
 }
@@ -361,16 +415,17 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, int n, int c
 enum RnKernel { kStats = 0, kApply = 1, kBwdReduce = 2, kBwdApply = 3 };
 
 // One full wave of resident blocks (grid-stride rows): blocks = SMs x occupancy of the kernel,
-// never more than the rows need.
+// never more than the rows need. Reductions: every block gets >= 8 row iterations (the per-block
+// merge is paid once per block).
 static int rn_grid(int n, int c, int v, int resident_per_sm, bool reduction) {
   const int vecs = (c + v - 1) / v;
   const int rpb = kRnThreads / vecs;
-  // reductions end with 2c fp64 atomics per block: give every block >= 32 row iterations
-  const long long rows_per_block = (long long)rpb * (reduction ? 32 : 1);
+  const long long rows_per_block = (long long)rpb * (reduction ? 8 : 1);
   long long blocks = ((long long)n + rows_per_block - 1) / rows_per_block;
   const long long cap = (long long)kNumSMsB200 * resident_per_sm;
   if (blocks > cap) blocks = cap;
-  return blocks < 1 ? 1 : (int)blocks;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
 }
 
 template <typename K>
@@ -384,12 +439,12 @@ static int rn_occupancy(K kernel, size_t smem) {
 
 template <typename T, int V>
 static int rn_launch_tv(int which, const RowNormParams& p, cudaStream_t s) {
-  const size_t sh = (size_t)2 * p.c * sizeof(float);
+  const size_t sh = (size_t)(kRnThreads / ((p.c + V - 1) / V)) * 2 * p.c * sizeof(float);  // [rpb][2c]
   static int occ[4] = {0, 0, 0, 0};  // per instantiation and kernel
   if (occ[which] == 0) {
     switch (which) {
       case kStats: occ[which] = rn_occupancy(bn_stats_kernel<T, V>, sh); break;
-      case kApply: occ[which] = rn_occupancy(scale_shift_act_kernel<T, V>, 0); break;
+      case kApply: occ[which] = rn_occupancy(scale_shift_act_kernel<T, V, true>, 0); break;
       case kBwdReduce: occ[which] = rn_occupancy(bn_bwd_reduce_kernel<T, V, 2>, sh); break;
       default: occ[which] = rn_occupancy(bn_bwd_apply_kernel<T, V, 2, true>, 0); break;
     }
@@ -397,7 +452,10 @@ static int rn_launch_tv(int which, const RowNormParams& p, cudaStream_t s) {
   const int grid = rn_grid(p.n, p.c, V, occ[which], which == kStats || which == kBwdReduce);
   switch (which) {
     case kStats: wcn_launch(bn_stats_kernel<T, V>, dim3(grid), dim3(kRnThreads), sh, s, p); break;
-    case kApply: wcn_launch(scale_shift_act_kernel<T, V>, dim3(grid), dim3(kRnThreads), 0, s, p); break;
+    case kApply:
+      if (p.res != nullptr) wcn_launch(scale_shift_act_kernel<T, V, true>, dim3(grid), dim3(kRnThreads), 0, s, p);
+      else wcn_launch(scale_shift_act_kernel<T, V, false>, dim3(grid), dim3(kRnThreads), 0, s, p);
+      break;
     case kBwdReduce: {
       const int mask = p.mask_scale != nullptr ? 2 : (p.y_in != nullptr ? 1 : 0);
       if (mask == 2) wcn_launch(bn_bwd_reduce_kernel<T, V, 2>, dim3(grid), dim3(kRnThreads), sh, s, p);
