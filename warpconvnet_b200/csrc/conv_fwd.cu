@@ -620,28 +620,45 @@ gather_gemm_kernel(const __grid_constant__ GatherGemmParams p) {
             __syncwarp();
             const int piece = lane & 15;
             const bool piece_ok = c0 * kElem + piece * 16 < p.bn * kElem;
+            // Branch-free store loop: the shared-memory read of an iteration never sits behind a
+            // branch, so the unrolled iterations overlap their shuffle / LDS / STG latencies. The
+            // statistics of this column chunk are accumulated from a zero-selected piece (rows
+            // past the end of the plan and pieces past bn contribute +0) and folded into the
+            // per-chunk registers once per chunk. (With a branch per row the STATS epilogue cost
+            // ~10 k cycles per 256-row tile against ~5 k without, profiles/r2v_epilogue.md.)
+            float cs[STATS ? kPieceElems : 1], cq[STATS ? kPieceElems : 1];
+            if constexpr (STATS) {
+#pragma unroll
+              for (int e = 0; e < kPieceElems; ++e) cs[e] = cq[e] = 0.f;
+            }
 #pragma unroll 4
             for (int rr = 0; rr < 16; ++rr) {
               const int row = 2 * rr + (lane >> 4);
               const int orow = __shfl_sync(0xffffffffu, out_row, row);
               const uint4 val =
                   ld_shared_v4(stage_warp + row * 256 + ((piece ^ (row & 15)) << 4));
-              if (orow >= 0 && piece_ok && !WCN_DBG(p, 1))  // debug 1: skip stores (bring-up)
+              const bool ok = orow >= 0 && piece_ok;
+              if (ok && !WCN_DBG(p, 1))  // debug 1: skip stores (bring-up)
                 *reinterpret_cast<uint4*>(out + (long long)orow * out_ld_bytes +
                                           (long long)(col_base + c0) * kElem + piece * 16) = val;
               if constexpr (STATS && !SWAP) {
-                if (orow >= 0 && piece_ok) {
-                  float fe[kPieceElems];
-                  unpack_piece<T>(val, fe);
+                float fe[kPieceElems];
+                unpack_piece<T>(ok ? val : make_uint4(0u, 0u, 0u, 0u), fe);  // +0.0 in every type
 #pragma unroll
-                  for (int cc = 0; cc < kStatChunks; ++cc) {  // static register indexing
-                    if (cc == ci) {
+                for (int e = 0; e < kPieceElems; ++e) {
+                  cs[e] += fe[e];
+                  cq[e] = fmaf(fe[e], fe[e], cq[e]);
+                }
+              }
+            }
+            if constexpr (STATS && !SWAP) {
 #pragma unroll
-                      for (int e = 0; e < kPieceElems; ++e) {
-                        st_s[cc][e] += fe[e];
-                        st_q[cc][e] = fmaf(fe[e], fe[e], st_q[cc][e]);
-                      }
-                    }
+              for (int cc = 0; cc < kStatChunks; ++cc) {  // static register indexing
+                if (cc == ci) {
+#pragma unroll
+                  for (int e = 0; e < kPieceElems; ++e) {
+                    st_s[cc][e] += cs[e];
+                    st_q[cc][e] += cq[e];
                   }
                 }
               }
