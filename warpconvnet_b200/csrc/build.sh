@@ -24,5 +24,5 @@ for f in cuhash coords conv_fwd conv_wgrad weight_prep knn rownorm conv_depthwis
   pids+=($!)
 done
 for p in "${pids[@]}"; do wait $p; done
-$NVCC -shared -o libwcn_b200.so build/cuhash.o build/coords.o build/conv_fwd.o build/conv_wgrad.o build/weight_prep.o build/knn.o build/rownorm.o build/conv_depthwise.o build/peer_allreduce.o build/capi.o
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o libwcn_b200.so build/cuhash.o build/coords.o build/conv_fwd.o build/conv_wgrad.o build/weight_prep.o build/knn.o build/rownorm.o build/conv_depthwise.o build/peer_allreduce.o build/capi.o
 echo "built $(pwd)/libwcn_b200.so"
