@@ -166,6 +166,14 @@ int wcn_build_tiles(const int32_t* table, int K, int M, const int32_t* sorted_ro
                     int m_pad, int32_t* step_nbr, int32_t* step_k, int32_t* rows_padded,
                     int32_t* tile_nk, int32_t* tile_cum, int n_range_ctas, int32_t* cta_units,
                     void* stream);
+/* Same, with the per-row offset masks of wcn_mask_keys / wcn_kernel_map_stats (bit k of
+ * row_masks[row] <=> table[k][row] >= 0; exact for K <= 64, ignored above; may be NULL): every row
+ * then reads only the table entries it has instead of all K. */
+int wcn_build_tiles_masked(const int32_t* table, int K, int M, const int32_t* sorted_rows,
+                           int tile_rows, int m_pad, int32_t* step_nbr, int32_t* step_k,
+                           int32_t* rows_padded, int32_t* tile_nk, int32_t* tile_cum,
+                           int n_range_ctas, int32_t* cta_units,
+                           const unsigned long long* row_masks, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Batched exact k-nearest-neighbour search for Points / PointConv                            */

@@ -71,6 +71,9 @@ SIGNATURES = {
                                        c_void_p]),
     "wcn_build_tiles": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "wcn_build_tiles_masked": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p,
+                                       c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                                       c_void_p, c_void_p]),
     "wcn_knn_workspace_bytes": (c_size_t, [c_int, c_int]),
     "wcn_knn_search": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int,
                                c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

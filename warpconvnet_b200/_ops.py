@@ -283,9 +283,14 @@ def build_tile_plan(table: Tensor, keys: Optional[Tensor] = None,
     # more than 128-row units): computed by the plan's scan kernel, read by the GEMM prologue
     n_range = min(_sm_count(dev), num_tiles * (tile_rows // TILE_M))
     cta_units = torch.empty(n_range + 1, dtype=torch.int32, device=dev) if n_range > 0 else None
-    check(lib.wcn_build_tiles(_p(table), K, M, _p(rows_sorted), tile_rows, m_pad, _p(step_nbr),
-                              _p(step_k), _p(rows), _p(tile_nk), _p(tile_cum), n_range,
-                              _p(cta_units), _stream()),
+    # the 64-bit row masks (when the caller has them: kernel_map_stats / mask_keys) let every row
+    # read only the table entries it has
+    row_masks = keys if (keys is not None and key_bits is None and K <= 64
+                         and keys.dtype in (torch.int64, torch.uint64)) else None
+    check(lib.wcn_build_tiles_masked(_p(table), K, M, _p(rows_sorted), tile_rows, m_pad,
+                                     _p(step_nbr), _p(step_k), _p(rows), _p(tile_nk),
+                                     _p(tile_cum), n_range, _p(cta_units), _p(row_masks),
+                                     _stream()),
           "build_tiles")
     return TilePlan(step_nbr, step_k, rows, tile_nk, tile_cum, K, M, m_pad, num_tiles, tile_rows,
                     cta_units, n_range)

@@ -29,7 +29,7 @@ size_t sort_workspace_bytes(int);
 int sort_rows_by_key(const unsigned long long*, int, int, int*, void*, size_t, cudaStream_t);
 int sort_rows_by_table(const int*, int, int, int*, void*, size_t, cudaStream_t);
 int build_tiles(const int*, int, int, const int*, int, int, int*, int*, int*, int*, int*, int, int*,
-                cudaStream_t);
+                const unsigned long long*, cudaStream_t);
 // coords.cu
 size_t coords_unique_workspace_bytes(long long);
 int coords_unique(const int*, int, int, int, int, const int*, int, int, int*, int*, int*, void*,
@@ -230,16 +230,36 @@ int wcn_sort_rows_by_table(const int32_t* table, int K, int M, int32_t* rows_out
   if (M > 0 && (!table || !rows_out || !workspace)) return kErrInvalidArg;
   return sort_rows_by_table(table, K, M, rows_out, workspace, workspace_bytes, S(stream));
 }
-int wcn_build_tiles(const int32_t* table, int K, int M, const int32_t* sorted_rows, int tile_rows,
-                    int m_pad, int32_t* step_nbr, int32_t* step_k, int32_t* rows_padded,
-                    int32_t* tile_nk, int32_t* tile_cum, int n_range_ctas, int32_t* cta_units,
-                    void* stream) {
+static int build_tiles_checked(const int32_t* table, int K, int M, const int32_t* sorted_rows,
+                               int tile_rows, int m_pad, int32_t* step_nbr, int32_t* step_k,
+                               int32_t* rows_padded, int32_t* tile_nk, int32_t* tile_cum,
+                               int n_range_ctas, int32_t* cta_units,
+                               const unsigned long long* row_masks, void* stream) {
   if (!tile_cum || !tile_nk) return kErrInvalidArg;
   if (m_pad > 0 && (!table || !sorted_rows || !step_nbr || !step_k || !rows_padded))
     return kErrInvalidArg;
   if (n_range_ctas < 0 || (n_range_ctas > 0 && !cta_units)) return kErrInvalidArg;
   return build_tiles(table, K, M, sorted_rows, tile_rows, m_pad, step_nbr, step_k, rows_padded,
-                     tile_nk, tile_cum, n_range_ctas, cta_units, S(stream));
+                     tile_nk, tile_cum, n_range_ctas, cta_units, row_masks, S(stream));
+}
+
+int wcn_build_tiles(const int32_t* table, int K, int M, const int32_t* sorted_rows, int tile_rows,
+                    int m_pad, int32_t* step_nbr, int32_t* step_k, int32_t* rows_padded,
+                    int32_t* tile_nk, int32_t* tile_cum, int n_range_ctas, int32_t* cta_units,
+                    void* stream) {
+  return build_tiles_checked(table, K, M, sorted_rows, tile_rows, m_pad, step_nbr, step_k,
+                             rows_padded, tile_nk, tile_cum, n_range_ctas, cta_units, nullptr,
+                             stream);
+}
+
+int wcn_build_tiles_masked(const int32_t* table, int K, int M, const int32_t* sorted_rows,
+                           int tile_rows, int m_pad, int32_t* step_nbr, int32_t* step_k,
+                           int32_t* rows_padded, int32_t* tile_nk, int32_t* tile_cum,
+                           int n_range_ctas, int32_t* cta_units,
+                           const unsigned long long* row_masks, void* stream) {
+  return build_tiles_checked(table, K, M, sorted_rows, tile_rows, m_pad, step_nbr, step_k,
+                             rows_padded, tile_nk, tile_cum, n_range_ctas, cta_units, row_masks,
+                             stream);
 }
 
 size_t wcn_knn_workspace_bytes(int n_ref, int n_batches) {

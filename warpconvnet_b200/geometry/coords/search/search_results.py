@@ -28,9 +28,78 @@ _PENDING_STATUS: List[tuple] = []
 _MAX_PENDING = 256
 
 
-def _register_pending(host: Tensor, event, on_ready) -> None:
-    if event is not None and on_ready is not None:
-        _PENDING_STATUS.append((host, event, on_ready))
+class _PinnedArena:
+    """ONE pinned allocation, cut into slots that the kernel-map builder takes round robin for its
+    asynchronous (offsets, status) read-back. ``torch.empty(pin_memory=True)`` per map looked free
+    (the caching host allocator reuses blocks) but is not: a block is only reusable once the copy
+    that wrote it has completed, so whenever the host runs further ahead of the GPU than ever
+    before, the allocator falls through to ``cudaHostAlloc`` — 10-30 ms of blocked host thread in
+    the middle of a step (the sporadic stalls of back-to-back eager steps: single steps of 4-33 ms
+    in a 1 ms/step loop, profiles/r2x_e2e_stalls.md)."""
+    SLOTS, WIDTH = 1024, 128
+
+    def __init__(self):
+        self.buf = torch.empty((self.SLOTS, self.WIDTH), dtype=torch.int32, pin_memory=True)
+        self.events = [None] * self.SLOTS
+        self.gen = [0] * self.SLOTS
+        self.next = 0
+
+    def acquire(self, n: int):
+        i = self.next
+        self.next = (i + 1) % self.SLOTS
+        ev = self.events[i]
+        if ev is not None and not ev.query():   # the GPU is 1024 maps behind: wait for it
+            ev.synchronize()
+        self.gen[i] += 1
+        return i, self.gen[i], self.buf[i, :n]
+
+
+_ARENA: Optional[_PinnedArena] = None
+
+
+class HostCopy:
+    """(offsets[K+1], status) of one deferred kernel map on its way to the host: a slot of the
+    pinned arena plus the event recorded behind the copy, or — built under CUDA-graph capture,
+    or when the slot has been handed out again since — the device tensor itself (read
+    synchronously when somebody asks)."""
+
+    def __init__(self, meta_dev: Tensor, asynchronous: bool):
+        global _ARENA
+        self.meta_dev = meta_dev
+        self.value: Optional[Tensor] = None
+        self.event = None
+        self.slot = -1
+        self.gen = 0
+        n = meta_dev.numel()
+        if asynchronous and n <= _PinnedArena.WIDTH:
+            if _ARENA is None:
+                _ARENA = _PinnedArena()
+            self.slot, self.gen, view = _ARENA.acquire(n)
+            view.copy_(meta_dev, non_blocking=True)
+            self.view = view
+            self.event = torch.cuda.Event()
+            self.event.record(torch.cuda.current_stream(meta_dev.device))
+            _ARENA.events[self.slot] = self.event
+
+    def ready(self) -> bool:
+        return self.value is not None or (self.event is not None and self.event.query())
+
+    def read(self) -> Tensor:
+        """CPU int32 [K + 2]; waits for the copy (or reads the device tensor) on first use."""
+        if self.value is None:
+            if self.event is not None:
+                self.event.synchronize()
+                if _ARENA.gen[self.slot] == self.gen:
+                    self.value = self.view.clone()
+            if self.value is None:              # no slot / slot reused since: synchronous read
+                self.value = self.meta_dev.cpu()
+            self.meta_dev = None
+        return self.value
+
+
+def _register_pending(host: "HostCopy", on_ready) -> None:
+    if host.event is not None and on_ready is not None:
+        _PENDING_STATUS.append((host, on_ready))
 
 
 def check_pending_kernel_maps(block: bool = False) -> int:
@@ -38,12 +107,11 @@ def check_pending_kernel_maps(block: bool = False) -> int:
     the host (``block=True``: waits for all of them — call it at the end of a step when a
     guaranteed check is wanted). Returns the number still in flight."""
     while _PENDING_STATUS:
-        host, event, on_ready = _PENDING_STATUS[0]
-        if not (block or len(_PENDING_STATUS) > _MAX_PENDING or event.query()):
+        host, on_ready = _PENDING_STATUS[0]
+        if not (block or len(_PENDING_STATUS) > _MAX_PENDING or host.ready()):
             break
-        event.synchronize()
         _PENDING_STATUS.pop(0)
-        on_ready(int(host[-1]))
+        on_ready(int(host.read()[-1]))
     return len(_PENDING_STATUS)
 
 
@@ -115,35 +183,31 @@ class IntSearchResult:
         self._symmetric = False
 
     @classmethod
-    def _from_device(cls, in_buf: Tensor, out_buf: Tensor, offsets_dev: Tensor, host: Tensor,
-                     event, on_ready, identity_map_index: Optional[int]) -> "IntSearchResult":
-        """host: pinned int32 [K + 2] receiving (offsets, status) asynchronously; event: recorded
-        after that copy; on_ready(status): raises the deferred hash-table errors."""
+    def _from_device(cls, in_buf: Tensor, out_buf: Tensor, offsets_dev: Tensor, host: "HostCopy",
+                     on_ready, identity_map_index: Optional[int]) -> "IntSearchResult":
+        """host: the (offsets, status) read-back in flight; on_ready(status): raises the deferred
+        hash-table errors."""
         self = cls.__new__(cls)
         self._in_maps = self._out_maps = self._offsets = None
         self._in_buf, self._out_buf = in_buf, out_buf
-        self._pending = (host, event, on_ready)
-        _register_pending(host, event, on_ready)
+        self._pending = (host, on_ready)
+        _register_pending(host, on_ready)
         self._init_common(identity_map_index, offsets_dev)
         return self
 
     def _resolve(self) -> None:
         if self._pending is None:
             return
-        host, event, on_ready = self._pending
+        host, on_ready = self._pending
         self._pending = None
         for i, entry in enumerate(_PENDING_STATUS):  # this map is checked right here
             if entry[0] is host:
                 del _PENDING_STATUS[i]
                 break
-        if event is not None:
-            event.synchronize()
-        else:
-            # built under CUDA-graph capture: `host` is the device tensor (offsets, status)
-            host = host.cpu()
+        meta = host.read()
         if on_ready is not None:
-            on_ready(int(host[-1]))
-        self._offsets = host[:-1].clone()
+            on_ready(int(meta[-1]))
+        self._offsets = meta[:-1].clone()
         n = int(self._offsets[-1])
         self._in_maps = self._in_buf[:n]
         self._out_maps = self._out_buf[:n]

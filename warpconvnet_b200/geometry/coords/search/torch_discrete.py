@@ -20,7 +20,7 @@ from torch import Tensor
 from warpconvnet_b200 import _ops
 from warpconvnet_b200.utils.ntuple import ntuple
 from .packed_hashmap import PackedHashTable
-from .search_results import IntSearchResult, check_pending_kernel_maps
+from .search_results import HostCopy, IntSearchResult, check_pending_kernel_maps
 
 _OFFSET_CACHE: Dict[tuple, Tensor] = {}
 _STATS_ON_SIDE = False  # True: statistics pass of a submanifold map on the CSR side stream (no gain
@@ -29,10 +29,6 @@ _STATS_ON_SIDE = False  # True: statistics pass of a submanifold map on the CSR 
 # it on surface data): a 27-offset map of 2.4 M voxels (MinkUNet-14 full resolution, 8 scenes)
 # stays on the sync-free path. Above it the exact length is read back (one host sync).
 _DEFERRED_MAX_PAIRS = 1 << 27
-
-
-def _pinned_host(n: int) -> Tensor:
-    return torch.empty(n, dtype=torch.int32, pin_memory=True)
 
 
 _SIDE_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
@@ -177,17 +173,13 @@ def generate_kernel_map(
             # travel to pinned host memory asynchronously and are only waited for when somebody
             # reads `offsets` / `in_maps` / `out_maps` on the host (IntSearchResult._resolve).
             meta = torch.cat([offsets_dev, table.status_tensor])
-            if torch.cuda.is_current_stream_capturing():
-                host, event = meta, None  # read back (synchronously) only if somebody asks later
-            else:
-                host = _pinned_host(K + 2)
-                host.copy_(meta, non_blocking=True)
-                event = torch.cuda.Event()
-                event.record(side)
+            # under capture: read back (synchronously) only if somebody asks later
+            host = HostCopy(meta, asynchronous=not torch.cuda.is_current_stream_capturing())
             in_maps, out_maps = _ops.kernel_map_scatter(pair_table, block_counts, offsets_dev,
                                                         K * n_out)
-            result = IntSearchResult._from_device(in_maps, out_maps, offsets_dev, host, event,
+            result = IntSearchResult._from_device(in_maps, out_maps, offsets_dev, host,
                                                   table.raise_if_failed, identity_map_index)
+            host = meta
         else:
             # very large K * M: allocate the exact length instead (one host sync)
             host = torch.cat([offsets_dev, table.status_tensor]).cpu()
