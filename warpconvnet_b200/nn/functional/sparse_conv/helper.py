@@ -91,9 +91,10 @@ def spatially_sparse_conv(input_sparse_tensor, weight, kernel_size, stride=1, ke
         w0 = weight[0]
         if w0.dim() == 3:  # grouped [G, cin_g, cout_g] -> block diagonal
             w0 = torch.block_diag(*w0.unbind(0))
-        out = feats @ w0.to(feats.dtype)
-        if bias is not None:
-            out = out + bias.to(out.dtype)
+        if bias is not None:  # bias in the GEMM epilogue (one pass less over the output)
+            out = torch.addmm(bias.to(feats.dtype), feats, w0.to(feats.dtype))
+        else:
+            out = feats @ w0.to(feats.dtype)
         return input_sparse_tensor.replace(batched_features=out)
 
     in_tensor_stride = input_sparse_tensor.tensor_stride
