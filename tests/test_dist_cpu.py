@@ -86,3 +86,16 @@ def test_two_rank_wgrad_allreduce_gloo():
     assert np.allclose(wgrad, full.float().numpy(), rtol=1e-5, atol=1e-5)
     assert np.allclose(t, full.float().numpy(), rtol=1e-5, atol=1e-5)
     assert np.allclose(bgrad, 3.0)
+
+
+def test_flat_grad_bucket_peer_request_without_a_process_group_uses_the_plain_buffer():
+    """peer=True needs an initialised multi-rank group (symmetric memory); in a single process the
+    bucket silently keeps its ordinary buffer and all_reduce is a no-op."""
+    import torch
+    from warpconvnet_b200.dist import FlatGradBucket
+    lin = torch.nn.Linear(4, 3)
+    bucket = FlatGradBucket(lin.parameters(), peer=True)
+    assert bucket.peer is None and bucket.flat.numel() == 4 * 3 + 3
+    lin(torch.ones(2, 4)).sum().backward()
+    assert lin.weight.grad.data_ptr() == bucket.flat.data_ptr()
+    assert bucket.all_reduce(average=True) is None

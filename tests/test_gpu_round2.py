@@ -658,3 +658,51 @@ def test_peer_allreduce_rejects_bad_arguments():
     assert lib.wcn_peer_allreduce_f32(arr, arr, 0, 2, 1024, ctypes.c_float(1.0), 8, None) < 0
     assert lib.wcn_peer_allreduce_f32(arr, arr, 0, 2, 1023, ctypes.c_float(1.0), 8, None) < 0
     assert lib.wcn_peer_allreduce_f32(arr, arr, 2, 2, 1024, ctypes.c_float(1.0), 8, None) < 0
+
+
+# ------------------------------------------------------------------------------------------------
+# masked tile build, pinned arena
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_build_tiles_masked_equals_the_unmasked_build():
+    """wcn_build_tiles_masked (rows read only the table entries their mask has) produces the same
+    plan as wcn_build_tiles, for a submanifold and a strided map."""
+    from warpconvnet_b200 import _ops
+    from warpconvnet_b200.geometry.coords.search.torch_discrete import generate_kernel_map
+    c = torch.from_numpy(surface_coords(150, 3))
+    bc = torch.cat([torch.zeros(len(c), 1, dtype=torch.int32), c], 1).cuda()
+    from warpconvnet_b200.geometry.coords.ops.stride import stride_coords
+    out_bc, _ = stride_coords(bc, (2, 2, 2), n_batches=1)
+    for in_c, out_c, stride, ks in ((bc, bc, (1, 1, 1), (3, 3, 3)), (bc, out_bc, (2, 2, 2), (2, 2, 2))):
+        km = generate_kernel_map(in_c, out_c, stride, ks, build_plan=False)
+        table = km.pair_table(out_c.shape[0])
+        keys = _ops.mask_keys(table)
+        masked = _ops.build_tile_plan(table, keys)          # passes the row masks
+        plain = _ops.build_tile_plan(table, keys, key_bits=table.shape[0])  # same order, no masks
+        assert torch.equal(masked.rows, plain.rows)
+        assert torch.equal(masked.tile_nk, plain.tile_nk) and torch.equal(masked.tile_cum, plain.tile_cum)
+        for t in range(masked.num_tiles):
+            n = int(masked.tile_nk[t])
+            assert torch.equal(masked.step_k[t, :n], plain.step_k[t, :n])
+            assert torch.equal(masked.step_nbr[t, :n], plain.step_nbr[t, :n])
+
+
+@pytest.mark.gpu
+def test_deferred_read_back_survives_reuse_of_its_pinned_slot(monkeypatch):
+    """The (offsets, status) read-back of a kernel map goes through a slot of one pinned arena; a
+    map that is only resolved after its slot has been handed out again reads the device copy."""
+    from warpconvnet_b200.geometry.coords.search import search_results as sr
+    from warpconvnet_b200.geometry.coords.search.torch_discrete import generate_kernel_map
+    monkeypatch.setattr(sr._PinnedArena, "SLOTS", 4)
+    monkeypatch.setattr(sr, "_ARENA", None)
+    maps, want = [], []
+    for seed in range(10):
+        c = torch.from_numpy(random_coords(400 + 37 * seed, 0.3, seed))
+        bc = torch.cat([torch.zeros(len(c), 1, dtype=torch.int32), c], 1).cuda()
+        maps.append(generate_kernel_map(bc, bc, (1, 1, 1), (3, 3, 3), same_coords=True))
+        ref = okm.generate_kernel_map(bc.cpu().numpy(), bc.cpu().numpy(), (1, 1, 1), (3, 3, 3))
+        want.append(np.asarray(ref["offsets"]))
+    torch.cuda.synchronize()
+    for km, w in zip(maps, want):          # the first six lost their slots to later maps
+        assert np.array_equal(km.offsets.numpy().astype(np.int64), np.asarray(w).astype(np.int64))
+    monkeypatch.setattr(sr, "_ARENA", None)
