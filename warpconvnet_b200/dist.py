@@ -121,10 +121,21 @@ class PeerAllReduce:
         self.n_ctas = int(n_ctas)
         words = int(lib.wcn_peer_allreduce_flag_words())
         self._timeout_word = int(lib.wcn_peer_allreduce_timeout_word())
-        self._data = symm_mem.empty(self.n, dtype=torch.float32, device=device)
-        self._flags = symm_mem.empty(words, dtype=torch.int32, device=device)
-        self._data.zero_()
-        self._flags.zero_()
+        # the allocation is local and may fail on one rank only; the rendezvous below is collective:
+        # agree first, so that every rank either goes on or raises (callers fall back to NCCL)
+        err = None
+        try:
+            self._data = symm_mem.empty(self.n, dtype=torch.float32, device=device)
+            self._flags = symm_mem.empty(words, dtype=torch.int32, device=device)
+            self._data.zero_()
+            self._flags.zero_()
+        except Exception as exc:  # pragma: no cover - depends on the driver / allocator state
+            err = exc
+        ok = torch.tensor([0 if err is not None else 1], dtype=torch.int32, device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 0:
+            raise RuntimeError("symmetric memory allocation failed on some rank"
+                               + (f": {err}" if err is not None else ""))
         try:
             self._h_data = symm_mem.rendezvous(self._data, group)
             self._h_flags = symm_mem.rendezvous(self._flags, group)
