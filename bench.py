@@ -212,7 +212,7 @@ def run_c4(dev, rank, world, dist, steps=10, warmup=3):
     bucket = None
     if world > 1:
         try:  # gradients in NVLink peer-mapped memory, reduced by the library's own kernel
-            bucket = FlatGradBucket(net.parameters(), peer=True)
+            bucket = FlatGradBucket(net.parameters(), peer=True, sections=4)
         except Exception:  # symmetric memory unavailable: NCCL
             bucket = FlatGradBucket(net.parameters())
     cached_vox = Voxels(coords, feats)
@@ -299,7 +299,8 @@ def run_c4(dev, rank, world, dist, steps=10, warmup=3):
                   "as one CUDA graph; eager_wall = host wall clock of the same eager steps",
         "grad_allreduce_bytes": int(bucket.flat.numel() * 4) if bucket is not None else 0,
         "grad_allreduce": ("none" if bucket is None else
-                           "own peer-memory kernel (wcn_peer_allreduce_f32)" if bucket.peer is not None
+                           "own peer-memory kernel (wcn_peer_allreduce_f32), 4 sections launched by "
+                           "post-accumulate hooks during backward" if bucket.peer is not None
                            else "NCCL"),
         "peak_mem_GiB": torch.cuda.max_memory_allocated() / 2 ** 30,
         "steps": steps, "warmup": warmup,

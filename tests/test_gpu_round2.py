@@ -706,3 +706,22 @@ def test_deferred_read_back_survives_reuse_of_its_pinned_slot(monkeypatch):
     for km, w in zip(maps, want):          # the first six lost their slots to later maps
         assert np.array_equal(km.offsets.numpy().astype(np.int64), np.asarray(w).astype(np.int64))
     monkeypatch.setattr(sr, "_ARENA", None)
+
+
+@pytest.mark.gpu
+def test_peer_gradient_bucket_sections_two_ranks():
+    """FlatGradBucket(peer=True, sections=k): sections reduced by post-accumulate hooks during
+    backward equal the NCCL mean, eagerly and replayed from a CUDA graph (needs two GPUs)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import json
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", "29534",
+           os.path.join(root, "tools", "exp_peer_bucket.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr[-2000:]
+    out = json.loads([ln for ln in res.stdout.splitlines() if ln.startswith("{")][-1])
+    for k in ("sections1", "sections3", "sections5"):
+        assert out[k]["max_rel_err_vs_nccl_mean"] < 1e-5 and out[k]["timeouts"] == 0

@@ -37,18 +37,26 @@ class FlatGradBucket:
     ``zero_grad(set_to_none=False)``) between steps to keep the views and skip that copy."""
 
     def __init__(self, params: Iterable[torch.nn.Parameter], peer: bool = False,
-                 peer_ctas: int = 64):
+                 peer_ctas: int = 64, sections: int = 1):
         """``peer``: keep the buffer in NVLink peer-mapped memory and reduce it with this
-        library's own kernel (``PeerAllReduce``) instead of an NCCL collective."""
+        library's own kernel (``PeerAllReduce``) instead of an NCCL collective. ``sections`` > 1
+        (peer only): the buffer is cut into that many pieces and the reduction of a piece is
+        launched — on a side stream, by a post-accumulate hook — as soon as every gradient that
+        overlaps it has been produced, so it runs under the rest of backward (what DDP does with
+        its buckets); ``all_reduce()`` launches what is left and joins."""
         self.params = [p for p in params if p.requires_grad]
         if not self.params:
             raise ValueError("no trainable parameters")
         dev = self.params[0].device
         total = sum(p.numel() for p in self.params)
         self.peer = None
+        self._sections: List[tuple] = []
         if peer and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            self.peer = PeerAllReduce(total, dev, n_ctas=peer_ctas)
+            n_sec = max(1, int(sections))
+            self.peer = PeerAllReduce(total, dev, n_ctas=peer_ctas, n_sections=n_sec)
             self.flat = self.peer.buffer
+            if n_sec > 1:
+                self._setup_sections(n_sec, total)
         else:
             self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
         self._slots = []
@@ -58,6 +66,50 @@ class FlatGradBucket:
             self._slots.append(self.flat[off:off + n].view_as(p))
             off += n
         self.bind()
+
+    # ---- sections: pieces of the peer buffer reduced while backward is still running ------------
+    def _setup_sections(self, n_sec: int, total: int) -> None:
+        n_pad = self.peer.n
+        bounds = [min(n_pad, (n_pad * k // n_sec) // 4 * 4) for k in range(n_sec)] + [n_pad]
+        starts, off = [], 0
+        for p in self.params:
+            starts.append(off)
+            off += p.numel()
+        for k in range(n_sec):
+            lo, hi = bounds[k], bounds[k + 1]
+            members = [i for i, p in enumerate(self.params)
+                       if starts[i] < hi and starts[i] + p.numel() > lo]
+            self._sections.append((lo, hi - lo, members))
+        self._of_param = [[k for k, (_, _, m) in enumerate(self._sections) if i in m]
+                          for i in range(len(self.params))]
+        self._ar_stream = torch.cuda.Stream(device=self.flat.device)
+        self._average = True
+        self._reset_sections()
+        for i, p in enumerate(self.params):
+            p.register_post_accumulate_grad_hook(lambda _p, i=i: self._grad_ready(i))
+
+    def _reset_sections(self) -> None:
+        self._seen = [False] * len(self.params)
+        self._left = [len(m) for _, _, m in self._sections]
+        self._launched = [False] * len(self._sections)
+
+    def _launch_section(self, k: int) -> None:
+        lo, length, _ = self._sections[k]
+        self._launched[k] = True
+        cur = torch.cuda.current_stream(self.flat.device)
+        self._ar_stream.wait_stream(cur)
+        with torch.cuda.stream(self._ar_stream):
+            self.peer.all_reduce_section_(k, lo, length, average=self._average)
+
+    def _grad_ready(self, i: int) -> None:
+        p = self.params[i]
+        if self._seen[i] or p.grad is None or p.grad.data_ptr() != self._slots[i].data_ptr():
+            return  # accumulated twice (shared parameter) or not bound: all_reduce() picks it up
+        self._seen[i] = True
+        for k in self._of_param[i]:
+            self._left[k] -= 1
+            if self._left[k] == 0 and not self._launched[k]:
+                self._launch_section(k)
 
     def bind(self) -> int:
         """Point every ``param.grad`` at its slot; returns how many had to be re-bound."""
@@ -74,6 +126,10 @@ class FlatGradBucket:
             rebound += 1
         return rebound
 
+    def set_average(self, average: bool) -> None:
+        """What the section launches made during backward apply (default: the mean)."""
+        self._average = bool(average)
+
     def zero(self) -> None:
         self.flat.zero_()
         self.bind()
@@ -85,7 +141,24 @@ class FlatGradBucket:
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
             self.bind()
             return None
-        self.bind()
+        rebound = self.bind()
+        if self.peer is not None and self._sections:
+            # sections launched by the hooks reduced what their gradients held at that time: if a
+            # gradient had to be re-bound (copied into its slot just now) the early launches were
+            # made with the wrong ``average`` or stale data — not supported, say so
+            if rebound and any(self._launched):
+                raise RuntimeError("FlatGradBucket(sections > 1) needs .grad to stay bound during "
+                                   "backward: use bucket.zero() instead of zero_grad(set_to_none=True)")
+            if average != self._average and any(self._launched):
+                raise RuntimeError("FlatGradBucket(sections > 1): all_reduce(average=...) must match "
+                                   "bucket.set_average(...) used by the early launches")
+            self._average = average
+            for k in range(len(self._sections)):
+                if not self._launched[k]:
+                    self._launch_section(k)
+            torch.cuda.current_stream(self.flat.device).wait_stream(self._ar_stream)
+            self._reset_sections()
+            return None
         if self.peer is not None:  # stream-ordered kernel: nothing to wait for
             self.peer.all_reduce_(average=average)
             return None
@@ -106,7 +179,10 @@ class PeerAllReduce:
     ``torch.distributed._symmetric_memory`` is used for the allocation and the handle exchange
     only. Single node; every rank constructs it and calls ``all_reduce_()`` in the same order."""
 
-    def __init__(self, numel: int, device, group=None, n_ctas: int = 32):
+    def __init__(self, numel: int, device, group=None, n_ctas: int = 32, n_sections: int = 1):
+        """``n_sections`` > 1: the buffer can also be reduced piecewise (``all_reduce_section_``),
+        every section through its own flag block, so several sections may be in flight at once
+        (gradient buckets launched while backward is still running)."""
         import ctypes
 
         import torch.distributed._symmetric_memory as symm_mem
@@ -120,13 +196,15 @@ class PeerAllReduce:
         self.n = (int(numel) + 3) // 4 * 4
         self.n_ctas = int(n_ctas)
         words = int(lib.wcn_peer_allreduce_flag_words())
+        self._words = words
+        self.n_sections = max(1, int(n_sections))
         self._timeout_word = int(lib.wcn_peer_allreduce_timeout_word())
         # the allocation is local and may fail on one rank only; the rendezvous below is collective:
         # agree first, so that every rank either goes on or raises (callers fall back to NCCL)
         err = None
         try:
             self._data = symm_mem.empty(self.n, dtype=torch.float32, device=device)
-            self._flags = symm_mem.empty(words, dtype=torch.int32, device=device)
+            self._flags = symm_mem.empty(words * self.n_sections, dtype=torch.int32, device=device)
             self._data.zero_()
             self._flags.zero_()
         except Exception as exc:  # pragma: no cover - depends on the driver / allocator state
@@ -152,17 +230,33 @@ class PeerAllReduce:
     def timeouts(self) -> int:
         """Barrier waits that gave up (10 s) since construction — synchronises; non-zero means a
         peer never arrived and the buffer is not a valid sum."""
-        return int(self._flags[self._timeout_word].item())
+        return int(self._flags.view(self.n_sections, self._words)[:, self._timeout_word].sum().item())
 
     def all_reduce_(self, average: bool = False) -> torch.Tensor:
-        from ._lib import check, lib
-        import ctypes
-        scale = ctypes.c_float(1.0 / self.world if average else 1.0)   # applied inside the kernel
-        check(lib.wcn_peer_allreduce_f32(self._bufs, self._flag_ptrs, self.rank, self.world, self.n,
-                                         scale, self.n_ctas,
-                                         torch.cuda.current_stream().cuda_stream),
-              "peer_allreduce")
+        """The whole buffer (through the flag block of section 0)."""
+        self.all_reduce_section_(0, 0, self.n, average)
         return self.buffer
+
+    def all_reduce_section_(self, section: int, start: int, length: int, average: bool = False) -> None:
+        """Elements [start, start + length) (both multiples of 4) through flag block ``section``.
+        Every rank issues the same sections; a section must not be issued again before its
+        previous reduction has been ordered before the new one on this rank (same stream, or a
+        stream dependency)."""
+        import ctypes
+
+        from ._lib import check, lib
+        if not (0 <= section < self.n_sections) or start % 4 or length % 4 or start < 0 \
+                or start + length > self.n:
+            raise ValueError("bad section / range")
+        if length == 0:
+            return
+        arr = ctypes.c_void_p * self.world
+        bufs = arr(*[int(p) + 4 * start for p in self._bufs])
+        flags = arr(*[int(p) + 4 * self._words * section for p in self._flag_ptrs])
+        scale = ctypes.c_float(1.0 / self.world if average else 1.0)   # applied inside the kernel
+        check(lib.wcn_peer_allreduce_f32(bufs, flags, self.rank, self.world, length, scale,
+                                         self.n_ctas, torch.cuda.current_stream().cuda_stream),
+              "peer_allreduce")
 
 
 def all_reduce_wgrad(tensors: Sequence[torch.Tensor], average: bool = False) -> None:
