@@ -451,6 +451,94 @@ def run_side_blocks(dev, flush):
     return blocks
 
 
+def run_c5(dev, rank, world, dist, flush):
+    """BASELINE config C5 at its stated scale, STRONG scaling over the ranks: 8 scenes x 125 316
+    voxels (1.0 M voxels) through SparseConv3d(512, 512, 3, groups=64) fwd + dgrad + wgrad (+ the
+    all-reduce of dW), and 8 clouds x 125 000 points (1.0 M points) through
+    PointConv(64, 64, knn_k=16) fwd + bwd; every rank owns 8 / world scenes and clouds."""
+    from warpconvnet_b200.dist import shard_scenes
+    from warpconvnet_b200.geometry.coords.search.search_configs import RealSearchConfig
+    from warpconvnet_b200.geometry.coords.search.torch_discrete import generate_kernel_map
+    from warpconvnet_b200.geometry.types.points import Points
+    from warpconvnet_b200.nn.functional.sparse_conv import (sparse_conv_dgrad, sparse_conv_forward,
+                                                            sparse_conv_wgrad)
+    from warpconvnet_b200.nn.modules.point_conv import PointConv
+    mine = shard_scenes(8, rank, world)
+
+    def timed(fn, k=5, w=2):
+        for _ in range(w):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+        evs = []
+        for _ in range(k):
+            flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        t = torch.tensor([float(np.mean([a.elapsed_time(b) for a, b in evs]))], device=dev,
+                         dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    base = make_coords("S", 0)
+    c5 = base[(base[:, 0] < 354) & (base[:, 1] < 354)]
+    per = len(c5)
+    bc = torch.from_numpy(np.concatenate(
+        [np.concatenate([np.full((per, 1), b, np.int32), c5], 1) for b in range(len(mine))], 0)).to(dev)
+    n_local = bc.shape[0]
+    km = generate_kernel_map(bc, bc, (1, 1, 1), (3, 3, 3), same_coords=True)
+    g = torch.Generator(device=dev).manual_seed(50 + rank)
+    x = torch.randn(n_local, 512, device=dev, generator=g).bfloat16()
+    gy = torch.randn(n_local, 512, device=dev, generator=g).bfloat16()
+    w = (torch.randn(27, 64, 8, 8, device=dev, generator=g) * (27 * 8) ** -0.5).bfloat16()
+
+    def gstep():
+        sparse_conv_forward(x, w, km, n_local, groups=64)
+        sparse_conv_dgrad(gy, w, km, n_local, groups=64)
+        dw = sparse_conv_wgrad(x, gy, tuple(w.shape), km, groups=64)
+        if world > 1:
+            dist.all_reduce(dw)
+
+    t_g = timed(gstep)
+    npts = 125000
+    gp = torch.Generator().manual_seed(5 + rank)
+    pts = torch.rand(npts * len(mine), 3, generator=gp).to(dev)
+    pf = torch.randn(npts * len(mine), 64, generator=gp).to(dev)
+    offs = torch.arange(len(mine) + 1, dtype=torch.int64) * npts
+    torch.manual_seed(0)
+    pconv = PointConv(64, 64, RealSearchConfig("knn", knn_k=16)).to(dev)
+
+    def pstep():
+        pconv.zero_grad(set_to_none=True)
+        pc = Points(pts, pf.detach().requires_grad_(True), offsets=offs)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out_pc = pconv(pc)
+        out_pc.feature_tensor.float().square().mean().backward()
+        if world > 1:
+            for q in pconv.parameters():
+                if q.grad is not None:
+                    dist.all_reduce(q.grad)
+
+    t_pc = timed(pstep, k=3, w=2)
+    out = {"workload": "C5: SparseConv3d(512,512,3,groups=64) on 8 scenes x %d voxels fwd+dgrad+wgrad"
+                       "(+all-reduce dW); PointConv(64,64,knn_k=16) on 8 clouds x %d points fwd+bwd"
+                       "(+all-reduce grads), bf16, kernel map / kNN built once for the group conv, "
+                       "kNN rebuilt every PointConv step" % (per, npts),
+           "scaling": "strong", "n_gpus": world, "scenes_per_rank": len(mine),
+           "voxels_total": 8 * per, "points_total": 8 * npts,
+           "group_conv_fwd_bwd_ms": t_g, "group_conv_voxels_per_s": 8 * per / (t_g * 1e-3),
+           "pointconv_fwd_bwd_ms": t_pc, "pointconv_points_per_s": 8 * npts / (t_pc * 1e-3),
+           "timing": "CUDA events per step, mean over steps, max over ranks; L2 flushed before each step"}
+    del x, gy, km, pts, pf, pconv
+    torch.cuda.empty_cache()
+    return out
+
+
 def bind_to_gpu_numa_node(local_rank: int):
     """Pin this process (and therefore the pinned host buffers it allocates afterwards) to the CPU
     cores of the NUMA node its GPU hangs off, so the per-step H2D copies of the e2e loop do not
@@ -770,6 +858,16 @@ def run_ours(args):
                   "trace": traceback.format_exc()[-800:]}
             torch.cuda.synchronize()
 
+    c5 = None
+    if not args.no_c4:
+        try:
+            c5 = run_c5(dev, rank, world, dist, flush)
+        except Exception as exc:  # pragma: no cover
+            import traceback
+            c5 = {"error": f"{type(exc).__name__}: {str(exc)[:300]}",
+                  "trace": traceback.format_exc()[-800:]}
+            torch.cuda.synchronize()
+
     peaks = load_peaks()
     steps_total = int(plan.tile_nk.sum().item())
     # Secondary (informational) bound, DESIGN.md 4.3: every gathered row crosses the L2->SM path
@@ -841,6 +939,7 @@ def run_ours(args):
         "phases_ms": phases,
         "wall_s_timed_region": wall,
         "c4": c4,
+        "c5": c5,
         "ref_gpu": ref_gpu,
     }
     out.update(side)
@@ -900,7 +999,7 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA graph replay")
-    ap.add_argument("--no-c4", action="store_true", help="skip the MinkUNet-14 (config C4) block")
+    ap.add_argument("--no-c4", action="store_true", help="skip the MinkUNet-14 (config C4) and C5 blocks")
     ap.add_argument("--no-side", action="store_true", help="skip the C3-R / C2 / C5 side blocks")
     ap.add_argument("--ref-gpu", default="kmap,c3s", help="sections of tools/ref_gpu_bench.py to run "
                     "against the built reference (N = 1 only): kmap,c3s,c3r,c4 or 'none'; c4 needs "
